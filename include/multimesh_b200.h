@@ -1,0 +1,198 @@
+/*
+ * multimesh_b200.h -- C-ABI of the B200-native mesh-to-mesh interpolation path.
+ *
+ * This is the drop-in boundary for the hot path of solvithrastar/MultiMesh: every entry point
+ * below names the reference interface it replaces (paths relative to the reference root).
+ * Conventions:
+ *   - extern "C", plain pointers and sizes, no torch / C++ types;
+ *   - mm_* functions take DEVICE pointers (sm_100a, CUDA 12.9), caller-owned buffers,
+ *     a cudaStream_t passed as void*, and return 0 (MM_OK) or a negative error code;
+ *     mm_last_error() returns a thread-local message for the last failure;
+ *   - base pointers of double arrays must be 16-byte aligned (bulk-async copies);
+ *   - no hidden allocation except the opaque mm_index handle (create/destroy);
+ *   - no global mutable state besides per-device constant tables; thread-safe per handle+stream;
+ *   - the two legacy symbols `centroid` and `triLinearInterpolator` keep the reference's exact
+ *     signatures and operate on HOST pointers, so multi_mesh/helpers.py:load_lib() keeps working.
+ * There is NO CPU fallback: without a CUDA device every mm_* call fails with MM_ERR_CUDA.
+ *
+ * All floating-point work is IEEE binary64 in a documented operation order and
+ * matches the CPU oracle bit for bit.
+ */
+#ifndef MULTIMESH_B200_H
+#define MULTIMESH_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MM_OK 0
+#define MM_ERR_INVALID (-1)     /* bad argument (order/dim/k/alignment/null pointer) */
+#define MM_ERR_CUDA (-2)        /* CUDA runtime error or no device */
+#define MM_ERR_UNSUPPORTED (-3) /* valid request outside the implemented range */
+#define MM_ERR_NOMEM (-4)
+
+#define MM_VERSION 100
+
+int mm_version(void);
+const char *mm_last_error(void);
+
+/* ------------------------------------------------------------------------------------------
+ * K0  element geometry: centroid (sequential mean of the P control nodes) and inclusive AABB.
+ * Replaces: SalvusMesh.get_element_centroids (components/salvus_mesh_reader.py:99-100),
+ *           _find_gll_centroids (components/interpolator.py:1389-1406),
+ *           the min/max of boundary_box_check (components/interpolator.py:1360).
+ *   nodes    [E][P][dim] f64, P = (order+1)^dim
+ *   centroid [E][dim]    f64 (out, may be NULL)
+ *   aabb     [E][2][dim] f64 (out, may be NULL): row 0 = min, row 1 = max
+ * ---------------------------------------------------------------------------------------- */
+int mm_element_geometry(int order, int dim, int64_t E, const double *nodes, double *centroid,
+                        double *aabb, void *stream);
+
+/* In-place x <- x * r_earth * z_node_1D / |x| for |x| > 0.
+ * Replaces: map_to_sphere (components/interpolator.py:1125-1144). nodes [n][3], radius_1d [n]. */
+int mm_map_to_sphere(int64_t n, double *nodes, const double *radius_1d, double r_earth,
+                     void *stream);
+
+/* ------------------------------------------------------------------------------------------
+ * K1  spatial index (uniform grid, counting-sorted) + exact k-nearest-neighbour query.
+ * Replaces: pykdtree KDTree(data) and .query(pts, k)  (components/interpolator.py:101-105,
+ *           255-264, 363-373, 515-522, 678, 751-756, 898-902, 949-951, 1053, 1176-1178;
+ *           utils.py:199-200).
+ * Neighbour order is the canonical total order (d2, index) with
+ *   d2 = (dx*dx + dy*dy) + dz*dz evaluated in binary64 without FMA,
+ * which fixes the tie order a KD-tree leaves implementation-defined.
+ * ---------------------------------------------------------------------------------------- */
+typedef struct mm_index mm_index_t;
+
+/* points [M][dim] f64 (device); the index keeps its own sorted copy. Synchronises the stream. */
+int mm_index_create(mm_index_t **out, int dim, int64_t M, const double *points, void *stream);
+int mm_index_destroy(mm_index_t *index);
+/* info[0]=M, info[1]=dim, info[2..4]=cells per axis, info[5]=non-empty cells, info[6]=bytes held */
+int mm_index_info(const mm_index_t *index, int64_t info[8], double *cell_size);
+
+/* idx [N][k] int32 (out): neighbour ids divided (integer division) by `divisor`
+ *   divisor = 1: plain ids;  divisor = P: the reference's GLL-point form `idx // P`
+ *   (components/interpolator.py:116-118, 754-756).  Missing neighbours (k > M) are -1.
+ * d2  [N][k] f64  (out, may be NULL): squared distances. 1 <= k <= 64. */
+int mm_knn(const mm_index_t *index, int64_t N, const double *pts, int k, int32_t divisor,
+           int32_t *idx, double *d2, void *stream);
+
+/* ------------------------------------------------------------------------------------------
+ * K2  point-in-element location: candidate iteration, optional AABB prefilter, fp64 Newton
+ *     inversion of the order-n isoparametric map, accept test and fallback.
+ * Replaces: inverse_transform -> salvus.fem InverseCoordinateTransformWrapper
+ *             (components/interpolator.py:1370-1386),
+ *           boundary_box_check (components/interpolator.py:1350-1367),
+ *           _check_if_inside_element  V1 (components/interpolator.py:1409-1473),
+ *           get_element_weights.check_inside V2 (components/interpolator.py:1181-1233),
+ *           get_element_weights_layered.check_inside V3 (components/interpolator.py:1271-1297),
+ *           v2_interpolation_tools.get_element_weights V4 (v2_interpolation_tools.py:71-164),
+ *           cli._check_if_inside_element V5 (scripts/cli.py:401-430),
+ *           and the per-point loops find_gll_coeffs / fill_value_array
+ *             (components/interpolator.py:1476-1597).
+ * ---------------------------------------------------------------------------------------- */
+enum { MM_FB_FAIL = 0, MM_FB_MAGIC = 1, MM_FB_SNAP = 2, MM_FB_MINL1 = 3 };
+enum {
+    MM_ST_ACCEPTED = 0,
+    MM_ST_FB_INSIDE_MAGIC = 1,
+    MM_ST_FB_NEAR_OK = 2,
+    MM_ST_FB_NEAR_MAGIC = 3,
+    MM_ST_FB_NAN_MAGIC = 4, /* reference raises ValueError unless ignore_hard_elements */
+    MM_ST_SNAPPED = 5,
+    MM_ST_FAILED = 6, /* elem = -1, zero weights */
+    MM_ST_MINL1 = 7,
+    MM_ST_SNAP_NONE = 8
+};
+
+typedef struct {
+    int32_t aabb_prefilter; /* V1 */
+    int32_t strict;         /* 1: all |xi| < tol, 0: all |xi| <= tol */
+    int32_t fallback;       /* MM_FB_* */
+    int32_t reserved;
+    double tol;
+    double snap_clip;
+    double magic_xi[3];
+} mm_locate_params;
+
+/*   nodes    [E][P][dim]   source control nodes
+ *   centroid [E][dim]      from mm_element_geometry (needed when aabb_prefilter)
+ *   aabb     [E][2][dim]   from mm_element_geometry (needed when aabb_prefilter)
+ *   pts      [N][dim]
+ *   cands    [N][k] int32  candidate element ids in neighbour order; negatives are skipped
+ *   elem     [N] int32 (out), xi [N][dim] f64 (out), status [N] u8 (out, may be NULL)
+ *   num_failed : device int64 (out, may be NULL) = number of points with elem = -1 */
+int mm_locate(int order, int dim, int64_t E, const double *nodes, const double *centroid,
+              const double *aabb, int64_t N, const double *pts, int k, const int32_t *cands,
+              const mm_locate_params *params, int32_t *elem, double *xi, uint8_t *status,
+              int64_t *num_failed, void *stream);
+
+/* ------------------------------------------------------------------------------------------
+ * K3  fused Lagrange weights + multi-field gather.
+ *   out[n][f] = sum_a w_a(xi_n) * fields[elem_n][f][a];  rows with elem < 0 are zero.
+ * Replaces: get_coefficients -> salvus.fem GetInterpolationCoefficients
+ *             (components/interpolator.py:1337-1347) and the gathers
+ *             np.sum(data[element] * coeffs, axis=...) (components/interpolator.py:136-138,
+ *             279, 406-414, 598-605, 814-826, 974-976, 1072-1081).
+ *   fields [E][F][P] f64 (MODEL/data layout), out [N][F] f64.
+ * ---------------------------------------------------------------------------------------- */
+int mm_interp(int order, int dim, int64_t E, int F, const double *fields, int64_t N,
+              const int32_t *elem, const double *xi, double *out, void *stream);
+
+/* coeffs [N][P] f64 (out) = w_a(xi_n), zero rows where elem < 0 (elem may be NULL).
+ * For the reference's stored interpolation matrices (components/interpolator.py:391-398,
+ * 797-810). */
+int mm_coeffs(int order, int dim, int64_t N, const int32_t *elem, const double *xi,
+              double *coeffs, void *stream);
+
+/* Explicit-matrix gather for cached (elements, coeffs):
+ *   out[n][f] = sum_a fields[elem_n][f][a] * coeffs[n][a]   (sequential in a). */
+int mm_gather_coeffs(int P, int64_t E, int F, const double *fields, int64_t N,
+                     const int32_t *elem, const double *coeffs, double *out, void *stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Order-1 nodal (Exodus HEX8) path, device pointers.  Arithmetic is bit-identical to
+ * multi_mesh/src/trilinearinterpolator.c:40-305 (same argument meaning as
+ * triLinearInterpolator) and multi_mesh/src/centroid.c:3-25.
+ *   num_failed: device int64 (out).
+ * ---------------------------------------------------------------------------------------- */
+int mm_trilinear(int64_t nelem_to_search, int64_t npoints, const int64_t *nearest,
+                 const int64_t *connectivity, int64_t *enclosing, const double *nodes,
+                 double *weights, const double *points, int64_t *num_failed, void *stream);
+int mm_centroid_conn(int64_t ndim, int64_t nelem, int64_t npe, const int64_t *connectivity,
+                     const double *points, double *centroid, void *stream);
+/* values[f][n] = sum_a param[f][enclosing[n][a]] * weights[n][a]  (a = 0..7, sequential);
+ * replaces np.sum(param_exodus[:, enc] * w, axis=2) (components/interpolator.py:219-222). */
+int mm_gather_nodal(int F, int64_t npoints_mesh, const double *param, int64_t N,
+                    const int64_t *enclosing, const double *weights, double *values,
+                    void *stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Legacy symbols, HOST pointers, exact reference signatures (helpers.py:43-81).
+ * They copy to the current CUDA device, run the kernels above and copy back.
+ * ---------------------------------------------------------------------------------------- */
+void centroid(long long int ndim, long long int nelem, long long int npointsperelem,
+              long long int *connectivity, double *points, double *centroid);
+long long int triLinearInterpolator(long long int nelem_to_search, long long int npoints,
+                                    long long int *nearest_element_indices,
+                                    long long int *connectivity,
+                                    long long int *enclosing_elem_indices, double *nodes,
+                                    double *weights, double *points);
+
+/* ------------------------------------------------------------------------------------------
+ * End-to-end convenience over HOST buffers (the call the e2e benchmark times):
+ * H2D of the source mesh and targets, index build over centroids (gll_points_form = 0) or over
+ * all GLL points (gll_points_form = 1, the gll_2_gll form), k-NN, locate, gather, D2H.
+ *   values [N][F] f64 (out, host), elem [N] int32 (out, host, may be NULL),
+ *   xi [N][dim] (out, host, may be NULL).  Returns MM_OK or an error; *num_failed (host).
+ * ---------------------------------------------------------------------------------------- */
+int mm_interpolate_host(int order, int dim, int64_t E, const double *nodes, int F,
+                        const double *fields, int64_t N, const double *pts, int k,
+                        int gll_points_form, const mm_locate_params *params, double *values,
+                        int32_t *elem, double *xi, int64_t *num_failed);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MULTIMESH_B200_H */

@@ -1,0 +1,78 @@
+"""
+Builds the CUDA library IN-TREE for sm_100a:  multimesh_b200/lib/multi_mesh_b200.so
+
+The name matches the glob `multi_mesh*.so` the reference's loader uses (multi_mesh/helpers.py:33).
+Flags that matter for correctness:
+    -fmad=false                      no FMA contraction on the device   } canonical arithmetic,
+    -Xcompiler -ffp-contract=off     nor in host code                   } DESIGN.md section 3
+    (no --use_fast_math; IEEE division and square root are the nvcc defaults for binary64)
+"""
+import os
+import subprocess
+import sys
+from concurrent.futures import ThreadPoolExecutor
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+CSRC = os.path.join(HERE, "csrc")
+LIB_DIR = os.path.join(HERE, "lib")
+OBJ_DIR = os.path.join(HERE, "lib", "obj")
+LIB_PATH = os.path.join(LIB_DIR, "multi_mesh_b200.so")
+SOURCES = ["mm_core.cu", "mm_geometry.cu", "mm_index.cu", "mm_locate.cu", "mm_interp.cu",
+           "mm_trilinear.cu", "mm_host.cu"]
+NVCC_FLAGS = [
+    "-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
+    "-fmad=false", "-Xcompiler", "-fPIC,-ffp-contract=off,-fno-fast-math", "-Xptxas", "-v",
+]
+
+
+def _nvcc():
+    for cand in (os.environ.get("NVCC"), "/usr/local/cuda/bin/nvcc", "nvcc"):
+        if cand and (os.path.isabs(cand) and os.path.exists(cand) or not os.path.isabs(cand)):
+            return cand
+    return "nvcc"
+
+
+def _stale(target, deps):
+    if not os.path.exists(target):
+        return True
+    t = os.path.getmtime(target)
+    return any(os.path.getmtime(d) > t for d in deps)
+
+
+def build(force=False, verbose=False):
+    os.makedirs(OBJ_DIR, exist_ok=True)
+    headers = [os.path.join(CSRC, "mm_common.cuh"),
+               os.path.join(HERE, "..", "include", "multimesh_b200.h"), __file__]
+    nvcc = _nvcc()
+    jobs = []
+    for s in SOURCES:
+        src = os.path.join(CSRC, s)
+        obj = os.path.join(OBJ_DIR, s.replace(".cu", ".o"))
+        if force or _stale(obj, [src] + headers):
+            jobs.append((src, obj))
+
+    def compile_one(job):
+        src, obj = job
+        cmd = [nvcc] + NVCC_FLAGS + ["-c", src, "-o", obj]
+        r = subprocess.run(cmd, capture_output=True, text=True)
+        log = obj + ".log"
+        with open(log, "w") as fh:
+            fh.write(" ".join(cmd) + "\n" + r.stdout + r.stderr)
+        if r.returncode != 0:
+            raise RuntimeError(f"nvcc failed for {src}:\n{r.stdout}\n{r.stderr}")
+        if verbose:
+            print(r.stderr)
+        return obj
+
+    if jobs:
+        with ThreadPoolExecutor(max_workers=min(8, len(jobs))) as ex:
+            list(ex.map(compile_one, jobs))
+    objs = [os.path.join(OBJ_DIR, s.replace(".cu", ".o")) for s in SOURCES]
+    if force or jobs or _stale(LIB_PATH, objs):
+        cmd = [nvcc, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", LIB_PATH] + objs + ["-lcudart"]
+        subprocess.check_call(cmd)
+    return LIB_PATH
+
+
+if __name__ == "__main__":
+    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))

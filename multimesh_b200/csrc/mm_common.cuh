@@ -1,0 +1,169 @@
+// mm_common.cuh -- shared device helpers for the sm_100a kernels.
+//
+// CANONICAL ARITHMETIC: every floating-point operation below is a single
+// IEEE binary64 operation in the order written.  The library is compiled with -fmad=false so the
+// compiler never contracts a*b+c; nothing here may be re-associated.  The CPU oracle
+// (oracle/mm_oracle.c, test infrastructure) restates the same order independently.
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <math.h>
+
+#include "../../include/multimesh_b200.h"
+
+#define MM_MAXM 5
+#define MM_NEWTON_MAXIT 50
+#define MM_NEWTON_TOL 1e-13
+#define MM_NEWTON_DIVERGE 1e10
+
+// ------------------------------------------------------------------------------------------------
+// error plumbing
+// ------------------------------------------------------------------------------------------------
+void mm_set_error(const char *fmt, ...);
+int mm_cuda_fail(cudaError_t e, const char *what, const char *file, int line);
+
+#define MM_CUDA(call)                                                          \
+    do {                                                                       \
+        cudaError_t _e = (call);                                               \
+        if (_e != cudaSuccess) return mm_cuda_fail(_e, #call, __FILE__, __LINE__); \
+    } while (0)
+
+#define MM_REQUIRE(cond, code, ...)  \
+    do {                             \
+        if (!(cond)) {               \
+            mm_set_error(__VA_ARGS__); \
+            return (code);           \
+        }                            \
+    } while (0)
+
+int mm_num_sms();                 // SM count of the current device
+
+static inline bool mm_valid_order(int order) { return order == 1 || order == 2 || order == 4; }
+static inline int mm_pow(int m, int dim) { return dim == 2 ? m * m : m * m * m; }
+
+// ------------------------------------------------------------------------------------------------
+// GLL table of one order, built on the host in binary64 and passed to kernels BY VALUE (kernel
+// parameters live in the constant bank, so reads are uniform constant loads):
+//   z : nodes;   c : 1 / prod_{j != i, ascending}(z_i - z_j)
+// ------------------------------------------------------------------------------------------------
+struct mm_gll_table {
+    double z[MM_MAXM];
+    double c[MM_MAXM];
+};
+int mm_make_table(int order, mm_gll_table *t);  // host; returns m = order + 1 or 0
+
+// L_i(x) = c_i * prod_{j != i, ascending}(x - z_j)
+template <int ORDER>
+__device__ __forceinline__ void lagrange_values(const mm_gll_table &T, double x,
+                                                double (&L)[ORDER + 1])
+{
+    constexpr int M = ORDER + 1;
+    double d[M];
+#pragma unroll
+    for (int j = 0; j < M; ++j) d[j] = x - T.z[j];
+#pragma unroll
+    for (int i = 0; i < M; ++i) {
+        double prod = T.c[i];
+#pragma unroll
+        for (int j = 0; j < M; ++j)
+            if (j != i) prod = prod * d[j];
+        L[i] = prod;
+    }
+}
+
+// L_i(x) and L_i'(x) = sum_{q != i, ascending} c_i * prod_{j != i,q, ascending}(x - z_j)
+template <int ORDER>
+__device__ __forceinline__ void lagrange_values_derivs(const mm_gll_table &T, double x,
+                                                       double (&L)[ORDER + 1],
+                                                       double (&dL)[ORDER + 1])
+{
+    constexpr int M = ORDER + 1;
+    double d[M];
+#pragma unroll
+    for (int j = 0; j < M; ++j) d[j] = x - T.z[j];
+#pragma unroll
+    for (int i = 0; i < M; ++i) {
+        double prod = T.c[i];
+#pragma unroll
+        for (int j = 0; j < M; ++j)
+            if (j != i) prod = prod * d[j];
+        L[i] = prod;
+        double sum = 0.0;
+#pragma unroll
+        for (int q = 0; q < M; ++q) {
+            if (q == i) continue;
+            double term = T.c[i];
+#pragma unroll
+            for (int j = 0; j < M; ++j)
+                if (j != i && j != q) term = term * d[j];
+            sum = sum + term;
+        }
+        dL[i] = sum;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// mbarrier + bulk-async-copy (TMA 1-D, cp.async.bulk) wrappers.  SASS: UBLKCP / SYNCS.
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void *p)
+{
+    return static_cast<uint32_t>(__cvta_generic_to_shared(p));
+}
+
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+
+__device__ __forceinline__ void fence_mbar_init()
+{
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t *bar, uint32_t bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)),
+                 "r"(bytes)
+                 : "memory");
+}
+
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity)
+{
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "WAIT_LOOP:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra WAIT_DONE;\n\t"
+        "bra WAIT_LOOP;\n\t"
+        "WAIT_DONE:\n\t"
+        "}" ::"r"(smem_u32(bar)),
+        "r"(parity)
+        : "memory");
+}
+
+// global -> shared bulk copy; dst/src 16-byte aligned, bytes a multiple of 16.
+__device__ __forceinline__ void bulk_copy_g2s(void *dst_smem, const void *src_gmem, uint32_t bytes,
+                                              uint64_t *bar)
+{
+    asm volatile(
+        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::
+            "r"(smem_u32(dst_smem)),
+        "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
+        : "memory");
+}
+
+// orders generic-proxy accesses to shared memory before later async-proxy (TMA) writes
+__device__ __forceinline__ void fence_proxy_async_smem()
+{
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+
+// slot stride for per-thread shared-memory staging: >= bytes, a multiple of 16 whose
+// 16-byte count is odd (at most a 2-way bank conflict for 8-byte accesses by a half-warp)
+__host__ __device__ constexpr int mm_slot_bytes(int bytes)
+{
+    int q = (bytes + 15) / 16;
+    return ((q % 2) ? q : q + 1) * 16;
+}

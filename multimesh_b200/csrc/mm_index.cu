@@ -1,0 +1,577 @@
+// mm_index.cu -- K1: GPU spatial index (counting-sorted uniform grid) and exact k-NN query.
+//
+// Replaces pykdtree's KDTree(data).query(pts, k) (call sites listed in include/multimesh_b200.h).
+// The result is the UNIQUE k-prefix of the data points under the strict total order
+// (d2, index), d2 = (dx*dx + dy*dy) + dz*dz in binary64 without FMA, so it does not depend on the
+// grid resolution, on the order points are visited in, or on the atomics used while building.
+//
+// Layout in HBM:  recs  [M]  32-byte records {x, y, z, id}  sorted by linear cell id
+//                             (x fastest, so a row of cells is ONE contiguous record range)
+//                 cell_start [ncells + 1] int32
+#include <algorithm>
+#include <cmath>
+#include <vector>
+
+#include "mm_common.cuh"
+
+struct mm_index {
+    int dim = 0;
+    int64_t M = 0;
+    double origin[3] = {0, 0, 0};
+    double cell = 1.0, inv_cell = 1.0;
+    int n[3] = {1, 1, 1};
+    int64_t ncells = 1;
+    int64_t nonempty = 0;
+    double4 *recs = nullptr;
+    int32_t *cell_start = nullptr;
+    size_t bytes = 0;
+};
+
+namespace {
+
+constexpr int64_t MAX_CELLS = (int64_t)1 << 26;
+constexpr int KNN_BLOCK = 128;
+
+struct grid_t {
+    double origin[3];
+    double cell, inv_cell;
+    int n[3];
+    int dim;
+};
+
+__device__ __forceinline__ int cell_coord(const grid_t &g, double x, int c)
+{
+    double f = floor((x - g.origin[c]) * g.inv_cell);
+    double hi = (double)(g.n[c] - 1);
+    f = f < 0.0 ? 0.0 : (f > hi ? hi : f);  // NaN maps to hi; clamping keeps monotonicity
+    return (int)f;
+}
+
+__device__ __forceinline__ int64_t cell_of(const grid_t &g, const double *p)
+{
+    int cx = cell_coord(g, p[0], 0), cy = cell_coord(g, p[1], 1);
+    int cz = g.dim == 3 ? cell_coord(g, p[2], 2) : 0;
+    return cx + (int64_t)g.n[0] * (cy + (int64_t)g.n[1] * cz);
+}
+
+// ---- bounding box: per-block partial min/max, finished on the host ------------------------------
+__global__ void __launch_bounds__(256)
+bbox_kernel(int dim, int64_t M, const double *__restrict__ pts, double *__restrict__ partial)
+{
+    double lo[3] = {INFINITY, INFINITY, INFINITY}, hi[3] = {-INFINITY, -INFINITY, -INFINITY};
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < M;
+         i += (int64_t)gridDim.x * blockDim.x)
+        for (int c = 0; c < dim; ++c) {
+            double v = pts[i * dim + c];
+            lo[c] = fmin(lo[c], v);
+            hi[c] = fmax(hi[c], v);
+        }
+    __shared__ double s[6][256];
+    for (int c = 0; c < 3; ++c) {
+        s[c][threadIdx.x] = lo[c];
+        s[3 + c][threadIdx.x] = hi[c];
+    }
+    __syncthreads();
+    for (int w = 128; w > 0; w >>= 1) {
+        if (threadIdx.x < w)
+            for (int c = 0; c < 3; ++c) {
+                s[c][threadIdx.x] = fmin(s[c][threadIdx.x], s[c][threadIdx.x + w]);
+                s[3 + c][threadIdx.x] = fmax(s[3 + c][threadIdx.x], s[3 + c][threadIdx.x + w]);
+            }
+        __syncthreads();
+    }
+    if (threadIdx.x < 6) partial[blockIdx.x * 6 + threadIdx.x] = s[threadIdx.x][0];
+}
+
+__global__ void __launch_bounds__(256)
+histogram_kernel(grid_t g, int64_t M, const double *__restrict__ pts, int32_t *__restrict__ counts)
+{
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < M;
+         i += (int64_t)gridDim.x * blockDim.x)
+        atomicAdd(&counts[cell_of(g, pts + i * g.dim)], 1);
+}
+
+__global__ void __launch_bounds__(256)
+count_nonempty_kernel(int64_t ncells, const int32_t *__restrict__ counts,
+                      unsigned long long *__restrict__ nonempty)
+{
+    unsigned long long local = 0;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < ncells;
+         i += (int64_t)gridDim.x * blockDim.x)
+        local += counts[i] > 0;
+    for (int o = 16; o > 0; o >>= 1) local += __shfl_xor_sync(0xffffffffu, local, o);
+    if ((threadIdx.x & 31) == 0 && local) atomicAdd(nonempty, local);
+}
+
+// ---- exclusive scan of int32 counts (n entries -> n + 1 starts), three small kernels -----------
+constexpr int SCAN_BLOCK = 256;
+constexpr int SCAN_ITEMS = 16;
+constexpr int SCAN_TILE = SCAN_BLOCK * SCAN_ITEMS;
+
+__global__ void __launch_bounds__(SCAN_BLOCK)
+scan_tile_sums(int64_t n, const int32_t *__restrict__ in, int32_t *__restrict__ tile_sums)
+{
+    int64_t base = (int64_t)blockIdx.x * SCAN_TILE;
+    int32_t s = 0;
+    for (int i = threadIdx.x; i < SCAN_TILE; i += SCAN_BLOCK)
+        if (base + i < n) s += in[base + i];
+    __shared__ int32_t sh[SCAN_BLOCK];
+    sh[threadIdx.x] = s;
+    __syncthreads();
+    for (int w = SCAN_BLOCK / 2; w > 0; w >>= 1) {
+        if (threadIdx.x < w) sh[threadIdx.x] += sh[threadIdx.x + w];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) tile_sums[blockIdx.x] = sh[0];
+}
+
+__global__ void __launch_bounds__(1024)
+scan_tile_offsets(int64_t ntiles, int32_t *__restrict__ tile_sums)  // in-place exclusive, 1 block
+{
+    __shared__ int32_t sh[1024];
+    __shared__ int32_t carry;
+    if (threadIdx.x == 0) carry = 0;
+    __syncthreads();
+    for (int64_t base = 0; base < ntiles; base += 1024) {
+        int64_t i = base + threadIdx.x;
+        int32_t v = i < ntiles ? tile_sums[i] : 0;
+        sh[threadIdx.x] = v;
+        __syncthreads();
+        for (int o = 1; o < 1024; o <<= 1) {
+            int32_t t = threadIdx.x >= o ? sh[threadIdx.x - o] : 0;
+            __syncthreads();
+            sh[threadIdx.x] += t;
+            __syncthreads();
+        }
+        if (i < ntiles) tile_sums[i] = carry + sh[threadIdx.x] - v;
+        __syncthreads();
+        if (threadIdx.x == 0) carry += sh[1023];
+        __syncthreads();
+    }
+}
+
+__global__ void __launch_bounds__(SCAN_BLOCK)
+scan_apply(int64_t n, const int32_t *__restrict__ in, const int32_t *__restrict__ tile_offsets,
+           int32_t *__restrict__ out /* n + 1 */)
+{
+    int64_t base = (int64_t)blockIdx.x * SCAN_TILE + (int64_t)threadIdx.x * SCAN_ITEMS;
+    int32_t v[SCAN_ITEMS];
+    int32_t s = 0;
+#pragma unroll
+    for (int i = 0; i < SCAN_ITEMS; ++i) {
+        v[i] = base + i < n ? in[base + i] : 0;
+        s += v[i];
+    }
+    __shared__ int32_t sh[SCAN_BLOCK];
+    sh[threadIdx.x] = s;
+    __syncthreads();
+    for (int o = 1; o < SCAN_BLOCK; o <<= 1) {
+        int32_t t = threadIdx.x >= o ? sh[threadIdx.x - o] : 0;
+        __syncthreads();
+        sh[threadIdx.x] += t;
+        __syncthreads();
+    }
+    int32_t run = tile_offsets[blockIdx.x] + sh[threadIdx.x] - s;
+#pragma unroll
+    for (int i = 0; i < SCAN_ITEMS; ++i) {
+        if (base + i < n) out[base + i] = run;
+        run += v[i];
+        if (base + i == n - 1) out[n] = run;
+    }
+}
+
+__global__ void __launch_bounds__(256)
+scatter_kernel(grid_t g, int64_t M, const double *__restrict__ pts,
+               const int32_t *__restrict__ cell_start, int32_t *__restrict__ cursor,
+               double4 *__restrict__ recs)
+{
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < M;
+         i += (int64_t)gridDim.x * blockDim.x) {
+        const double *p = pts + i * g.dim;
+        int64_t c = cell_of(g, p);
+        int32_t pos = cell_start[c] + atomicAdd(&cursor[c], 1);
+        double4 r;
+        r.x = p[0];
+        r.y = p[1];
+        r.z = g.dim == 3 ? p[2] : 0.0;
+        r.w = __longlong_as_double((long long)i);
+        recs[pos] = r;
+    }
+}
+
+// ---- k-NN query: one thread per query point, sorted top-k list in shared memory ----------------
+struct knn_list {
+    double *d2;   // [k][KNN_BLOCK] slot-major: conflict-free whatever slot each lane touches
+    int32_t *id;
+    int k, cnt;
+    double kth_d2;
+    int32_t kth_id;
+
+    __device__ __forceinline__ double &D(int s) { return d2[s * KNN_BLOCK + threadIdx.x]; }
+    __device__ __forceinline__ int32_t &I(int s) { return id[s * KNN_BLOCK + threadIdx.x]; }
+
+    __device__ __forceinline__ void insert(double nd, int32_t ni)
+    {
+        int pos;
+        if (cnt == k) {
+            if (!(nd < kth_d2 || (nd == kth_d2 && ni < kth_id))) return;
+            pos = k - 1;
+        } else {
+            pos = cnt++;
+        }
+        while (pos > 0) {
+            double pd = D(pos - 1);
+            int32_t pi = I(pos - 1);
+            if (!(nd < pd || (nd == pd && ni < pi))) break;
+            D(pos) = pd;
+            I(pos) = pi;
+            --pos;
+        }
+        D(pos) = nd;
+        I(pos) = ni;
+        if (cnt == k) {
+            kth_d2 = D(k - 1);
+            kth_id = I(k - 1);
+        }
+    }
+};
+
+__device__ __forceinline__ void scan_range(knn_list &L, const double4 *__restrict__ recs,
+                                           int32_t lo, int32_t hi, double px, double py, double pz,
+                                           bool three_d)
+{
+    for (int32_t j = lo; j < hi; ++j) {
+        const double2 *q = reinterpret_cast<const double2 *>(&recs[j]);  // 2 x LDG.128
+        const double2 xy = __ldg(q), zw = __ldg(q + 1);
+        double dx = px - xy.x, dy = py - xy.y;
+        double s = dx * dx + dy * dy;
+        if (three_d) {
+            double dz = pz - zw.x;
+            s = s + dz * dz;
+        }
+        L.insert(s, (int32_t)__double_as_longlong(zw.y));
+    }
+}
+
+__global__ void __launch_bounds__(KNN_BLOCK)
+knn_kernel(grid_t g, int64_t N, const double *__restrict__ pts, int k, int32_t divisor,
+           const double4 *__restrict__ recs, const int32_t *__restrict__ cell_start,
+           int32_t *__restrict__ out_idx, double *__restrict__ out_d2)
+{
+    extern __shared__ __align__(16) unsigned char smem[];
+    knn_list L;
+    L.d2 = reinterpret_cast<double *>(smem);
+    L.id = reinterpret_cast<int32_t *>(smem + (size_t)k * KNN_BLOCK * sizeof(double));
+    L.k = k;
+
+    const bool three_d = g.dim == 3;
+    const double h = g.cell;
+    const double margin = h * 1e-6;
+
+    for (int64_t n = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; n < N;
+         n += (int64_t)gridDim.x * blockDim.x) {
+        const double px = pts[n * g.dim + 0], py = pts[n * g.dim + 1];
+        const double pz = three_d ? pts[n * g.dim + 2] : 0.0;
+        const double p[3] = {px, py, pz};
+        int ci[3];
+        ci[0] = cell_coord(g, px, 0);
+        ci[1] = cell_coord(g, py, 1);
+        ci[2] = three_d ? cell_coord(g, pz, 2) : 0;
+        L.cnt = 0;
+        L.kth_d2 = INFINITY;
+        L.kth_id = 0x7fffffff;
+
+        for (int r = 0;; ++r) {
+            const int zlo = max(ci[2] - r, 0), zhi = min(ci[2] + r, g.n[2] - 1);
+            const int ylo = max(ci[1] - r, 0), yhi = min(ci[1] + r, g.n[1] - 1);
+            const int xlo = max(ci[0] - r, 0), xhi = min(ci[0] + r, g.n[0] - 1);
+            for (int zz = zlo; zz <= zhi; ++zz) {
+                double gz = 0.0;
+                if (three_d) {
+                    double zl = g.origin[2] + zz * h, zh = zl + h;
+                    gz = fmax(fmax(zl - pz, pz - zh) - margin, 0.0);
+                }
+                const bool zedge = three_d && (abs(zz - ci[2]) == r);
+                for (int yy = ylo; yy <= yhi; ++yy) {
+                    double yl = g.origin[1] + yy * h, yh = yl + h;
+                    double gy = fmax(fmax(yl - py, py - yh) - margin, 0.0);
+                    // rows farther than the current k-th neighbour cannot contribute
+                    if (L.cnt == k && (gy * gy + gz * gz) > L.kth_d2) continue;
+                    const int64_t base = (int64_t)g.n[0] * (yy + (int64_t)g.n[1] * zz);
+                    if (zedge || abs(yy - ci[1]) == r) {
+                        scan_range(L, recs, cell_start[base + xlo], cell_start[base + xhi + 1], px,
+                                   py, pz, three_d);
+                    } else {
+                        int xa = ci[0] - r, xb = ci[0] + r;
+                        if (xa >= 0)
+                            scan_range(L, recs, cell_start[base + xa], cell_start[base + xa + 1],
+                                       px, py, pz, three_d);
+                        if (xb < g.n[0] && r > 0)
+                            scan_range(L, recs, cell_start[base + xb], cell_start[base + xb + 1],
+                                       px, py, pz, three_d);
+                    }
+                }
+            }
+            // every point not yet visited lies outside the block of cells [ci-r, ci+r]; its
+            // distance to p is at least the gap to the nearest block face that has cells beyond it
+            double bound = INFINITY;
+            bool remaining = false;
+            for (int c = 0; c < g.dim; ++c) {
+                if (ci[c] - r > 0) {
+                    remaining = true;
+                    bound = fmin(bound, p[c] - (g.origin[c] + (ci[c] - r) * h));
+                }
+                if (ci[c] + r < g.n[c] - 1) {
+                    remaining = true;
+                    bound = fmin(bound, (g.origin[c] + (ci[c] + r + 1) * h) - p[c]);
+                }
+            }
+            if (!remaining) break;
+            bound = fmax(bound - margin, 0.0);
+            if (L.cnt == k && L.kth_d2 < bound * bound) break;
+        }
+        for (int t = 0; t < k; ++t) {
+            bool have = t < L.cnt;
+            out_idx[n * k + t] = have ? L.I(t) / divisor : -1;
+            if (out_d2) out_d2[n * k + t] = have ? L.D(t) : INFINITY;
+        }
+    }
+}
+
+int launch_blocks(int64_t work, int block, int per_sm)
+{
+    int sms = mm_num_sms();
+    int64_t need = (work + block - 1) / block;
+    int64_t cap = (int64_t)(sms > 0 ? sms : 148) * per_sm;
+    return (int)(need < 1 ? 1 : (need > cap ? cap : need));
+}
+
+void choose_dims(const double ext[3], int dim, double h, int n[3])
+{
+    for (int c = 0; c < 3; ++c) {
+        n[c] = 1;
+        if (c < dim && ext[c] > 0.0) {
+            double q = std::ceil(ext[c] / h);
+            if (!(q >= 1.0)) q = 1.0;
+            if (q > 4096.0) q = 4096.0;
+            n[c] = (int)q;
+        }
+    }
+}
+
+}  // namespace
+
+extern "C" int mm_index_destroy(mm_index_t *ix)
+{
+    if (!ix) return MM_OK;
+    if (ix->recs) cudaFree(ix->recs);
+    if (ix->cell_start) cudaFree(ix->cell_start);
+    delete ix;
+    return MM_OK;
+}
+
+extern "C" int mm_index_info(const mm_index_t *ix, int64_t info[8], double *cell_size)
+{
+    MM_REQUIRE(ix && info, MM_ERR_INVALID, "mm_index_info: null");
+    info[0] = ix->M;
+    info[1] = ix->dim;
+    info[2] = ix->n[0];
+    info[3] = ix->n[1];
+    info[4] = ix->n[2];
+    info[5] = ix->nonempty;
+    info[6] = (int64_t)ix->bytes;
+    info[7] = 0;
+    if (cell_size) *cell_size = ix->cell;
+    return MM_OK;
+}
+
+extern "C" int mm_index_create(mm_index_t **out, int dim, int64_t M, const double *points,
+                               void *stream_)
+{
+    cudaStream_t stream = (cudaStream_t)stream_;
+    MM_REQUIRE(out, MM_ERR_INVALID, "mm_index_create: null out");
+    *out = nullptr;
+    MM_REQUIRE(dim == 2 || dim == 3, MM_ERR_INVALID, "mm_index_create: dim %d", dim);
+    MM_REQUIRE(M >= 0 && M < ((int64_t)1 << 31), MM_ERR_INVALID,
+               "mm_index_create: M=%lld outside [0, 2^31)", (long long)M);
+    MM_REQUIRE(M == 0 || points, MM_ERR_INVALID, "mm_index_create: null points");
+
+    mm_index *ix = new mm_index();
+    ix->dim = dim;
+    ix->M = M;
+    struct guard_t {
+        mm_index *p;
+        ~guard_t() { if (p) mm_index_destroy(p); }
+    } guard{ix};
+
+    grid_t g{};
+    g.dim = dim;
+    g.n[0] = g.n[1] = g.n[2] = 1;
+    g.cell = g.inv_cell = 1.0;
+    int32_t *counts = nullptr;
+    int32_t *tile_sums = nullptr;
+    unsigned long long *d_nonempty = nullptr;
+    double *d_partial = nullptr;
+    struct scratch_t {
+        int32_t *&a;
+        int32_t *&b;
+        unsigned long long *&c;
+        double *&d;
+        ~scratch_t()
+        {
+            if (a) cudaFree(a);
+            if (b) cudaFree(b);
+            if (c) cudaFree(c);
+            if (d) cudaFree(d);
+        }
+    } scratch{counts, tile_sums, d_nonempty, d_partial};
+
+    if (M > 0) {
+        // 1. bounding box
+        int nb = launch_blocks(M, 256, 8);
+        MM_CUDA(cudaMalloc(&d_partial, sizeof(double) * 6 * nb));
+        bbox_kernel<<<nb, 256, 0, stream>>>(dim, M, points, d_partial);
+        MM_CUDA(cudaGetLastError());
+        std::vector<double> part(6 * (size_t)nb);
+        MM_CUDA(cudaMemcpyAsync(part.data(), d_partial, sizeof(double) * 6 * nb,
+                                cudaMemcpyDeviceToHost, stream));
+        MM_CUDA(cudaStreamSynchronize(stream));
+        double lo[3] = {INFINITY, INFINITY, INFINITY}, hi[3] = {-INFINITY, -INFINITY, -INFINITY};
+        for (int b = 0; b < nb; ++b)
+            for (int c = 0; c < 3; ++c) {
+                lo[c] = std::fmin(lo[c], part[b * 6 + c]);
+                hi[c] = std::fmax(hi[c], part[b * 6 + 3 + c]);
+            }
+        double ext[3] = {0, 0, 0};
+        int nd = 0;
+        double vol = 1.0;
+        for (int c = 0; c < dim; ++c) {
+            MM_REQUIRE(std::isfinite(lo[c]) && std::isfinite(hi[c]), MM_ERR_INVALID,
+                       "mm_index_create: non-finite coordinates");
+            g.origin[c] = lo[c];
+            ext[c] = hi[c] - lo[c];
+            if (ext[c] > 0.0) {
+                ++nd;
+                vol *= ext[c];
+            }
+        }
+        // 2. cell size: ~2 points per cell by volume, then refine while cells stay crowded and
+        //    halving the cell still separates points (duplicated points never separate)
+        double h = 1.0;
+        if (nd > 0) {
+            h = std::pow(vol * 2.0 / (double)M, 1.0 / nd);
+            double emax = std::max(ext[0], std::max(ext[1], ext[2]));
+            if (!(h > 0.0) || !std::isfinite(h)) h = emax;
+            h = std::max(h, emax / 4096.0);
+        }
+        MM_CUDA(cudaMalloc(&d_nonempty, sizeof(unsigned long long)));
+        auto evaluate = [&](double hh, int64_t *nonempty) -> int {
+            choose_dims(ext, dim, hh, g.n);
+            g.cell = hh;
+            g.inv_cell = 1.0 / hh;
+            int64_t ncells = (int64_t)g.n[0] * g.n[1] * g.n[2];
+            if (counts) { cudaFree(counts); counts = nullptr; }
+            MM_CUDA(cudaMalloc(&counts, sizeof(int32_t) * (size_t)(ncells + 1)));
+            MM_CUDA(cudaMemsetAsync(counts, 0, sizeof(int32_t) * (size_t)(ncells + 1), stream));
+            MM_CUDA(cudaMemsetAsync(d_nonempty, 0, sizeof(unsigned long long), stream));
+            histogram_kernel<<<launch_blocks(M, 256, 8), 256, 0, stream>>>(g, M, points, counts);
+            count_nonempty_kernel<<<launch_blocks(ncells, 256, 8), 256, 0, stream>>>(
+                ncells, counts, d_nonempty);
+            MM_CUDA(cudaGetLastError());
+            unsigned long long ne = 0;
+            MM_CUDA(cudaMemcpyAsync(&ne, d_nonempty, sizeof ne, cudaMemcpyDeviceToHost, stream));
+            MM_CUDA(cudaStreamSynchronize(stream));
+            *nonempty = (int64_t)ne;
+            return MM_OK;
+        };
+        auto cells_at = [&](double hh) {
+            int nn[3];
+            choose_dims(ext, dim, hh, nn);
+            return (int64_t)nn[0] * nn[1] * nn[2];
+        };
+        while (cells_at(h) > MAX_CELLS) h *= 1.25;
+        int64_t nonempty = 0;
+        int rc = evaluate(h, &nonempty);
+        if (rc != MM_OK) return rc;
+        for (int it = 0; it < 8 && nd > 0; ++it) {
+            if ((double)M / (double)std::max<int64_t>(nonempty, 1) <= 4.0) break;
+            double h2 = 0.5 * h;
+            double emax = std::max(ext[0], std::max(ext[1], ext[2]));
+            if (h2 < emax / 4096.0) break;  // keep every axis below the per-axis cell cap
+            if (cells_at(h2) > MAX_CELLS || cells_at(h2) == cells_at(h)) break;
+            int64_t ne2 = 0;
+            rc = evaluate(h2, &ne2);
+            if (rc != MM_OK) return rc;
+            if ((double)ne2 >= 1.5 * (double)nonempty) {
+                h = h2;
+                nonempty = ne2;
+            } else {
+                rc = evaluate(h, &nonempty);  // restore the coarser grid
+                if (rc != MM_OK) return rc;
+                break;
+            }
+        }
+        ix->nonempty = nonempty;
+    }
+    for (int c = 0; c < 3; ++c) {
+        ix->origin[c] = g.origin[c];
+        ix->n[c] = g.n[c];
+    }
+    ix->cell = g.cell;
+    ix->inv_cell = g.inv_cell;
+    ix->ncells = (int64_t)g.n[0] * g.n[1] * g.n[2];
+
+    // 3. exclusive scan of the histogram -> cell_start
+    MM_CUDA(cudaMalloc(&ix->cell_start, sizeof(int32_t) * (size_t)(ix->ncells + 1)));
+    ix->bytes += sizeof(int32_t) * (size_t)(ix->ncells + 1);
+    if (M == 0) {
+        MM_CUDA(cudaMemsetAsync(ix->cell_start, 0, sizeof(int32_t) * (size_t)(ix->ncells + 1),
+                                stream));
+    } else {
+        int64_t ntiles = (ix->ncells + SCAN_TILE - 1) / SCAN_TILE;
+        MM_CUDA(cudaMalloc(&tile_sums, sizeof(int32_t) * (size_t)ntiles));
+        scan_tile_sums<<<(int)ntiles, SCAN_BLOCK, 0, stream>>>(ix->ncells, counts, tile_sums);
+        scan_tile_offsets<<<1, 1024, 0, stream>>>(ntiles, tile_sums);
+        scan_apply<<<(int)ntiles, SCAN_BLOCK, 0, stream>>>(ix->ncells, counts, tile_sums,
+                                                           ix->cell_start);
+        MM_CUDA(cudaGetLastError());
+        // 4. scatter the points into cell order (the histogram buffer becomes the cursor)
+        MM_CUDA(cudaMalloc(&ix->recs, sizeof(double4) * (size_t)M));
+        ix->bytes += sizeof(double4) * (size_t)M;
+        MM_CUDA(cudaMemsetAsync(counts, 0, sizeof(int32_t) * (size_t)(ix->ncells + 1), stream));
+        scatter_kernel<<<launch_blocks(M, 256, 8), 256, 0, stream>>>(g, M, points, ix->cell_start,
+                                                                     counts, ix->recs);
+        MM_CUDA(cudaGetLastError());
+    }
+    MM_CUDA(cudaStreamSynchronize(stream));
+    guard.p = nullptr;
+    *out = ix;
+    return MM_OK;
+}
+
+extern "C" int mm_knn(const mm_index_t *ix, int64_t N, const double *pts, int k, int32_t divisor,
+                      int32_t *idx, double *d2, void *stream)
+{
+    MM_REQUIRE(ix, MM_ERR_INVALID, "mm_knn: null index");
+    MM_REQUIRE(k >= 1 && k <= 64, MM_ERR_INVALID, "mm_knn: k=%d outside [1, 64]", k);
+    MM_REQUIRE(divisor >= 1, MM_ERR_INVALID, "mm_knn: divisor %d", (int)divisor);
+    MM_REQUIRE(N >= 0, MM_ERR_INVALID, "mm_knn: N");
+    if (N == 0) return MM_OK;
+    MM_REQUIRE(pts && idx, MM_ERR_INVALID, "mm_knn: null buffer");
+    grid_t g{};
+    g.dim = ix->dim;
+    for (int c = 0; c < 3; ++c) {
+        g.origin[c] = ix->origin[c];
+        g.n[c] = ix->n[c];
+    }
+    g.cell = ix->cell;
+    g.inv_cell = ix->inv_cell;
+    size_t smem = (size_t)k * KNN_BLOCK * (sizeof(double) + sizeof(int32_t));
+    MM_CUDA(cudaFuncSetAttribute(knn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 (int)smem));
+    int per_sm = (int)std::max<size_t>(1, std::min<size_t>(8, (200 * 1024) / smem));
+    knn_kernel<<<launch_blocks(N, KNN_BLOCK, per_sm), KNN_BLOCK, smem, (cudaStream_t)stream>>>(
+        g, N, pts, k, divisor, ix->recs, ix->cell_start, idx, d2);
+    MM_CUDA(cudaGetLastError());
+    return MM_OK;
+}

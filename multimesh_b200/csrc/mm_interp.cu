@@ -1,0 +1,335 @@
+// mm_interp.cu -- K3: fused Lagrange weights + multi-field gather (the roofline-graded kernel),
+//                 plus coefficient write-out and the explicit-matrix gather for cached weights.
+//
+// out[n][f] = sum_a w_a(xi_n) * fields[elem_n][f][a]
+//
+// Data movement.  In the reference's MODEL/data layout [E][F][P] the F*P values a point needs are
+// ONE contiguous block (1 080 B at order 2 / F=5, 5 000 B at order 4 / F=5).  Each lane owns one
+// target point and fetches its block -- in chunks of FC fields -- with a single bulk-async copy
+// (cp.async.bulk, SASS UBLKCP) into a private shared-memory slot.  A warp keeps S stages of 32
+// slots in flight on per-stage mbarriers, so the copy engine streams whole contiguous blocks from
+// HBM/L2 while the lanes contract the previous chunk out of shared memory.  No thread ever issues
+// a scattered global load for field data.
+//
+// Arithmetic: nested tensor contraction, i innermost --
+//   t[j,k] = sum_i Lx[i] v[i,j,k];  u[k] = sum_j Ly[j] t[j,k];  out = sum_k Lz[k] u[k]
+// one rounding per operation, no FMA; bit-identical to oracle/mm_oracle.c:mmo_interp.
+#include <algorithm>
+
+#include "mm_common.cuh"
+
+namespace {
+
+constexpr int INTERP_WARPS = 2;
+
+struct interp_cfg {
+    int F;           // fields
+    int FC;          // fields per staged chunk
+    int chunks;      // ceil(F / FC)
+    int stages;      // pipeline depth per warp
+    int slot_bytes;  // per-lane slot stride
+    int odd_p;       // P odd: chunk starts alternate between 0 and 8 (mod 16)
+};
+
+__host__ __device__ inline int chunk_copy_bytes(int nf, int P, int odd_p)
+{
+    int b = nf * P * 8;
+    return odd_p ? ((b + 8 + 15) / 16) * 16 : b;
+}
+
+template <int ORDER, int DIM>
+__device__ __forceinline__ double contract_field(const double *__restrict__ v,
+                                                 const double (&L)[DIM][ORDER + 1])
+{
+    constexpr int M = ORDER + 1;
+    if constexpr (DIM == 2) {
+        double u = 0.0;
+#pragma unroll
+        for (int j = 0; j < M; ++j) {
+            double t = 0.0;
+#pragma unroll
+            for (int i = 0; i < M; ++i) t = t + L[0][i] * v[i + M * j];
+            u = u + L[1][j] * t;
+        }
+        return u;
+    } else {
+        double acc = 0.0;
+#pragma unroll
+        for (int k = 0; k < M; ++k) {
+            double u = 0.0;
+#pragma unroll
+            for (int j = 0; j < M; ++j) {
+                double t = 0.0;
+#pragma unroll
+                for (int i = 0; i < M; ++i) t = t + L[0][i] * v[i + M * j + M * M * k];
+                u = u + L[1][j] * t;
+            }
+            acc = acc + L[2][k] * u;
+        }
+        return acc;
+    }
+}
+
+template <int ORDER, int DIM>
+__global__ void __launch_bounds__(INTERP_WARPS * 32)
+interp_kernel(const mm_gll_table T, const interp_cfg cfg, int64_t E,
+              const double *__restrict__ fields, int64_t N, const int32_t *__restrict__ elem,
+              const double *__restrict__ xi, double *__restrict__ out)
+{
+    constexpr int M = ORDER + 1;
+    constexpr int P = DIM == 2 ? M * M : M * M * M;
+    extern __shared__ __align__(128) unsigned char smem[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const size_t stage_bytes = (size_t)32 * cfg.slot_bytes;
+    unsigned char *wbase = smem + (size_t)warp * cfg.stages * stage_bytes;
+    uint64_t *bars = reinterpret_cast<uint64_t *>(smem + (size_t)INTERP_WARPS * cfg.stages * stage_bytes) +
+                     warp * cfg.stages;
+    if (lane < cfg.stages) mbar_init(&bars[lane], 1);
+    fence_mbar_init();
+    __syncthreads();
+
+    const int64_t total_bytes = E * (int64_t)cfg.F * P * 8;
+    const int64_t nbatch = (N + 31) / 32;
+    const int64_t warps_total = (int64_t)gridDim.x * INTERP_WARPS;
+    const int64_t first = (int64_t)blockIdx.x * INTERP_WARPS + warp;
+    // this warp's batches: first, first + warps_total, ...
+    const int64_t my_batches = first < nbatch ? (nbatch - first + warps_total - 1) / warps_total : 0;
+    const int64_t items = my_batches * cfg.chunks;
+
+    // producer side: stage item `q` (batch q / chunks, chunk q % chunks)
+    auto issue = [&](int64_t q) {
+        const int64_t b = first + (q / cfg.chunks) * warps_total;
+        const int ch = (int)(q % cfg.chunks);
+        const int f0 = ch * cfg.FC;
+        const int nf = min(cfg.FC, cfg.F - f0);
+        const int bytes = chunk_copy_bytes(nf, P, cfg.odd_p);
+        const int s = (int)(q % cfg.stages);
+        const int64_t n = b * 32 + lane;
+        const int32_t e = n < N ? elem[n] : -1;
+        int shift = 0;
+        bool use_tma = false;
+        int64_t off = 0;
+        if (e >= 0) {
+            off = (((int64_t)e * cfg.F + f0) * P) * 8;
+            shift = cfg.odd_p ? (int)(off & 8) : 0;
+            use_tma = (off - shift + bytes) <= total_bytes;
+        }
+        const unsigned mask = __ballot_sync(0xffffffffu, use_tma);
+        // always arrive (tx may be 0) so that every use of a stage completes exactly one phase
+        if (lane == 0) mbar_arrive_expect_tx(&bars[s], (uint32_t)__popc(mask) * bytes);
+        __syncwarp();
+        unsigned char *slot = wbase + s * stage_bytes + (size_t)lane * cfg.slot_bytes;
+        if (use_tma) {
+            bulk_copy_g2s(slot, reinterpret_cast<const unsigned char *>(fields) + off - shift,
+                          (uint32_t)bytes, &bars[s]);
+        } else if (e >= 0) {  // last bytes of the array: plain loads
+            const double *src = reinterpret_cast<const double *>(
+                reinterpret_cast<const unsigned char *>(fields) + off);
+            double *dst = reinterpret_cast<double *>(slot + shift);
+            for (int q2 = 0; q2 < nf * P; ++q2) dst[q2] = src[q2];
+        }
+    };
+
+    const int prefetch = cfg.stages - 1;
+    for (int64_t q = 0; q < prefetch && q < items; ++q) issue(q);
+
+    double L[DIM][M];
+    for (int64_t q = 0; q < items; ++q) {
+        if (q + prefetch < items) {
+            // the stage being refilled was consumed at item q-1; order those generic reads
+            // before the async-proxy writes
+            fence_proxy_async_smem();
+            __syncwarp();
+            issue(q + prefetch);
+        }
+        const int64_t b = first + (q / cfg.chunks) * warps_total;
+        const int ch = (int)(q % cfg.chunks);
+        const int f0 = ch * cfg.FC;
+        const int nf = min(cfg.FC, cfg.F - f0);
+        const int bytes = chunk_copy_bytes(nf, P, cfg.odd_p);
+        const int s = (int)(q % cfg.stages);
+        const int64_t n = b * 32 + lane;
+        const int32_t e = n < N ? elem[n] : -1;
+        int shift = 0;
+        bool use_tma = false;
+        if (e >= 0) {
+            const int64_t off = (((int64_t)e * cfg.F + f0) * P) * 8;
+            shift = cfg.odd_p ? (int)(off & 8) : 0;
+            use_tma = (off - shift + bytes) <= total_bytes;
+        }
+        if (ch == 0 && e >= 0) {
+#pragma unroll
+            for (int ax = 0; ax < DIM; ++ax) lagrange_values<ORDER>(T, xi[n * DIM + ax], L[ax]);
+        }
+        mbar_wait(&bars[s], (uint32_t)((q / cfg.stages) & 1));
+        if (n < N) {
+            const double *v = reinterpret_cast<const double *>(
+                wbase + s * stage_bytes + (size_t)lane * cfg.slot_bytes + shift);
+            double *o = out + n * cfg.F + f0;
+            if (e >= 0) {
+                for (int f = 0; f < nf; ++f) o[f] = contract_field<ORDER, DIM>(v + f * P, L);
+            } else {
+                for (int f = 0; f < nf; ++f) o[f] = 0.0;
+            }
+        }
+    }
+}
+
+template <int ORDER, int DIM>
+int launch_interp(int64_t E, int F, const double *fields, int64_t N, const int32_t *elem,
+                  const double *xi, double *out, cudaStream_t stream)
+{
+    constexpr int M = ORDER + 1;
+    constexpr int P = DIM == 2 ? M * M : M * M * M;
+    mm_gll_table T;
+    mm_make_table(ORDER, &T);
+    interp_cfg cfg;
+    cfg.F = F;
+    cfg.odd_p = P % 2;
+    // chunk size: keep a lane's slot near 512 B (a 32-lane stage near 16 KB) so that several
+    // CTAs of 2 warps x 3 stages share an SM; one field is the minimum (1 008 B at order 4)
+    int fc = std::max(1, std::min(F, 504 / (P * 8)));
+    cfg.FC = fc;
+    cfg.chunks = (F + fc - 1) / fc;
+    cfg.slot_bytes = mm_slot_bytes(chunk_copy_bytes(fc, P, cfg.odd_p));
+    cfg.stages = 3;
+    auto kern = interp_kernel<ORDER, DIM>;
+    size_t smem = (size_t)INTERP_WARPS * cfg.stages * 32 * cfg.slot_bytes +
+                  INTERP_WARPS * cfg.stages * sizeof(uint64_t);
+    MM_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int per_sm = 1;
+    MM_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, INTERP_WARPS * 32, smem));
+    if (per_sm < 1) per_sm = 1;
+    const int sms = mm_num_sms() > 0 ? mm_num_sms() : 148;
+    int64_t nbatch = (N + 31) / 32;
+    int64_t grid = (int64_t)sms * per_sm;  // persistent CTAs, multiple of the SM count
+    int64_t need = (nbatch + INTERP_WARPS - 1) / INTERP_WARPS;
+    if (grid > need) grid = need;
+    if (grid < 1) grid = 1;
+    kern<<<(int)grid, INTERP_WARPS * 32, smem, stream>>>(T, cfg, E, fields, N, elem, xi, out);
+    MM_CUDA(cudaGetLastError());
+    return MM_OK;
+}
+
+// ---- coefficient write-out: coeffs[n][a] = (Lx[i] * Ly[j]) * Lz[k] -----------------------------
+template <int ORDER, int DIM>
+__global__ void __launch_bounds__(256)
+coeffs_kernel(const mm_gll_table T, int64_t N, const int32_t *__restrict__ elem,
+              const double *__restrict__ xi, double *__restrict__ coeffs)
+{
+    constexpr int M = ORDER + 1;
+    constexpr int P = DIM == 2 ? M * M : M * M * M;
+    for (int64_t n = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; n < N;
+         n += (int64_t)gridDim.x * blockDim.x) {
+        double *w = coeffs + n * P;
+        if (elem && elem[n] < 0) {
+            for (int a = 0; a < P; ++a) w[a] = 0.0;
+            continue;
+        }
+        double L[DIM][M];
+#pragma unroll
+        for (int ax = 0; ax < DIM; ++ax) lagrange_values<ORDER>(T, xi[n * DIM + ax], L[ax]);
+        if constexpr (DIM == 2) {
+#pragma unroll
+            for (int j = 0; j < M; ++j)
+#pragma unroll
+                for (int i = 0; i < M; ++i) w[i + M * j] = L[0][i] * L[1][j];
+        } else {
+#pragma unroll
+            for (int k = 0; k < M; ++k)
+#pragma unroll
+                for (int j = 0; j < M; ++j)
+#pragma unroll
+                    for (int i = 0; i < M; ++i)
+                        w[i + M * j + M * M * k] = (L[0][i] * L[1][j]) * L[2][k];
+        }
+    }
+}
+
+// ---- explicit-matrix gather (cached elements/coeffs): one warp per point -----------------------
+// out[n][f] = sum_a fields[e][f][a] * coeffs[n][a], a ascending (sequential, lane 0 finishes).
+__global__ void __launch_bounds__(256)
+gather_coeffs_kernel(int P, int64_t E, int F, const double *__restrict__ fields, int64_t N,
+                     const int32_t *__restrict__ elem, const double *__restrict__ coeffs,
+                     double *__restrict__ out)
+{
+    // thread per (point, field): the P-long dot product walks one contiguous row
+    int64_t total = N * F;
+    for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < total;
+         t += (int64_t)gridDim.x * blockDim.x) {
+        int64_t n = t / F;
+        int f = (int)(t - n * F);
+        int32_t e = elem[n];
+        double acc = 0.0;
+        if (e >= 0) {
+            const double *v = fields + ((int64_t)e * F + f) * P;
+            const double *w = coeffs + n * P;
+            for (int a = 0; a < P; ++a) acc = acc + v[a] * w[a];
+        }
+        out[t] = acc;
+    }
+}
+
+int blocks_for(int64_t work, int block)
+{
+    int sms = mm_num_sms() > 0 ? mm_num_sms() : 148;
+    int64_t need = (work + block - 1) / block;
+    int64_t cap = (int64_t)sms * 16;
+    return (int)(need < 1 ? 1 : (need > cap ? cap : need));
+}
+
+}  // namespace
+
+extern "C" int mm_interp(int order, int dim, int64_t E, int F, const double *fields, int64_t N,
+                         const int32_t *elem, const double *xi, double *out, void *stream_)
+{
+    cudaStream_t stream = (cudaStream_t)stream_;
+    MM_REQUIRE(mm_valid_order(order), MM_ERR_INVALID, "mm_interp: order %d (supported 1, 2, 4)", order);
+    MM_REQUIRE(dim == 2 || dim == 3, MM_ERR_INVALID, "mm_interp: dim %d", dim);
+    MM_REQUIRE(F >= 1 && N >= 0 && E >= 0, MM_ERR_INVALID, "mm_interp: sizes");
+    if (N == 0) return MM_OK;
+    MM_REQUIRE(fields && elem && xi && out, MM_ERR_INVALID, "mm_interp: null buffer");
+    MM_REQUIRE(((uintptr_t)fields & 15) == 0, MM_ERR_INVALID,
+               "mm_interp: fields must be 16-byte aligned");
+#define MM_INT(O, D) \
+    if (order == O && dim == D) return launch_interp<O, D>(E, F, fields, N, elem, xi, out, stream);
+    MM_INT(1, 2) MM_INT(2, 2) MM_INT(4, 2) MM_INT(1, 3) MM_INT(2, 3) MM_INT(4, 3)
+#undef MM_INT
+    mm_set_error("mm_interp: unsupported order/dim");
+    return MM_ERR_UNSUPPORTED;
+}
+
+extern "C" int mm_coeffs(int order, int dim, int64_t N, const int32_t *elem, const double *xi,
+                         double *coeffs, void *stream_)
+{
+    cudaStream_t stream = (cudaStream_t)stream_;
+    MM_REQUIRE(mm_valid_order(order), MM_ERR_INVALID, "mm_coeffs: order %d", order);
+    MM_REQUIRE(dim == 2 || dim == 3, MM_ERR_INVALID, "mm_coeffs: dim %d", dim);
+    if (N == 0) return MM_OK;
+    MM_REQUIRE(N > 0 && xi && coeffs, MM_ERR_INVALID, "mm_coeffs: arguments");
+    mm_gll_table T;
+    mm_make_table(order, &T);
+#define MM_COE(O, D)                                                                       \
+    if (order == O && dim == D) {                                                          \
+        coeffs_kernel<O, D><<<blocks_for(N, 256), 256, 0, stream>>>(T, N, elem, xi, coeffs); \
+        MM_CUDA(cudaGetLastError());                                                       \
+        return MM_OK;                                                                      \
+    }
+    MM_COE(1, 2) MM_COE(2, 2) MM_COE(4, 2) MM_COE(1, 3) MM_COE(2, 3) MM_COE(4, 3)
+#undef MM_COE
+    mm_set_error("mm_coeffs: unsupported order/dim");
+    return MM_ERR_UNSUPPORTED;
+}
+
+extern "C" int mm_gather_coeffs(int P, int64_t E, int F, const double *fields, int64_t N,
+                                const int32_t *elem, const double *coeffs, double *out,
+                                void *stream)
+{
+    MM_REQUIRE(P >= 1 && F >= 1 && N >= 0 && E >= 0, MM_ERR_INVALID, "mm_gather_coeffs: sizes");
+    if (N == 0) return MM_OK;
+    MM_REQUIRE(fields && elem && coeffs && out, MM_ERR_INVALID, "mm_gather_coeffs: null buffer");
+    gather_coeffs_kernel<<<blocks_for(N * F, 256), 256, 0, (cudaStream_t)stream>>>(
+        P, E, F, fields, N, elem, coeffs, out);
+    MM_CUDA(cudaGetLastError());
+    return MM_OK;
+}

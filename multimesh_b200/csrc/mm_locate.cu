@@ -1,0 +1,442 @@
+// mm_locate.cu -- K2: batched point-in-element location (fp64 Newton inverse map + accept/fallback).
+//
+// One thread per target point, warp-synchronous rounds:
+//   1. every unresolved lane advances through its candidate list (skipping negatives, repeats
+//      and -- for V1 -- candidates whose node AABB excludes the point) to its next candidate;
+//   2. all lanes with a candidate stage that element's control nodes ([P][dim] f64, contiguous
+//      in HBM) into their private shared-memory slot with ONE bulk-async copy each
+//      (cp.async.bulk -> UBLKCP), completion tracked by a per-warp mbarrier;
+//   3. each lane shifts its nodes by the point (Y = X - p) and runs Newton on the order-n map with
+//      the sum-factorised canonical evaluation order, reading Y from its slot;
+//   4. accept test / best tracking; lanes that run out of candidates take the variant's fallback.
+// Rounds repeat until every lane is resolved (~1-2 rounds typically).
+//
+// Arithmetic = DESIGN.md section 3 (no FMA, fixed order); mirrors oracle/mm_oracle.c.
+#include "mm_common.cuh"
+
+namespace {
+
+template <int ORDER, int DIM>
+struct elem_traits {
+    static constexpr int M = ORDER + 1;
+    static constexpr int P = DIM == 2 ? M * M : M * M * M;
+    static constexpr int DOUBLES = P * DIM;
+    static constexpr int BYTES = DOUBLES * 8;
+    static constexpr bool MISALIGNED = (BYTES % 16) != 0;  // odd elements start at 8 mod 16
+    static constexpr int COPY_BYTES = MISALIGNED ? BYTES + 8 : BYTES;
+    static constexpr int SLOT_BYTES = mm_slot_bytes(COPY_BYTES);
+};
+
+// x[c] = sum_a w_a Y_a[c],  J[c][s] = sum_a dw_a/dxi_s Y_a[c]; i innermost, then j, then k.
+template <int ORDER, int DIM>
+__device__ __forceinline__ void eval_map(const mm_gll_table &T, const double *__restrict__ Y,
+                                         const double (&xi)[DIM], double (&x)[DIM],
+                                         double (&J)[DIM][DIM])
+{
+    constexpr int M = ORDER + 1;
+    double L[DIM][M], dL[DIM][M];
+#pragma unroll
+    for (int ax = 0; ax < DIM; ++ax) lagrange_values_derivs<ORDER>(T, xi[ax], L[ax], dL[ax]);
+
+    if constexpr (DIM == 2) {
+        double V[2] = {0, 0}, Dxi[2] = {0, 0}, Deta[2] = {0, 0};
+#pragma unroll
+        for (int j = 0; j < M; ++j) {
+            double a[2] = {0, 0}, b[2] = {0, 0};
+#pragma unroll
+            for (int i = 0; i < M; ++i) {
+#pragma unroll
+                for (int c = 0; c < 2; ++c) {
+                    double y = Y[(i + M * j) * 2 + c];
+                    a[c] = a[c] + L[0][i] * y;
+                    b[c] = b[c] + dL[0][i] * y;
+                }
+            }
+#pragma unroll
+            for (int c = 0; c < 2; ++c) {
+                V[c] = V[c] + L[1][j] * a[c];
+                Deta[c] = Deta[c] + dL[1][j] * a[c];
+                Dxi[c] = Dxi[c] + L[1][j] * b[c];
+            }
+        }
+#pragma unroll
+        for (int c = 0; c < 2; ++c) {
+            x[c] = V[c];
+            J[c][0] = Dxi[c];
+            J[c][1] = Deta[c];
+        }
+    } else {
+        double X[3] = {0, 0, 0}, Jx[3] = {0, 0, 0}, Jy[3] = {0, 0, 0}, Jz[3] = {0, 0, 0};
+#pragma unroll
+        for (int k = 0; k < M; ++k) {
+            double V[3] = {0, 0, 0}, Dxi[3] = {0, 0, 0}, Deta[3] = {0, 0, 0};
+#pragma unroll
+            for (int j = 0; j < M; ++j) {
+                double a[3] = {0, 0, 0}, b[3] = {0, 0, 0};
+#pragma unroll
+                for (int i = 0; i < M; ++i) {
+#pragma unroll
+                    for (int c = 0; c < 3; ++c) {
+                        double y = Y[(i + M * j + M * M * k) * 3 + c];
+                        a[c] = a[c] + L[0][i] * y;
+                        b[c] = b[c] + dL[0][i] * y;
+                    }
+                }
+#pragma unroll
+                for (int c = 0; c < 3; ++c) {
+                    V[c] = V[c] + L[1][j] * a[c];
+                    Deta[c] = Deta[c] + dL[1][j] * a[c];
+                    Dxi[c] = Dxi[c] + L[1][j] * b[c];
+                }
+            }
+#pragma unroll
+            for (int c = 0; c < 3; ++c) {
+                X[c] = X[c] + L[2][k] * V[c];
+                Jz[c] = Jz[c] + dL[2][k] * V[c];
+                Jx[c] = Jx[c] + L[2][k] * Dxi[c];
+                Jy[c] = Jy[c] + L[2][k] * Deta[c];
+            }
+        }
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+            x[c] = X[c];
+            J[c][0] = Jx[c];
+            J[c][1] = Jy[c];
+            J[c][2] = Jz[c];
+        }
+    }
+}
+
+// Newton from xi = 0 on point-shifted nodes Y; returns true when max|delta| <= 1e-13.
+template <int ORDER, int DIM>
+__device__ __forceinline__ bool newton_inverse(const mm_gll_table &T,
+                                               const double *__restrict__ Y, double (&xi)[DIM])
+{
+#pragma unroll
+    for (int c = 0; c < DIM; ++c) xi[c] = 0.0;
+#pragma unroll 1
+    for (int it = 0; it < MM_NEWTON_MAXIT; ++it) {
+        double x[DIM], J[DIM][DIM], delta[DIM];
+        eval_map<ORDER, DIM>(T, Y, xi, x, J);
+        if constexpr (DIM == 2) {
+            double r0 = -x[0], r1 = -x[1];
+            double det = J[0][0] * J[1][1] - J[0][1] * J[1][0];
+            delta[0] = (J[1][1] * r0 - J[0][1] * r1) / det;
+            delta[1] = (J[0][0] * r1 - J[1][0] * r0) / det;
+        } else {
+            double r0 = -x[0], r1 = -x[1], r2 = -x[2];
+            double C00 = J[1][1] * J[2][2] - J[1][2] * J[2][1];
+            double C01 = J[1][2] * J[2][0] - J[1][0] * J[2][2];
+            double C02 = J[1][0] * J[2][1] - J[1][1] * J[2][0];
+            double C10 = J[0][2] * J[2][1] - J[0][1] * J[2][2];
+            double C11 = J[0][0] * J[2][2] - J[0][2] * J[2][0];
+            double C12 = J[0][1] * J[2][0] - J[0][0] * J[2][1];
+            double C20 = J[0][1] * J[1][2] - J[0][2] * J[1][1];
+            double C21 = J[0][2] * J[1][0] - J[0][0] * J[1][2];
+            double C22 = J[0][0] * J[1][1] - J[0][1] * J[1][0];
+            double det = (J[0][0] * C00 + J[0][1] * C01) + J[0][2] * C02;
+            delta[0] = ((C00 * r0 + C10 * r1) + C20 * r2) / det;
+            delta[1] = ((C01 * r0 + C11 * r1) + C21 * r2) / det;
+            delta[2] = ((C02 * r0 + C12 * r1) + C22 * r2) / det;
+        }
+        double dmax = 0.0;
+        bool bad = false;
+#pragma unroll
+        for (int c = 0; c < DIM; ++c) {
+            double ad = fabs(delta[c]);
+            if (!(ad <= MM_NEWTON_DIVERGE)) bad = true;
+            if (ad > dmax) dmax = ad;
+            xi[c] = xi[c] + delta[c];
+        }
+        if (bad) return false;
+        if (dmax <= MM_NEWTON_TOL) return true;
+    }
+    return false;
+}
+
+template <int DIM>
+__device__ __forceinline__ bool accept_xi(const mm_locate_params &prm, const double (&xi)[DIM])
+{
+    bool ok = true;
+#pragma unroll
+    for (int c = 0; c < DIM; ++c) {
+        double a = fabs(xi[c]);
+        if (prm.strict ? !(a < prm.tol) : !(a <= prm.tol)) ok = false;
+    }
+    return ok;
+}
+
+template <int ORDER, int DIM, int WARPS>
+__global__ void __launch_bounds__(WARPS * 32)
+locate_kernel(const mm_gll_table T, const mm_locate_params prm, int64_t E,
+              const double *__restrict__ nodes, const double *__restrict__ centroid,
+              const double *__restrict__ aabb, int64_t N, const double *__restrict__ pts, int k,
+              const int32_t *__restrict__ cands, int32_t *__restrict__ elem_out,
+              double *__restrict__ xi_out, uint8_t *__restrict__ status_out,
+              unsigned long long *__restrict__ num_failed)
+{
+    using tr = elem_traits<ORDER, DIM>;
+    extern __shared__ __align__(128) unsigned char smem[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    unsigned char *slot = smem + ((size_t)warp * 32 + lane) * tr::SLOT_BYTES;
+    uint64_t *bar = reinterpret_cast<uint64_t *>(smem + (size_t)WARPS * 32 * tr::SLOT_BYTES) + warp;
+    if (lane == 0) mbar_init(bar, 1);
+    fence_mbar_init();
+    __syncthreads();
+    uint32_t phase = 0;
+    const int64_t total_bytes = E * (int64_t)tr::BYTES;
+    unsigned long long failed_local = 0;
+
+    const int64_t warps_total = (int64_t)gridDim.x * WARPS;
+    for (int64_t batch = (int64_t)blockIdx.x * WARPS + warp; batch * 32 < N; batch += warps_total) {
+        const int64_t n = batch * 32 + lane;
+        bool done = n >= N;
+        double p[DIM];
+#pragma unroll
+        for (int c = 0; c < DIM; ++c) p[c] = done ? 0.0 : pts[n * DIM + c];
+        const int32_t *cl = cands + (done ? 0 : n * (int64_t)k);
+        int t = 0;
+        int32_t r_elem = -1;
+        uint8_t r_status = MM_ST_FAILED;
+        double r_xi[DIM];
+#pragma unroll
+        for (int c = 0; c < DIM; ++c) r_xi[c] = 0.0;
+        int32_t first_inside = -1, near_elem = -1, best_elem = -1;
+        double near_dist = INFINITY;
+        double best_key = prm.fallback == MM_FB_SNAP ? 10e9 : INFINITY;
+        double best_xi[DIM];
+#pragma unroll
+        for (int c = 0; c < DIM; ++c) best_xi[c] = 0.0;
+
+        while (true) {
+            int32_t e = -1;
+            bool fb_newton = false;
+            if (!done) {
+                while (t < k) {
+                    int32_t c = cl[t];
+                    ++t;
+                    if (c < 0) continue;
+                    bool dup = false;
+                    for (int u = 0; u < t - 1; ++u) dup = dup || (cl[u] == c);
+                    if (dup) continue;
+                    if (prm.aabb_prefilter) {
+                        const double *lo = aabb + ((int64_t)c * 2 + 0) * DIM;
+                        const double *hi = lo + DIM;
+                        bool inside = true;
+#pragma unroll
+                        for (int q = 0; q < DIM; ++q)
+                            if (!(p[q] >= lo[q] && p[q] <= hi[q])) inside = false;
+                        if (!inside) {
+                            const double *cc = centroid + (int64_t)c * DIM;
+                            double dx = p[0] - cc[0], dy = p[1] - cc[1];
+                            double s = dx * dx + dy * dy;
+                            if constexpr (DIM == 3) {
+                                double dz = p[2] - cc[2];
+                                s = s + dz * dz;
+                            }
+                            double d = sqrt(s);
+                            if (d < near_dist) {
+                                near_dist = d;
+                                near_elem = c;
+                            }
+                            continue;
+                        }
+                        if (first_inside < 0) first_inside = c;
+                    }
+                    e = c;
+                    break;
+                }
+                if (e < 0) {  // candidates exhausted without acceptance: fallback
+                    done = true;
+                    if (prm.fallback == MM_FB_MAGIC) {
+                        if (first_inside >= 0) {
+                            r_elem = first_inside;
+                            r_status = MM_ST_FB_INSIDE_MAGIC;
+#pragma unroll
+                            for (int c = 0; c < DIM; ++c) r_xi[c] = prm.magic_xi[c];
+                        } else if (near_elem >= 0) {
+                            e = near_elem;
+                            fb_newton = true;
+                            done = false;
+                        }
+                    } else if (prm.fallback == MM_FB_SNAP) {
+                        if (best_elem >= 0) {
+                            r_elem = best_elem;
+                            r_status = MM_ST_SNAPPED;
+#pragma unroll
+                            for (int c = 0; c < DIM; ++c) {
+                                double v = best_xi[c];
+                                if (v < -prm.snap_clip) v = -prm.snap_clip;
+                                if (v > prm.snap_clip) v = prm.snap_clip;
+                                r_xi[c] = v;
+                            }
+                        } else {
+                            r_elem = 0;
+                            r_status = MM_ST_SNAP_NONE;
+#pragma unroll
+                            for (int c = 0; c < DIM; ++c) r_xi[c] = prm.snap_clip;
+                        }
+                    } else if (prm.fallback == MM_FB_MINL1) {
+                        if (best_elem >= 0) {
+                            r_elem = best_elem;
+                            r_status = MM_ST_MINL1;
+#pragma unroll
+                            for (int c = 0; c < DIM; ++c) r_xi[c] = best_xi[c];
+                        }
+                    }
+                }
+            }
+            const unsigned active = __ballot_sync(0xffffffffu, e >= 0);
+            if (!active) break;
+
+            // ---- stage the candidate elements' control nodes: one bulk copy per lane ----------
+            int shift = 0;
+            bool use_tma = false;
+            const double *src = nodes;
+            if (e >= 0) {
+                const int64_t off = (int64_t)e * tr::BYTES;
+                shift = tr::MISALIGNED ? (int)(off & 8) : 0;
+                use_tma = (off - shift + tr::COPY_BYTES) <= total_bytes;
+                src = nodes + (int64_t)e * tr::DOUBLES;
+            }
+            const unsigned tma_mask = __ballot_sync(0xffffffffu, use_tma);
+            if (lane == 0 && tma_mask)
+                mbar_arrive_expect_tx(bar, (uint32_t)__popc(tma_mask) * tr::COPY_BYTES);
+            __syncwarp();
+            double *Y = reinterpret_cast<double *>(slot + shift);
+            if (use_tma) {
+                bulk_copy_g2s(slot, reinterpret_cast<const unsigned char *>(src) - shift,
+                              tr::COPY_BYTES, bar);
+            } else if (e >= 0) {
+                for (int q = 0; q < tr::DOUBLES; ++q) Y[q] = src[q];  // array tail: plain loads
+            }
+            if (tma_mask) {
+                mbar_wait(bar, phase);
+                phase ^= 1;
+            }
+            if (e >= 0) {
+                for (int a = 0; a < tr::P; ++a) {
+#pragma unroll
+                    for (int c = 0; c < DIM; ++c) Y[a * DIM + c] = Y[a * DIM + c] - p[c];
+                }
+                double x[DIM];
+                const bool ok = newton_inverse<ORDER, DIM>(T, Y, x);
+                if (fb_newton) {  // V1: nearest-centre element, interpolator.py:1460-1473
+                    bool big = false;
+#pragma unroll
+                    for (int c = 0; c < DIM; ++c)
+                        if (ok && fabs(x[c]) >= prm.tol) big = true;
+                    r_elem = e;
+                    r_status = !ok ? MM_ST_FB_NAN_MAGIC : (big ? MM_ST_FB_NEAR_MAGIC : MM_ST_FB_NEAR_OK);
+#pragma unroll
+                    for (int c = 0; c < DIM; ++c)
+                        r_xi[c] = (r_status == MM_ST_FB_NEAR_OK) ? x[c] : prm.magic_xi[c];
+                    done = true;
+                } else if (ok) {
+                    if (prm.fallback == MM_FB_SNAP || prm.fallback == MM_FB_MINL1) {
+                        double key = 0.0;
+#pragma unroll
+                        for (int c = 0; c < DIM; ++c) {
+                            double a = fabs(x[c]);
+                            if (prm.fallback == MM_FB_SNAP) key = a > key ? a : key;
+                            else key = key + a;
+                        }
+                        if (key < best_key) {
+                            best_key = key;
+                            best_elem = e;
+#pragma unroll
+                            for (int c = 0; c < DIM; ++c) best_xi[c] = x[c];
+                        }
+                    }
+                    if (accept_xi<DIM>(prm, x)) {
+                        r_elem = e;
+                        r_status = MM_ST_ACCEPTED;
+#pragma unroll
+                        for (int c = 0; c < DIM; ++c) r_xi[c] = x[c];
+                        done = true;
+                    }
+                }
+            }
+            // generic-proxy reads/writes of the slots must be ordered before the next round's
+            // async-proxy (bulk copy) writes into the same slots
+            fence_proxy_async_smem();
+            __syncwarp();
+        }
+        if (n < N) {
+            elem_out[n] = r_elem;
+#pragma unroll
+            for (int c = 0; c < DIM; ++c) xi_out[n * DIM + c] = r_elem < 0 ? 0.0 : r_xi[c];
+            if (status_out) status_out[n] = r_status;
+            if (r_elem < 0) failed_local += 1;
+        }
+    }
+    if (num_failed) {
+        for (int o = 16; o > 0; o >>= 1) failed_local += __shfl_xor_sync(0xffffffffu, failed_local, o);
+        if (lane == 0 && failed_local) atomicAdd(num_failed, failed_local);
+    }
+}
+
+template <int ORDER, int DIM, int WARPS>
+int launch_locate(const mm_locate_params &prm, int64_t E, const double *nodes,
+                  const double *centroid, const double *aabb, int64_t N, const double *pts, int k,
+                  const int32_t *cands, int32_t *elem, double *xi, uint8_t *status,
+                  int64_t *num_failed, cudaStream_t stream)
+{
+    using tr = elem_traits<ORDER, DIM>;
+    mm_gll_table T;
+    mm_make_table(ORDER, &T);
+    auto kern = locate_kernel<ORDER, DIM, WARPS>;
+    const size_t smem = (size_t)WARPS * 32 * tr::SLOT_BYTES + WARPS * sizeof(uint64_t);
+    MM_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int per_sm = 1;
+    MM_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, WARPS * 32, smem));
+    if (per_sm < 1) per_sm = 1;
+    const int sms = mm_num_sms() > 0 ? mm_num_sms() : 148;
+    int64_t batches = (N + 32 * WARPS - 1) / (32 * WARPS);
+    int64_t grid = (int64_t)sms * per_sm;  // persistent: resident CTAs loop over point batches
+    if (grid > batches) grid = batches;
+    if (grid < 1) grid = 1;
+    kern<<<(int)grid, WARPS * 32, smem, stream>>>(T, prm, E, nodes, centroid, aabb, N, pts, k,
+                                                  cands, elem, xi, status,
+                                                  reinterpret_cast<unsigned long long *>(num_failed));
+    MM_CUDA(cudaGetLastError());
+    return MM_OK;
+}
+
+}  // namespace
+
+extern "C" int mm_locate(int order, int dim, int64_t E, const double *nodes,
+                         const double *centroid, const double *aabb, int64_t N, const double *pts,
+                         int k, const int32_t *cands, const mm_locate_params *params,
+                         int32_t *elem, double *xi, uint8_t *status, int64_t *num_failed,
+                         void *stream_)
+{
+    cudaStream_t stream = (cudaStream_t)stream_;
+    MM_REQUIRE(mm_valid_order(order), MM_ERR_INVALID, "mm_locate: order %d (supported 1, 2, 4)", order);
+    MM_REQUIRE(dim == 2 || dim == 3, MM_ERR_INVALID, "mm_locate: dim %d", dim);
+    MM_REQUIRE(params, MM_ERR_INVALID, "mm_locate: null params");
+    MM_REQUIRE(params->fallback >= MM_FB_FAIL && params->fallback <= MM_FB_MINL1, MM_ERR_INVALID,
+               "mm_locate: fallback %d", (int)params->fallback);
+    MM_REQUIRE(k >= 1, MM_ERR_INVALID, "mm_locate: k=%d", k);
+    MM_REQUIRE(N >= 0 && E >= 0, MM_ERR_INVALID, "mm_locate: sizes");
+    if (num_failed) MM_CUDA(cudaMemsetAsync(num_failed, 0, sizeof(int64_t), stream));
+    if (N == 0) return MM_OK;
+    MM_REQUIRE(nodes && pts && cands && elem && xi, MM_ERR_INVALID, "mm_locate: null buffer");
+    MM_REQUIRE(((uintptr_t)nodes & 15) == 0, MM_ERR_INVALID,
+               "mm_locate: nodes must be 16-byte aligned");
+    MM_REQUIRE(!params->aabb_prefilter || (centroid && aabb), MM_ERR_INVALID,
+               "mm_locate: aabb_prefilter needs centroid and aabb (mm_element_geometry)");
+#define MM_LOC(O, D, W)                                                                          \
+    if (order == O && dim == D)                                                                  \
+        return launch_locate<O, D, W>(*params, E, nodes, centroid, aabb, N, pts, k, cands, elem, \
+                                      xi, status, num_failed, stream);
+    MM_LOC(1, 2, 4)
+    MM_LOC(2, 2, 4)
+    MM_LOC(4, 2, 4)
+    MM_LOC(1, 3, 4)
+    MM_LOC(2, 3, 4)
+    MM_LOC(4, 3, 2)
+#undef MM_LOC
+    mm_set_error("mm_locate: unsupported order/dim");
+    return MM_ERR_UNSUPPORTED;
+}

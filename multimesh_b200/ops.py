@@ -1,0 +1,343 @@
+"""
+PyTorch custom ops over the C-ABI (include/multimesh_b200.h).
+
+torch is plumbing here: device memory, the current CUDA stream and `torch.library` registration.
+Every op takes CUDA tensors, launches the hand-written sm_100a kernels through ctypes on torch's
+current stream and returns CUDA tensors.  CPU tensors are rejected -- there is no CPU path.
+
+Inner operator boundary of the reference that these ops replace:
+    KDTree(...).query(pts, k)                       -> GridIndex.query          (K1)
+    inverse_transform + _check_if_inside_element... -> locate                   (K2)
+    get_coefficients + np.sum(data[elem] * coeffs)  -> interp / coeffs          (K3)
+"""
+import ctypes as C
+from dataclasses import dataclass
+from typing import Tuple
+
+import torch
+
+from . import _lib
+from ._lib import (FB_FAIL, FB_MAGIC, FB_MINL1, FB_SNAP, LocateParams, MultiMeshError, check,  # noqa: F401
+                   load_lib)
+from .gll import SUPPORTED_ORDERS
+
+__all__ = [
+    "LocateSpec", "V1", "V2", "V3", "V4", "V5", "GridIndex", "element_geometry", "locate", "interp",
+    "coeffs", "gather_coeffs", "trilinear", "centroid_conn", "gather_nodal", "map_to_sphere_",
+]
+
+
+# ----------------------------------------------------------------------------------------------
+# location-logic variants of the reference, as parameter sets of ONE kernel
+# ----------------------------------------------------------------------------------------------
+@dataclass(frozen=True)
+class LocateSpec:
+    aabb_prefilter: bool
+    tol: float
+    strict: bool
+    fallback: int
+    snap_clip: float = 1.02
+    magic_xi: Tuple[float, float, float] = (0.645, -0.5, 0.22)
+
+    def to_c(self) -> LocateParams:
+        p = LocateParams()
+        p.aabb_prefilter = int(self.aabb_prefilter)
+        p.strict = int(self.strict)
+        p.fallback = int(self.fallback)
+        p.tol = float(self.tol)
+        p.snap_clip = float(self.snap_clip)
+        for i in range(3):
+            p.magic_xi[i] = float(self.magic_xi[i])
+        return p
+
+
+def V1() -> LocateSpec:
+    """_check_if_inside_element (interpolator.py:1409-1473): AABB prefilter, |xi| <= 1.04,
+    fallback = first AABB hit / nearest centre with the reference's magic xi."""
+    return LocateSpec(True, 1.04, False, FB_MAGIC)
+
+
+def V2(tolerance: float = 1.05, snap_to_nearest: bool = False) -> LocateSpec:
+    """get_element_weights.check_inside (interpolator.py:1181-1233)."""
+    return LocateSpec(False, tolerance, True, FB_SNAP if snap_to_nearest else FB_FAIL)
+
+
+def V3() -> LocateSpec:
+    """get_element_weights_layered.check_inside (interpolator.py:1271-1297)."""
+    return LocateSpec(False, 1.03, True, FB_FAIL)
+
+
+def V4() -> LocateSpec:
+    """v2_interpolation_tools.get_element_weights (v2_interpolation_tools.py:71-164)."""
+    return LocateSpec(False, 1.05, True, FB_FAIL)
+
+
+def V5() -> LocateSpec:
+    """cli._check_if_inside_element (scripts/cli.py:401-430)."""
+    return LocateSpec(False, 1.02, False, FB_MINL1)
+
+
+# ----------------------------------------------------------------------------------------------
+# helpers
+# ----------------------------------------------------------------------------------------------
+def _stream() -> C.c_void_p:
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _ptr(t):
+    return C.c_void_p(0 if t is None else t.data_ptr())
+
+
+def _need_cuda(t: torch.Tensor, name: str, dtype=None) -> torch.Tensor:
+    if not isinstance(t, torch.Tensor):
+        raise TypeError(f"{name}: expected a torch.Tensor, got {type(t)}")
+    if not t.is_cuda:
+        raise MultiMeshError(
+            f"{name}: tensor is on {t.device}; multimesh_b200 runs on CUDA only (no CPU fallback)")
+    if dtype is not None and t.dtype != dtype:
+        raise TypeError(f"{name}: expected dtype {dtype}, got {t.dtype}")
+    if not t.is_contiguous():
+        t = t.contiguous()
+    if t.data_ptr() % 16 != 0:  # bulk-async copies need 16-byte aligned bases
+        t = t.clone()
+    return t
+
+
+def _order_dim(P: int, dim: int) -> int:
+    for o in SUPPORTED_ORDERS:
+        if (o + 1) ** dim == P:
+            return o
+    raise ValueError(f"{P} nodes per element is not (order+1)^{dim} for order in {SUPPORTED_ORDERS}")
+
+
+# ----------------------------------------------------------------------------------------------
+# K0
+# ----------------------------------------------------------------------------------------------
+@torch.library.custom_op("multimesh::element_geometry", mutates_args=())
+def element_geometry(nodes: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor]:
+    """nodes [E,P,d] -> (centroid [E,d], aabb [E,2,d])."""
+    nodes = _need_cuda(nodes, "nodes", torch.float64)
+    E, P, d = nodes.shape
+    order = _order_dim(P, d)
+    with torch.cuda.device(nodes.device):
+        cent = torch.empty((E, d), dtype=torch.float64, device=nodes.device)
+        box = torch.empty((E, 2, d), dtype=torch.float64, device=nodes.device)
+        check(load_lib().mm_element_geometry(order, d, E, _ptr(nodes), _ptr(cent), _ptr(box),
+                                             _stream()), "mm_element_geometry")
+    return cent, box
+
+
+def map_to_sphere_(points: torch.Tensor, radius_1d: torch.Tensor, r_earth: float = 6371000.0):
+    """In place; points [..., 3], radius_1d [...] (interpolator.py:1125-1144)."""
+    p = _need_cuda(points, "points", torch.float64)
+    r = _need_cuda(radius_1d, "radius_1d", torch.float64)
+    if p.data_ptr() != points.data_ptr():
+        raise ValueError("map_to_sphere_: points must be contiguous (in-place op)")
+    n = r.numel()
+    assert p.numel() == 3 * n
+    with torch.cuda.device(p.device):
+        check(load_lib().mm_map_to_sphere(n, _ptr(p), _ptr(r), float(r_earth), _stream()),
+              "mm_map_to_sphere")
+    return points
+
+
+# ----------------------------------------------------------------------------------------------
+# K1
+# ----------------------------------------------------------------------------------------------
+@torch.library.custom_op("multimesh::knn", mutates_args=())
+def _knn_op(handle: int, pts: torch.Tensor, k: int, divisor: int) -> torch.Tensor:
+    pts = _need_cuda(pts, "pts", torch.float64)
+    N = pts.shape[0]
+    with torch.cuda.device(pts.device):
+        idx = torch.empty((N, k), dtype=torch.int32, device=pts.device)
+        check(load_lib().mm_knn(C.c_void_p(handle), N, _ptr(pts), k, divisor, _ptr(idx), None,
+                                _stream()), "mm_knn")
+    return idx
+
+
+class GridIndex:
+    """GPU replacement for `pykdtree.kdtree.KDTree(data)`: exact k-NN in the canonical
+    (d2, index) order.  `query` mirrors KDTree.query's (dist, idx) return."""
+
+    def __init__(self, data: torch.Tensor):
+        data = _need_cuda(data, "data", torch.float64)
+        if data.dim() != 2 or data.shape[1] not in (2, 3):
+            raise ValueError("GridIndex: data must be [M, 2] or [M, 3]")
+        self.device = data.device
+        self.n, self.dim = data.shape
+        h = C.c_void_p()
+        with torch.cuda.device(self.device):
+            check(load_lib().mm_index_create(C.byref(h), self.dim, self.n, _ptr(data), _stream()),
+                  "mm_index_create")
+        self._h = h.value
+
+    def info(self):
+        arr = (C.c_int64 * 8)()
+        cell = C.c_double()
+        check(load_lib().mm_index_info(C.c_void_p(self._h), C.byref(arr), C.byref(cell)),
+              "mm_index_info")
+        return {"M": arr[0], "dim": arr[1], "cells": (arr[2], arr[3], arr[4]),
+                "nonempty_cells": arr[5], "bytes": arr[6], "cell_size": cell.value}
+
+    def query_idx(self, pts: torch.Tensor, k: int, divisor: int = 1) -> torch.Tensor:
+        if self._h is None:
+            raise MultiMeshError("GridIndex used after close()")
+        if pts.dim() != 2 or pts.shape[1] != self.dim:
+            raise ValueError(f"query points must be [N, {self.dim}]")
+        return _knn_op(self._h, pts, int(k), int(divisor))
+
+    def query(self, pts: torch.Tensor, k: int = 1):
+        """(dist [N,k], idx [N,k]); dist = sqrt(d2)."""
+        pts = _need_cuda(pts, "pts", torch.float64)
+        N = pts.shape[0]
+        with torch.cuda.device(self.device):
+            idx = torch.empty((N, k), dtype=torch.int32, device=self.device)
+            d2 = torch.empty((N, k), dtype=torch.float64, device=self.device)
+            check(load_lib().mm_knn(C.c_void_p(self._h), N, _ptr(pts), int(k), 1, _ptr(idx),
+                                    _ptr(d2), _stream()), "mm_knn")
+        return torch.sqrt(d2), idx
+
+    def close(self):
+        if getattr(self, "_h", None):
+            load_lib().mm_index_destroy(C.c_void_p(self._h))
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+# ----------------------------------------------------------------------------------------------
+# K2
+# ----------------------------------------------------------------------------------------------
+@torch.library.custom_op("multimesh::locate", mutates_args=())
+def _locate_op(nodes: torch.Tensor, centroid: torch.Tensor, aabb: torch.Tensor, pts: torch.Tensor,
+               cands: torch.Tensor, aabb_prefilter: bool, tol: float, strict: bool, fallback: int,
+               snap_clip: float, m0: float, m1: float, m2: float
+               ) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor, torch.Tensor]:
+    nodes = _need_cuda(nodes, "nodes", torch.float64)
+    pts = _need_cuda(pts, "pts", torch.float64)
+    cands = _need_cuda(cands, "cands", torch.int32)
+    centroid = _need_cuda(centroid, "centroid", torch.float64)
+    aabb = _need_cuda(aabb, "aabb", torch.float64)
+    E, P, d = nodes.shape
+    order = _order_dim(P, d)
+    N, k = cands.shape
+    if pts.shape != (N, d):
+        raise ValueError(f"pts must be [{N}, {d}], got {tuple(pts.shape)}")
+    prm = LocateSpec(aabb_prefilter, tol, strict, fallback, snap_clip, (m0, m1, m2)).to_c()
+    dev = nodes.device
+    with torch.cuda.device(dev):
+        elem = torch.empty((N,), dtype=torch.int32, device=dev)
+        xi = torch.empty((N, d), dtype=torch.float64, device=dev)
+        status = torch.empty((N,), dtype=torch.uint8, device=dev)
+        nfail = torch.zeros((1,), dtype=torch.int64, device=dev)
+        check(load_lib().mm_locate(order, d, E, _ptr(nodes), _ptr(centroid), _ptr(aabb), N,
+                                   _ptr(pts), k, _ptr(cands), C.byref(prm), _ptr(elem), _ptr(xi),
+                                   _ptr(status), _ptr(nfail), _stream()), "mm_locate")
+    return elem, xi, status, nfail
+
+
+def locate(nodes, centroid, aabb, pts, cands, spec: LocateSpec):
+    """-> (elem [N] i32, xi [N,d] f64, status [N] u8, num_failed [1] i64 on device)."""
+    return _locate_op(nodes, centroid, aabb, pts, cands, spec.aabb_prefilter, spec.tol,
+                      spec.strict, spec.fallback, spec.snap_clip, *spec.magic_xi)
+
+
+# ----------------------------------------------------------------------------------------------
+# K3
+# ----------------------------------------------------------------------------------------------
+@torch.library.custom_op("multimesh::interp", mutates_args=())
+def interp(fields: torch.Tensor, elem: torch.Tensor, xi: torch.Tensor) -> torch.Tensor:
+    """fields [E,F,P], elem [N] i32, xi [N,d] -> out [N,F]."""
+    fields = _need_cuda(fields, "fields", torch.float64)
+    elem = _need_cuda(elem, "elem", torch.int32)
+    xi = _need_cuda(xi, "xi", torch.float64)
+    E, F, P = fields.shape
+    N, d = xi.shape
+    order = _order_dim(P, d)
+    with torch.cuda.device(fields.device):
+        out = torch.empty((N, F), dtype=torch.float64, device=fields.device)
+        check(load_lib().mm_interp(order, d, E, F, _ptr(fields), N, _ptr(elem), _ptr(xi),
+                                   _ptr(out), _stream()), "mm_interp")
+    return out
+
+
+@torch.library.custom_op("multimesh::coeffs", mutates_args=())
+def coeffs(elem: torch.Tensor, xi: torch.Tensor, order: int) -> torch.Tensor:
+    """-> coeffs [N,P]; zero rows where elem < 0."""
+    elem = _need_cuda(elem, "elem", torch.int32)
+    xi = _need_cuda(xi, "xi", torch.float64)
+    N, d = xi.shape
+    P = (order + 1) ** d
+    with torch.cuda.device(xi.device):
+        out = torch.empty((N, P), dtype=torch.float64, device=xi.device)
+        check(load_lib().mm_coeffs(order, d, N, _ptr(elem), _ptr(xi), _ptr(out), _stream()),
+              "mm_coeffs")
+    return out
+
+
+def gather_coeffs(fields: torch.Tensor, elem: torch.Tensor, coeff: torch.Tensor) -> torch.Tensor:
+    """Cached-matrix gather: out[n,f] = sum_a fields[elem_n,f,a] * coeff[n,a]."""
+    fields = _need_cuda(fields, "fields", torch.float64)
+    elem = _need_cuda(elem, "elem", torch.int32)
+    coeff = _need_cuda(coeff, "coeffs", torch.float64)
+    E, F, P = fields.shape
+    N = elem.shape[0]
+    assert coeff.shape == (N, P)
+    with torch.cuda.device(fields.device):
+        out = torch.empty((N, F), dtype=torch.float64, device=fields.device)
+        check(load_lib().mm_gather_coeffs(P, E, F, _ptr(fields), N, _ptr(elem), _ptr(coeff),
+                                          _ptr(out), _stream()), "mm_gather_coeffs")
+    return out
+
+
+# ----------------------------------------------------------------------------------------------
+# order-1 nodal (Exodus) path
+# ----------------------------------------------------------------------------------------------
+def trilinear(nearest: torch.Tensor, connectivity: torch.Tensor, nodes: torch.Tensor,
+              points: torch.Tensor):
+    """Device twin of lib.triLinearInterpolator.  nearest [N,k] i64, connectivity [E,8] i64 (C
+    vertex order), nodes [Np,3], points [N,3] -> (num_failed [1] i64, enclosing [N,8] i64,
+    weights [N,8]); failed points keep zero weights / zero node ids."""
+    nearest = _need_cuda(nearest, "nearest", torch.int64)
+    connectivity = _need_cuda(connectivity, "connectivity", torch.int64)
+    nodes = _need_cuda(nodes, "nodes", torch.float64)
+    points = _need_cuda(points, "points", torch.float64)
+    N, k = nearest.shape
+    dev = points.device
+    with torch.cuda.device(dev):
+        enc = torch.zeros((N, 8), dtype=torch.int64, device=dev)
+        w = torch.zeros((N, 8), dtype=torch.float64, device=dev)
+        nfail = torch.zeros((1,), dtype=torch.int64, device=dev)
+        check(load_lib().mm_trilinear(k, N, _ptr(nearest), _ptr(connectivity), _ptr(enc),
+                                      _ptr(nodes), _ptr(w), _ptr(points), _ptr(nfail), _stream()),
+              "mm_trilinear")
+    return nfail, enc, w
+
+
+def centroid_conn(connectivity: torch.Tensor, points: torch.Tensor) -> torch.Tensor:
+    connectivity = _need_cuda(connectivity, "connectivity", torch.int64)
+    points = _need_cuda(points, "points", torch.float64)
+    E, npe = connectivity.shape
+    with torch.cuda.device(points.device):
+        out = torch.empty((E, points.shape[1]), dtype=torch.float64, device=points.device)
+        check(load_lib().mm_centroid_conn(points.shape[1], E, npe, _ptr(connectivity),
+                                          _ptr(points), _ptr(out), _stream()), "mm_centroid_conn")
+    return out
+
+
+def gather_nodal(param: torch.Tensor, enclosing: torch.Tensor, weights: torch.Tensor) -> torch.Tensor:
+    """param [F,Np], enclosing [N,8] i64, weights [N,8] -> values [F,N]."""
+    param = _need_cuda(param, "param", torch.float64)
+    enclosing = _need_cuda(enclosing, "enclosing", torch.int64)
+    weights = _need_cuda(weights, "weights", torch.float64)
+    F, npm = param.shape
+    N = enclosing.shape[0]
+    with torch.cuda.device(param.device):
+        out = torch.empty((F, N), dtype=torch.float64, device=param.device)
+        check(load_lib().mm_gather_nodal(F, npm, _ptr(param), N, _ptr(enclosing), _ptr(weights),
+                                         _ptr(out), _stream()), "mm_gather_nodal")
+    return out

@@ -1,0 +1,392 @@
+"""
+GPU parity tests (the parity tests proper): every CUDA kernel, called through the C-ABI via the
+torch custom ops, against the CPU oracle on the same seeded inputs.
+
+Bar (BASELINE.json north_star): element ownership and k-NN indices bit-exact; reference
+coordinates within 1e-12 absolute; interpolated values within 1e-10 relative.  Because the
+kernels and the oracle share one documented operation order, the tests additionally assert
+bit-identity and report it -- the tolerance asserts are the contract, bit-identity the design goal.
+"""
+import numpy as np
+import pytest
+
+from multimesh_b200 import meshgen
+
+pytestmark = pytest.mark.gpu
+
+XI_ATOL = 1e-12
+VAL_RTOL = 1e-10
+
+
+def _t(a, dev, dtype=None):
+    import torch
+
+    return torch.as_tensor(np.ascontiguousarray(a), dtype=dtype).to(dev)
+
+
+def _mesh(order, dim, n, warp, lo=None, hi=None):
+    shape = (n,) * dim
+    return meshgen.box_mesh(shape, order, lo=lo, hi=hi, warp=warp)
+
+
+def _targets(rng, dim, n, lo=-0.03, hi=1.03):
+    return rng.uniform(lo, hi, size=(n, dim))
+
+
+# ---------------------------------------------------------------------------------------------
+# K0
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("order,dim", [(1, 2), (2, 2), (4, 2), (1, 3), (2, 3), (4, 3)])
+def test_element_geometry_bit_exact(cuda, oracle, order, dim):
+    from multimesh_b200 import ops
+
+    nodes = _mesh(order, dim, 5, 0.04)
+    cent, box = ops.element_geometry(_t(nodes, cuda))
+    assert np.array_equal(cent.cpu().numpy(), oracle.centroids(nodes))
+    assert np.array_equal(box.cpu().numpy(), oracle.aabb(nodes))
+    # and bit-equal to the reference's np.mean(points, axis=1) (salvus_mesh_reader.py:99-100)
+    assert np.array_equal(cent.cpu().numpy(), np.mean(nodes, axis=1))
+
+
+# ---------------------------------------------------------------------------------------------
+# K1
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("dim,k", [(3, 20), (3, 25), (3, 30), (2, 20), (3, 1), (3, 64)])
+def test_knn_random_bit_exact(cuda, oracle, dim, k):
+    from multimesh_b200 import ops
+
+    rng = np.random.default_rng(10 + dim + k)
+    data = rng.random((5000, dim))
+    pts = _targets(rng, dim, 3000, -0.2, 1.2)
+    ix = ops.GridIndex(_t(data, cuda))
+    got = ix.query_idx(_t(pts, cuda), k).cpu().numpy()
+    want = oracle.knn_bruteforce(data, pts, k)
+    assert np.array_equal(got, want)
+    dist, idx = ix.query(_t(pts, cuda), k)
+    _, d2 = oracle.knn_bruteforce(data, pts, k, return_d2=True)
+    assert np.array_equal(dist.cpu().numpy(), np.sqrt(d2))
+    ix.close()
+
+
+def test_knn_structured_ties_bit_exact(cuda, oracle):
+    """Structured-grid centroids with targets ON mesh nodes: 8-way exact distance ties
+    (SURVEY fact 5); the canonical order is (d2, index)."""
+    from multimesh_b200 import ops
+
+    nodes = _mesh(2, 3, 8, 0.0)
+    cent = oracle.centroids(nodes)
+    pts = nodes.reshape(-1, 3)[::7]
+    ix = ops.GridIndex(_t(cent, cuda))
+    got = ix.query_idx(_t(pts, cuda), 20).cpu().numpy()
+    assert np.array_equal(got, oracle.knn_bruteforce(cent, pts, 20))
+
+
+def test_knn_gll_point_form_duplicates(cuda, oracle):
+    """gll_2_gll form: tree over ALL GLL points (shared nodes appear up to 8 times),
+    idx // P -> element ids (interpolator.py:674-678,751-756)."""
+    from multimesh_b200 import ops
+
+    nodes = _mesh(2, 3, 6, 0.02)
+    allp = nodes.reshape(-1, 3)
+    rng = np.random.default_rng(3)
+    pts = np.concatenate([_targets(rng, 3, 1500), allp[::11]])
+    ix = ops.GridIndex(_t(allp, cuda))
+    got = ix.query_idx(_t(pts, cuda), 20, divisor=27).cpu().numpy()
+    want = oracle.knn_bruteforce(allp, pts, 20) // 27
+    assert np.array_equal(got, want)
+
+
+def test_knn_edge_cases(cuda, oracle):
+    from multimesh_b200 import ops
+    import torch
+
+    rng = np.random.default_rng(5)
+    data = rng.random((7, 3))
+    pts = rng.random((33, 3))
+    ix = ops.GridIndex(_t(data, cuda))
+    got = ix.query_idx(_t(pts, cuda), 20).cpu().numpy()  # k > M: padded with -1
+    assert np.array_equal(got, oracle.knn_bruteforce(data, pts, 20))
+    assert (got[:, 7:] == -1).all()
+    # empty query
+    assert ix.query_idx(torch.empty((0, 3), dtype=torch.float64, device=cuda), 5).shape == (0, 5)
+    # all data points identical / coplanar data
+    same = np.tile(rng.random((1, 3)), (50, 1))
+    got = ops.GridIndex(_t(same, cuda)).query_idx(_t(pts, cuda), 10).cpu().numpy()
+    assert np.array_equal(got, oracle.knn_bruteforce(same, pts, 10))
+    flat = rng.random((400, 3))
+    flat[:, 2] = 0.25
+    got = ops.GridIndex(_t(flat, cuda)).query_idx(_t(pts, cuda), 10).cpu().numpy()
+    assert np.array_equal(got, oracle.knn_bruteforce(flat, pts, 10))
+    # strongly non-uniform density
+    clus = np.concatenate([rng.random((2000, 3)) * 0.01, rng.random((200, 3))])
+    q = np.concatenate([rng.random((200, 3)) * 0.01, rng.random((200, 3))])
+    got = ops.GridIndex(_t(clus, cuda)).query_idx(_t(q, cuda), 20).cpu().numpy()
+    assert np.array_equal(got, oracle.knn_bruteforce(clus, q, 20))
+
+
+# ---------------------------------------------------------------------------------------------
+# K2
+# ---------------------------------------------------------------------------------------------
+def _variants(oracle):
+    from multimesh_b200 import ops
+
+    return [
+        ("V1", ops.V1(), oracle.V1()),
+        ("V2", ops.V2(), oracle.V2()),
+        ("V2snap", ops.V2(1.05, True), oracle.V2(1.05, True)),
+        ("V3", ops.V3(), oracle.V3()),
+        ("V4", ops.V4(), oracle.V4()),
+        ("V5", ops.V5(), oracle.V5()),
+    ]
+
+
+def _locate_both(cuda, oracle, nodes, pts, cands, spec, prm):
+    from multimesh_b200 import ops
+
+    order = round(nodes.shape[1] ** (1.0 / nodes.shape[2])) - 1
+    dim = nodes.shape[2]
+    tn = _t(nodes, cuda)
+    cent, box = ops.element_geometry(tn)
+    elem, xi, status, nfail = ops.locate(tn, cent, box, _t(pts, cuda), _t(cands, cuda), spec)
+    o_elem, o_xi, o_status, o_nfail = oracle.locate(order, dim, nodes, pts, cands, prm)
+    return (elem.cpu().numpy(), xi.cpu().numpy(), status.cpu().numpy(), int(nfail.item()),
+            o_elem, o_xi, o_status, o_nfail)
+
+
+@pytest.mark.parametrize("order,dim,n,warp", [
+    (1, 3, 6, 0.03), (2, 3, 6, 0.03), (4, 3, 4, 0.03), (2, 3, 7, 0.0),
+    (1, 2, 9, 0.03), (2, 2, 9, 0.03), (4, 2, 6, 0.03),
+])
+def test_locate_all_variants(cuda, oracle, order, dim, n, warp):
+    rng = np.random.default_rng(100 * order + dim)
+    nodes = _mesh(order, dim, n, warp)
+    # inside points, points outside the mesh (fallbacks), and points exactly on nodes (ties)
+    pts = np.concatenate([_targets(rng, dim, 1501, -0.08, 1.08), nodes.reshape(-1, dim)[::5]])
+    cands = oracle.knn_bruteforce(oracle.centroids(nodes), pts, 20)
+    for name, spec, prm in _variants(oracle):
+        elem, xi, st, nf, o_elem, o_xi, o_st, o_nf = _locate_both(cuda, oracle, nodes, pts, cands, spec, prm)
+        assert np.array_equal(elem, o_elem), name          # ownership: bit-exact
+        assert np.array_equal(st, o_st), name
+        assert nf == o_nf == int((o_elem < 0).sum()), name
+        assert np.max(np.abs(xi - o_xi), initial=0.0) <= XI_ATOL, name
+        assert np.array_equal(xi, o_xi), f"{name}: xi not bit-identical"
+    # sanity: most points are accepted by the plain V2 search
+    assert (o_elem >= 0).mean() > 0.5
+
+
+def test_locate_gll_point_form_duplicates_and_padding(cuda, oracle):
+    rng = np.random.default_rng(77)
+    nodes = _mesh(2, 3, 5, 0.02)
+    pts = _targets(rng, 3, 700)
+    cands = (oracle.knn_bruteforce(nodes.reshape(-1, 3), pts, 20) // 27).astype(np.int32)
+    cands[::9, 3:] = -1  # ragged candidate lists
+    cands[5] = -1        # a point with no candidates at all
+    from multimesh_b200 import ops
+
+    for spec, prm in [(ops.V1(), oracle.V1()), (ops.V3(), oracle.V3())]:
+        elem, xi, st, nf, o_elem, o_xi, o_st, o_nf = _locate_both(cuda, oracle, nodes, pts, cands, spec, prm)
+        assert np.array_equal(elem, o_elem) and np.array_equal(st, o_st) and nf == o_nf
+        assert np.array_equal(xi, o_xi)
+    assert o_elem[5] == -1
+
+
+def test_locate_last_element_alignment(cuda, oracle):
+    """The last element of an odd-sized mesh ends the array: exercises the plain-load tail path
+    next to the bulk-copy path (3-D order 2/4 element blocks are 8 mod 16 bytes)."""
+    from multimesh_b200 import ops
+
+    for order in (2, 4):
+        nodes = _mesh(order, 3, 3, 0.01)  # 27 elements: last id 26 is even
+        assert nodes.shape[0] % 2 == 1
+        rng = np.random.default_rng(order)
+        pts = _targets(rng, 3, 257, 0.6, 1.0)
+        cands = np.tile(np.array([26, 25, 13], dtype=np.int32), (len(pts), 1))
+        elem, xi, st, nf, o_elem, o_xi, o_st, o_nf = _locate_both(
+            cuda, oracle, nodes, pts, cands, ops.V2(), oracle.V2())
+        assert np.array_equal(elem, o_elem) and np.array_equal(xi, o_xi)
+        assert (o_elem == 26).any()
+
+
+# ---------------------------------------------------------------------------------------------
+# K3
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("order,dim,F", [
+    (1, 3, 5), (2, 3, 5), (4, 3, 5), (2, 3, 8), (4, 3, 1), (2, 3, 3), (1, 3, 11),
+    (1, 2, 3), (2, 2, 3), (4, 2, 3), (4, 2, 8),
+])
+def test_interp_bit_exact(cuda, oracle, order, dim, F):
+    from multimesh_b200 import ops
+
+    rng = np.random.default_rng(1000 + 10 * order + F)
+    n = 3
+    nodes = _mesh(order, dim, n, 0.0)
+    E, P, _ = nodes.shape
+    fields = rng.normal(size=(E, F, P)) * 1000.0
+    N = 2049  # ragged: not a multiple of 32
+    elem = rng.integers(0, E, size=N).astype(np.int32)
+    elem[::13] = E - 1  # hit the array tail
+    elem[5::17] = -1    # failed points -> zero rows
+    xi = rng.uniform(-1.04, 1.04, size=(N, dim))
+    out = ops.interp(_t(fields, cuda), _t(elem, cuda), _t(xi, cuda)).cpu().numpy()
+    want = oracle.interp(order, dim, fields, elem, xi)
+    scale = np.abs(fields).max() * P
+    assert np.max(np.abs(out - want)) <= VAL_RTOL * scale
+    assert np.array_equal(out, want), "K3 not bit-identical to the oracle"
+    assert (out[elem < 0] == 0).all()
+    c = ops.coeffs(_t(elem, cuda), _t(xi, cuda), order).cpu().numpy()
+    assert np.array_equal(c, oracle.coeffs(order, dim, elem, xi))
+    g = ops.gather_coeffs(_t(fields, cuda), _t(elem, cuda), _t(c, cuda)).cpu().numpy()
+    ref = np.sum(fields[np.maximum(elem, 0)] * c[:, None, :], axis=2)  # numpy, as interpolator.py:822
+    assert np.max(np.abs(g - ref)) <= VAL_RTOL * scale
+    assert np.max(np.abs(out - ref)) <= VAL_RTOL * scale
+
+
+def test_interp_empty(cuda):
+    import torch
+    from multimesh_b200 import ops
+
+    f = torch.zeros((4, 5, 27), dtype=torch.float64, device=cuda)
+    out = ops.interp(f, torch.empty((0,), dtype=torch.int32, device=cuda),
+                     torch.empty((0, 3), dtype=torch.float64, device=cuda))
+    assert out.shape == (0, 5)
+
+
+# ---------------------------------------------------------------------------------------------
+# whole pipeline: k-NN -> locate -> gather, polynomial reproduction and identity interpolation
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("order", [1, 2, 4])
+def test_pipeline_polynomial_reproduction(cuda, oracle, order):
+    from multimesh_b200 import ops
+
+    rng = np.random.default_rng(order)
+    nodes = _mesh(order, 3, 5, 0.0)
+    v, coef = meshgen.polynomial_field(nodes, order, rng)
+    fields = np.ascontiguousarray(v[:, None, :])
+    pts = rng.uniform(0.0, 1.0, size=(4000, 3))
+    tn = _t(nodes, cuda)
+    cent, box = ops.element_geometry(tn)
+    cands = ops.GridIndex(cent).query_idx(_t(pts, cuda), 20)
+    elem, xi, st, nf = ops.locate(tn, cent, box, _t(pts, cuda), cands, ops.V1())
+    out = ops.interp(_t(fields, cuda), elem, xi).cpu().numpy()[:, 0]
+    exact, _ = meshgen.polynomial_field(pts[None, :, :], order, rng) if False else (None, None)
+    exact = np.zeros(len(pts))
+    for idx in np.ndindex(*coef.shape):
+        exact += coef[idx] * pts[:, 0] ** idx[0] * pts[:, 1] ** idx[1] * pts[:, 2] ** idx[2]
+    assert int(nf.item()) == 0
+    assert np.max(np.abs(out - exact)) < 1e-11
+
+
+def test_pipeline_identity_mesh(cuda, oracle):
+    """mesh -> same mesh returns the fields (every target sits on a node shared by up to 8
+    elements: exercises the tie-break)."""
+    from multimesh_b200 import ops
+
+    nodes = _mesh(2, 3, 6, 0.02)
+    names = ["QKAPPA", "QMU", "RHO", "VP", "VS"]
+    fields = meshgen.analytic_fields(nodes, names)
+    pts = nodes.reshape(-1, 3)
+    tn = _t(nodes, cuda)
+    cent, box = ops.element_geometry(tn)
+    cands = ops.GridIndex(cent).query_idx(_t(pts, cuda), 20)
+    elem, xi, st, nf = ops.locate(tn, cent, box, _t(pts, cuda), cands, ops.V1())
+    out = ops.interp(_t(fields, cuda), elem, xi).cpu().numpy()
+    want = np.swapaxes(fields, 1, 2).reshape(-1, len(names))
+    assert np.max(np.abs(out - want) / np.abs(want)) < VAL_RTOL
+    o_cands = oracle.knn_bruteforce(oracle.centroids(nodes), pts, 20)
+    assert np.array_equal(cands.cpu().numpy(), o_cands)
+    o_elem, o_xi, _, _ = oracle.locate(2, 3, nodes, pts, o_cands, oracle.V1())
+    assert np.array_equal(elem.cpu().numpy(), o_elem)
+
+
+# ---------------------------------------------------------------------------------------------
+# order-1 nodal (exodus) path
+# ---------------------------------------------------------------------------------------------
+def test_trilinear_bit_exact(cuda, oracle):
+    from multimesh_b200 import ops
+
+    rng = np.random.default_rng(8)
+    points, conn = meshgen.hex8_mesh((7, 6, 5), warp=0.03)
+    perm = np.argsort([0, 3, 2, 1, 4, 5, 6, 7])
+    connC = np.ascontiguousarray(conn[:, perm])
+    cent = ops.centroid_conn(_t(conn, cuda), _t(points, cuda))
+    assert np.array_equal(cent.cpu().numpy(), oracle.centroid_conn(conn, points))
+    q = np.concatenate([rng.uniform(-0.05, 1.05, (3000, 3)), points[::3]])
+    nn = oracle.knn_bruteforce(cent.cpu().numpy(), q, 20).astype(np.int64)
+    nfail, enc, w = ops.trilinear(_t(nn, cuda), _t(connC, cuda), _t(points, cuda), _t(q, cuda))
+    o_nf, o_enc, o_w = oracle.trilinear_interpolator(20, nn, connC, points, q)
+    assert int(nfail.item()) == o_nf
+    assert np.array_equal(enc.cpu().numpy(), o_enc)
+    assert np.array_equal(w.cpu().numpy(), o_w)
+    if oracle.ref_lib() is not None:  # the compiled reference itself
+        r_nf, r_enc, r_w = oracle.ref_trilinear_interpolator(20, nn, connC, points, q)
+        assert r_nf == int(nfail.item())
+        assert np.array_equal(enc.cpu().numpy(), r_enc) and np.array_equal(w.cpu().numpy(), r_w)
+    param = rng.normal(size=(4, len(points)))
+    vals = ops.gather_nodal(_t(param, cuda), enc, w).cpu().numpy()
+    want = np.sum(param[:, o_enc] * o_w, axis=2)
+    assert np.max(np.abs(vals - want)) < 1e-12
+
+
+def test_legacy_host_symbols(cuda, oracle):
+    """helpers.load_lib()-style ctypes calls on HOST numpy buffers (helpers.py:43-81)."""
+    import ctypes as C
+    from multimesh_b200 import _lib
+
+    lib = _lib.load_lib()
+    rng = np.random.default_rng(9)
+    points, conn = meshgen.hex8_mesh((4, 4, 4), warp=0.02)
+    cent = np.zeros((len(conn), 3))
+    lib.centroid(3, len(conn), 8, conn.ctypes.data_as(C.c_void_p), points.ctypes.data_as(C.c_void_p),
+                 cent.ctypes.data_as(C.c_void_p))
+    assert np.array_equal(cent, oracle.centroid_conn(conn, points))
+    connC = np.ascontiguousarray(conn[:, np.argsort([0, 3, 2, 1, 4, 5, 6, 7])])
+    q = rng.uniform(0.0, 1.0, (500, 3))
+    nn = oracle.knn_bruteforce(cent, q, 20).astype(np.int64)
+    enc = np.zeros((len(q), 8), dtype=np.int64)
+    w = np.zeros((len(q), 8))
+    nf = lib.triLinearInterpolator(20, len(q), nn.ctypes.data_as(C.c_void_p),
+                                   connC.ctypes.data_as(C.c_void_p), enc.ctypes.data_as(C.c_void_p),
+                                   points.ctypes.data_as(C.c_void_p), w.ctypes.data_as(C.c_void_p),
+                                   q.ctypes.data_as(C.c_void_p))
+    o_nf, o_enc, o_w = oracle.trilinear_interpolator(20, nn, connC, points, q)
+    assert nf == o_nf == 0
+    assert np.array_equal(enc, o_enc) and np.array_equal(w, o_w)
+
+
+def test_interpolate_host_entry_point(cuda, oracle):
+    import ctypes as C
+    from multimesh_b200 import _lib, ops
+
+    lib = _lib.load_lib()
+    rng = np.random.default_rng(12)
+    nodes = _mesh(2, 3, 5, 0.02)
+    fields = meshgen.analytic_fields(nodes, ["QKAPPA", "QMU", "RHO", "VP", "VS"])
+    pts = _targets(rng, 3, 999, 0.0, 1.0)
+    for form in (0, 1):
+        vals = np.zeros((len(pts), 5))
+        elem = np.zeros(len(pts), dtype=np.int32)
+        xi = np.zeros((len(pts), 3))
+        nf = C.c_int64(-1)
+        prm = ops.V1().to_c()
+        rc = lib.mm_interpolate_host(2, 3, nodes.shape[0], nodes.ctypes.data_as(C.c_void_p), 5,
+                                     fields.ctypes.data_as(C.c_void_p), len(pts),
+                                     pts.ctypes.data_as(C.c_void_p), 20, form, C.byref(prm),
+                                     vals.ctypes.data_as(C.c_void_p), elem.ctypes.data_as(C.c_void_p),
+                                     xi.ctypes.data_as(C.c_void_p), C.byref(nf))
+        assert rc == 0, lib.mm_last_error()
+        if form == 0:
+            cands = oracle.knn_bruteforce(oracle.centroids(nodes), pts, 20)
+        else:
+            cands = oracle.knn_bruteforce(nodes.reshape(-1, 3), pts, 20) // 27
+        o_elem, o_xi, _, o_nf = oracle.locate(2, 3, nodes, pts, cands, oracle.V1())
+        assert np.array_equal(elem, o_elem) and np.array_equal(xi, o_xi) and nf.value == o_nf
+        assert np.array_equal(vals, oracle.interp(2, 3, fields, o_elem, o_xi))
+
+
+def test_cpu_tensors_are_rejected(cuda):
+    import torch
+    from multimesh_b200 import ops
+
+    with pytest.raises(Exception):
+        ops.interp(torch.zeros((1, 1, 8), dtype=torch.float64), torch.zeros(1, dtype=torch.int32),
+                   torch.zeros((1, 3), dtype=torch.float64))
