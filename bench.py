@@ -1,0 +1,394 @@
+#!/usr/bin/env python
+"""
+bench.py -- headline benchmark of the mesh-to-mesh interpolation hot path (BASELINE.json metric:
+target GLL points interpolated per second; % of HBM roofline; host CPU path timed beside it).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload S2|small]
+
+A step = one pass of the hot path over one batch of target points, all resident in HBM:
+    K1 k-NN over the source GLL points (gll_2_gll form, idx // P)  ->  K2 locate (V1)  ->  K3 gather.
+Workload S2 (BASELINE.json configs[1]): source 100^3 hex elements, order 2, F = 5
+(QKAPPA, QMU, RHO, VP, VS); targets = all 23.9 M GLL points of a non-nested 96^3 order-2 mesh.
+Inputs are far larger than the 126 MB L2 (source 1.7 GB, targets 0.57 GB), so no L2 flush is needed.
+N > 1: one process per GPU (torchrun), source mesh + index replicated, every rank processes its own
+target set of the same size (weak scaling); no data-path collective.
+
+One JSON line is printed by rank 0; see the task contract for the keys.  `--impl reference` times
+the CPU port of the same path (oracle/, test infrastructure: scipy cKDTree + the C oracle with
+OpenMP on all host threads) on a bounded spatial crop of the same workload.
+"""
+import argparse
+import ctypes as C
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+NAMES = ["QKAPPA", "QMU", "RHO", "VP", "VS"]
+METRIC = "target GLL points interpolated/sec"
+UNIT = "points/s"
+
+WORKLOADS = {
+    # name: (source elements per axis, target elements per axis, order, k)
+    "S2": dict(src=100, tgt=96, order=2, k=20),
+    "small": dict(src=24, tgt=22, order=2, k=20),
+    "S2o4": dict(src=60, tgt=50, order=4, k=20),
+}
+
+
+def workload_name(w):
+    return (f"{w['name']}: gll_2_gll, source {w['src']}^3 hex order-{w['order']} F=5, targets = GLL points of a "
+            f"non-nested {w['tgt']}^3 order-{w['order']} mesh, k={w['k']}, V1 location, GLL-point k-NN form")
+
+
+def make_source(w):
+    from multimesh_b200 import meshgen
+
+    nodes = meshgen.box_mesh((w["src"],) * 3, w["order"])
+    fields = meshgen.analytic_fields(nodes, NAMES)
+    return nodes, fields
+
+
+def make_targets(w, rank=0, crop=None):
+    """GLL points of the target mesh.  Ranks > 0 get the same mesh shifted by a fraction of a
+    target element so that every rank has distinct points of identical difficulty."""
+    from multimesh_b200 import meshgen
+
+    n = w["tgt"]
+    h = 1.0 / n
+    shift = (rank % 8) * 0.11 * h
+    lo = np.full(3, 0.001 + shift * 0.1)
+    hi = np.full(3, 0.999 - shift)
+    if crop is None:
+        pts = meshgen.box_mesh((n,) * 3, w["order"], lo=lo, hi=hi)
+    else:
+        m = crop
+        span = (hi - lo) * (m / n)
+        pts = meshgen.box_mesh((m,) * 3, w["order"], lo=lo, hi=lo + span)
+    return np.ascontiguousarray(pts.reshape(-1, 3))
+
+
+# ----------------------------------------------------------------------------------------------
+# clocks sampling during the timed region
+# ----------------------------------------------------------------------------------------------
+class ClockSampler:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.gpu = gpu_index
+        self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+        self.p = None
+
+    def start(self):
+        try:
+            self.p = subprocess.Popen(
+                ["nvidia-smi", f"--id={self.gpu}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                 "-lms", "100"], stdout=self.f, stderr=subprocess.DEVNULL)
+        except Exception:
+            self.p = None
+
+    def stop(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        if self.p is None:
+            return out
+        time.sleep(0.15)
+        self.p.terminate()
+        try:
+            self.p.wait(timeout=5)
+        except Exception:
+            self.p.kill()
+        self.f.flush()
+        rows = [r.strip().split(",") for r in open(self.f.name) if r.strip()]
+        os.unlink(self.f.name)
+        sm, reasons, smmax = [], set(), None
+        for r in rows:
+            try:
+                sm.append(float(r[1]))
+                smmax = float(r[2])
+                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"),
+                                   r[5:9]):
+                    if v.strip().lower().startswith("active"):
+                        reasons.add(name)
+            except Exception:
+                continue
+        if sm:
+            out.update(sm_mhz=float(np.median(sm)), sm_max_mhz=smmax, reasons=sorted(reasons), samples=len(sm))
+        return out
+
+
+# ----------------------------------------------------------------------------------------------
+# CPU port of the path (oracle/ = test infrastructure; allowed here only as the timed baseline)
+# ----------------------------------------------------------------------------------------------
+def cpu_port_run(w, crop_src, crop_tgt, steps=1, warmup=0):
+    """Times the reference's algorithm on the host: cKDTree over the GLL points of a spatial crop
+    of the source mesh (scipy's KD-tree is what the reference's cli.py:66 uses; pykdtree is absent),
+    query k nearest GLL points -> idx // P, V1 location + GLL weights + gather in the C oracle
+    (OpenMP, all host threads)."""
+    from multimesh_b200 import meshgen
+    from oracle import capi as oracle
+    from scipy.spatial import cKDTree
+
+    order, k = w["order"], w["k"]
+    P = (order + 1) ** 3
+    frac = crop_src / w["src"]
+    nodes = meshgen.box_mesh((crop_src,) * 3, order, lo=np.zeros(3), hi=np.full(3, frac))
+    fields = meshgen.analytic_fields(nodes, NAMES, scale=np.ones(3))
+    # targets strictly inside the crop
+    h = 1.0 / w["tgt"]
+    lo = np.full(3, 0.001)
+    pts = meshgen.box_mesh((crop_tgt,) * 3, order, lo=lo, hi=lo + crop_tgt * h * 0.998)
+    pts = np.ascontiguousarray(pts.reshape(-1, 3))
+    assert pts.max() < frac
+    t0 = time.perf_counter()
+    tree = cKDTree(nodes.reshape(-1, 3))
+    cent = oracle.centroids(nodes)
+    box = oracle.aabb(nodes)
+    t_build = time.perf_counter() - t0
+    times = []
+    for it in range(warmup + steps):
+        t0 = time.perf_counter()
+        _, nn = tree.query(pts, k=k, workers=-1)
+        cands = (nn // P).astype(np.int32)
+        elem, xi, _, nfail = oracle.locate(order, 3, nodes, pts, cands, oracle.V1(), cent=cent, box=box)
+        vals = oracle.interp(order, 3, fields, elem, xi)
+        dt = time.perf_counter() - t0
+        if it >= warmup:
+            times.append(dt)
+    t = float(np.mean(times))
+    return {
+        "points": int(len(pts)), "seconds_per_step": t, "build_seconds": t_build,
+        "value": len(pts) / t, "cores": int(oracle.num_threads()), "nfailed": int(nfail),
+        "checksum": float(vals.sum()),
+        "sample": (f"spatial crop of {w['name']}: source {crop_src}^3 of {w['src']}^3 elements, targets = "
+                   f"{len(pts)} GLL points of the {crop_tgt}^3 target elements inside the crop; KD-tree build "
+                   f"({t_build:.1f} s) excluded like the GPU index build"),
+    }
+
+
+def run_reference(args, w):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    crop_src, crop_tgt = (40, 36) if w["src"] >= 40 else (w["src"], w["tgt"] - 2)
+    r = cpu_port_run(w, crop_src, crop_tgt, steps=args.steps, warmup=min(args.warmup, 1))
+    line = {
+        "impl": "reference", "metric": METRIC, "value": r["value"], "unit": UNIT, "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": min(args.warmup, 1), "ms_per_step": r["seconds_per_step"] * 1e3,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": workload_name(w)},
+        "cpu_baseline": {"value": r["value"], "unit": UNIT, "cores": r["cores"], "kind": "port",
+                         "sample": r["sample"]},
+        "e2e": {"value": r["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ----------------------------------------------------------------------------------------------
+# our arm
+# ----------------------------------------------------------------------------------------------
+def run_ours(args, w):
+    import torch
+    import torch.distributed as dist
+
+    from multimesh_b200 import _lib, ops
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device -- the product path has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    lib = _lib.load_lib()
+
+    order, k = w["order"], w["k"]
+    P = (order + 1) ** 3
+    F = len(NAMES)
+    nodes_h, fields_h = make_source(w)
+    pts_h = make_targets(w, rank)
+    E, N = nodes_h.shape[0], pts_h.shape[0]
+
+    # ---- setup (untimed): source mesh resident, geometry + index built once per source mesh -----
+    nodes = torch.from_numpy(nodes_h).to(dev)
+    fields = torch.from_numpy(fields_h).to(dev)
+    pts = torch.from_numpy(pts_h).to(dev)
+    ev = lambda: torch.cuda.Event(enable_timing=True)  # noqa: E731
+    e0, e1 = ev(), ev()
+    e0.record()
+    cent, box = ops.element_geometry(nodes)
+    index = ops.GridIndex(nodes.view(E * P, 3))
+    e1.record()
+    torch.cuda.synchronize()
+    build_ms = e0.elapsed_time(e1)
+    spec = ops.V1()
+
+    def step(events=None):
+        if events is not None:
+            events[0].record()
+        cands = index.query_idx(pts, k, divisor=P)
+        if events is not None:
+            events[1].record()
+        elem, xi, status, nfail = ops.locate(nodes, cent, box, pts, cands, spec)
+        if events is not None:
+            events[2].record()
+        out = ops.interp(fields, elem, xi)
+        if events is not None:
+            events[3].record()
+        return cands, elem, xi, status, nfail, out
+
+    for _ in range(max(args.warmup, 3)):
+        res = step()
+    torch.cuda.synchronize()
+    cands, elem, xi, status, nfail, out = res
+    nfailed = int(nfail.item())
+    tested = None
+    checksum = float(out.sum().item())
+    st = torch.bincount(status.to(torch.int64), minlength=9).cpu().tolist()
+    del res
+
+    # ---- timed region: EXACTLY K steps, events on torch's current stream ------------------------
+    sampler = ClockSampler(local_rank)
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    sampler.start()
+    kev = [[ev() for _ in range(4)] for _ in range(args.steps)]
+    t_start, t_end = ev(), ev()
+    t_start.record()
+    for s in range(args.steps):
+        step(kev[s])
+    t_end.record()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    clocks = sampler.stop()
+    total_ms = t_start.elapsed_time(t_end)
+    kms = np.array([[kev[s][i].elapsed_time(kev[s][i + 1]) for i in range(3)] for s in range(args.steps)])
+    k_avg = kms.mean(axis=0)  # K1, K2, K3 average launch durations (ms)
+    if world > 1:
+        t = torch.tensor([total_ms], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        total_ms = float(t.item())
+    ms_per_step = total_ms / args.steps
+    value = world * N / (ms_per_step * 1e-3)
+
+    # ---- e2e: the C-ABI call on HOST buffers (pinned), H2D + index build + K1-K3 + D2H per step --
+    pin = lambda a: torch.from_numpy(a).pin_memory()  # noqa: E731
+    nodes_p, fields_p, pts_p = pin(nodes_h), pin(fields_h), pin(pts_h)
+    vals_p = torch.empty((N, F), dtype=torch.float64).pin_memory()
+    prm = spec.to_c()
+    nf = C.c_int64(0)
+    del cands, elem, xi, status, out
+    torch.cuda.empty_cache()
+
+    def e2e_step():
+        rc = lib.mm_interpolate_host(order, 3, E, C.c_void_p(nodes_p.data_ptr()), F,
+                                     C.c_void_p(fields_p.data_ptr()), N, C.c_void_p(pts_p.data_ptr()), k, 1,
+                                     C.byref(prm), C.c_void_p(vals_p.data_ptr()), None, None, C.byref(nf))
+        _lib.check(rc, "mm_interpolate_host")
+
+    e2e_steps = max(1, min(args.steps, 3))
+    e2e_step()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        e2e_step()  # synchronous: returns after the D2H copy of the values completed
+    torch.cuda.synchronize()
+    e2e_s = (time.perf_counter() - t0) / e2e_steps
+    if world > 1:
+        t = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_s = float(t.item())
+    e2e_value = world * N / e2e_s
+    e2e_checksum = float(vals_p.sum().item())
+    h2d = int(nodes_h.nbytes + fields_h.nbytes + pts_h.nbytes)
+    d2h = int(N * F * 8 + 8)
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    # ---- roofline of the dominant kernel (SURVEY 8d algorithmic bytes) --------------------------
+    peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(peaks_path):
+        peak = float(json.load(open(peaks_path))["hbm_gbs"])
+        peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)"
+    else:
+        peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
+    d = 3
+    accepted_first = None
+    bytes_pt = {
+        "K1_knn": 8 * d + 4 * k,
+        "K2_locate": 8 * d + 1.0 * (8 * d * P + 16 * d) + (4 + 8 * d),
+        "K3_interp": (8 * d + 4) + 8 * F * P + 8 * F,
+    }
+    kernels = {}
+    for name, ms in zip(("K1_knn", "K2_locate", "K3_interp"), k_avg):
+        gbs = bytes_pt[name] * N / (ms * 1e-3) / 1e9
+        kernels[name] = {"ms": round(float(ms), 4), "alg_bytes_per_point": bytes_pt[name],
+                         "achieved_gbs": round(gbs, 1), "frac": round(gbs / peak, 4)}
+    dom = max(kernels, key=lambda n: kernels[n]["ms"])
+    roofline = {"bound": "hbm", "kernel": dom, "achieved": kernels[dom]["achieved_gbs"], "peak": peak,
+                "unit": "GB/s", "frac": kernels[dom]["frac"], "traffic": None, "peak_source": peak_src,
+                "graded_kernel_K3": kernels["K3_interp"]}
+
+    # ---- CPU baseline, rank 0, N = 1 only -------------------------------------------------------
+    cpu = None
+    if world == 1 and not args.no_cpu:
+        crop_src, crop_tgt = (40, 36) if w["src"] >= 40 else (w["src"], w["tgt"] - 2)
+        r = cpu_port_run(w, crop_src, crop_tgt, steps=1, warmup=0)
+        cpu = {"value": r["value"], "unit": UNIT, "cores": r["cores"], "kind": "port", "sample": r["sample"]}
+
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+        "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": workload_name(w), "points_per_gpu": N, "source_elements": E, "fields": F,
+                   "l2": "inputs larger than L2 (source 1.7 GB + targets 0.57 GB per step), no flush"},
+        "roofline": roofline, "kernels": kernels, "cpu_baseline": cpu,
+        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                "ms_per_step": e2e_s * 1e3, "steps": e2e_steps,
+                "call": "mm_interpolate_host (C-ABI, pinned host buffers; H2D source mesh + targets, index "
+                        "build, K1-K3, D2H values every step)"},
+        "gpu_launches": 3 * args.steps, "clocks": clocks, "index_build_ms": build_ms, "nfailed": nfailed,
+        "status_histogram": st, "checksum": checksum, "e2e_checksum": e2e_checksum,
+    }
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="S2", choices=sorted(WORKLOADS))
+    ap.add_argument("--no-cpu", action="store_true", help="skip the CPU baseline leg")
+    args = ap.parse_args()
+    w = dict(WORKLOADS[args.workload], name=args.workload)
+    if args.impl == "reference":
+        run_reference(args, w)
+    else:
+        run_ours(args, w)
+
+
+if __name__ == "__main__":
+    main()
