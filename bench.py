@@ -40,6 +40,7 @@ WORKLOADS = {
     # name: (source elements per axis, target elements per axis, order, k)
     "S2": dict(src=100, tgt=96, order=2, k=20),
     "small": dict(src=24, tgt=22, order=2, k=20),
+    "medium": dict(src=60, tgt=56, order=2, k=20),
     "S2o4": dict(src=60, tgt=50, order=4, k=20),
 }
 

@@ -1,0 +1,529 @@
+"""
+Interpolation drivers and inner operators -- the host-side mirror of
+multi_mesh/components/interpolator.py (line numbers below refer to that file).
+
+The Python per-point loops, the pybind11 calls into salvus.fem and the pykdtree queries of the
+reference are replaced by three CUDA kernels (k-NN, locate, gather) reached through `ops`;
+everything here is orchestration: array preparation, layer bookkeeping, file I/O and the
+reference's return layouts.  Names, argument meaning, return order and error behaviour follow the
+reference; its bit-rot (np.int, undefined names, ...) is not replicated.
+Mesh arguments accept a path or an in-memory object (SalvusMesh / Exodus).
+"""
+import os
+import pathlib
+from typing import Dict, List, Tuple, Union
+
+import numpy as np
+import torch
+
+from .. import ops, utils
+from ..gll import order_from_npoints
+from ..io.exodus import Exodus
+from ..io.store import open_store
+from ..kdtree import KDTree, _device
+from .salvus_mesh_reader import SalvusMesh
+
+R_EARTH = 6371000
+
+
+# ================================================================================================
+# device-side engine shared by all drivers
+# ================================================================================================
+def _dev_f64(a, device):
+    if isinstance(a, torch.Tensor):
+        return a.to(device=device, dtype=torch.float64)
+    return torch.from_numpy(np.ascontiguousarray(a, dtype=np.float64)).to(device)
+
+
+class _Source:
+    """Source element nodes resident on the device with their geometry (K0) and, lazily, the
+    spatial indices over centroids / over all GLL points (K1)."""
+
+    def __init__(self, nodes, device=None):
+        self.device = _device(device)
+        self.nodes = _dev_f64(nodes, self.device).contiguous()
+        self.E, self.P, self.dim = self.nodes.shape
+        self.order = order_from_npoints(self.P, self.dim)
+        self.centroid, self.aabb = ops.element_geometry(self.nodes)
+        self._cent_index = None
+        self._gll_index = None
+
+    def centroid_index(self):
+        if self._cent_index is None:
+            self._cent_index = ops.GridIndex(self.centroid)
+        return self._cent_index
+
+    def gll_index(self):
+        if self._gll_index is None:
+            self._gll_index = ops.GridIndex(self.nodes.view(self.E * self.P, self.dim))
+        return self._gll_index
+
+    def candidates(self, pts, k, form="centroid"):
+        if form == "gll":  # tree over all GLL points, idx // P  (:674-678, :751-756)
+            return self.gll_index().query_idx(pts, k, divisor=self.P)
+        return self.centroid_index().query_idx(pts, k)
+
+    def locate(self, pts, cands, spec):
+        return ops.locate(self.nodes, self.centroid, self.aabb, pts, cands, spec)
+
+
+def _raise_if_hard(status, ignore_hard_elements):
+    if not ignore_hard_elements and bool((status == ops._lib.ST_FB_NAN_MAGIC).any().item()):
+        raise ValueError("Can't find an appropriate element.")  # :1465-1467
+
+
+def _stack_fields(mesh, parameters, mask=None):
+    """[E, F, P] device layout from a dict of element-nodal fields."""
+    arrs = [mesh.element_nodal_fields[p] if mask is None else mesh.element_nodal_fields[p][mask]
+            for p in parameters]
+    return np.ascontiguousarray(np.stack(arrs, axis=1), dtype=np.float64)
+
+
+def _as_salvus_mesh(m, fast_mode=False):
+    if isinstance(m, SalvusMesh):
+        if not fast_mode:
+            m.get_elemental_fields()
+            m.get_element_nodal_fields()
+        return m
+    return SalvusMesh(m, fast_mode=fast_mode)
+
+
+# ================================================================================================
+# inner operators (same names / signatures as the reference)
+# ================================================================================================
+def get_coefficients(a, b, c, ref_coord, dimension):
+    """Tensor-product GLL Lagrange weights at `ref_coord` for order `a` (:1337-1347).
+    Unlike the reference, 2-D supports orders 1/2/4 (the reference returns order 4 regardless)."""
+    dev = _device()
+    xi = _dev_f64(np.asarray(ref_coord, dtype=np.float64).reshape(1, dimension), dev)
+    elem = torch.zeros(1, dtype=torch.int32, device=dev)
+    return ops.coeffs(elem, xi, int(a))[0].cpu().numpy()
+
+
+def inverse_transform(point, gll_points, dimension):
+    """Reference coordinates of `point` in the element with control nodes `gll_points` [P, d];
+    NaNs when Newton does not converge (:1370-1386)."""
+    src = _Source(np.asarray(gll_points, dtype=np.float64)[None])
+    pts = _dev_f64(np.asarray(point, dtype=np.float64).reshape(1, dimension), src.device)
+    cands = torch.zeros((1, 1), dtype=torch.int32, device=src.device)
+    elem, xi, _, _ = src.locate(pts, cands, ops.LocateSpec(False, float("inf"), False, ops.FB_FAIL))
+    if int(elem.item()) < 0:
+        return np.full(dimension, np.nan)
+    return xi[0].cpu().numpy()
+
+
+def boundary_box_check(point, gll_points) -> Tuple[bool, float]:
+    """Inclusive AABB test; distance to the node mean when outside (:1350-1367)."""
+    src = _Source(np.asarray(gll_points, dtype=np.float64)[None])
+    p = _dev_f64(np.asarray(point, dtype=np.float64), src.device)
+    inside = bool(((p >= src.aabb[0, 0]) & (p <= src.aabb[0, 1])).all().item())
+    if inside:
+        return True, 0
+    return False, float(torch.sqrt(((p - src.centroid[0]) ** 2).sum()).item())
+
+
+def _find_gll_centroids(gll_coordinates, dimensions=3):
+    """[E, d] element centroids of a GLL model (:1389-1406)."""
+    if dimensions != gll_coordinates.shape[2]:
+        raise ValueError("Dimensions of GLL model not the same as input")
+    return _Source(gll_coordinates).centroid.cpu().numpy()
+
+
+def _check_if_inside_element(gll_model, nearest_elements, point, dimension, ignore_hard_elements=True):
+    """(element, ref_coord) for ONE point: the reference's V1 logic (:1409-1473)."""
+    src = gll_model if isinstance(gll_model, _Source) else _Source(gll_model)
+    pts = _dev_f64(np.asarray(point, dtype=np.float64).reshape(1, dimension), src.device)
+    cands = torch.as_tensor(np.asarray(nearest_elements).reshape(1, -1).astype(np.int32)).to(src.device)
+    elem, xi, status, _ = src.locate(pts, cands, ops.V1())
+    _raise_if_hard(status, ignore_hard_elements)
+    return int(elem.item()), xi[0].cpu().numpy()
+
+
+def find_gll_coeffs(original_coordinates, coordinates, nearest_elements, coeffs, element, dimensions,
+                    from_gll_order, ignore_hard_elements):
+    """Batched V1 location + weights (:1540-1597).  Layouts as in the reference: coordinates
+    [d, N], nearest_elements [k, N], coeffs [F, P, N] (only coeffs[0] is filled, as there),
+    element [N].  Returns (element, coeffs)."""
+    src = original_coordinates if isinstance(original_coordinates, _Source) else _Source(original_coordinates)
+    pts = _dev_f64(np.ascontiguousarray(np.asarray(coordinates).T), src.device)
+    cands = torch.as_tensor(np.ascontiguousarray(np.asarray(nearest_elements).T).astype(np.int32)).to(src.device)
+    elem, xi, status, _ = src.locate(pts, cands, ops.V1())
+    _raise_if_hard(status, ignore_hard_elements)
+    w = ops.coeffs(elem, xi, int(from_gll_order))  # zero rows where elem = -1 (:1581-1583)
+    element[:] = elem.cpu().numpy()
+    coeffs[0, :, :] = w.cpu().numpy().T
+    return element, coeffs
+
+
+def fill_value_array(new_coordinates: Dict[str, tuple], nearest_elements: Dict[str, np.ndarray], original_mesh,
+                     original_mask: Dict[str, np.ndarray], parameters: List[str], dimensions: int = 3,
+                     from_gll_order: int = 2):
+    """Per layer: V1 location with layer-local element ids + weights (:1476-1537).
+    Returns (coeffs {layer: [N, P]}, element {layer: [N]}) -- coeffs first, as in the reference."""
+    element, coeffs = {}, {}
+    for key, val in new_coordinates.items():
+        print(f"Interpolating layer: {key}")
+        src = _Source(original_mesh.points[original_mask[key]])
+        pts = _dev_f64(val[0], src.device)
+        cands = torch.as_tensor(np.ascontiguousarray(nearest_elements[key]).astype(np.int32)).to(src.device)
+        elem, xi, _, _ = src.locate(pts, cands, ops.V1())  # ignore_hard_elements=True (:1528)
+        coeffs[key] = ops.coeffs(elem, xi, int(from_gll_order)).cpu().numpy()
+        element[key] = elem.cpu().numpy().astype(int)
+    return coeffs, element
+
+
+def get_element_weights(gll_points, shape_order, centroid_tree, points, nelem_to_search=25, tolerance=1.05,
+                        snap_to_nearest=False):
+    """Enclosing element + weights for a point cloud, V2 logic (:1147-1255).
+    Returns (elems [N] int, coeffs [N, P]); elems = -1 and zero weights when nothing is found."""
+    src = gll_points if isinstance(gll_points, _Source) else _Source(gll_points)
+    pts = _dev_f64(points, src.device)
+    if isinstance(centroid_tree, KDTree):
+        _, cands = centroid_tree.query(pts, k=nelem_to_search, return_distance=False)
+    elif centroid_tree is None:
+        cands = src.candidates(pts, nelem_to_search)
+    else:  # any tree object exposing its data (scipy cKDTree, pykdtree): rebuild the index on the GPU
+        _, cands = KDTree(np.asarray(centroid_tree.data), device=src.device).query(
+            pts, k=nelem_to_search, return_distance=False)
+    elem, xi, _, _ = src.locate(pts, cands, ops.V2(tolerance, snap_to_nearest))
+    w = ops.coeffs(elem, xi, int(shape_order))
+    return elem.cpu().numpy().astype(int), w.cpu().numpy()
+
+
+def get_element_weights_layered(new_coordinates: Dict[str, tuple], nearest_elements: Dict[str, np.ndarray],
+                                original_mesh, original_mask: Dict[str, np.ndarray], dimensions: int = 3,
+                                from_gll_order: int = 2):
+    """Per layer V3 logic: all |xi| < 1.03, no fallback (:1258-1334). Returns (elems{}, coeffs{})."""
+    elems, coeffs = {}, {}
+    for layer, point in new_coordinates.items():
+        src = _Source(original_mesh.points[original_mask[layer]])
+        pts = _dev_f64(point[0], src.device)
+        cands = torch.as_tensor(np.ascontiguousarray(nearest_elements[layer]).astype(np.int32)).to(src.device)
+        elem, xi, _, _ = src.locate(pts, cands, ops.V3())
+        elems[layer] = elem.cpu().numpy().astype(int)
+        coeffs[layer] = ops.coeffs(elem, xi, int(from_gll_order)).cpu().numpy()
+        print(f"Done with layer: {layer}")
+    return elems, coeffs
+
+
+def map_to_sphere(mesh):
+    """x <- x * r_earth * z_node_1D / |x| for every node with |x| > 0, in place (:1125-1144)."""
+    dev = _device()
+    rad = np.ascontiguousarray(mesh.element_nodal_fields["z_node_1D"], dtype=np.float64)
+    pts = _dev_f64(mesh.points, dev).contiguous()
+    ops.map_to_sphere_(pts, _dev_f64(rad, dev), float(R_EARTH))
+    mesh.points[...] = pts.cpu().numpy().reshape(mesh.points.shape)
+
+
+# ================================================================================================
+# gather helpers
+# ================================================================================================
+def _gather(src: _Source, fields_np, elem, xi):
+    """values [N, F] for located points (fused weights + gather, K3)."""
+    return ops.interp(_dev_f64(fields_np, src.device), elem, xi)
+
+
+def _gather_cached(device, fields_np, elements, coeffs):
+    """values [N, F] from stored (elements, coeffs [N, P])."""
+    elem = torch.as_tensor(np.asarray(elements).astype(np.int32)).to(device)
+    return ops.gather_coeffs(_dev_f64(fields_np, device), elem, _dev_f64(coeffs, device))
+
+
+# ================================================================================================
+# drivers
+# ================================================================================================
+def query_model(coordinates, model, nelem_to_search, model_path, coordinates_path):
+    """Model parameters at (lat, lon, depth_in_m) coordinates (:60-139)."""
+    print("Initialization stage")
+    original_points, original_data, original_params = utils.load_hdf5_params_to_memory(
+        model, model_path, coordinates_path)
+    assert coordinates.shape[1] == 3, "Make sure coordinates array has shape N,3"
+    xyz = utils.latlondepth_to_xyz(latlondepth=coordinates)
+    src = _Source(original_points)
+    pts = _dev_f64(xyz, src.device)
+    cands = src.candidates(pts, nelem_to_search, form="gll")
+    elem, xi, status, _ = src.locate(pts, cands, ops.V1())
+    _raise_if_hard(status, False)  # ignore_hard_elements=False (:128)
+    print("Interpolation done, need to organize the results")
+    return _gather(src, original_data, elem, xi).cpu().numpy()
+
+
+def interpolate_to_points(mesh, points, params_to_interp, make_spherical=False):
+    """Mesh -> point cloud, V2 logic with k = 25, tolerance 1.05; points that are not found get
+    zero (:931-977).  `mesh`: SalvusMesh (or path) -- or any object with `.points [Np,3]`,
+    `.connectivity [E,P]`, `.element_nodal_fields`, `.shape_order` (UnstructuredMesh-like)."""
+    if isinstance(mesh, (str, pathlib.Path)):
+        mesh = SalvusMesh(mesh, fast_mode=False)
+    if make_spherical:
+        map_to_sphere(mesh)
+    if hasattr(mesh, "connectivity") and np.ndim(mesh.points) == 2:
+        gll_points = mesh.points[mesh.connectivity]  # (:954)
+    else:
+        gll_points = mesh.points
+    print("Initializing KDtree...")
+    src = _Source(gll_points)
+    print("Retrieving interpolation weights")
+    pts = _dev_f64(points, src.device)
+    cands = src.candidates(pts, 25)
+    elem, xi, _, nfail = src.locate(pts, cands, ops.V2())
+    num_failed = int(nfail.item())
+    if num_failed > 0:
+        print(num_failed, "points could not find an enclosing element. These points will be set to zero. "
+              "Please check your domain or the interpolation tuning parameters")
+    print("Interpolating fields...")
+    return _gather(src, _stack_fields(mesh, params_to_interp), elem, xi).cpu().numpy()
+
+
+def _layer_setup(from_gll, to_gll, layers, parameters, make_spherical):
+    print("Initialization stage")
+    original_mesh = _as_salvus_mesh(from_gll)
+    if make_spherical:
+        map_to_sphere(original_mesh)
+    original_mask, layers = utils.create_layer_mask(mesh=original_mesh, layers=layers)
+    if isinstance(parameters, str) and parameters == "all":
+        parameters = list(original_mesh.element_nodal_fields.keys())
+    new_mesh = _as_salvus_mesh(to_gll)
+    if make_spherical:
+        map_to_sphere(new_mesh)
+    unique_new_points, mask, layers = utils.get_unique_points(points=new_mesh, mesh=True, layers=layers)
+    parameters = utils.pick_parameters(parameters)
+    return original_mesh, original_mask, new_mesh, unique_new_points, mask, layers, parameters
+
+
+def _interp_info_path(stored_array):
+    for name in ("interp_info.h5", "interp_info.npz"):
+        p = os.path.join(stored_array, name)
+        if os.path.exists(p):
+            return p
+    return None
+
+
+def _load_interp_info(stored_array, layer_keys):
+    """coeffs/<layer> [N,P] and elements/<layer> [N] (:342-349, :1035-1044)."""
+    p = None if stored_array is None else _interp_info_path(stored_array)
+    if p is None:
+        return None
+    print("No need for looping, we have the matrices")
+    with open_store(p, "r") as st:
+        return ({k: st.read(f"coeffs/{k}") for k in layer_keys},
+                {k: st.read(f"elements/{k}") for k in layer_keys})
+
+
+def _save_interp_info(stored_array, coeffs, elements):
+    print("Saving interpolation matrices")  # (:391-398)
+    os.makedirs(stored_array, exist_ok=True)
+    try:
+        import h5py  # noqa: F401
+        name = "interp_info.h5"
+    except ImportError:
+        name = "interp_info.npz"
+    with open_store(os.path.join(stored_array, name), "w") as st:
+        for k, v in coeffs.items():
+            st.write(f"coeffs/{k}", np.asarray(v))
+        for k, v in elements.items():
+            st.write(f"elements/{k}", np.asarray(v))
+
+
+def _layered_write_back(original_mesh, original_mask, new_mesh, unique_new_points, mask, parameters, located):
+    """values[inverse] -> reshape -> new_field[mask] per parameter, then attach (:415-427)."""
+    dev = _device()
+    new_fields = {p: np.zeros_like(new_mesh.element_nodal_fields[p]) for p in parameters}
+    num_failed = 0
+    for layer, loc in located.items():
+        fields = _stack_fields(original_mesh, parameters, original_mask[layer])
+        if "xi" in loc:
+            vals = ops.interp(_dev_f64(fields, dev), loc["elem"], loc["xi"])
+            num_failed += int((loc["elem"] < 0).sum().item())
+        else:
+            vals = _gather_cached(dev, fields, loc["elements"], loc["coeffs"])
+            num_failed += int((np.asarray(loc["elements"]) < 0).sum())
+        vals = vals.cpu().numpy()[unique_new_points[layer][1]]  # scatter back to all GLL nodes
+        shape = new_mesh.element_nodal_fields[parameters[0]][mask[layer]].shape
+        for f, p in enumerate(parameters):
+            new_fields[p][mask[layer]] = vals[:, f].reshape(shape)
+    for p in parameters:
+        new_mesh.attach_field(name=p, data=new_fields[p])
+    return num_failed
+
+
+def _gll_2_gll_layered_impl(from_gll, to_gll, layers, nelem_to_search, parameters, stored_array, make_spherical,
+                            spec):
+    (original_mesh, original_mask, new_mesh, unique_new_points, mask, layers,
+     parameters) = _layer_setup(from_gll, to_gll, layers, parameters, make_spherical)
+    order = original_mesh.shape_order
+    keys = list(unique_new_points.keys())
+    cached = _load_interp_info(stored_array, keys)
+    located = {}
+    if cached is not None:
+        for k in keys:
+            located[k] = {"coeffs": cached[0][k], "elements": cached[1][k]}
+    else:
+        for k in keys:
+            print(f"Interpolating layer: {k}")
+            # one index per layer over that layer's centroids => layer-local element ids (:363-373)
+            src = _Source(original_mesh.points[original_mask[k]])
+            pts = _dev_f64(unique_new_points[k][0], src.device)
+            cands = src.candidates(pts, nelem_to_search)
+            elem, xi, _, _ = src.locate(pts, cands, spec)
+            located[k] = {"elem": elem, "xi": xi}
+        if stored_array is not None:
+            _save_interp_info(
+                stored_array,
+                {k: ops.coeffs(v["elem"], v["xi"], order).cpu().numpy() for k, v in located.items()},
+                {k: v["elem"].cpu().numpy().astype(int) for k, v in located.items()})
+    num_failed = _layered_write_back(original_mesh, original_mask, new_mesh, unique_new_points, mask,
+                                     parameters, located)
+    if num_failed > 0:
+        print(f"{num_failed} points could not be interpolated")
+    return new_mesh
+
+
+def gll_2_gll_layered(from_gll, to_gll, layers, nelem_to_search: int = 20, parameters="ISO", stored_array=None,
+                      make_spherical: bool = False):
+    """Layer-restricted GLL -> GLL interpolation, V1 location (:288-439)."""
+    print(f"Stored array: {stored_array}")
+    return _gll_2_gll_layered_impl(from_gll, to_gll, layers, nelem_to_search, parameters, stored_array,
+                                   make_spherical, ops.V1())
+
+
+def gll_2_gll_layered_multi(from_gll, to_gll, layers, nelem_to_search: int = 20, parameters="all", threads=None,
+                            stored_array=None, make_spherical: bool = False):
+    """Same as gll_2_gll_layered; the reference parallelises over layers with a process pool
+    (:442-618) -- `threads` is accepted and ignored, the layers run back to back on the GPU."""
+    return _gll_2_gll_layered_impl(from_gll, to_gll, layers, nelem_to_search, parameters, stored_array,
+                                   make_spherical, ops.V1())
+
+
+def gll_2_gll_layered_multi_two(from_gll, to_gll, layers, nelem_to_search: int = 30, parameters="all",
+                                stored_array=None, make_spherical: bool = False, tolerance: float = 1.05):
+    """Layered interpolation with V2 location and snap_to_nearest=True (:980-1082)."""
+    return _gll_2_gll_layered_impl(from_gll, to_gll, layers, nelem_to_search, parameters, stored_array,
+                                   make_spherical, ops.V2(tolerance, True))
+
+
+def interpolate_to_points_layered(from_mesh, to_mesh, parameters, layers="nocore", make_spherical=False,
+                                  nelem_to_search=20):
+    """Layered mesh -> mesh with V3 location (|xi| < 1.03, failures get zero) (:855-928)."""
+    return _gll_2_gll_layered_impl(from_mesh, to_mesh, layers, nelem_to_search, parameters, None,
+                                   make_spherical, ops.V3())
+
+
+def gll_2_gll(from_gll, to_gll, nelem_to_search=20, parameters="ISO", from_model_path="MODEL/data",
+              to_model_path="MODEL/data", from_coordinates_path="MODEL/coordinates",
+              to_coordinates_path="MODEL/coordinates", gradient=False, stored_array=None):
+    """GLL -> GLL interpolation of ALL parameters of the source model onto the unique GLL points of
+    the target, V1 location over the k nearest source GLL points (:621-852).  The target file is
+    modified in place.  `stored_array`: directory with elements.npy / coeffs.npy ([F, P, N_unique],
+    F identical copies, as the reference stores them)."""
+    print("Initialization stage")
+    print(f"Stored array: {stored_array}")
+    original_points, original_data, original_params = utils.load_hdf5_params_to_memory(
+        from_gll, from_model_path, from_coordinates_path)
+    dimensions = original_points.shape[2]
+    from_gll_order = order_from_npoints(original_data.shape[2], dimensions)
+    parameters = original_params  # the reference interpolates every source parameter (:668)
+    src = _Source(original_points)
+
+    with open_store(to_gll, "r+") as new:
+        new_points = np.array(new.read(to_coordinates_path), dtype=np.float64)
+        elem_params = new.labels("MODEL/element_data")
+        fluid_elements = new.read("MODEL/element_data")[:, elem_params.index("fluid")].astype(bool)
+        solid_elements = np.invert(fluid_elements)
+        new_values = np.copy(new.read(to_model_path))
+        gll_points = new_points.shape[1]
+
+        element = coeffs = None
+        if stored_array and os.path.exists(os.path.join(stored_array, "coeffs.npy")) and os.path.exists(
+                os.path.join(stored_array, "elements.npy")):
+            coeffs = np.load(os.path.join(stored_array, "coeffs.npy"), allow_pickle=True)
+            element = np.load(os.path.join(stored_array, "elements.npy"), allow_pickle=True)
+            assert not np.isnan(coeffs).any(), "Stored coeffs matrix has NaNs"
+            print("Matrix was already stored. Will use that one")
+
+        unique_new_points, recon = utils.get_unique_points(points=new_points)
+        if element is None:
+            print("Now we start interpolating")
+            pts = _dev_f64(unique_new_points, src.device)
+            cands = src.candidates(pts, nelem_to_search, form="gll")
+            elem, xi, status, nfail = src.locate(pts, cands, ops.V1())  # ignore_hard_elements=True (:781)
+            print("Interpolation done, Need to organize the results and write to file")
+            num_failed = int(nfail.item())
+            if num_failed > 0:
+                print(f"{num_failed} points could not find an enclosing element.")
+            if stored_array:
+                os.makedirs(stored_array, exist_ok=True)
+                print("Will save matrices for later usage")
+                w = ops.coeffs(elem, xi, from_gll_order).cpu().numpy()  # [N, P]
+                assert not np.isnan(w).any(), "Interpolation failed somehow"
+                np.save(os.path.join(stored_array, "elements.npy"), elem.cpu().numpy().astype(int),
+                        allow_pickle=True)
+                np.save(os.path.join(stored_array, "coeffs.npy"),
+                        np.broadcast_to(w.T[None], (len(parameters),) + w.T.shape).copy(), allow_pickle=True)
+            vals = _gather(src, original_data, elem, xi)
+        else:
+            vals = _gather_cached(src.device, original_data, element, np.ascontiguousarray(coeffs[0].T))
+        # [N_unique, F] -> all GLL nodes -> [E_t, F, P_t]  (:822-826)
+        values = vals.cpu().numpy()[recon, :].reshape((new_points.shape[0], gll_points, len(parameters)))
+        values = np.ascontiguousarray(values.swapaxes(1, 2))
+        assert not np.isnan(values).any(), "Interpolation failed somehow"
+        if not gradient:
+            # keep fluid elements untouched and repair solids that picked up fluid (VS = 0) values
+            values[~solid_elements] = new_values[~solid_elements]
+            vs_index = parameters.index("VS") if "VS" in parameters else parameters.index("VSV")
+            zero_vs = np.where(values[:, vs_index, :] == 0.0)
+            print("If any fluid values accidentally went to the solid part we fix it")
+            for elem_id in np.unique(zero_vs[0]):
+                if solid_elements[elem_id]:
+                    values[elem_id, :, :] = new_values[elem_id, :, :]
+        utils.remove_and_create_empty_dataset(new, parameters, to_model_path, to_coordinates_path)
+        new.write(to_model_path, values)
+
+
+def exodus_2_gll(mesh, gll_model, gll_order=4, dimensions=3, nelem_to_search=20, parameters="TTI",
+                 model_path="MODEL/data", coordinates_path="MODEL/coordinates"):
+    """Nodal HEX8 (Exodus) model -> GLL model through the order-1 trilinear path (:142-224).
+    Every target GLL point is located in the k nearest source elements by centroid; arithmetic is
+    bit-identical to the reference's C routine."""
+    exodus, centroid_tree = utils.load_exodus(mesh, find_centroids=True)
+    dev = centroid_tree.device
+    parameters = utils.pick_parameters(parameters)
+    with open_store(gll_model, "r+") as gll:
+        gll_coords = np.array(gll.read(coordinates_path), dtype=np.float64)
+        npoints, gll_points = gll_coords.shape[:2]
+        # Exodus HEX8 -> vertex order of the C routine (:186-190)
+        perm = np.argsort([0, 3, 2, 1, 4, 5, 6, 7])
+        connectivity = torch.from_numpy(np.ascontiguousarray(exodus.connectivity[:, perm])).to(dev)
+        exopoints = _dev_f64(exodus.points, dev)
+        param_exodus = _dev_f64(np.stack([exodus.get_nodal_field(p) for p in parameters]), dev)
+        utils.remove_and_create_empty_dataset(gll, parameters, model_path, coordinates_path)
+        # all GLL points in one batch (the reference loops over the P node slots, :205-224)
+        pts = _dev_f64(gll_coords.reshape(-1, 3), dev)
+        _, nearest = centroid_tree.query(pts, k=nelem_to_search, return_distance=False)
+        nfail, enclosing, weights = ops.trilinear(nearest.to(torch.int64), connectivity, exopoints, pts)
+        nfailed = int(nfail.item())
+        assert nfailed == 0, f"{nfailed} points could not be interpolated."
+        values = ops.gather_nodal(param_exodus, enclosing, weights)  # [F, N]
+        values = values.cpu().numpy().reshape(len(parameters), npoints, gll_points)
+        gll.write(model_path, np.ascontiguousarray(values.swapaxes(0, 1)))
+
+
+def gll_2_exodus(gll_model, exodus_model, gll_order=4, dimensions=3, nelem_to_search=20, parameters="TTI",
+                 model_path="MODEL/data", coordinates_path="MODEL/coordinates", gradient=False):
+    """GLL model -> nodal fields of an Exodus mesh, V1 location over centroids (:227-285).
+    All parameters stored in the GLL model are interpolated (as in the reference, :248-249)."""
+    with open_store(gll_model, "r") as st:
+        gll_points = np.array(st.read(coordinates_path), dtype=np.float64)
+        gll_data = np.array(st.read(model_path))
+        parameters = st.labels(model_path)
+    src = _Source(gll_points)
+    print("Read in mesh")
+    exodus = exodus_model if isinstance(exodus_model, Exodus) else Exodus(exodus_model, mode="a")
+    print("Querying the KDTree")
+    pts = _dev_f64(exodus.points[:, :dimensions], src.device)
+    cands = src.candidates(pts, nelem_to_search)
+    elem, xi, _, _ = src.locate(pts, cands, ops.V1())
+    values = _gather(src, gll_data, elem, xi).cpu().numpy()
+    for i, param in enumerate(parameters):
+        exodus.attach_field(param, np.zeros_like(values[:, i]))
+        exodus.attach_field(param, values[:, i])
+    return exodus

@@ -15,12 +15,13 @@
 //   t[j,k] = sum_i Lx[i] v[i,j,k];  u[k] = sum_j Ly[j] t[j,k];  out = sum_k Lz[k] u[k]
 // one rounding per operation, no FMA; bit-identical to oracle/mm_oracle.c:mmo_interp.
 #include <algorithm>
+#include <cstdlib>
 
 #include "mm_common.cuh"
 
 namespace {
 
-constexpr int INTERP_WARPS = 2;
+constexpr int INTERP_MAX_WARPS = 8;
 
 struct interp_cfg {
     int F;           // fields
@@ -29,6 +30,7 @@ struct interp_cfg {
     int stages;      // pipeline depth per warp
     int slot_bytes;  // per-lane slot stride
     int odd_p;       // P odd: chunk starts alternate between 0 and 8 (mod 16)
+    int warps;       // warps per CTA (each warp runs its own pipeline)
 };
 
 __host__ __device__ inline int chunk_copy_bytes(int nf, int P, int odd_p)
@@ -71,7 +73,7 @@ __device__ __forceinline__ double contract_field(const double *__restrict__ v,
 }
 
 template <int ORDER, int DIM>
-__global__ void __launch_bounds__(INTERP_WARPS * 32)
+__global__ void __launch_bounds__(INTERP_MAX_WARPS * 32)
 interp_kernel(const mm_gll_table T, const interp_cfg cfg, int64_t E,
               const double *__restrict__ fields, int64_t N, const int32_t *__restrict__ elem,
               const double *__restrict__ xi, double *__restrict__ out)
@@ -82,7 +84,7 @@ interp_kernel(const mm_gll_table T, const interp_cfg cfg, int64_t E,
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const size_t stage_bytes = (size_t)32 * cfg.slot_bytes;
     unsigned char *wbase = smem + (size_t)warp * cfg.stages * stage_bytes;
-    uint64_t *bars = reinterpret_cast<uint64_t *>(smem + (size_t)INTERP_WARPS * cfg.stages * stage_bytes) +
+    uint64_t *bars = reinterpret_cast<uint64_t *>(smem + (size_t)cfg.warps * cfg.stages * stage_bytes) +
                      warp * cfg.stages;
     if (lane < cfg.stages) mbar_init(&bars[lane], 1);
     fence_mbar_init();
@@ -90,8 +92,8 @@ interp_kernel(const mm_gll_table T, const interp_cfg cfg, int64_t E,
 
     const int64_t total_bytes = E * (int64_t)cfg.F * P * 8;
     const int64_t nbatch = (N + 31) / 32;
-    const int64_t warps_total = (int64_t)gridDim.x * INTERP_WARPS;
-    const int64_t first = (int64_t)blockIdx.x * INTERP_WARPS + warp;
+    const int64_t warps_total = (int64_t)gridDim.x * cfg.warps;
+    const int64_t first = (int64_t)blockIdx.x * cfg.warps + warp;
     // this warp's batches: first, first + warps_total, ...
     const int64_t my_batches = first < nbatch ? (nbatch - first + warps_total - 1) / warps_total : 0;
     const int64_t items = my_batches * cfg.chunks;
@@ -193,20 +195,29 @@ int launch_interp(int64_t E, int F, const double *fields, int64_t N, const int32
     cfg.chunks = (F + fc - 1) / fc;
     cfg.slot_bytes = mm_slot_bytes(chunk_copy_bytes(fc, P, cfg.odd_p));
     cfg.stages = 3;
+    cfg.warps = 2;
+    // tuning overrides (profiling only)
+    if (const char *e = getenv("MM_INTERP_FC")) fc = std::max(1, std::min(F, atoi(e)));
+    if (const char *e = getenv("MM_INTERP_STAGES")) cfg.stages = std::max(2, std::min(8, atoi(e)));
+    if (const char *e = getenv("MM_INTERP_WARPS")) cfg.warps = std::max(1, std::min(INTERP_MAX_WARPS, atoi(e)));
+    cfg.FC = fc;
+    cfg.chunks = (F + fc - 1) / fc;
+    cfg.slot_bytes = mm_slot_bytes(chunk_copy_bytes(fc, P, cfg.odd_p));
     auto kern = interp_kernel<ORDER, DIM>;
-    size_t smem = (size_t)INTERP_WARPS * cfg.stages * 32 * cfg.slot_bytes +
-                  INTERP_WARPS * cfg.stages * sizeof(uint64_t);
+    size_t smem = (size_t)cfg.warps * cfg.stages * 32 * cfg.slot_bytes +
+                  cfg.warps * cfg.stages * sizeof(uint64_t);
+    MM_REQUIRE(smem <= 227 * 1024, MM_ERR_UNSUPPORTED, "mm_interp: staging needs %zu B of shared memory", smem);
     MM_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int per_sm = 1;
-    MM_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, INTERP_WARPS * 32, smem));
+    MM_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, cfg.warps * 32, smem));
     if (per_sm < 1) per_sm = 1;
     const int sms = mm_num_sms() > 0 ? mm_num_sms() : 148;
     int64_t nbatch = (N + 31) / 32;
     int64_t grid = (int64_t)sms * per_sm;  // persistent CTAs, multiple of the SM count
-    int64_t need = (nbatch + INTERP_WARPS - 1) / INTERP_WARPS;
+    int64_t need = (nbatch + cfg.warps - 1) / cfg.warps;
     if (grid > need) grid = need;
     if (grid < 1) grid = 1;
-    kern<<<(int)grid, INTERP_WARPS * 32, smem, stream>>>(T, cfg, E, fields, N, elem, xi, out);
+    kern<<<(int)grid, cfg.warps * 32, smem, stream>>>(T, cfg, E, fields, N, elem, xi, out);
     MM_CUDA(cudaGetLastError());
     return MM_OK;
 }

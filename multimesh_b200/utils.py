@@ -1,0 +1,134 @@
+"""
+Host-side helpers on the interpolation path; counterparts of the functions of the same name in
+multi_mesh/utils.py (line numbers below refer to that file).  Visualisation / xarray / geodesy
+helpers of the reference are out of scope.
+"""
+from typing import List, Union
+
+import numpy as np
+
+from .io.store import open_store
+
+R_EARTH = 6371000.0
+
+_PRESETS = {
+    "TTI": ["VPV", "VPH", "VSV", "VSH", "RHO", "ETA", "QKAPPA", "QMU"],  # :172-182
+    "ISO": ["QKAPPA", "QMU", "RHO", "VP", "VS"],  # :183-184
+}
+
+
+def pick_parameters(parameters):
+    """'TTI' / 'ISO' presets, anything else is passed through (:171-188)."""
+    if isinstance(parameters, str) and parameters in _PRESETS:
+        return list(_PRESETS[parameters])
+    return parameters
+
+
+def load_hdf5_params_to_memory(gll: str, model: str, coordinates: str):
+    """(points [E,P,d] f64, data [E,F,P], params) with 'grad' stripped from the labels (:206-217)."""
+    with open_store(gll, "r") as st:
+        points = np.array(st.read(coordinates), dtype=np.float64)
+        data = np.array(st.read(model))
+        params = [p.replace("grad", "") for p in st.labels(model)]
+    return points, data, params
+
+
+def remove_and_create_empty_dataset(gll_model, parameters: list, model: str, coordinates: str):
+    """Replace `model` by an empty [E, len(parameters), P] float64 dataset with fresh dimension
+    labels (:137-168).  `gll_model` is an open store."""
+    E, P = gll_model.shape(coordinates)[:2]
+    gll_model.write(model, np.zeros((E, len(parameters), P), dtype=np.float64))
+    gll_model.set_labels(model, list(parameters))
+
+
+def _layer_field(mesh):
+    fields = mesh.get_elemental_fields() if hasattr(mesh, "get_elemental_fields") else mesh.elemental_fields
+    return fields
+
+
+def _assess_layers(mesh, layers: Union[List[int], str, int]):
+    """Resolve a layer request into the list of numerical layers (descending, so that moho_idx
+    indexes from the surface) and whether masking is needed (:382-440)."""
+    fields = _layer_field(mesh)
+    mesh_layers = np.sort(np.unique(fields["layer"]))[::-1].astype(int)
+    if isinstance(layers, (list, tuple, np.ndarray)):
+        if np.max(layers) > np.max(mesh_layers) or np.min(layers) < np.min(mesh_layers):
+            raise ValueError("Requested layers not in mesh")
+        return list(layers), set(mesh_layers.tolist()) != set(int(x) for x in layers)
+    if isinstance(layers, (int, np.integer)):
+        if layers not in mesh_layers:
+            raise ValueError("Requested layer not in mesh")
+        return [int(layers)], True
+    available = ["all", "crust", "mantle", "core", "nocore"]
+    if not isinstance(layers, str):
+        raise ValueError(f"Input for layers needs to be a list of one of: {available}")
+    if layers == "all":
+        return mesh_layers, False
+    if layers not in available:
+        raise ValueError(f"Only allowed string layer inputs are: {available}")
+    if layers == "crust":
+        return mesh_layers[: int(mesh.global_strings["moho_idx"])], True
+    fluid = np.where(fields["fluid"] == 1)[0]
+    if fluid.size == 0:
+        # no fluid element: the reference would raise IndexError; treat as "no core present"
+        o_core_idx = len(mesh_layers)
+    else:
+        o_core_idx = int(np.where(mesh_layers == fields["layer"][fluid[0]])[0][0])
+    if layers == "mantle":
+        return mesh_layers[int(mesh.global_strings["moho_idx"]):o_core_idx], True
+    if layers == "core":
+        return mesh_layers[o_core_idx:], True
+    return mesh_layers[:o_core_idx], True  # nocore
+
+
+def _create_mask(mesh, layers):
+    """{str(layer): bool[E]} (:355-379)."""
+    lay = _layer_field(mesh)["layer"]
+    return {str(layer): (lay == layer) for layer in layers}, layers
+
+
+def create_layer_mask(mesh, layers):
+    layers, _ = _assess_layers(mesh=mesh, layers=layers)
+    return _create_mask(mesh=mesh, layers=layers)
+
+
+def get_unique_points(points, mesh=False, layers=None):
+    """Lexicographic unique rows + inverse (np.unique(axis=0, return_inverse=True)), for a
+    coordinate array [E,P,d] or, per layer, for a mesh object (:465-515)."""
+    if isinstance(points, np.ndarray):
+        allp = points.reshape(points.shape[0] * points.shape[1], points.shape[2])
+        u, inv = np.unique(allp, return_inverse=True, axis=0)
+        return u, inv.reshape(-1)
+    layers, _ = _assess_layers(mesh=points, layers=layers)
+    mask, _ = _create_mask(mesh=points, layers=layers)
+    unique_points = {}
+    for layer in layers:
+        nodes = points.get_element_nodes()[mask[str(layer)]]
+        u, inv = np.unique(nodes.reshape(nodes.shape[0] * nodes.shape[1], nodes.shape[2]),
+                           return_inverse=True, axis=0)
+        unique_points[str(layer)] = (u, inv.reshape(-1))
+    return unique_points, mask, layers
+
+
+def lat2colat(lat):
+    return 90.0 - lat
+
+
+def latlondepth_to_xyz(latlondepth: np.ndarray):
+    """[lat, lon, depth_m] rows -> geocentric xyz on a 6371 km sphere (:526-542)."""
+    r = R_EARTH - latlondepth[:, 2]
+    colat = np.deg2rad(lat2colat(latlondepth[:, 0]))
+    lon = np.deg2rad(latlondepth[:, 1])
+    return np.array([r * np.sin(colat) * np.cos(lon), r * np.sin(colat) * np.sin(lon),
+                     r * np.cos(colat)]).T
+
+
+def load_exodus(file, find_centroids=True):
+    """Exodus object (+ KD-tree over its element centroids) (:191-203)."""
+    from .io.exodus import Exodus
+    from .kdtree import KDTree
+
+    exodus = file if isinstance(file, Exodus) else Exodus(file)
+    if not find_centroids:
+        return exodus
+    return exodus, KDTree(exodus.get_element_centroid())

@@ -1,0 +1,120 @@
+"""CPU tests of the host-side logic: layer handling, unique points, stores, readers, partitioning."""
+import os
+
+import numpy as np
+import pytest
+
+from multimesh_b200 import meshgen, utils
+from multimesh_b200.components.salvus_mesh_reader import SalvusMesh
+from multimesh_b200.io.store import open_store, write_gll_model
+
+
+def _shell(order=2, n_lat=2):
+    layers = [(3480e3, 5000e3, 2, 4, 1), (5000e3, 6291e3, 2, 3, 0), (6291e3, 6346e3, 1, 2, 0), (6346e3, 6371e3, 1, 1, 0)]
+    coords, elemental, z1d = meshgen.shell_mesh(n_lat, layers, order)
+    names = ["VP", "VS", "z_node_1D"]
+    data = meshgen.analytic_fields(coords, names)
+    data[:, 2, :] = z1d
+    ed = np.stack([elemental["layer"], elemental["fluid"]], axis=1)
+    return SalvusMesh.from_arrays(coords, data, names, ed, ["layer", "fluid"], {"moho_idx": "2"})
+
+
+def test_pick_parameters():
+    assert utils.pick_parameters("ISO") == ["QKAPPA", "QMU", "RHO", "VP", "VS"]
+    assert utils.pick_parameters("TTI")[:2] == ["VPV", "VPH"] and len(utils.pick_parameters("TTI")) == 8
+    assert utils.pick_parameters(["A"]) == ["A"]
+
+
+def test_assess_layers_and_masks():
+    m = _shell()
+    layers, mask = utils._assess_layers(m, "all")
+    assert list(layers) == [4, 3, 2, 1] and mask is False
+    assert list(utils._assess_layers(m, "crust")[0]) == [4, 3]  # first moho_idx layers of the descending list
+    assert list(utils._assess_layers(m, "nocore")[0]) == []  # fluid layer 4 is first in the descending list
+    assert list(utils._assess_layers(m, "core")[0]) == [4, 3, 2, 1]
+    assert utils._assess_layers(m, [1, 2]) == ([1, 2], True)
+    assert utils._assess_layers(m, 3) == ([3], True)
+    with pytest.raises(ValueError):
+        utils._assess_layers(m, [9])
+    with pytest.raises(ValueError):
+        utils._assess_layers(m, "nonsense")
+    masks, layers = utils.create_layer_mask(m, [1, 3])
+    assert set(masks) == {"1", "3"}
+    assert masks["1"].sum() + masks["3"].sum() == (m.elemental_fields["layer"] == 1).sum() + (m.elemental_fields["layer"] == 3).sum()
+    assert not (masks["1"] & masks["3"]).any()
+
+
+def test_get_unique_points_array_and_mesh():
+    nodes = meshgen.box_mesh((3, 3, 3), 2)
+    u, inv = utils.get_unique_points(nodes)
+    assert u.shape == (7 ** 3, 3)
+    assert np.array_equal(u[inv].reshape(nodes.shape), nodes)
+    assert (np.diff(u.view([("x", "f8"), ("y", "f8"), ("z", "f8")]).ravel().argsort(order=("x", "y", "z"))) == 1).all()
+    m = _shell()
+    up, mask, layers = utils.get_unique_points(m, mesh=True, layers=[1, 2])
+    for k in ("1", "2"):
+        pts, inv = up[k]
+        assert np.array_equal(pts[inv].reshape(-1, m.n_gll_points, 3), m.points[mask[k]])
+
+
+def test_latlondepth_to_xyz():
+    xyz = utils.latlondepth_to_xyz(np.array([[90.0, 0.0, 0.0], [0.0, 0.0, 1000.0], [0.0, 90.0, 0.0]]))
+    assert np.allclose(xyz[0], [0, 0, 6371000.0], atol=1e-6)
+    assert np.allclose(xyz[1], [6370000.0, 0, 0], atol=1e-6)
+    assert np.allclose(xyz[2], [0, 6371000.0, 0], atol=1e-6)
+
+
+def test_npz_store_and_salvus_mesh_round_trip(tmp_path):
+    nodes = meshgen.box_mesh((2, 2, 2), 2)
+    names = ["QKAPPA", "QMU", "RHO", "VP", "VS"]
+    data = meshgen.analytic_fields(nodes, names)
+    ed = np.zeros((8, 2))
+    path = str(tmp_path / "model.npz")
+    write_gll_model(path, nodes, data, names, ed, ["fluid", "layer"], {"moho_idx": "1"})
+    pts, dat, params = utils.load_hdf5_params_to_memory(path, "MODEL/data", "MODEL/coordinates")
+    assert np.array_equal(pts, nodes) and np.array_equal(dat, data) and params == names
+    m = SalvusMesh(path, fast_mode=False)
+    assert (m.nelem, m.n_gll_points, m.dimensions, m.shape_order) == (8, 27, 3, 2)
+    assert m.global_strings["moho_idx"] == "1"
+    assert np.array_equal(m.get_element_centroids(), nodes.mean(axis=1))
+    new = np.full((8, 27), 7.0)
+    m.attach_field("VP", new)
+    assert np.array_equal(SalvusMesh(path, fast_mode=False).element_nodal_fields["VP"], new)
+    with pytest.raises(ValueError):
+        m.attach_field("NOPE", new)
+    with pytest.raises(ValueError):
+        m.attach_field("VP", np.zeros((3, 3)))
+    with open_store(path, "r+") as st:
+        utils.remove_and_create_empty_dataset(st, ["A", "B"], "MODEL/data", "MODEL/coordinates")
+    with open_store(path, "r") as st:
+        assert st.shape("MODEL/data") == (8, 2, 27) and st.labels("MODEL/data") == ["A", "B"]
+
+
+def test_grad_labels_are_stripped(tmp_path):
+    nodes = meshgen.box_mesh((2, 2, 2), 1)
+    path = str(tmp_path / "g.npz")
+    write_gll_model(path, nodes, np.zeros((8, 2, 8)), ["gradVP", "gradVS"])
+    assert utils.load_hdf5_params_to_memory(path, "MODEL/data", "MODEL/coordinates")[2] == ["VP", "VS"]
+
+
+def test_shard_bounds():
+    from multimesh_b200.parallel import local_slice, shard_bounds
+
+    for n, w in [(10, 3), (7, 8), (0, 2), (100, 1), (23887872, 8)]:
+        b = shard_bounds(n, w)
+        assert b[0] == 0 and b[-1] == n and len(b) == w + 1
+        sizes = np.diff(b)
+        assert sizes.max() - sizes.min() <= 1
+        assert sum(local_slice(n, r, w).stop - local_slice(n, r, w).start for r in range(w)) == n
+
+
+def test_meshgen_shapes_and_shell_radii():
+    c = meshgen.box_mesh((3, 2), 4, lo=[0, 0], hi=[3, 2])
+    assert c.shape == (6, 25, 2) and c.min() == 0 and c[..., 0].max() == 3
+    coords, el, z1d = meshgen.shell_mesh(2, meshgen.default_shell_layers(), 2)
+    r = np.linalg.norm(coords, axis=2)
+    assert np.allclose(r, z1d * 6371000.0, rtol=1e-13)
+    assert r.min() >= 3480e3 - 1 and r.max() <= 6371e3 + 1
+    assert set(np.unique(el["layer"])) == {1.0, 2.0, 3.0}
+    pts, conn = meshgen.hex8_mesh((2, 3, 4))
+    assert pts.shape == (3 * 4 * 5, 3) and conn.shape == (24, 8) and conn.max() == len(pts) - 1
