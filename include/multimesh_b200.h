@@ -21,6 +21,7 @@
 #ifndef MULTIMESH_B200_H
 #define MULTIMESH_B200_H
 
+#include <stddef.h>
 #include <stdint.h>
 
 #ifdef __cplusplus
@@ -103,7 +104,8 @@ enum {
     MM_ST_SNAPPED = 5,
     MM_ST_FAILED = 6, /* elem = -1, zero weights */
     MM_ST_MINL1 = 7,
-    MM_ST_SNAP_NONE = 8
+    MM_ST_SNAP_NONE = 8,
+    MM_ST_UNRESOLVED = 9 /* internal to the progressive search; never returned */
 };
 
 typedef struct {
@@ -140,6 +142,12 @@ int mm_locate(int order, int dim, int64_t E, const double *nodes, const double *
 int mm_interp(int order, int dim, int64_t E, int F, const double *fields, int64_t N,
               const int32_t *elem, const double *xi, double *out, void *stream);
 
+/* Same with an output permutation: row n is written to out[perm[n]] (perm may be NULL). Used by
+ * mm_interpolate, which processes the points in spatially sorted order. */
+int mm_interp_perm(int order, int dim, int64_t E, int F, const double *fields, int64_t N,
+                   const int32_t *elem, const double *xi, const int32_t *perm, double *out,
+                   void *stream);
+
 /* coeffs [N][P] f64 (out) = w_a(xi_n), zero rows where elem < 0 (elem may be NULL).
  * For the reference's stored interpolation matrices (components/interpolator.py:391-398,
  * 797-810). */
@@ -167,6 +175,31 @@ int mm_centroid_conn(int64_t ndim, int64_t nelem, int64_t npe, const int64_t *co
 int mm_gather_nodal(int F, int64_t npoints_mesh, const double *param, int64_t N,
                     const int64_t *enclosing, const double *weights, double *values,
                     void *stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Fused device pipeline K1 -> K2 -> K3 over one batch of target points (the bench's "step").
+ * Replaces the body of the reference's drivers between "arrays loaded" and "values computed":
+ *   KDTree.query + find_gll_coeffs / fill_value_array / get_element_weights + the gather
+ *   (components/interpolator.py:744-826, 363-427, 949-976).
+ * Same results as mm_knn -> mm_locate -> mm_interp, but
+ *   - the points are first counting-sorted by index cell (coherent warps, L2 locality) and the
+ *     results are written back through the permutation;
+ *   - the search is progressive: a first pass with the min(k, 8) nearest candidates resolves
+ *     most points (any prefix of the canonical k-NN list is the k'-NN list); only points whose
+ *     prefix is exhausted are re-run with all k candidates and the variant's fallback.
+ *   index    : over element centroids (divisor = 1) or over all GLL points (divisor = P)
+ *   fields   : [E][F][P], may be NULL (locate only; out ignored)
+ *   out      : [N][F];  elem [N], xi [N][dim], status [N]: optional (NULL to skip)
+ *   num_failed: device int64 (may be NULL)
+ *   workspace: device scratch of at least mm_interpolate_workspace_bytes(...) bytes
+ * ---------------------------------------------------------------------------------------- */
+size_t mm_interpolate_workspace_bytes(const mm_index_t *index, int dim, int64_t N, int k);
+int mm_interpolate(const mm_index_t *index, int32_t divisor, int order, int dim, int64_t E,
+                   const double *nodes, const double *centroid, const double *aabb, int F,
+                   const double *fields, int64_t N, const double *pts, int k,
+                   const mm_locate_params *params, double *out, int32_t *elem, double *xi,
+                   uint8_t *status, int64_t *num_failed, void *workspace, size_t workspace_bytes,
+                   void *stream);
 
 /* ------------------------------------------------------------------------------------------
  * Legacy symbols, HOST pointers, exact reference signatures (helpers.py:43-81).

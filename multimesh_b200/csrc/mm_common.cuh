@@ -39,6 +39,17 @@ int mm_cuda_fail(cudaError_t e, const char *what, const char *file, int line);
 
 int mm_num_sms();                 // SM count of the current device
 
+// internal (C++) entry points shared between translation units
+int mm_locate_impl(int order, int dim, int64_t E, const double *nodes, const double *centroid,
+                   const double *aabb, int64_t N, const double *pts, int k, const int32_t *cands,
+                   const mm_locate_params *params, int32_t *elem, double *xi, uint8_t *status,
+                   int64_t *num_failed, bool zero_num_failed, int32_t *unresolved_list,
+                   int64_t *unresolved_count, void *stream);
+size_t mm_index_sort_scratch_bytes(const mm_index_t *ix);
+// counting sort of query points by index cell: sorted[i] = pts[perm[i]]
+int mm_index_sort_queries(const mm_index_t *ix, int64_t N, const double *pts, double *sorted,
+                          int32_t *perm, void *scratch, void *stream);
+
 static inline bool mm_valid_order(int order) { return order == 1 || order == 2 || order == 4; }
 static inline int mm_pow(int m, int dim) { return dim == 2 ? m * m : m * m * m; }
 

@@ -37,17 +37,16 @@ extern "C" int mm_interpolate_host(int order, int dim, int64_t E, const double *
     if (N == 0) return MM_OK;
     const int P = mm_pow(order + 1, dim);
     cudaStream_t stream = nullptr;
-    dev_buf d_nodes, d_fields, d_pts, d_cent, d_aabb, d_cands, d_elem, d_xi, d_out, d_nf;
+    dev_buf d_nodes, d_fields, d_pts, d_cent, d_aabb, d_elem, d_xi, d_out, d_nf, d_ws;
     MM_CUDA(d_nodes.alloc(sizeof(double) * E * P * dim));
     MM_CUDA(d_fields.alloc(sizeof(double) * E * F * P));
     MM_CUDA(d_pts.alloc(sizeof(double) * N * dim));
     MM_CUDA(d_cent.alloc(sizeof(double) * E * dim));
     MM_CUDA(d_aabb.alloc(sizeof(double) * E * 2 * dim));
-    MM_CUDA(d_cands.alloc(sizeof(int32_t) * N * k));
-    MM_CUDA(d_elem.alloc(sizeof(int32_t) * N));
-    MM_CUDA(d_xi.alloc(sizeof(double) * N * dim));
     MM_CUDA(d_out.alloc(sizeof(double) * N * F));
     MM_CUDA(d_nf.alloc(sizeof(int64_t)));
+    if (elem) MM_CUDA(d_elem.alloc(sizeof(int32_t) * N));
+    if (xi) MM_CUDA(d_xi.alloc(sizeof(double) * N * dim));
     MM_CUDA(cudaMemcpyAsync(d_nodes.p, nodes, sizeof(double) * E * P * dim, cudaMemcpyHostToDevice, stream));
     MM_CUDA(cudaMemcpyAsync(d_pts.p, pts, sizeof(double) * N * dim, cudaMemcpyHostToDevice, stream));
     MM_TRY(mm_element_geometry(order, dim, E, d_nodes.as<double>(), d_cent.as<double>(),
@@ -58,13 +57,13 @@ extern "C" int mm_interpolate_host(int order, int dim, int64_t E, const double *
     else
         MM_TRY(mm_index_create(&ih.ix, dim, E, d_cent.as<double>(), stream));
     MM_CUDA(cudaMemcpyAsync(d_fields.p, fields, sizeof(double) * E * F * P, cudaMemcpyHostToDevice, stream));
-    MM_TRY(mm_knn(ih.ix, N, d_pts.as<double>(), k, gll_points_form ? P : 1, d_cands.as<int32_t>(),
-                  nullptr, stream));
-    MM_TRY(mm_locate(order, dim, E, d_nodes.as<double>(), d_cent.as<double>(), d_aabb.as<double>(),
-                     N, d_pts.as<double>(), k, d_cands.as<int32_t>(), params, d_elem.as<int32_t>(),
-                     d_xi.as<double>(), nullptr, d_nf.as<int64_t>(), stream));
-    MM_TRY(mm_interp(order, dim, E, F, d_fields.as<double>(), N, d_elem.as<int32_t>(),
-                     d_xi.as<double>(), d_out.as<double>(), stream));
+    const size_t ws_bytes = mm_interpolate_workspace_bytes(ih.ix, dim, N, k);
+    MM_CUDA(d_ws.alloc(ws_bytes));
+    MM_TRY(mm_interpolate(ih.ix, gll_points_form ? P : 1, order, dim, E, d_nodes.as<double>(),
+                          d_cent.as<double>(), d_aabb.as<double>(), F, d_fields.as<double>(), N,
+                          d_pts.as<double>(), k, params, d_out.as<double>(),
+                          elem ? d_elem.as<int32_t>() : nullptr, xi ? d_xi.as<double>() : nullptr,
+                          nullptr, d_nf.as<int64_t>(), d_ws.p, ws_bytes, stream));
     MM_CUDA(cudaMemcpyAsync(values, d_out.p, sizeof(double) * N * F, cudaMemcpyDeviceToHost, stream));
     if (elem) MM_CUDA(cudaMemcpyAsync(elem, d_elem.p, sizeof(int32_t) * N, cudaMemcpyDeviceToHost, stream));
     if (xi) MM_CUDA(cudaMemcpyAsync(xi, d_xi.p, sizeof(double) * N * dim, cudaMemcpyDeviceToHost, stream));

@@ -199,16 +199,35 @@ scatter_kernel(grid_t g, int64_t M, const double *__restrict__ pts,
     }
 }
 
-// ---- k-NN query: one thread per query point, sorted top-k list in shared memory ----------------
-struct knn_list {
-    double *d2;   // [k][KNN_BLOCK] slot-major: conflict-free whatever slot each lane touches
+// ---- k-NN query: one thread per query point -----------------------------------------------------
+// Two list policies with the same interface:
+//   smem_list   sorted top-k list in shared memory (any k <= 64); slot-major layout, so the
+//               accesses are conflict-free whatever slot each lane touches
+//   reg_list<K> sorted top-K list in registers (K = 4 or 8), used for small k: the first pass
+//               of the progressive search (mm_pipeline.cu) and plain queries with k <= 8
+struct smem_list {
+    double *d2;
     int32_t *id;
     int k, cnt;
     double kth_d2;
     int32_t kth_id;
 
+    __device__ __forceinline__ void init(unsigned char *smem, int k_)
+    {
+        d2 = reinterpret_cast<double *>(smem);
+        id = reinterpret_cast<int32_t *>(smem + (size_t)k_ * KNN_BLOCK * sizeof(double));
+        k = k_;
+    }
+    __device__ __forceinline__ void reset()
+    {
+        cnt = 0;
+        kth_d2 = INFINITY;
+        kth_id = 0x7fffffff;
+    }
     __device__ __forceinline__ double &D(int s) { return d2[s * KNN_BLOCK + threadIdx.x]; }
     __device__ __forceinline__ int32_t &I(int s) { return id[s * KNN_BLOCK + threadIdx.x]; }
+    __device__ __forceinline__ bool full() const { return cnt == k; }
+    __device__ __forceinline__ double worst() const { return kth_d2; }
 
     __device__ __forceinline__ void insert(double nd, int32_t ni)
     {
@@ -234,10 +253,79 @@ struct knn_list {
             kth_id = I(k - 1);
         }
     }
+    __device__ __forceinline__ void write(int32_t *oi, double *od, int32_t divisor)
+    {
+        for (int t = 0; t < k; ++t) {
+            bool have = t < cnt;
+            oi[t] = have ? I(t) / divisor : -1;
+            if (od) od[t] = have ? D(t) : INFINITY;
+        }
+    }
 };
 
-__device__ __forceinline__ void scan_range(knn_list &L, const double4 *__restrict__ recs,
-                                           int32_t lo, int32_t hi, double px, double py, double pz,
+template <int K>
+struct reg_list {
+    // ascending in slots [K - k, K); slots below hold -inf sentinels that never move, so the
+    // worst kept entry is always slot K-1 (a compile-time register) for any runtime k <= K
+    double d2[K];
+    int32_t id[K];
+    int k;
+
+    __device__ __forceinline__ void init(unsigned char *, int k_) { k = k_; }
+    __device__ __forceinline__ void reset()
+    {
+#pragma unroll
+        for (int j = 0; j < K; ++j) {
+            d2[j] = j < K - k ? -INFINITY : INFINITY;
+            id[j] = j < K - k ? -1 : 0x7fffffff;
+        }
+    }
+    __device__ __forceinline__ bool full() const { return d2[K - 1] < INFINITY; }
+    __device__ __forceinline__ double worst() const { return d2[K - 1]; }
+
+    __device__ __forceinline__ void insert(double nd, int32_t ni)
+    {
+        if (!(nd < d2[K - 1] || (nd == d2[K - 1] && ni < id[K - 1]))) return;
+        // one bubble pass from the top: shift entries that the new one precedes
+#pragma unroll
+        for (int j = K - 1; j > 0; --j) {
+            bool before = nd < d2[j - 1] || (nd == d2[j - 1] && ni < id[j - 1]);
+            bool here = !before && (nd < d2[j] || (nd == d2[j] && ni < id[j]) || j == K - 1);
+            // entries above j were already shifted; slot j takes its lower neighbour or the new one
+            double od = d2[j - 1];
+            int32_t oi = id[j - 1];
+            if (before) {
+                d2[j] = od;
+                id[j] = oi;
+            } else if (here) {
+                d2[j] = nd;
+                id[j] = ni;
+                nd = INFINITY;  // placed: nothing below compares as "before"
+                ni = 0x7fffffff;
+            }
+        }
+        if (nd < d2[0] || (nd == d2[0] && ni < id[0])) {  // new best of a full-width list (k == K)
+            d2[0] = nd;
+            id[0] = ni;
+        }
+    }
+    __device__ __forceinline__ void write(int32_t *oi, double *od, int32_t divisor)
+    {
+#pragma unroll
+        for (int j = 0; j < K; ++j) {
+            int t = j - (K - k);
+            if (t >= 0) {
+                bool have = d2[j] < INFINITY;
+                oi[t] = have ? id[j] / divisor : -1;
+                if (od) od[t] = have ? d2[j] : INFINITY;
+            }
+        }
+    }
+};
+
+template <class List>
+__device__ __forceinline__ void scan_range(List &L, const double4 *__restrict__ recs, int32_t lo,
+                                           int32_t hi, double px, double py, double pz,
                                            bool three_d)
 {
     for (int32_t j = lo; j < hi; ++j) {
@@ -253,16 +341,15 @@ __device__ __forceinline__ void scan_range(knn_list &L, const double4 *__restric
     }
 }
 
+template <class List>
 __global__ void __launch_bounds__(KNN_BLOCK)
 knn_kernel(grid_t g, int64_t N, const double *__restrict__ pts, int k, int32_t divisor,
            const double4 *__restrict__ recs, const int32_t *__restrict__ cell_start,
            int32_t *__restrict__ out_idx, double *__restrict__ out_d2)
 {
     extern __shared__ __align__(16) unsigned char smem[];
-    knn_list L;
-    L.d2 = reinterpret_cast<double *>(smem);
-    L.id = reinterpret_cast<int32_t *>(smem + (size_t)k * KNN_BLOCK * sizeof(double));
-    L.k = k;
+    List L;
+    L.init(smem, k);
 
     const bool three_d = g.dim == 3;
     const double h = g.cell;
@@ -277,9 +364,7 @@ knn_kernel(grid_t g, int64_t N, const double *__restrict__ pts, int k, int32_t d
         ci[0] = cell_coord(g, px, 0);
         ci[1] = cell_coord(g, py, 1);
         ci[2] = three_d ? cell_coord(g, pz, 2) : 0;
-        L.cnt = 0;
-        L.kth_d2 = INFINITY;
-        L.kth_id = 0x7fffffff;
+        L.reset();
 
         for (int r = 0;; ++r) {
             const int zlo = max(ci[2] - r, 0), zhi = min(ci[2] + r, g.n[2] - 1);
@@ -295,19 +380,29 @@ knn_kernel(grid_t g, int64_t N, const double *__restrict__ pts, int k, int32_t d
                 for (int yy = ylo; yy <= yhi; ++yy) {
                     double yl = g.origin[1] + yy * h, yh = yl + h;
                     double gy = fmax(fmax(yl - py, py - yh) - margin, 0.0);
-                    // rows farther than the current k-th neighbour cannot contribute
-                    if (L.cnt == k && (gy * gy + gz * gz) > L.kth_d2) continue;
+                    const double g2 = gy * gy + gz * gz;
+                    int xa = xlo, xb = xhi;
+                    if (L.full()) {
+                        // rows farther than the current k-th neighbour cannot contribute, and
+                        // inside a row only the cells that the k-th-neighbour ball reaches can
+                        const double w2 = L.worst() - g2;
+                        if (w2 < 0.0) continue;
+                        const double wx = sqrt(w2) + margin;
+                        xa = max(xa, cell_coord(g, px - wx, 0));
+                        xb = min(xb, cell_coord(g, px + wx, 0));
+                        if (xa > xb) continue;
+                    }
                     const int64_t base = (int64_t)g.n[0] * (yy + (int64_t)g.n[1] * zz);
                     if (zedge || abs(yy - ci[1]) == r) {
-                        scan_range(L, recs, cell_start[base + xlo], cell_start[base + xhi + 1], px,
+                        scan_range(L, recs, cell_start[base + xa], cell_start[base + xb + 1], px,
                                    py, pz, three_d);
-                    } else {
-                        int xa = ci[0] - r, xb = ci[0] + r;
-                        if (xa >= 0)
-                            scan_range(L, recs, cell_start[base + xa], cell_start[base + xa + 1],
+                    } else {  // interior row of the shell: only its two end cells are new
+                        const int x0 = ci[0] - r, x1 = ci[0] + r;
+                        if (x0 >= xa && x0 <= xb)
+                            scan_range(L, recs, cell_start[base + x0], cell_start[base + x0 + 1],
                                        px, py, pz, three_d);
-                        if (xb < g.n[0] && r > 0)
-                            scan_range(L, recs, cell_start[base + xb], cell_start[base + xb + 1],
+                        if (r > 0 && x1 >= xa && x1 <= xb)
+                            scan_range(L, recs, cell_start[base + x1], cell_start[base + x1 + 1],
                                        px, py, pz, three_d);
                     }
                 }
@@ -328,14 +423,32 @@ knn_kernel(grid_t g, int64_t N, const double *__restrict__ pts, int k, int32_t d
             }
             if (!remaining) break;
             bound = fmax(bound - margin, 0.0);
-            if (L.cnt == k && L.kth_d2 < bound * bound) break;
+            if (L.full() && L.worst() < bound * bound) break;
         }
-        for (int t = 0; t < k; ++t) {
-            bool have = t < L.cnt;
-            out_idx[n * k + t] = have ? L.I(t) / divisor : -1;
-            if (out_d2) out_d2[n * k + t] = have ? L.D(t) : INFINITY;
-        }
+        L.write(out_idx + n * k, out_d2 ? out_d2 + n * k : nullptr, divisor);
     }
+}
+
+// ---- counting sort of QUERY points by index cell (coherent warps in K1-K3) -----------------------
+__global__ void __launch_bounds__(256)
+query_scatter_kernel(grid_t g, int64_t N, const double *__restrict__ pts,
+                     const int32_t *__restrict__ start, int32_t *__restrict__ cursor,
+                     double *__restrict__ sorted, int32_t *__restrict__ perm)
+{
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < N;
+         i += (int64_t)gridDim.x * blockDim.x) {
+        const double *p = pts + i * g.dim;
+        int64_t c = cell_of(g, p);
+        int32_t pos = start[c] + atomicAdd(&cursor[c], 1);
+        for (int q = 0; q < g.dim; ++q) sorted[(int64_t)pos * g.dim + q] = p[q];
+        perm[pos] = (int32_t)i;
+    }
+}
+
+grid_t grid_of(const mm_index *ix)
+{
+    grid_t g = grid_of(ix);
+    return g;
 }
 
 int launch_blocks(int64_t work, int block, int per_sm)
@@ -558,20 +671,57 @@ extern "C" int mm_knn(const mm_index_t *ix, int64_t N, const double *pts, int k,
     MM_REQUIRE(N >= 0, MM_ERR_INVALID, "mm_knn: N");
     if (N == 0) return MM_OK;
     MM_REQUIRE(pts && idx, MM_ERR_INVALID, "mm_knn: null buffer");
-    grid_t g{};
-    g.dim = ix->dim;
-    for (int c = 0; c < 3; ++c) {
-        g.origin[c] = ix->origin[c];
-        g.n[c] = ix->n[c];
+    grid_t g = grid_of(ix);
+    cudaStream_t st = (cudaStream_t)stream;
+    if (k <= 4) {
+        knn_kernel<reg_list<4>><<<launch_blocks(N, KNN_BLOCK, 8), KNN_BLOCK, 0, st>>>(
+            g, N, pts, k, divisor, ix->recs, ix->cell_start, idx, d2);
+    } else if (k <= 8) {
+        knn_kernel<reg_list<8>><<<launch_blocks(N, KNN_BLOCK, 8), KNN_BLOCK, 0, st>>>(
+            g, N, pts, k, divisor, ix->recs, ix->cell_start, idx, d2);
+    } else {
+        size_t smem = (size_t)k * KNN_BLOCK * (sizeof(double) + sizeof(int32_t));
+        MM_CUDA(cudaFuncSetAttribute(knn_kernel<smem_list>,
+                                     cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        int per_sm = (int)std::max<size_t>(1, std::min<size_t>(8, (200 * 1024) / smem));
+        knn_kernel<smem_list><<<launch_blocks(N, KNN_BLOCK, per_sm), KNN_BLOCK, smem, st>>>(
+            g, N, pts, k, divisor, ix->recs, ix->cell_start, idx, d2);
     }
-    g.cell = ix->cell;
-    g.inv_cell = ix->inv_cell;
-    size_t smem = (size_t)k * KNN_BLOCK * (sizeof(double) + sizeof(int32_t));
-    MM_CUDA(cudaFuncSetAttribute(knn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                 (int)smem));
-    int per_sm = (int)std::max<size_t>(1, std::min<size_t>(8, (200 * 1024) / smem));
-    knn_kernel<<<launch_blocks(N, KNN_BLOCK, per_sm), KNN_BLOCK, smem, (cudaStream_t)stream>>>(
-        g, N, pts, k, divisor, ix->recs, ix->cell_start, idx, d2);
+    MM_CUDA(cudaGetLastError());
+    return MM_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// internal: counting sort of query points by the index's cell id.  The order inside a cell depends
+// on atomics and is NOT deterministic; results of the pipeline do not depend on it (every point's
+// result is a pure function of the point) and are written back through `perm`.
+// scratch layout: counts[ncells + 1] | starts[ncells + 1] | tile_sums[ntiles]
+// ------------------------------------------------------------------------------------------------
+size_t mm_index_sort_scratch_bytes(const mm_index_t *ix)
+{
+    int64_t ntiles = (ix->ncells + SCAN_TILE - 1) / SCAN_TILE;
+    return sizeof(int32_t) * (size_t)(2 * (ix->ncells + 1) + ntiles + 4);
+}
+
+int mm_index_sort_queries(const mm_index_t *ix, int64_t N, const double *pts, double *sorted,
+                          int32_t *perm, void *scratch, void *stream_)
+{
+    cudaStream_t stream = (cudaStream_t)stream_;
+    MM_REQUIRE(N < ((int64_t)1 << 31), MM_ERR_INVALID, "mm_interpolate: N=%lld >= 2^31 per call",
+               (long long)N);
+    grid_t g = grid_of(ix);
+    int32_t *counts = static_cast<int32_t *>(scratch);
+    int32_t *starts = counts + (ix->ncells + 1);
+    int32_t *tile_sums = starts + (ix->ncells + 1);
+    int64_t ntiles = (ix->ncells + SCAN_TILE - 1) / SCAN_TILE;
+    MM_CUDA(cudaMemsetAsync(counts, 0, sizeof(int32_t) * (size_t)(ix->ncells + 1), stream));
+    histogram_kernel<<<launch_blocks(N, 256, 8), 256, 0, stream>>>(g, N, pts, counts);
+    scan_tile_sums<<<(int)ntiles, SCAN_BLOCK, 0, stream>>>(ix->ncells, counts, tile_sums);
+    scan_tile_offsets<<<1, 1024, 0, stream>>>(ntiles, tile_sums);
+    scan_apply<<<(int)ntiles, SCAN_BLOCK, 0, stream>>>(ix->ncells, counts, tile_sums, starts);
+    MM_CUDA(cudaMemsetAsync(counts, 0, sizeof(int32_t) * (size_t)(ix->ncells + 1), stream));
+    query_scatter_kernel<<<launch_blocks(N, 256, 8), 256, 0, stream>>>(g, N, pts, starts, counts,
+                                                                       sorted, perm);
     MM_CUDA(cudaGetLastError());
     return MM_OK;
 }

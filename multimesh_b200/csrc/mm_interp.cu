@@ -76,7 +76,8 @@ template <int ORDER, int DIM>
 __global__ void __launch_bounds__(INTERP_MAX_WARPS * 32)
 interp_kernel(const mm_gll_table T, const interp_cfg cfg, int64_t E,
               const double *__restrict__ fields, int64_t N, const int32_t *__restrict__ elem,
-              const double *__restrict__ xi, double *__restrict__ out)
+              const double *__restrict__ xi, const int32_t *__restrict__ perm,
+              double *__restrict__ out)
 {
     constexpr int M = ORDER + 1;
     constexpr int P = DIM == 2 ? M * M : M * M * M;
@@ -167,7 +168,7 @@ interp_kernel(const mm_gll_table T, const interp_cfg cfg, int64_t E,
         if (n < N) {
             const double *v = reinterpret_cast<const double *>(
                 wbase + s * stage_bytes + (size_t)lane * cfg.slot_bytes + shift);
-            double *o = out + n * cfg.F + f0;
+            double *o = out + (perm ? (int64_t)perm[n] : n) * cfg.F + f0;
             if (e >= 0) {
                 for (int f = 0; f < nf; ++f) o[f] = contract_field<ORDER, DIM>(v + f * P, L);
             } else {
@@ -179,7 +180,7 @@ interp_kernel(const mm_gll_table T, const interp_cfg cfg, int64_t E,
 
 template <int ORDER, int DIM>
 int launch_interp(int64_t E, int F, const double *fields, int64_t N, const int32_t *elem,
-                  const double *xi, double *out, cudaStream_t stream)
+                  const double *xi, const int32_t *perm, double *out, cudaStream_t stream)
 {
     constexpr int M = ORDER + 1;
     constexpr int P = DIM == 2 ? M * M : M * M * M;
@@ -217,7 +218,7 @@ int launch_interp(int64_t E, int F, const double *fields, int64_t N, const int32
     int64_t need = (nbatch + cfg.warps - 1) / cfg.warps;
     if (grid > need) grid = need;
     if (grid < 1) grid = 1;
-    kern<<<(int)grid, cfg.warps * 32, smem, stream>>>(T, cfg, E, fields, N, elem, xi, out);
+    kern<<<(int)grid, cfg.warps * 32, smem, stream>>>(T, cfg, E, fields, N, elem, xi, perm, out);
     MM_CUDA(cudaGetLastError());
     return MM_OK;
 }
@@ -292,7 +293,14 @@ int blocks_for(int64_t work, int block)
 }  // namespace
 
 extern "C" int mm_interp(int order, int dim, int64_t E, int F, const double *fields, int64_t N,
-                         const int32_t *elem, const double *xi, double *out, void *stream_)
+                         const int32_t *elem, const double *xi, double *out, void *stream)
+{
+    return mm_interp_perm(order, dim, E, F, fields, N, elem, xi, nullptr, out, stream);
+}
+
+extern "C" int mm_interp_perm(int order, int dim, int64_t E, int F, const double *fields, int64_t N,
+                              const int32_t *elem, const double *xi, const int32_t *perm,
+                              double *out, void *stream_)
 {
     cudaStream_t stream = (cudaStream_t)stream_;
     MM_REQUIRE(mm_valid_order(order), MM_ERR_INVALID, "mm_interp: order %d (supported 1, 2, 4)", order);
@@ -303,7 +311,7 @@ extern "C" int mm_interp(int order, int dim, int64_t E, int F, const double *fie
     MM_REQUIRE(((uintptr_t)fields & 15) == 0, MM_ERR_INVALID,
                "mm_interp: fields must be 16-byte aligned");
 #define MM_INT(O, D) \
-    if (order == O && dim == D) return launch_interp<O, D>(E, F, fields, N, elem, xi, out, stream);
+    if (order == O && dim == D) return launch_interp<O, D>(E, F, fields, N, elem, xi, perm, out, stream);
     MM_INT(1, 2) MM_INT(2, 2) MM_INT(4, 2) MM_INT(1, 3) MM_INT(2, 3) MM_INT(4, 3)
 #undef MM_INT
     mm_set_error("mm_interp: unsupported order/dim");

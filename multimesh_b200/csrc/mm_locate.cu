@@ -173,7 +173,8 @@ locate_kernel(const mm_gll_table T, const mm_locate_params prm, int64_t E,
               const double *__restrict__ aabb, int64_t N, const double *__restrict__ pts, int k,
               const int32_t *__restrict__ cands, int32_t *__restrict__ elem_out,
               double *__restrict__ xi_out, uint8_t *__restrict__ status_out,
-              unsigned long long *__restrict__ num_failed)
+              unsigned long long *__restrict__ num_failed, int32_t *__restrict__ unresolved_list,
+              unsigned long long *__restrict__ unresolved_count)
 {
     using tr = elem_traits<ORDER, DIM>;
     extern __shared__ __align__(128) unsigned char smem[];
@@ -248,7 +249,11 @@ locate_kernel(const mm_gll_table T, const mm_locate_params prm, int64_t E,
                 }
                 if (e < 0) {  // candidates exhausted without acceptance: fallback
                     done = true;
-                    if (prm.fallback == MM_FB_MAGIC) {
+                    if (prm.reserved & 1) {
+                        // first pass of the progressive search: the list is only a PREFIX of the
+                        // k-NN list, so no fallback may be taken; the point is re-run with all k
+                        r_status = MM_ST_UNRESOLVED;
+                    } else if (prm.fallback == MM_FB_MAGIC) {
                         if (first_inside >= 0) {
                             r_elem = first_inside;
                             r_status = MM_ST_FB_INSIDE_MAGIC;
@@ -367,7 +372,17 @@ locate_kernel(const mm_gll_table T, const mm_locate_params prm, int64_t E,
 #pragma unroll
             for (int c = 0; c < DIM; ++c) xi_out[n * DIM + c] = r_elem < 0 ? 0.0 : r_xi[c];
             if (status_out) status_out[n] = r_status;
-            if (r_elem < 0) failed_local += 1;
+            if (r_elem < 0 && r_status != MM_ST_UNRESOLVED) failed_local += 1;
+        }
+        if (unresolved_list) {  // warp-aggregated append of the points that need the full search
+            const unsigned um = __ballot_sync(0xffffffffu, n < N && r_status == MM_ST_UNRESOLVED);
+            if (um) {
+                unsigned long long base = 0;
+                if (lane == 0) base = atomicAdd(unresolved_count, (unsigned long long)__popc(um));
+                base = __shfl_sync(0xffffffffu, base, 0);
+                if (um & (1u << lane))
+                    unresolved_list[base + __popc(um & ((1u << lane) - 1))] = (int32_t)n;
+            }
         }
     }
     if (num_failed) {
@@ -380,7 +395,8 @@ template <int ORDER, int DIM, int WARPS>
 int launch_locate(const mm_locate_params &prm, int64_t E, const double *nodes,
                   const double *centroid, const double *aabb, int64_t N, const double *pts, int k,
                   const int32_t *cands, int32_t *elem, double *xi, uint8_t *status,
-                  int64_t *num_failed, cudaStream_t stream)
+                  int64_t *num_failed, int32_t *unresolved_list, int64_t *unresolved_count,
+                  cudaStream_t stream)
 {
     using tr = elem_traits<ORDER, DIM>;
     mm_gll_table T;
@@ -398,18 +414,20 @@ int launch_locate(const mm_locate_params &prm, int64_t E, const double *nodes,
     if (grid < 1) grid = 1;
     kern<<<(int)grid, WARPS * 32, smem, stream>>>(T, prm, E, nodes, centroid, aabb, N, pts, k,
                                                   cands, elem, xi, status,
-                                                  reinterpret_cast<unsigned long long *>(num_failed));
+                                                  reinterpret_cast<unsigned long long *>(num_failed),
+                                                  unresolved_list,
+                                                  reinterpret_cast<unsigned long long *>(unresolved_count));
     MM_CUDA(cudaGetLastError());
     return MM_OK;
 }
 
 }  // namespace
 
-extern "C" int mm_locate(int order, int dim, int64_t E, const double *nodes,
-                         const double *centroid, const double *aabb, int64_t N, const double *pts,
-                         int k, const int32_t *cands, const mm_locate_params *params,
-                         int32_t *elem, double *xi, uint8_t *status, int64_t *num_failed,
-                         void *stream_)
+int mm_locate_impl(int order, int dim, int64_t E, const double *nodes, const double *centroid,
+                   const double *aabb, int64_t N, const double *pts, int k, const int32_t *cands,
+                   const mm_locate_params *params, int32_t *elem, double *xi, uint8_t *status,
+                   int64_t *num_failed, bool zero_num_failed, int32_t *unresolved_list,
+                   int64_t *unresolved_count, void *stream_)
 {
     cudaStream_t stream = (cudaStream_t)stream_;
     MM_REQUIRE(mm_valid_order(order), MM_ERR_INVALID, "mm_locate: order %d (supported 1, 2, 4)", order);
@@ -419,7 +437,7 @@ extern "C" int mm_locate(int order, int dim, int64_t E, const double *nodes,
                "mm_locate: fallback %d", (int)params->fallback);
     MM_REQUIRE(k >= 1, MM_ERR_INVALID, "mm_locate: k=%d", k);
     MM_REQUIRE(N >= 0 && E >= 0, MM_ERR_INVALID, "mm_locate: sizes");
-    if (num_failed) MM_CUDA(cudaMemsetAsync(num_failed, 0, sizeof(int64_t), stream));
+    if (num_failed && zero_num_failed) MM_CUDA(cudaMemsetAsync(num_failed, 0, sizeof(int64_t), stream));
     if (N == 0) return MM_OK;
     MM_REQUIRE(nodes && pts && cands && elem && xi, MM_ERR_INVALID, "mm_locate: null buffer");
     MM_REQUIRE(((uintptr_t)nodes & 15) == 0, MM_ERR_INVALID,
@@ -429,7 +447,8 @@ extern "C" int mm_locate(int order, int dim, int64_t E, const double *nodes,
 #define MM_LOC(O, D, W)                                                                          \
     if (order == O && dim == D)                                                                  \
         return launch_locate<O, D, W>(*params, E, nodes, centroid, aabb, N, pts, k, cands, elem, \
-                                      xi, status, num_failed, stream);
+                                      xi, status, num_failed, unresolved_list, unresolved_count,  \
+                                      stream);
     MM_LOC(1, 2, 4)
     MM_LOC(2, 2, 4)
     MM_LOC(4, 2, 4)
@@ -439,4 +458,17 @@ extern "C" int mm_locate(int order, int dim, int64_t E, const double *nodes,
 #undef MM_LOC
     mm_set_error("mm_locate: unsupported order/dim");
     return MM_ERR_UNSUPPORTED;
+}
+
+extern "C" int mm_locate(int order, int dim, int64_t E, const double *nodes,
+                         const double *centroid, const double *aabb, int64_t N, const double *pts,
+                         int k, const int32_t *cands, const mm_locate_params *params,
+                         int32_t *elem, double *xi, uint8_t *status, int64_t *num_failed,
+                         void *stream)
+{
+    MM_REQUIRE(params, MM_ERR_INVALID, "mm_locate: null params");
+    mm_locate_params prm = *params;
+    prm.reserved = 0;  // the partial (progressive first pass) mode is internal to mm_interpolate
+    return mm_locate_impl(order, dim, E, nodes, centroid, aabb, N, pts, k, cands, &prm, elem, xi,
+                          status, num_failed, true, nullptr, nullptr, stream);
 }

@@ -1,0 +1,194 @@
+// mm_pipeline.cu -- fused device pipeline K1 -> K2 -> K3 over one batch of target points.
+//
+//   1. counting-sort the points by index cell (coherent warps, L2 locality); everything below
+//      runs in sorted order and results are written back through the permutation;
+//   2. progressive search: K1 with k1 = min(k, 8) candidates (register top-k list), K2 in
+//      "prefix" mode -- a point is final if one of its first k1 candidates accepts it, which is
+//      exactly what the full list would have decided, because any prefix of the canonical k-NN
+//      list IS the k1-NN list; points that exhaust the prefix are appended to a work list;
+//   3. the work list (typically a few per cent) is re-run in chunks with all k candidates and
+//      the variant's complete fallback logic, and scattered back;
+//   4. K3 gathers in sorted order and writes out[perm[n]].
+// Results are identical to mm_knn -> mm_locate -> mm_interp (tests/test_gpu_parity.py).
+#include <algorithm>
+
+#include "mm_common.cuh"
+
+namespace {
+
+constexpr int64_t CHUNK_B = 1 << 20;  // points per re-run chunk
+
+inline size_t align_up(size_t x) { return (x + 255) & ~(size_t)255; }
+
+struct ws_layout {
+    size_t sorted, perm, cands1, elem, xi, status, list, counters, sort_scratch;
+    size_t b_pts, b_cands, b_elem, b_xi, b_status, total;
+};
+
+ws_layout make_layout(const mm_index_t *ix, int dim, int64_t N, int k)
+{
+    ws_layout L{};
+    size_t o = 0;
+    auto take = [&](size_t bytes) { size_t at = o; o += align_up(bytes); return at; };
+    const int k1 = std::min(k, 8);
+    L.sorted = take(sizeof(double) * N * dim);
+    L.perm = take(sizeof(int32_t) * N);
+    L.cands1 = take(sizeof(int32_t) * N * k1);
+    L.elem = take(sizeof(int32_t) * N);
+    L.xi = take(sizeof(double) * N * dim);
+    L.status = take(N);
+    L.list = take(sizeof(int32_t) * N);
+    L.counters = take(64);
+    L.sort_scratch = take(mm_index_sort_scratch_bytes(ix));
+    const int64_t cb = std::min<int64_t>(N, CHUNK_B);
+    L.b_pts = take(sizeof(double) * cb * dim);
+    L.b_cands = take(sizeof(int32_t) * cb * k);
+    L.b_elem = take(sizeof(int32_t) * cb);
+    L.b_xi = take(sizeof(double) * cb * dim);
+    L.b_status = take(cb);
+    L.total = o;
+    return L;
+}
+
+__global__ void __launch_bounds__(256)
+gather_points_kernel(int dim, int64_t n, const int32_t *__restrict__ list,
+                     const double *__restrict__ pts, double *__restrict__ out)
+{
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n;
+         i += (int64_t)gridDim.x * blockDim.x)
+        for (int c = 0; c < dim; ++c) out[i * dim + c] = pts[(int64_t)list[i] * dim + c];
+}
+
+__global__ void __launch_bounds__(256)
+scatter_results_kernel(int dim, int64_t n, const int32_t *__restrict__ list,
+                       const int32_t *__restrict__ elem_b, const double *__restrict__ xi_b,
+                       const uint8_t *__restrict__ status_b, int32_t *__restrict__ elem,
+                       double *__restrict__ xi, uint8_t *__restrict__ status)
+{
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n;
+         i += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t t = list[i];
+        elem[t] = elem_b[i];
+        status[t] = status_b[i];
+        for (int c = 0; c < dim; ++c) xi[t * dim + c] = xi_b[i * dim + c];
+    }
+}
+
+__global__ void __launch_bounds__(256)
+unpermute_kernel(int dim, int64_t n, const int32_t *__restrict__ perm,
+                 const int32_t *__restrict__ elem_s, const double *__restrict__ xi_s,
+                 const uint8_t *__restrict__ status_s, int32_t *__restrict__ elem,
+                 double *__restrict__ xi, uint8_t *__restrict__ status)
+{
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n;
+         i += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t t = perm[i];
+        if (elem) elem[t] = elem_s[i];
+        if (status) status[t] = status_s[i];
+        if (xi)
+            for (int c = 0; c < dim; ++c) xi[t * dim + c] = xi_s[i * dim + c];
+    }
+}
+
+int blocks_for(int64_t work)
+{
+    int sms = mm_num_sms() > 0 ? mm_num_sms() : 148;
+    int64_t need = (work + 255) / 256;
+    int64_t cap = (int64_t)sms * 16;
+    return (int)(need < 1 ? 1 : (need > cap ? cap : need));
+}
+
+}  // namespace
+
+#define MM_TRY(call)                  \
+    do {                              \
+        int _rc = (call);             \
+        if (_rc != MM_OK) return _rc; \
+    } while (0)
+
+extern "C" size_t mm_interpolate_workspace_bytes(const mm_index_t *index, int dim, int64_t N, int k)
+{
+    if (!index || N < 0 || k < 1) return 0;
+    return make_layout(index, dim, N, k).total;
+}
+
+extern "C" int mm_interpolate(const mm_index_t *index, int32_t divisor, int order, int dim,
+                              int64_t E, const double *nodes, const double *centroid,
+                              const double *aabb, int F, const double *fields, int64_t N,
+                              const double *pts, int k, const mm_locate_params *params,
+                              double *out, int32_t *elem, double *xi, uint8_t *status,
+                              int64_t *num_failed, void *workspace, size_t workspace_bytes,
+                              void *stream_)
+{
+    cudaStream_t stream = (cudaStream_t)stream_;
+    MM_REQUIRE(index && params, MM_ERR_INVALID, "mm_interpolate: null index/params");
+    MM_REQUIRE(k >= 1 && k <= 64, MM_ERR_INVALID, "mm_interpolate: k=%d outside [1, 64]", k);
+    MM_REQUIRE(N >= 0, MM_ERR_INVALID, "mm_interpolate: N");
+    if (num_failed) MM_CUDA(cudaMemsetAsync(num_failed, 0, sizeof(int64_t), stream));
+    if (N == 0) return MM_OK;
+    const ws_layout L = make_layout(index, dim, N, k);
+    MM_REQUIRE(workspace && workspace_bytes >= L.total, MM_ERR_INVALID,
+               "mm_interpolate: workspace of %zu bytes needed, %zu given", L.total, workspace_bytes);
+    MM_REQUIRE(((uintptr_t)workspace & 255) == 0, MM_ERR_INVALID, "mm_interpolate: workspace must be 256-byte aligned");
+    unsigned char *ws = static_cast<unsigned char *>(workspace);
+    double *sorted = reinterpret_cast<double *>(ws + L.sorted);
+    int32_t *perm = reinterpret_cast<int32_t *>(ws + L.perm);
+    int32_t *cands1 = reinterpret_cast<int32_t *>(ws + L.cands1);
+    int32_t *elem_s = reinterpret_cast<int32_t *>(ws + L.elem);
+    double *xi_s = reinterpret_cast<double *>(ws + L.xi);
+    uint8_t *status_s = ws + L.status;
+    int32_t *list = reinterpret_cast<int32_t *>(ws + L.list);
+    int64_t *counters = reinterpret_cast<int64_t *>(ws + L.counters);  // [0] unresolved, [1] failed
+    const int k1 = std::min(k, 8);
+
+    // 1. spatial sort of the target points
+    MM_TRY(mm_index_sort_queries(index, N, pts, sorted, perm, ws + L.sort_scratch, stream));
+    MM_CUDA(cudaMemsetAsync(counters, 0, 64, stream));
+
+    // 2. first pass: k1 nearest candidates, prefix mode (unless k1 == k: complete semantics)
+    MM_TRY(mm_knn(index, N, sorted, k1, divisor, cands1, nullptr, stream));
+    mm_locate_params p1 = *params;
+    p1.reserved = (k1 < k) ? 1 : 0;
+    MM_TRY(mm_locate_impl(order, dim, E, nodes, centroid, aabb, N, sorted, k1, cands1, &p1, elem_s,
+                          xi_s, status_s, counters + 1, false, (k1 < k) ? list : nullptr,
+                          (k1 < k) ? counters : nullptr, stream));
+
+    // 3. re-run the unresolved points with the full candidate list
+    if (k1 < k) {
+        int64_t n_un = 0;
+        MM_CUDA(cudaMemcpyAsync(&n_un, counters, sizeof(int64_t), cudaMemcpyDeviceToHost, stream));
+        MM_CUDA(cudaStreamSynchronize(stream));
+        mm_locate_params p2 = *params;
+        p2.reserved = 0;
+        double *b_pts = reinterpret_cast<double *>(ws + L.b_pts);
+        int32_t *b_cands = reinterpret_cast<int32_t *>(ws + L.b_cands);
+        int32_t *b_elem = reinterpret_cast<int32_t *>(ws + L.b_elem);
+        double *b_xi = reinterpret_cast<double *>(ws + L.b_xi);
+        uint8_t *b_status = ws + L.b_status;
+        for (int64_t at = 0; at < n_un; at += CHUNK_B) {
+            const int64_t nb = std::min<int64_t>(CHUNK_B, n_un - at);
+            gather_points_kernel<<<blocks_for(nb), 256, 0, stream>>>(dim, nb, list + at, sorted, b_pts);
+            MM_TRY(mm_knn(index, nb, b_pts, k, divisor, b_cands, nullptr, stream));
+            MM_TRY(mm_locate_impl(order, dim, E, nodes, centroid, aabb, nb, b_pts, k, b_cands, &p2,
+                                  b_elem, b_xi, b_status, counters + 1, false, nullptr, nullptr,
+                                  stream));
+            scatter_results_kernel<<<blocks_for(nb), 256, 0, stream>>>(
+                dim, nb, list + at, b_elem, b_xi, b_status, elem_s, xi_s, status_s);
+            MM_CUDA(cudaGetLastError());
+        }
+    }
+    if (num_failed)
+        MM_CUDA(cudaMemcpyAsync(num_failed, counters + 1, sizeof(int64_t), cudaMemcpyDeviceToDevice, stream));
+
+    // 4. gather in sorted order, written back through the permutation
+    if (fields) {
+        MM_REQUIRE(out, MM_ERR_INVALID, "mm_interpolate: null out");
+        MM_TRY(mm_interp_perm(order, dim, E, F, fields, N, elem_s, xi_s, perm, out, stream));
+    }
+    if (elem || xi || status) {
+        unpermute_kernel<<<blocks_for(N), 256, 0, stream>>>(dim, N, perm, elem_s, xi_s, status_s,
+                                                            elem, xi, status);
+        MM_CUDA(cudaGetLastError());
+    }
+    return MM_OK;
+}

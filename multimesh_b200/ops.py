@@ -24,6 +24,7 @@ from .gll import SUPPORTED_ORDERS
 __all__ = [
     "LocateSpec", "V1", "V2", "V3", "V4", "V5", "GridIndex", "element_geometry", "locate", "interp",
     "coeffs", "gather_coeffs", "trilinear", "centroid_conn", "gather_nodal", "map_to_sphere_",
+    "interpolate",
 ]
 
 
@@ -341,3 +342,63 @@ def gather_nodal(param: torch.Tensor, enclosing: torch.Tensor, weights: torch.Te
         check(load_lib().mm_gather_nodal(F, npm, _ptr(param), N, _ptr(enclosing), _ptr(weights),
                                          _ptr(out), _stream()), "mm_gather_nodal")
     return out
+
+
+# ----------------------------------------------------------------------------------------------
+# fused pipeline K1 -> K2 -> K3 (mm_interpolate): spatially sorted points, progressive search
+# ----------------------------------------------------------------------------------------------
+@torch.library.custom_op("multimesh::interpolate", mutates_args=())
+def _interpolate_op(handle: int, divisor: int, nodes: torch.Tensor, centroid: torch.Tensor,
+                    aabb: torch.Tensor, fields: torch.Tensor, pts: torch.Tensor, k: int,
+                    aabb_prefilter: bool, tol: float, strict: bool, fallback: int, snap_clip: float,
+                    m0: float, m1: float, m2: float, want_location: bool
+                    ) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor, torch.Tensor, torch.Tensor]:
+    nodes = _need_cuda(nodes, "nodes", torch.float64)
+    centroid = _need_cuda(centroid, "centroid", torch.float64)
+    aabb = _need_cuda(aabb, "aabb", torch.float64)
+    pts = _need_cuda(pts, "pts", torch.float64)
+    E, P, d = nodes.shape
+    order = _order_dim(P, d)
+    N = pts.shape[0]
+    have_fields = fields.numel() > 0
+    if have_fields:
+        fields = _need_cuda(fields, "fields", torch.float64)
+        F = fields.shape[1]
+        assert fields.shape[0] == E and fields.shape[2] == P
+    else:
+        F = 1
+    prm = LocateSpec(aabb_prefilter, tol, strict, fallback, snap_clip, (m0, m1, m2)).to_c()
+    dev = nodes.device
+    lib = load_lib()
+    with torch.cuda.device(dev):
+        nbytes = lib.mm_interpolate_workspace_bytes(C.c_void_p(handle), d, N, k)
+        ws = torch.empty((max(int(nbytes), 256),), dtype=torch.uint8, device=dev)
+        out = torch.empty((N, F) if have_fields else (0, 0), dtype=torch.float64, device=dev)
+        nfail = torch.zeros((1,), dtype=torch.int64, device=dev)
+        if want_location:
+            elem = torch.empty((N,), dtype=torch.int32, device=dev)
+            xi = torch.empty((N, d), dtype=torch.float64, device=dev)
+            status = torch.empty((N,), dtype=torch.uint8, device=dev)
+        else:
+            elem = torch.empty((0,), dtype=torch.int32, device=dev)
+            xi = torch.empty((0, d), dtype=torch.float64, device=dev)
+            status = torch.empty((0,), dtype=torch.uint8, device=dev)
+        check(lib.mm_interpolate(C.c_void_p(handle), divisor, order, d, E, _ptr(nodes), _ptr(centroid),
+                                 _ptr(aabb), F, _ptr(fields) if have_fields else None, N, _ptr(pts), k,
+                                 C.byref(prm), _ptr(out) if have_fields else None,
+                                 _ptr(elem) if want_location else None, _ptr(xi) if want_location else None,
+                                 _ptr(status) if want_location else None, _ptr(nfail), _ptr(ws),
+                                 ws.numel(), _stream()), "mm_interpolate")
+    return out, elem, xi, status, nfail
+
+
+def interpolate(index: "GridIndex", divisor: int, nodes, centroid, aabb, fields, pts, k: int,
+                spec: LocateSpec, want_location: bool = True):
+    """Fused k-NN -> locate -> gather.  `fields` may be None (locate only).
+    -> (out [N,F], elem [N], xi [N,d], status [N], num_failed [1]); identical to running
+    GridIndex.query_idx, locate and interp one after the other."""
+    if fields is None:
+        fields = torch.empty((0, 0, 0), dtype=torch.float64, device=nodes.device)
+    return _interpolate_op(index._h, int(divisor), nodes, centroid, aabb, fields, pts, int(k),
+                           spec.aabb_prefilter, spec.tol, spec.strict, spec.fallback, spec.snap_clip,
+                           *spec.magic_xi, bool(want_location))

@@ -390,3 +390,56 @@ def test_cpu_tensors_are_rejected(cuda):
     with pytest.raises(Exception):
         ops.interp(torch.zeros((1, 1, 8), dtype=torch.float64), torch.zeros(1, dtype=torch.int32),
                    torch.zeros((1, 3), dtype=torch.float64))
+
+
+# ---------------------------------------------------------------------------------------------
+# small-k (register list) k-NN and the fused, progressive pipeline
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("dim,k", [(3, 2), (3, 4), (3, 5), (3, 8), (2, 3), (2, 8)])
+def test_knn_small_k_register_list(cuda, oracle, dim, k):
+    from multimesh_b200 import ops
+
+    rng = np.random.default_rng(50 + dim + k)
+    nodes = _mesh(2, dim, 6, 0.0)
+    data = np.concatenate([nodes.reshape(-1, dim), rng.random((500, dim))])  # duplicates + random
+    pts = np.concatenate([_targets(rng, dim, 1500, -0.1, 1.1), nodes.reshape(-1, dim)[::13]])
+    got = ops.GridIndex(_t(data, cuda)).query_idx(_t(pts, cuda), k).cpu().numpy()
+    assert np.array_equal(got, oracle.knn_bruteforce(data, pts, k))
+
+
+@pytest.mark.parametrize("order,dim,form", [(2, 3, "gll"), (2, 3, "centroid"), (4, 3, "centroid"), (2, 2, "gll"),
+                                            (1, 3, "centroid")])
+def test_fused_pipeline_equals_separate_kernels(cuda, oracle, order, dim, form):
+    """mm_interpolate (spatial sort + progressive search) == mm_knn -> mm_locate -> mm_interp,
+    for every location variant, including points that need the full-k re-run and fallbacks."""
+    from multimesh_b200 import ops
+
+    rng = np.random.default_rng(7 * order + dim)
+    nodes = _mesh(order, dim, 5 if order == 4 else 7, 0.03)
+    E, P, _ = nodes.shape
+    F = 5
+    fields = rng.normal(size=(E, F, P)) * 100.0
+    pts = np.concatenate([_targets(rng, dim, 3001, -0.1, 1.1), nodes.reshape(-1, dim)[::7]])
+    tn, tf, tp = _t(nodes, cuda), _t(fields, cuda), _t(pts, cuda)
+    cent, box = ops.element_geometry(tn)
+    if form == "gll":
+        index, div = ops.GridIndex(tn.view(E * P, dim)), P
+        data = nodes.reshape(-1, dim)
+    else:
+        index, div = ops.GridIndex(cent), 1
+        data = oracle.centroids(nodes)
+    for k in (20, 6):
+        cands = (oracle.knn_bruteforce(data, pts, k) // div).astype(np.int32)
+        for name, spec, prm in _variants(oracle):
+            out, elem, xi, st, nf = ops.interpolate(index, div, tn, cent, box, tf, tp, k, spec)
+            o_elem, o_xi, o_st, o_nf = oracle.locate(order, dim, nodes, pts, cands, prm)
+            assert np.array_equal(elem.cpu().numpy(), o_elem), (name, k)
+            assert np.array_equal(st.cpu().numpy(), o_st), (name, k)
+            assert np.array_equal(xi.cpu().numpy(), o_xi), (name, k)
+            assert int(nf.item()) == o_nf, (name, k)
+            assert np.array_equal(out.cpu().numpy(), oracle.interp(order, dim, fields, o_elem, o_xi)), (name, k)
+    # locate-only mode, and no location outputs
+    out, elem, xi, st, nf = ops.interpolate(index, div, tn, cent, box, None, tp, 20, ops.V1())
+    assert out.numel() == 0 and elem.shape[0] == len(pts)
+    out2, e2, _, _, _ = ops.interpolate(index, div, tn, cent, box, tf, tp, 20, ops.V1(), want_location=False)
+    assert e2.numel() == 0 and out2.shape == (len(pts), F)
