@@ -10,6 +10,8 @@
 //                 cell_start [ncells + 1] int32
 #include <algorithm>
 #include <cmath>
+#include <cstdio>
+#include <cstdlib>
 #include <vector>
 
 #include "mm_common.cuh"
@@ -447,7 +449,14 @@ query_scatter_kernel(grid_t g, int64_t N, const double *__restrict__ pts,
 
 grid_t grid_of(const mm_index *ix)
 {
-    grid_t g = grid_of(ix);
+    grid_t g{};
+    g.dim = ix->dim;
+    for (int c = 0; c < 3; ++c) {
+        g.origin[c] = ix->origin[c];
+        g.n[c] = ix->n[c];
+    }
+    g.cell = ix->cell;
+    g.inv_cell = ix->inv_cell;
     return g;
 }
 
