@@ -191,12 +191,12 @@ int launch_interp(int64_t E, int F, const double *fields, int64_t N, const int32
     cfg.odd_p = P % 2;
     // chunk size: keep a lane's slot near 512 B (a 32-lane stage near 16 KB) so that several
     // CTAs of 2 warps x 3 stages share an SM; one field is the minimum (1 008 B at order 4)
-    int fc = std::max(1, std::min(F, 504 / (P * 8)));
+    int fc = std::max(1, std::min(F, 256 / (P * 8)));
     cfg.FC = fc;
     cfg.chunks = (F + fc - 1) / fc;
     cfg.slot_bytes = mm_slot_bytes(chunk_copy_bytes(fc, P, cfg.odd_p));
     cfg.stages = 3;
-    cfg.warps = 2;
+    cfg.warps = 4;
     // tuning overrides (profiling only)
     if (const char *e = getenv("MM_INTERP_FC")) fc = std::max(1, std::min(F, atoi(e)));
     if (const char *e = getenv("MM_INTERP_STAGES")) cfg.stages = std::max(2, std::min(8, atoi(e)));
@@ -215,6 +215,202 @@ int launch_interp(int64_t E, int F, const double *fields, int64_t N, const int32
     const int sms = mm_num_sms() > 0 ? mm_num_sms() : 148;
     int64_t nbatch = (N + 31) / 32;
     int64_t grid = (int64_t)sms * per_sm;  // persistent CTAs, multiple of the SM count
+    int64_t need = (nbatch + cfg.warps - 1) / cfg.warps;
+    if (grid > need) grid = need;
+    if (grid < 1) grid = 1;
+    kern<<<(int)grid, cfg.warps * 32, smem, stream>>>(T, cfg, E, fields, N, elem, xi, perm, out);
+    MM_CUDA(cudaGetLastError());
+    return MM_OK;
+}
+
+// ================================================================================================
+// K3, coherent variant (used by mm_interp_perm / the fused pipeline, where the points arrive
+// spatially sorted): the 32 points of a warp batch usually fall into a handful of source elements,
+// so the warp de-duplicates them (__match_any_sync), fetches each DISTINCT element block once with
+// one bulk-async copy into one of C shared slots, and every lane contracts out of the slot of its
+// element (lanes of one element read the same addresses: shared-memory broadcast).  Batches with
+// more than C distinct elements take several rounds.  Correct for any point order; fast when the
+// order is coherent.  Same arithmetic as interp_kernel (bit-identical results).
+// ================================================================================================
+struct coh_cfg {
+    int F, FC, chunks, stages, slots, slot_bytes, odd_p, warps;
+};
+
+template <int ORDER, int DIM>
+struct coh_cursor {  // walks this warp's (batch, round, chunk) items; identical on both pipeline ends
+    int64_t b;       // batch index
+    int r, c;        // round (groups [r*C, r*C+C)), field chunk
+    int D;           // distinct elements in the batch
+    int rank;        // this lane's group rank (-1: no element)
+    int32_t e;       // this lane's element
+    int64_t n;       // this lane's point
+};
+
+template <int ORDER, int DIM>
+__global__ void __launch_bounds__(INTERP_MAX_WARPS * 32)
+interp_coherent_kernel(const mm_gll_table T, const coh_cfg cfg, int64_t E,
+                       const double *__restrict__ fields, int64_t N,
+                       const int32_t *__restrict__ elem, const double *__restrict__ xi,
+                       const int32_t *__restrict__ perm, double *__restrict__ out)
+{
+    constexpr int M = ORDER + 1;
+    constexpr int P = DIM == 2 ? M * M : M * M * M;
+    extern __shared__ __align__(128) unsigned char smem[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const size_t stage_bytes = (size_t)cfg.slots * cfg.slot_bytes;
+    unsigned char *wbase = smem + (size_t)warp * cfg.stages * stage_bytes;
+    uint64_t *bars = reinterpret_cast<uint64_t *>(smem + (size_t)cfg.warps * cfg.stages * stage_bytes) +
+                     warp * cfg.stages;
+    if (lane < cfg.stages) mbar_init(&bars[lane], 1);
+    fence_mbar_init();
+    __syncthreads();
+
+    const int64_t total_bytes = E * (int64_t)cfg.F * P * 8;
+    const int64_t nbatch = (N + 31) / 32;
+    const int64_t stride = (int64_t)gridDim.x * cfg.warps;
+    const int64_t first = (int64_t)blockIdx.x * cfg.warps + warp;
+
+    using cur_t = coh_cursor<ORDER, DIM>;
+    auto load_batch = [&](cur_t &k) {  // group the lanes of batch k.b by element
+        k.n = k.b * 32 + lane;
+        k.e = (k.b < nbatch && k.n < N) ? elem[k.n] : -1;
+        const unsigned same = __match_any_sync(0xffffffffu, k.e);
+        const int leader = __ffs(same) - 1;
+        const unsigned leaders = __ballot_sync(0xffffffffu, lane == leader && k.e >= 0);
+        k.rank = k.e >= 0 ? __popc(leaders & ((1u << leader) - 1)) : -1;
+        k.D = __popc(leaders);
+        k.r = 0;
+        k.c = 0;
+    };
+    auto advance = [&](cur_t &k) {
+        if (++k.c < cfg.chunks) return;
+        k.c = 0;
+        if ((++k.r) * cfg.slots < k.D) return;
+        k.b += stride;
+        load_batch(k);
+    };
+    auto valid = [&](const cur_t &k) { return k.b < nbatch; };
+
+    auto issue = [&](const cur_t &k, int64_t q) {
+        const int f0 = k.c * cfg.FC;
+        const int nf = min(cfg.FC, cfg.F - f0);
+        const int bytes = chunk_copy_bytes(nf, P, cfg.odd_p);
+        const int s = (int)(q % cfg.stages);
+        const int slot_id = k.rank - k.r * cfg.slots;
+        // the group leader (lowest lane of the group) fetches the block for the whole group
+        const unsigned same = __match_any_sync(0xffffffffu, k.e);
+        const bool mine = k.e >= 0 && lane == __ffs(same) - 1 && slot_id >= 0 && slot_id < cfg.slots;
+        int shift = 0;
+        bool use_tma = false;
+        int64_t off = 0;
+        if (mine) {
+            off = (((int64_t)k.e * cfg.F + f0) * P) * 8;
+            shift = cfg.odd_p ? (int)(off & 8) : 0;
+            use_tma = (off - shift + bytes) <= total_bytes;
+        }
+        const unsigned mask = __ballot_sync(0xffffffffu, use_tma);
+        if (lane == 0) mbar_arrive_expect_tx(&bars[s], (uint32_t)__popc(mask) * bytes);
+        __syncwarp();
+        if (mine) {
+            unsigned char *slot = wbase + s * stage_bytes + (size_t)slot_id * cfg.slot_bytes;
+            if (use_tma) {
+                bulk_copy_g2s(slot, reinterpret_cast<const unsigned char *>(fields) + off - shift,
+                              (uint32_t)bytes, &bars[s]);
+            } else {  // last bytes of the array: plain loads
+                const double *src = reinterpret_cast<const double *>(
+                    reinterpret_cast<const unsigned char *>(fields) + off);
+                double *dst = reinterpret_cast<double *>(slot + shift);
+                for (int q2 = 0; q2 < nf * P; ++q2) dst[q2] = src[q2];
+            }
+        }
+    };
+
+    cur_t ci, cc;  // issue cursor runs `prefetch` items ahead of the consume cursor
+    ci.b = first;
+    load_batch(ci);
+    cc = ci;
+    const int prefetch = cfg.stages - 1;
+    int64_t qi = 0;
+    for (; qi < prefetch && valid(ci); ++qi) {
+        issue(ci, qi);
+        advance(ci);
+    }
+    double L[DIM][M];
+    int64_t last_b = -1;
+    for (int64_t q = 0; valid(cc); ++q) {
+        if (valid(ci)) {
+            fence_proxy_async_smem();  // reads of the stage being refilled happened at item q-1
+            __syncwarp();
+            issue(ci, qi);
+            advance(ci);
+            ++qi;
+        }
+        const int f0 = cc.c * cfg.FC;
+        const int nf = min(cfg.FC, cfg.F - f0);
+        const int s = (int)(q % cfg.stages);
+        if (cc.b != last_b) {  // new batch: Lagrange values of this lane's point
+            last_b = cc.b;
+            if (cc.e >= 0) {
+#pragma unroll
+                for (int ax = 0; ax < DIM; ++ax) lagrange_values<ORDER>(T, xi[cc.n * DIM + ax], L[ax]);
+            }
+        }
+        mbar_wait(&bars[s], (uint32_t)((q / cfg.stages) & 1));
+        const int slot_id = cc.rank - cc.r * cfg.slots;
+        if (cc.e >= 0) {
+            if (slot_id >= 0 && slot_id < cfg.slots) {
+                const int64_t off = (((int64_t)cc.e * cfg.F + f0) * P) * 8;
+                const int shift = cfg.odd_p ? (int)(off & 8) : 0;
+                const double *v = reinterpret_cast<const double *>(
+                    wbase + s * stage_bytes + (size_t)slot_id * cfg.slot_bytes + shift);
+                double *o = out + (perm ? (int64_t)perm[cc.n] : cc.n) * cfg.F + f0;
+                for (int f = 0; f < nf; ++f) o[f] = contract_field<ORDER, DIM>(v + f * P, L);
+            }
+        } else if (cc.n < N && cc.b < nbatch && cc.r == 0) {
+            double *o = out + (perm ? (int64_t)perm[cc.n] : cc.n) * cfg.F + f0;
+            for (int f = 0; f < nf; ++f) o[f] = 0.0;  // failed point: zero row
+        }
+        advance(cc);
+    }
+}
+
+template <int ORDER, int DIM>
+int launch_interp_coherent(int64_t E, int F, const double *fields, int64_t N, const int32_t *elem,
+                           const double *xi, const int32_t *perm, double *out, cudaStream_t stream)
+{
+    constexpr int M = ORDER + 1;
+    constexpr int P = DIM == 2 ? M * M : M * M * M;
+    mm_gll_table T;
+    mm_make_table(ORDER, &T);
+    coh_cfg cfg;
+    cfg.F = F;
+    cfg.odd_p = P % 2;
+    // whole element block per slot when it stays below ~5 KB, else chunks of fields
+    int fc = std::max(1, std::min(F, 5040 / (P * 8)));
+    cfg.stages = 3;
+    cfg.slots = P * 8 * fc > 2048 ? 2 : 4;
+    cfg.warps = 8;
+    if (const char *e = getenv("MM_COH_FC")) fc = std::max(1, std::min(F, atoi(e)));
+    if (const char *e = getenv("MM_COH_STAGES")) cfg.stages = std::max(2, std::min(8, atoi(e)));
+    if (const char *e = getenv("MM_COH_SLOTS")) cfg.slots = std::max(1, std::min(32, atoi(e)));
+    if (const char *e = getenv("MM_COH_WARPS")) cfg.warps = std::max(1, std::min(INTERP_MAX_WARPS, atoi(e)));
+    cfg.FC = fc;
+    cfg.chunks = (F + fc - 1) / fc;
+    cfg.slot_bytes = ((chunk_copy_bytes(fc, P, cfg.odd_p) + 15) / 16) * 16;
+    auto kern = interp_coherent_kernel<ORDER, DIM>;
+    auto smem_of = [&](int warps) {
+        return (size_t)warps * cfg.stages * cfg.slots * cfg.slot_bytes + warps * cfg.stages * sizeof(uint64_t);
+    };
+    while (cfg.warps > 1 && smem_of(cfg.warps) > 110 * 1024) --cfg.warps;  // two CTAs per SM
+    size_t smem = smem_of(cfg.warps);
+    MM_REQUIRE(smem <= 227 * 1024, MM_ERR_UNSUPPORTED, "mm_interp: staging needs %zu B of shared memory", smem);
+    MM_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int per_sm = 1;
+    MM_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, cfg.warps * 32, smem));
+    if (per_sm < 1) per_sm = 1;
+    const int sms = mm_num_sms() > 0 ? mm_num_sms() : 148;
+    int64_t nbatch = (N + 31) / 32;
+    int64_t grid = (int64_t)sms * per_sm;
     int64_t need = (nbatch + cfg.warps - 1) / cfg.warps;
     if (grid > need) grid = need;
     if (grid < 1) grid = 1;
@@ -292,15 +488,28 @@ int blocks_for(int64_t work, int block)
 
 }  // namespace
 
+static int interp_dispatch(bool coherent, int order, int dim, int64_t E, int F, const double *fields,
+                           int64_t N, const int32_t *elem, const double *xi, const int32_t *perm,
+                           double *out, void *stream_);
+
 extern "C" int mm_interp(int order, int dim, int64_t E, int F, const double *fields, int64_t N,
                          const int32_t *elem, const double *xi, double *out, void *stream)
 {
-    return mm_interp_perm(order, dim, E, F, fields, N, elem, xi, nullptr, out, stream);
+    return interp_dispatch(false, order, dim, E, F, fields, N, elem, xi, nullptr, out, stream);
 }
 
 extern "C" int mm_interp_perm(int order, int dim, int64_t E, int F, const double *fields, int64_t N,
                               const int32_t *elem, const double *xi, const int32_t *perm,
-                              double *out, void *stream_)
+                              double *out, void *stream)
+{
+    const char *mode = getenv("MM_INTERP_MODE");
+    const bool coherent = !(mode && mode[0] == 'l');
+    return interp_dispatch(coherent, order, dim, E, F, fields, N, elem, xi, perm, out, stream);
+}
+
+static int interp_dispatch(bool coherent, int order, int dim, int64_t E, int F, const double *fields,
+                           int64_t N, const int32_t *elem, const double *xi, const int32_t *perm,
+                           double *out, void *stream_)
 {
     cudaStream_t stream = (cudaStream_t)stream_;
     MM_REQUIRE(mm_valid_order(order), MM_ERR_INVALID, "mm_interp: order %d (supported 1, 2, 4)", order);
@@ -310,8 +519,10 @@ extern "C" int mm_interp_perm(int order, int dim, int64_t E, int F, const double
     MM_REQUIRE(fields && elem && xi && out, MM_ERR_INVALID, "mm_interp: null buffer");
     MM_REQUIRE(((uintptr_t)fields & 15) == 0, MM_ERR_INVALID,
                "mm_interp: fields must be 16-byte aligned");
-#define MM_INT(O, D) \
-    if (order == O && dim == D) return launch_interp<O, D>(E, F, fields, N, elem, xi, perm, out, stream);
+#define MM_INT(O, D)                                                                              \
+    if (order == O && dim == D)                                                                   \
+        return coherent ? launch_interp_coherent<O, D>(E, F, fields, N, elem, xi, perm, out, stream) \
+                        : launch_interp<O, D>(E, F, fields, N, elem, xi, perm, out, stream);
     MM_INT(1, 2) MM_INT(2, 2) MM_INT(4, 2) MM_INT(1, 3) MM_INT(2, 3) MM_INT(4, 3)
 #undef MM_INT
     mm_set_error("mm_interp: unsupported order/dim");

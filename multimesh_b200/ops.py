@@ -266,6 +266,24 @@ def interp(fields: torch.Tensor, elem: torch.Tensor, xi: torch.Tensor) -> torch.
     return out
 
 
+def interp_perm(fields: torch.Tensor, elem: torch.Tensor, xi: torch.Tensor, perm) -> torch.Tensor:
+    """K3, coherent variant (mm_interp_perm): row n of the result goes to out[perm[n]] (perm may be
+    None).  Meant for spatially sorted points; correct for any order."""
+    fields = _need_cuda(fields, "fields", torch.float64)
+    elem = _need_cuda(elem, "elem", torch.int32)
+    xi = _need_cuda(xi, "xi", torch.float64)
+    if perm is not None:
+        perm = _need_cuda(perm, "perm", torch.int32)
+    E, F, P = fields.shape
+    N, d = xi.shape
+    order = _order_dim(P, d)
+    with torch.cuda.device(fields.device):
+        out = torch.empty((N, F), dtype=torch.float64, device=fields.device)
+        check(load_lib().mm_interp_perm(order, d, E, F, _ptr(fields), N, _ptr(elem), _ptr(xi),
+                                        _ptr(perm), _ptr(out), _stream()), "mm_interp_perm")
+    return out
+
+
 @torch.library.custom_op("multimesh::coeffs", mutates_args=())
 def coeffs(elem: torch.Tensor, xi: torch.Tensor, order: int) -> torch.Tensor:
     """-> coeffs [N,P]; zero rows where elem < 0."""

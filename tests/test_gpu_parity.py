@@ -443,3 +443,30 @@ def test_fused_pipeline_equals_separate_kernels(cuda, oracle, order, dim, form):
     assert out.numel() == 0 and elem.shape[0] == len(pts)
     out2, e2, _, _, _ = ops.interpolate(index, div, tn, cent, box, tf, tp, 20, ops.V1(), want_location=False)
     assert e2.numel() == 0 and out2.shape == (len(pts), F)
+
+
+@pytest.mark.parametrize("order,dim,F", [(2, 3, 5), (4, 3, 5), (4, 3, 8), (1, 3, 5), (2, 2, 3), (2, 3, 40)])
+def test_interp_coherent_variant_bit_exact(cuda, oracle, order, dim, F):
+    """mm_interp_perm: warp-level de-duplication of element blocks; incoherent input (up to 32
+    distinct elements per warp -> several rounds), coherent input, failed points, permutation."""
+    import torch
+    from multimesh_b200 import ops
+
+    rng = np.random.default_rng(2000 + 10 * order + F)
+    nodes = _mesh(order, dim, 4, 0.0)
+    E, P, _ = nodes.shape
+    fields = rng.normal(size=(E, F, P)) * 1000.0
+    N = 3001
+    for coherent in (False, True):
+        elem = rng.integers(0, E, size=N).astype(np.int32)
+        if coherent:
+            elem = np.sort(elem)
+        elem[::13] = E - 1
+        elem[5::17] = -1
+        xi = rng.uniform(-1.04, 1.04, size=(N, dim))
+        perm = rng.permutation(N).astype(np.int32)
+        want = oracle.interp(order, dim, fields, elem, xi)
+        got = ops.interp_perm(_t(fields, cuda), _t(elem, cuda), _t(xi, cuda), None).cpu().numpy()
+        assert np.array_equal(got, want)
+        got = ops.interp_perm(_t(fields, cuda), _t(elem, cuda), _t(xi, cuda), _t(perm, cuda)).cpu().numpy()
+        assert np.array_equal(got[perm], want)
