@@ -205,8 +205,11 @@ int launch_interp(int64_t E, int F, const double *fields, int64_t N, const int32
     cfg.chunks = (F + fc - 1) / fc;
     cfg.slot_bytes = mm_slot_bytes(chunk_copy_bytes(fc, P, cfg.odd_p));
     auto kern = interp_kernel<ORDER, DIM>;
-    size_t smem = (size_t)cfg.warps * cfg.stages * 32 * cfg.slot_bytes +
-                  cfg.warps * cfg.stages * sizeof(uint64_t);
+    auto smem_of = [&](int warps) {
+        return (size_t)warps * cfg.stages * 32 * cfg.slot_bytes + warps * cfg.stages * sizeof(uint64_t);
+    };
+    while (cfg.warps > 1 && smem_of(cfg.warps) > 200 * 1024) --cfg.warps;
+    size_t smem = smem_of(cfg.warps);
     MM_REQUIRE(smem <= 227 * 1024, MM_ERR_UNSUPPORTED, "mm_interp: staging needs %zu B of shared memory", smem);
     MM_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int per_sm = 1;

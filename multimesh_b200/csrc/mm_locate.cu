@@ -3,11 +3,14 @@
 // One thread per target point, warp-synchronous rounds:
 //   1. every unresolved lane advances through its candidate list (skipping negatives, repeats
 //      and -- for V1 -- candidates whose node AABB excludes the point) to its next candidate;
-//   2. all lanes with a candidate stage that element's control nodes ([P][dim] f64, contiguous
-//      in HBM) into their private shared-memory slot with ONE bulk-async copy each
-//      (cp.async.bulk -> UBLKCP), completion tracked by a per-warp mbarrier;
-//   3. each lane shifts its nodes by the point (Y = X - p) and runs Newton on the order-n map with
-//      the sum-factorised canonical evaluation order, reading Y from its slot;
+//   2. the warp de-duplicates the candidate elements of its lanes (__match_any_sync): each
+//      DISTINCT element's control nodes ([P][dim] f64, contiguous in HBM) are staged ONCE, by the
+//      group's leader lane, with one bulk-async copy (cp.async.bulk -> UBLKCP) into one of SLOTS
+//      shared-memory slots, completion tracked by a per-warp mbarrier; groups beyond SLOTS wait
+//      for the next round.  With spatially sorted points (mm_interpolate) a warp needs 1-4 copies;
+//   3. each lane runs Newton on the order-n map with the sum-factorised canonical evaluation
+//      order, reading its element's nodes from the shared slot (lanes of one group read the same
+//      addresses: broadcast) and shifting them by its own point on the fly (Y = X - p);
 //   4. accept test / best tracking; lanes that run out of candidates take the variant's fallback.
 // Rounds repeat until every lane is resolved (~1-2 rounds typically).
 //
@@ -24,14 +27,14 @@ struct elem_traits {
     static constexpr int BYTES = DOUBLES * 8;
     static constexpr bool MISALIGNED = (BYTES % 16) != 0;  // odd elements start at 8 mod 16
     static constexpr int COPY_BYTES = MISALIGNED ? BYTES + 8 : BYTES;
-    static constexpr int SLOT_BYTES = mm_slot_bytes(COPY_BYTES);
+    static constexpr int SLOT_BYTES = ((COPY_BYTES + 15) / 16) * 16;
 };
 
 // x[c] = sum_a w_a Y_a[c],  J[c][s] = sum_a dw_a/dxi_s Y_a[c]; i innermost, then j, then k.
 template <int ORDER, int DIM>
-__device__ __forceinline__ void eval_map(const mm_gll_table &T, const double *__restrict__ Y,
-                                         const double (&xi)[DIM], double (&x)[DIM],
-                                         double (&J)[DIM][DIM])
+__device__ __forceinline__ void eval_map(const mm_gll_table &T, const double *__restrict__ X,
+                                         const double (&p)[DIM], const double (&xi)[DIM],
+                                         double (&x)[DIM], double (&J)[DIM][DIM])
 {
     constexpr int M = ORDER + 1;
     double L[DIM][M], dL[DIM][M];
@@ -47,7 +50,7 @@ __device__ __forceinline__ void eval_map(const mm_gll_table &T, const double *__
             for (int i = 0; i < M; ++i) {
 #pragma unroll
                 for (int c = 0; c < 2; ++c) {
-                    double y = Y[(i + M * j) * 2 + c];
+                    double y = X[(i + M * j) * 2 + c] - p[c];
                     a[c] = a[c] + L[0][i] * y;
                     b[c] = b[c] + dL[0][i] * y;
                 }
@@ -77,7 +80,7 @@ __device__ __forceinline__ void eval_map(const mm_gll_table &T, const double *__
                 for (int i = 0; i < M; ++i) {
 #pragma unroll
                     for (int c = 0; c < 3; ++c) {
-                        double y = Y[(i + M * j + M * M * k) * 3 + c];
+                        double y = X[(i + M * j + M * M * k) * 3 + c] - p[c];
                         a[c] = a[c] + L[0][i] * y;
                         b[c] = b[c] + dL[0][i] * y;
                     }
@@ -107,17 +110,18 @@ __device__ __forceinline__ void eval_map(const mm_gll_table &T, const double *__
     }
 }
 
-// Newton from xi = 0 on point-shifted nodes Y; returns true when max|delta| <= 1e-13.
+// Newton from xi = 0 on the point-shifted nodes Y = X - p; true when max|delta| <= 1e-13.
 template <int ORDER, int DIM>
 __device__ __forceinline__ bool newton_inverse(const mm_gll_table &T,
-                                               const double *__restrict__ Y, double (&xi)[DIM])
+                                               const double *__restrict__ X,
+                                               const double (&p)[DIM], double (&xi)[DIM])
 {
 #pragma unroll
     for (int c = 0; c < DIM; ++c) xi[c] = 0.0;
 #pragma unroll 1
     for (int it = 0; it < MM_NEWTON_MAXIT; ++it) {
         double x[DIM], J[DIM][DIM], delta[DIM];
-        eval_map<ORDER, DIM>(T, Y, xi, x, J);
+        eval_map<ORDER, DIM>(T, X, p, xi, x, J);
         if constexpr (DIM == 2) {
             double r0 = -x[0], r1 = -x[1];
             double det = J[0][0] * J[1][1] - J[0][1] * J[1][0];
@@ -166,7 +170,7 @@ __device__ __forceinline__ bool accept_xi(const mm_locate_params &prm, const dou
     return ok;
 }
 
-template <int ORDER, int DIM, int WARPS>
+template <int ORDER, int DIM, int WARPS, int SLOTS>
 __global__ void __launch_bounds__(WARPS * 32)
 locate_kernel(const mm_gll_table T, const mm_locate_params prm, int64_t E,
               const double *__restrict__ nodes, const double *__restrict__ centroid,
@@ -179,8 +183,8 @@ locate_kernel(const mm_gll_table T, const mm_locate_params prm, int64_t E,
     using tr = elem_traits<ORDER, DIM>;
     extern __shared__ __align__(128) unsigned char smem[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    unsigned char *slot = smem + ((size_t)warp * 32 + lane) * tr::SLOT_BYTES;
-    uint64_t *bar = reinterpret_cast<uint64_t *>(smem + (size_t)WARPS * 32 * tr::SLOT_BYTES) + warp;
+    unsigned char *wslots = smem + (size_t)warp * SLOTS * tr::SLOT_BYTES;
+    uint64_t *bar = reinterpret_cast<uint64_t *>(smem + (size_t)WARPS * SLOTS * tr::SLOT_BYTES) + warp;
     if (lane == 0) mbar_init(bar, 1);
     fence_mbar_init();
     __syncthreads();
@@ -209,10 +213,16 @@ locate_kernel(const mm_gll_table T, const mm_locate_params prm, int64_t E,
 #pragma unroll
         for (int c = 0; c < DIM; ++c) best_xi[c] = 0.0;
 
+        int32_t deferred_e = -1;  // candidate selected but not staged yet (more groups than SLOTS)
+        bool deferred_fb = false;
         while (true) {
             int32_t e = -1;
             bool fb_newton = false;
-            if (!done) {
+            if (deferred_e >= 0) {
+                e = deferred_e;
+                fb_newton = deferred_fb;
+                deferred_e = -1;
+            } else if (!done) {
                 while (t < k) {
                     int32_t c = cl[t];
                     ++t;
@@ -294,38 +304,46 @@ locate_kernel(const mm_gll_table T, const mm_locate_params prm, int64_t E,
             const unsigned active = __ballot_sync(0xffffffffu, e >= 0);
             if (!active) break;
 
-            // ---- stage the candidate elements' control nodes: one bulk copy per lane ----------
+            // ---- stage each DISTINCT candidate element once: the group's leader lane copies ----
+            const unsigned same = __match_any_sync(0xffffffffu, e);
+            const int leader = __ffs(same) - 1;
+            const unsigned leaders = __ballot_sync(0xffffffffu, e >= 0 && lane == leader);
+            const int rank = e >= 0 ? __popc(leaders & ((1u << leader) - 1)) : -1;
+            const bool served = e >= 0 && rank < SLOTS;
+            if (e >= 0 && !served) {  // wait for a later round, keep the candidate
+                deferred_e = e;
+                deferred_fb = fb_newton;
+            }
             int shift = 0;
             bool use_tma = false;
             const double *src = nodes;
-            if (e >= 0) {
+            if (served) {
                 const int64_t off = (int64_t)e * tr::BYTES;
                 shift = tr::MISALIGNED ? (int)(off & 8) : 0;
-                use_tma = (off - shift + tr::COPY_BYTES) <= total_bytes;
+                use_tma = lane == leader && (off - shift + tr::COPY_BYTES) <= total_bytes;
                 src = nodes + (int64_t)e * tr::DOUBLES;
             }
             const unsigned tma_mask = __ballot_sync(0xffffffffu, use_tma);
             if (lane == 0 && tma_mask)
                 mbar_arrive_expect_tx(bar, (uint32_t)__popc(tma_mask) * tr::COPY_BYTES);
             __syncwarp();
-            double *Y = reinterpret_cast<double *>(slot + shift);
+            unsigned char *slot = wslots + (size_t)(served ? rank : 0) * tr::SLOT_BYTES;
+            const double *X = reinterpret_cast<const double *>(slot + shift);
             if (use_tma) {
                 bulk_copy_g2s(slot, reinterpret_cast<const unsigned char *>(src) - shift,
                               tr::COPY_BYTES, bar);
-            } else if (e >= 0) {
-                for (int q = 0; q < tr::DOUBLES; ++q) Y[q] = src[q];  // array tail: plain loads
+            } else if (served && lane == leader) {  // array tail: plain loads
+                double *dst = reinterpret_cast<double *>(slot + shift);
+                for (int q = 0; q < tr::DOUBLES; ++q) dst[q] = src[q];
             }
             if (tma_mask) {
                 mbar_wait(bar, phase);
                 phase ^= 1;
             }
-            if (e >= 0) {
-                for (int a = 0; a < tr::P; ++a) {
-#pragma unroll
-                    for (int c = 0; c < DIM; ++c) Y[a * DIM + c] = Y[a * DIM + c] - p[c];
-                }
+            __syncwarp();  // plain-load tail path: make the leader's stores visible to its group
+            if (served) {
                 double x[DIM];
-                const bool ok = newton_inverse<ORDER, DIM>(T, Y, x);
+                const bool ok = newton_inverse<ORDER, DIM>(T, X, p, x);
                 if (fb_newton) {  // V1: nearest-centre element, interpolator.py:1460-1473
                     bool big = false;
 #pragma unroll
@@ -391,7 +409,7 @@ locate_kernel(const mm_gll_table T, const mm_locate_params prm, int64_t E,
     }
 }
 
-template <int ORDER, int DIM, int WARPS>
+template <int ORDER, int DIM, int WARPS, int SLOTS>
 int launch_locate(const mm_locate_params &prm, int64_t E, const double *nodes,
                   const double *centroid, const double *aabb, int64_t N, const double *pts, int k,
                   const int32_t *cands, int32_t *elem, double *xi, uint8_t *status,
@@ -401,8 +419,8 @@ int launch_locate(const mm_locate_params &prm, int64_t E, const double *nodes,
     using tr = elem_traits<ORDER, DIM>;
     mm_gll_table T;
     mm_make_table(ORDER, &T);
-    auto kern = locate_kernel<ORDER, DIM, WARPS>;
-    const size_t smem = (size_t)WARPS * 32 * tr::SLOT_BYTES + WARPS * sizeof(uint64_t);
+    auto kern = locate_kernel<ORDER, DIM, WARPS, SLOTS>;
+    const size_t smem = (size_t)WARPS * SLOTS * tr::SLOT_BYTES + WARPS * sizeof(uint64_t);
     MM_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int per_sm = 1;
     MM_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, WARPS * 32, smem));
@@ -446,7 +464,7 @@ int mm_locate_impl(int order, int dim, int64_t E, const double *nodes, const dou
                "mm_locate: aabb_prefilter needs centroid and aabb (mm_element_geometry)");
 #define MM_LOC(O, D, W)                                                                          \
     if (order == O && dim == D)                                                                  \
-        return launch_locate<O, D, W>(*params, E, nodes, centroid, aabb, N, pts, k, cands, elem, \
+        return launch_locate<O, D, W, 8>(*params, E, nodes, centroid, aabb, N, pts, k, cands, elem, \
                                       xi, status, num_failed, unresolved_list, unresolved_count,  \
                                       stream);
     MM_LOC(1, 2, 4)
