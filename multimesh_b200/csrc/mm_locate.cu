@@ -32,7 +32,7 @@ struct elem_traits {
 
 // x[c] = sum_a w_a Y_a[c],  J[c][s] = sum_a dw_a/dxi_s Y_a[c]; i innermost, then j, then k.
 template <int ORDER, int DIM>
-__device__ __forceinline__ void eval_map(const mm_gll_table &T, const double *__restrict__ X,
+__device__ __forceinline__ void eval_map(const mm_gll_table &T, const double *__restrict__ Xn,
                                          const double (&p)[DIM], const double (&xi)[DIM],
                                          double (&x)[DIM], double (&J)[DIM][DIM])
 {
@@ -50,7 +50,7 @@ __device__ __forceinline__ void eval_map(const mm_gll_table &T, const double *__
             for (int i = 0; i < M; ++i) {
 #pragma unroll
                 for (int c = 0; c < 2; ++c) {
-                    double y = X[(i + M * j) * 2 + c] - p[c];
+                    double y = Xn[(i + M * j) * 2 + c] - p[c];
                     a[c] = a[c] + L[0][i] * y;
                     b[c] = b[c] + dL[0][i] * y;
                 }
@@ -80,7 +80,7 @@ __device__ __forceinline__ void eval_map(const mm_gll_table &T, const double *__
                 for (int i = 0; i < M; ++i) {
 #pragma unroll
                     for (int c = 0; c < 3; ++c) {
-                        double y = X[(i + M * j + M * M * k) * 3 + c] - p[c];
+                        double y = Xn[(i + M * j + M * M * k) * 3 + c] - p[c];
                         a[c] = a[c] + L[0][i] * y;
                         b[c] = b[c] + dL[0][i] * y;
                     }
