@@ -288,25 +288,19 @@ struct reg_list {
     __device__ __forceinline__ void insert(double nd, int32_t ni)
     {
         if (!(nd < d2[K - 1] || (nd == d2[K - 1] && ni < id[K - 1]))) return;
-        // one bubble pass from the top: shift entries that the new one precedes
+        // branch-free: pos = number of kept entries that precede the new one; slots above pos
+        // take their lower neighbour, slot pos takes the new entry
+        int pos = 0;
+#pragma unroll
+        for (int j = 0; j < K - 1; ++j)
+            pos += (d2[j] < nd || (d2[j] == nd && id[j] < ni)) ? 1 : 0;
 #pragma unroll
         for (int j = K - 1; j > 0; --j) {
-            bool before = nd < d2[j - 1] || (nd == d2[j - 1] && ni < id[j - 1]);
-            bool here = !before && (nd < d2[j] || (nd == d2[j] && ni < id[j]) || j == K - 1);
-            // entries above j were already shifted; slot j takes its lower neighbour or the new one
-            double od = d2[j - 1];
-            int32_t oi = id[j - 1];
-            if (before) {
-                d2[j] = od;
-                id[j] = oi;
-            } else if (here) {
-                d2[j] = nd;
-                id[j] = ni;
-                nd = INFINITY;  // placed: nothing below compares as "before"
-                ni = 0x7fffffff;
-            }
+            const bool shift = j > pos, here = j == pos;
+            d2[j] = shift ? d2[j - 1] : (here ? nd : d2[j]);
+            id[j] = shift ? id[j - 1] : (here ? ni : id[j]);
         }
-        if (nd < d2[0] || (nd == d2[0] && ni < id[0])) {  // new best of a full-width list (k == K)
+        if (pos == 0) {
             d2[0] = nd;
             id[0] = ni;
         }
@@ -330,16 +324,23 @@ __device__ __forceinline__ void scan_range(List &L, const double4 *__restrict__ 
                                            int32_t hi, double px, double py, double pz,
                                            bool three_d)
 {
+    if (lo >= hi) return;
+    const double2 *q = reinterpret_cast<const double2 *>(&recs[lo]);  // 2 x LDG.128 per record
+    double2 xy = __ldg(q), zw = __ldg(q + 1);
     for (int32_t j = lo; j < hi; ++j) {
-        const double2 *q = reinterpret_cast<const double2 *>(&recs[j]);  // 2 x LDG.128
-        const double2 xy = __ldg(q), zw = __ldg(q + 1);
-        double dx = px - xy.x, dy = py - xy.y;
+        const double2 cxy = xy, czw = zw;
+        if (j + 1 < hi) {  // next record in flight while this one is ranked
+            q += 2;
+            xy = __ldg(q);
+            zw = __ldg(q + 1);
+        }
+        double dx = px - cxy.x, dy = py - cxy.y;
         double s = dx * dx + dy * dy;
         if (three_d) {
-            double dz = pz - zw.x;
+            double dz = pz - czw.x;
             s = s + dz * dz;
         }
-        L.insert(s, (int32_t)__double_as_longlong(zw.y));
+        L.insert(s, (int32_t)__double_as_longlong(czw.y));
     }
 }
 
@@ -372,14 +373,21 @@ knn_kernel(grid_t g, int64_t N, const double *__restrict__ pts, int k, int32_t d
             const int zlo = max(ci[2] - r, 0), zhi = min(ci[2] + r, g.n[2] - 1);
             const int ylo = max(ci[1] - r, 0), yhi = min(ci[1] + r, g.n[1] - 1);
             const int xlo = max(ci[0] - r, 0), xhi = min(ci[0] + r, g.n[0] - 1);
-            for (int zz = zlo; zz <= zhi; ++zz) {
+            // rows of the shell are visited nearest-first (offsets 0, -1, +1, -2, +2, ...), so the
+            // list tightens early and the farther rows are pruned
+            const int nz = three_d ? 2 * r + 1 : 1;
+            for (int iz = 0; iz < nz; ++iz) {
+                const int zz = ci[2] + ((iz & 1) ? -((iz + 1) >> 1) : ((iz + 1) >> 1));
+                if (zz < zlo || zz > zhi) continue;
                 double gz = 0.0;
                 if (three_d) {
                     double zl = g.origin[2] + zz * h, zh = zl + h;
                     gz = fmax(fmax(zl - pz, pz - zh) - margin, 0.0);
                 }
                 const bool zedge = three_d && (abs(zz - ci[2]) == r);
-                for (int yy = ylo; yy <= yhi; ++yy) {
+                for (int iy = 0; iy < 2 * r + 1; ++iy) {
+                    const int yy = ci[1] + ((iy & 1) ? -((iy + 1) >> 1) : ((iy + 1) >> 1));
+                    if (yy < ylo || yy > yhi) continue;
                     double yl = g.origin[1] + yy * h, yh = yl + h;
                     double gy = fmax(fmax(yl - py, py - yh) - margin, 0.0);
                     const double g2 = gy * gy + gz * gz;
