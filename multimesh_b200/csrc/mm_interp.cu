@@ -388,10 +388,11 @@ int launch_interp_coherent(int64_t E, int F, const double *fields, int64_t N, co
     coh_cfg cfg;
     cfg.F = F;
     cfg.odd_p = P % 2;
-    // whole element block per slot when it stays below ~5 KB, else chunks of fields
-    int fc = std::max(1, std::min(F, 5040 / (P * 8)));
-    cfg.stages = 3;
-    cfg.slots = P * 8 * fc > 2048 ? 2 : 4;
+    // slots of about 1 KB (whole block at order <= 2 / F = 5, one field at order 4), 4 slots x 2
+    // stages per warp, 8 warps per CTA: measured best on B200 (profiles/r1_*), ~3 CTAs per SM
+    int fc = std::max(1, std::min(F, 1100 / (P * 8)));
+    cfg.stages = 2;
+    cfg.slots = 4;
     cfg.warps = 8;
     if (const char *e = getenv("MM_COH_FC")) fc = std::max(1, std::min(F, atoi(e)));
     if (const char *e = getenv("MM_COH_STAGES")) cfg.stages = std::max(2, std::min(8, atoi(e)));

@@ -69,10 +69,19 @@ __device__ __forceinline__ void eval_map(const mm_gll_table &T, const double *__
             J[c][1] = Deta[c];
         }
     } else {
-        double X[3] = {0, 0, 0}, Jx[3] = {0, 0, 0}, Jy[3] = {0, 0, 0}, Jz[3] = {0, 0, 0};
+        // the z-direction values are indexed by the k loop; for order 4 that loop stays rolled
+        // (keeps the live register set and the code size down), so they live in their own arrays
+        double Lz[M], dLz[M];
 #pragma unroll
         for (int k = 0; k < M; ++k) {
+            Lz[k] = L[2][k];
+            dLz[k] = dL[2][k];
+        }
+        double X[3] = {0, 0, 0}, Jx[3] = {0, 0, 0}, Jy[3] = {0, 0, 0}, Jz[3] = {0, 0, 0};
+#pragma unroll(M == 5 ? 1 : M)
+        for (int k = 0; k < M; ++k) {
             double V[3] = {0, 0, 0}, Dxi[3] = {0, 0, 0}, Deta[3] = {0, 0, 0};
+            const double *Xk = Xn + (M * M * k) * 3;
 #pragma unroll
             for (int j = 0; j < M; ++j) {
                 double a[3] = {0, 0, 0}, b[3] = {0, 0, 0};
@@ -80,7 +89,7 @@ __device__ __forceinline__ void eval_map(const mm_gll_table &T, const double *__
                 for (int i = 0; i < M; ++i) {
 #pragma unroll
                     for (int c = 0; c < 3; ++c) {
-                        double y = Xn[(i + M * j + M * M * k) * 3 + c] - p[c];
+                        double y = Xk[(i + M * j) * 3 + c] - p[c];
                         a[c] = a[c] + L[0][i] * y;
                         b[c] = b[c] + dL[0][i] * y;
                     }
@@ -92,12 +101,13 @@ __device__ __forceinline__ void eval_map(const mm_gll_table &T, const double *__
                     Dxi[c] = Dxi[c] + L[1][j] * b[c];
                 }
             }
+            const double lz = Lz[k], dlz = dLz[k];
 #pragma unroll
             for (int c = 0; c < 3; ++c) {
-                X[c] = X[c] + L[2][k] * V[c];
-                Jz[c] = Jz[c] + dL[2][k] * V[c];
-                Jx[c] = Jx[c] + L[2][k] * Dxi[c];
-                Jy[c] = Jy[c] + L[2][k] * Deta[c];
+                X[c] = X[c] + lz * V[c];
+                Jz[c] = Jz[c] + dlz * V[c];
+                Jx[c] = Jx[c] + lz * Dxi[c];
+                Jy[c] = Jy[c] + lz * Deta[c];
             }
         }
 #pragma unroll
