@@ -287,13 +287,13 @@ struct reg_list {
 
     __device__ __forceinline__ void insert(double nd, int32_t ni)
     {
-        if (!(nd < d2[K - 1] || (nd == d2[K - 1] && ni < id[K - 1]))) return;
+        if (!((int)(nd < d2[K - 1]) | ((int)(nd == d2[K - 1]) & (int)(ni < id[K - 1])))) return;
         // branch-free: pos = number of kept entries that precede the new one; slots above pos
         // take their lower neighbour, slot pos takes the new entry
         int pos = 0;
 #pragma unroll
         for (int j = 0; j < K - 1; ++j)
-            pos += (d2[j] < nd || (d2[j] == nd && id[j] < ni)) ? 1 : 0;
+            pos += (int)(d2[j] < nd) | ((int)(d2[j] == nd) & (int)(id[j] < ni));
 #pragma unroll
         for (int j = K - 1; j > 0; --j) {
             const bool shift = j > pos, here = j == pos;
