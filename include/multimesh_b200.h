@@ -201,6 +201,20 @@ int mm_interpolate(const mm_index_t *index, int32_t divisor, int order, int dim,
                    uint8_t *status, int64_t *num_failed, void *workspace, size_t workspace_bytes,
                    void *stream);
 
+/* Stage timing of mm_interpolate with CUDA events recorded on the caller's stream (no sync inside
+ * mm_interpolate).  Stages: 0 query sort, 1 k-NN first pass, 2 locate first pass, 3 re-run of
+ * unresolved points (k-NN + locate with all k), 4 gather (K3), 5 un-permute of elem/xi/status.
+ * mm_profile_begin makes the CALLING THREAD's subsequent mm_interpolate calls record into `p`
+ * (up to max_calls); mm_profile_end stops it; mm_profile_read synchronises the events and returns
+ * the per-call stage durations in milliseconds, stage_ms[call][MM_N_STAGES]. */
+#define MM_N_STAGES 6
+typedef struct mm_profile mm_profile_t;
+int mm_profile_create(mm_profile_t **out, int max_calls);
+int mm_profile_destroy(mm_profile_t *p);
+int mm_profile_begin(mm_profile_t *p);
+int mm_profile_end(void);
+int mm_profile_read(mm_profile_t *p, int *n_calls, float *stage_ms);
+
 /* ------------------------------------------------------------------------------------------
  * Legacy symbols, HOST pointers, exact reference signatures (helpers.py:43-81).
  * They copy to the current CUDA device, run the kernels above and copy back.
@@ -224,6 +238,9 @@ int mm_interpolate_host(int order, int dim, int64_t E, const double *nodes, int 
                         const double *fields, int64_t N, const double *pts, int k,
                         int gll_points_form, const mm_locate_params *params, double *values,
                         int32_t *elem, double *xi, int64_t *num_failed);
+/* mm_interpolate_host keeps its device buffers and two streams in a per-thread pool between calls
+ * (repeated interpolations re-use them); this releases the pool. */
+int mm_host_release(void);
 
 #ifdef __cplusplus
 }

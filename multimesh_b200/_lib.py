@@ -64,6 +64,12 @@ _SIGNATURES = {
     "mm_gather_nodal": (_int, [_int, _i64, _vp, _i64, _vp, _vp, _vp, _vp]),
     "mm_interpolate_host": (_int, [_int, _int, _i64, _vp, _int, _vp, _i64, _vp, _int, _int,
                                    C.POINTER(LocateParams), _vp, _vp, _vp, C.POINTER(_i64)]),
+    "mm_host_release": (_int, []),
+    "mm_profile_create": (_int, [C.POINTER(_vp), _int]),
+    "mm_profile_destroy": (_int, [_vp]),
+    "mm_profile_begin": (_int, [_vp]),
+    "mm_profile_end": (_int, []),
+    "mm_profile_read": (_int, [_vp, C.POINTER(_int), _vp]),
     # legacy symbols with the reference's signatures (host pointers)
     "centroid": (None, [C.c_longlong, C.c_longlong, C.c_longlong, _vp, _vp, _vp]),
     "triLinearInterpolator": (C.c_longlong, [C.c_longlong, C.c_longlong, _vp, _vp, _vp, _vp, _vp, _vp]),

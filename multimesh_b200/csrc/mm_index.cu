@@ -31,6 +31,25 @@ struct mm_index {
 
 namespace {
 
+// stream-ordered allocation from the device's default memory pool; the pool is told to keep freed
+// memory, so rebuilding an index for every call (as the reference rebuilds its KD-tree) does not
+// pay cudaMalloc/cudaFree each time
+cudaError_t pool_alloc(void **p, size_t bytes, cudaStream_t st)
+{
+    static thread_local int configured_dev = -1;
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (configured_dev != dev) {
+        cudaMemPool_t pool;
+        if (cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
+            uint64_t keep = UINT64_MAX;
+            cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+        }
+        configured_dev = dev;
+    }
+    return cudaMallocAsync(p, bytes ? bytes : 16, st);
+}
+
 constexpr int64_t MAX_CELLS = (int64_t)1 << 26;
 constexpr int KNN_BLOCK = 128;
 
@@ -494,8 +513,8 @@ void choose_dims(const double ext[3], int dim, double h, int n[3])
 extern "C" int mm_index_destroy(mm_index_t *ix)
 {
     if (!ix) return MM_OK;
-    if (ix->recs) cudaFree(ix->recs);
-    if (ix->cell_start) cudaFree(ix->cell_start);
+    if (ix->recs) cudaFreeAsync(ix->recs, nullptr);
+    if (ix->cell_start) cudaFreeAsync(ix->cell_start, nullptr);
     delete ix;
     return MM_OK;
 }
@@ -547,19 +566,20 @@ extern "C" int mm_index_create(mm_index_t **out, int dim, int64_t M, const doubl
         int32_t *&b;
         unsigned long long *&c;
         double *&d;
+        cudaStream_t st;
         ~scratch_t()
         {
-            if (a) cudaFree(a);
-            if (b) cudaFree(b);
-            if (c) cudaFree(c);
-            if (d) cudaFree(d);
+            if (a) cudaFreeAsync(a, st);
+            if (b) cudaFreeAsync(b, st);
+            if (c) cudaFreeAsync(c, st);
+            if (d) cudaFreeAsync(d, st);
         }
-    } scratch{counts, tile_sums, d_nonempty, d_partial};
+    } scratch{counts, tile_sums, d_nonempty, d_partial, stream};
 
     if (M > 0) {
         // 1. bounding box
         int nb = launch_blocks(M, 256, 8);
-        MM_CUDA(cudaMalloc(&d_partial, sizeof(double) * 6 * nb));
+        MM_CUDA(pool_alloc((void **)&d_partial, sizeof(double) * 6 * nb, stream));
         bbox_kernel<<<nb, 256, 0, stream>>>(dim, M, points, d_partial);
         MM_CUDA(cudaGetLastError());
         std::vector<double> part(6 * (size_t)nb);
@@ -594,14 +614,14 @@ extern "C" int mm_index_create(mm_index_t **out, int dim, int64_t M, const doubl
             if (!(h > 0.0) || !std::isfinite(h)) h = emax;
             h = std::max(h, emax / 4096.0);
         }
-        MM_CUDA(cudaMalloc(&d_nonempty, sizeof(unsigned long long)));
+        MM_CUDA(pool_alloc((void **)&d_nonempty, sizeof(unsigned long long), stream));
         auto evaluate = [&](double hh, int64_t *nonempty) -> int {
             choose_dims(ext, dim, hh, g.n);
             g.cell = hh;
             g.inv_cell = 1.0 / hh;
             int64_t ncells = (int64_t)g.n[0] * g.n[1] * g.n[2];
-            if (counts) { cudaFree(counts); counts = nullptr; }
-            MM_CUDA(cudaMalloc(&counts, sizeof(int32_t) * (size_t)(ncells + 1)));
+            if (counts) { cudaFreeAsync(counts, stream); counts = nullptr; }
+            MM_CUDA(pool_alloc((void **)&counts, sizeof(int32_t) * (size_t)(ncells + 1), stream));
             MM_CUDA(cudaMemsetAsync(counts, 0, sizeof(int32_t) * (size_t)(ncells + 1), stream));
             MM_CUDA(cudaMemsetAsync(d_nonempty, 0, sizeof(unsigned long long), stream));
             histogram_kernel<<<launch_blocks(M, 256, 8), 256, 0, stream>>>(g, M, points, counts);
@@ -652,21 +672,21 @@ extern "C" int mm_index_create(mm_index_t **out, int dim, int64_t M, const doubl
     ix->ncells = (int64_t)g.n[0] * g.n[1] * g.n[2];
 
     // 3. exclusive scan of the histogram -> cell_start
-    MM_CUDA(cudaMalloc(&ix->cell_start, sizeof(int32_t) * (size_t)(ix->ncells + 1)));
+    MM_CUDA(pool_alloc((void **)&ix->cell_start, sizeof(int32_t) * (size_t)(ix->ncells + 1), stream));
     ix->bytes += sizeof(int32_t) * (size_t)(ix->ncells + 1);
     if (M == 0) {
         MM_CUDA(cudaMemsetAsync(ix->cell_start, 0, sizeof(int32_t) * (size_t)(ix->ncells + 1),
                                 stream));
     } else {
         int64_t ntiles = (ix->ncells + SCAN_TILE - 1) / SCAN_TILE;
-        MM_CUDA(cudaMalloc(&tile_sums, sizeof(int32_t) * (size_t)ntiles));
+        MM_CUDA(pool_alloc((void **)&tile_sums, sizeof(int32_t) * (size_t)ntiles, stream));
         scan_tile_sums<<<(int)ntiles, SCAN_BLOCK, 0, stream>>>(ix->ncells, counts, tile_sums);
         scan_tile_offsets<<<1, 1024, 0, stream>>>(ntiles, tile_sums);
         scan_apply<<<(int)ntiles, SCAN_BLOCK, 0, stream>>>(ix->ncells, counts, tile_sums,
                                                            ix->cell_start);
         MM_CUDA(cudaGetLastError());
         // 4. scatter the points into cell order (the histogram buffer becomes the cursor)
-        MM_CUDA(cudaMalloc(&ix->recs, sizeof(double4) * (size_t)M));
+        MM_CUDA(pool_alloc((void **)&ix->recs, sizeof(double4) * (size_t)M, stream));
         ix->bytes += sizeof(double4) * (size_t)M;
         MM_CUDA(cudaMemsetAsync(counts, 0, sizeof(int32_t) * (size_t)(ix->ncells + 1), stream));
         scatter_kernel<<<launch_blocks(M, 256, 8), 256, 0, stream>>>(g, M, points, ix->cell_start,

@@ -11,8 +11,17 @@
 //   4. K3 gathers in sorted order and writes out[perm[n]].
 // Results are identical to mm_knn -> mm_locate -> mm_interp (tests/test_gpu_parity.py).
 #include <algorithm>
+#include <vector>
 
 #include "mm_common.cuh"
+
+struct mm_profile {
+    int max_calls = 0;
+    int calls = 0;
+    std::vector<cudaEvent_t> ev;  // [max_calls][MM_N_STAGES + 1]
+};
+
+static thread_local mm_profile *g_profile = nullptr;
 
 namespace {
 
@@ -141,18 +150,29 @@ extern "C" int mm_interpolate(const mm_index_t *index, int32_t divisor, int orde
     int64_t *counters = reinterpret_cast<int64_t *>(ws + L.counters);  // [0] unresolved, [1] failed
     const int k1 = std::min(k, 8);
 
+    cudaEvent_t *pev = nullptr;  // stage-boundary events of this call, if profiling is on
+    if (g_profile && g_profile->calls < g_profile->max_calls)
+        pev = g_profile->ev.data() + (size_t)(g_profile->calls++) * (MM_N_STAGES + 1);
+    auto mark = [&](int i) {
+        if (pev) cudaEventRecord(pev[i], stream);
+    };
+    mark(0);
+
     // 1. spatial sort of the target points
     MM_TRY(mm_index_sort_queries(index, N, pts, sorted, perm, ws + L.sort_scratch, stream));
     MM_CUDA(cudaMemsetAsync(counters, 0, 64, stream));
 
+    mark(1);
     // 2. first pass: k1 nearest candidates, prefix mode (unless k1 == k: complete semantics)
     MM_TRY(mm_knn(index, N, sorted, k1, divisor, cands1, nullptr, stream));
+    mark(2);
     mm_locate_params p1 = *params;
     p1.reserved = (k1 < k) ? 1 : 0;
     MM_TRY(mm_locate_impl(order, dim, E, nodes, centroid, aabb, N, sorted, k1, cands1, &p1, elem_s,
                           xi_s, status_s, counters + 1, false, (k1 < k) ? list : nullptr,
                           (k1 < k) ? counters : nullptr, stream));
 
+    mark(3);
     // 3. re-run the unresolved points with the full candidate list
     if (k1 < k) {
         int64_t n_un = 0;
@@ -180,15 +200,71 @@ extern "C" int mm_interpolate(const mm_index_t *index, int32_t divisor, int orde
     if (num_failed)
         MM_CUDA(cudaMemcpyAsync(num_failed, counters + 1, sizeof(int64_t), cudaMemcpyDeviceToDevice, stream));
 
+    mark(4);
     // 4. gather in sorted order, written back through the permutation
     if (fields) {
         MM_REQUIRE(out, MM_ERR_INVALID, "mm_interpolate: null out");
         MM_TRY(mm_interp_perm(order, dim, E, F, fields, N, elem_s, xi_s, perm, out, stream));
     }
+    mark(5);
     if (elem || xi || status) {
         unpermute_kernel<<<blocks_for(N), 256, 0, stream>>>(dim, N, perm, elem_s, xi_s, status_s,
                                                             elem, xi, status);
         MM_CUDA(cudaGetLastError());
+    }
+    mark(6);
+    return MM_OK;
+}
+
+extern "C" int mm_profile_create(mm_profile_t **out, int max_calls)
+{
+    MM_REQUIRE(out && max_calls > 0, MM_ERR_INVALID, "mm_profile_create: arguments");
+    mm_profile *p = new mm_profile();
+    p->max_calls = max_calls;
+    p->ev.resize((size_t)max_calls * (MM_N_STAGES + 1));
+    for (auto &e : p->ev) {
+        cudaError_t rc = cudaEventCreate(&e);
+        if (rc != cudaSuccess) {
+            delete p;
+            return mm_cuda_fail(rc, "cudaEventCreate", __FILE__, __LINE__);
+        }
+    }
+    *out = p;
+    return MM_OK;
+}
+
+extern "C" int mm_profile_destroy(mm_profile_t *p)
+{
+    if (!p) return MM_OK;
+    if (g_profile == p) g_profile = nullptr;
+    for (auto &e : p->ev) cudaEventDestroy(e);
+    delete p;
+    return MM_OK;
+}
+
+extern "C" int mm_profile_begin(mm_profile_t *p)
+{
+    MM_REQUIRE(p, MM_ERR_INVALID, "mm_profile_begin: null");
+    p->calls = 0;
+    g_profile = p;
+    return MM_OK;
+}
+
+extern "C" int mm_profile_end(void)
+{
+    g_profile = nullptr;
+    return MM_OK;
+}
+
+extern "C" int mm_profile_read(mm_profile_t *p, int *n_calls, float *stage_ms)
+{
+    MM_REQUIRE(p && n_calls && stage_ms, MM_ERR_INVALID, "mm_profile_read: null");
+    *n_calls = p->calls;
+    for (int c = 0; c < p->calls; ++c) {
+        cudaEvent_t *e = p->ev.data() + (size_t)c * (MM_N_STAGES + 1);
+        MM_CUDA(cudaEventSynchronize(e[MM_N_STAGES]));
+        for (int s = 0; s < MM_N_STAGES; ++s)
+            MM_CUDA(cudaEventElapsedTime(&stage_ms[c * MM_N_STAGES + s], e[s], e[s + 1]));
     }
     return MM_OK;
 }
