@@ -227,13 +227,17 @@ def run_ours(args, w):
     fields = torch.from_numpy(fields_h).to(dev)
     pts = torch.from_numpy(pts_h).to(dev)
     ev = lambda: torch.cuda.Event(enable_timing=True)  # noqa: E731
+    cent, box = ops.element_geometry(nodes)
+    index = ops.GridIndex(nodes.view(E * P, 3))  # first build: includes one-off module loading
+    torch.cuda.synchronize()
+    del index
     e0, e1 = ev(), ev()
     e0.record()
     cent, box = ops.element_geometry(nodes)
     index = ops.GridIndex(nodes.view(E * P, 3))
     e1.record()
     torch.cuda.synchronize()
-    build_ms = e0.elapsed_time(e1)
+    build_ms = e0.elapsed_time(e1)  # K0 geometry + index build, amortised per source mesh
     spec = ops.V1()
 
     def step():
