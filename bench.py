@@ -139,6 +139,7 @@ def cpu_port_run(w, crop_src, crop_tgt, steps=1, warmup=0):
     from oracle import capi as oracle
     from scipy.spatial import cKDTree
 
+    oracle.set_num_threads(len(os.sched_getaffinity(0)))  # torchrun sets OMP_NUM_THREADS=1
     order, k = w["order"], w["k"]
     P = (order + 1) ** 3
     frac = crop_src / w["src"]

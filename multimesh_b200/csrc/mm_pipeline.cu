@@ -34,12 +34,16 @@ struct ws_layout {
     size_t b_pts, b_cands, b_elem, b_xi, b_status, total;
 };
 
+// first-pass list length: 8 for the GLL-point form (a shared node appears up to 8 times, and its
+// copies are consecutive in the k-NN order), 4 for the centroid form
+inline int first_pass_k(int k, int32_t divisor) { return std::min(k, divisor > 1 ? 8 : 4); }
+
 ws_layout make_layout(const mm_index_t *ix, int dim, int64_t N, int k)
 {
     ws_layout L{};
     size_t o = 0;
     auto take = [&](size_t bytes) { size_t at = o; o += align_up(bytes); return at; };
-    const int k1 = std::min(k, 8);
+    const int k1 = std::min(k, 8);  // sized for the larger first pass
     L.sorted = take(sizeof(double) * N * dim);
     L.perm = take(sizeof(int32_t) * N);
     L.cands1 = take(sizeof(int32_t) * N * k1);
@@ -148,7 +152,7 @@ extern "C" int mm_interpolate(const mm_index_t *index, int32_t divisor, int orde
     uint8_t *status_s = ws + L.status;
     int32_t *list = reinterpret_cast<int32_t *>(ws + L.list);
     int64_t *counters = reinterpret_cast<int64_t *>(ws + L.counters);  // [0] unresolved, [1] failed
-    const int k1 = std::min(k, 8);
+    const int k1 = first_pass_k(k, divisor);
 
     cudaEvent_t *pev = nullptr;  // stage-boundary events of this call, if profiling is on
     if (g_profile && g_profile->calls < g_profile->max_calls)

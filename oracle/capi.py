@@ -108,6 +108,8 @@ def lib():
     L.mmo_hex8_inverse.restype = C.c_int
     L.mmo_hex8_inverse.argtypes = [_f64, _f64, _f64]
     L.mmo_num_threads.restype = C.c_int
+    L.mmo_set_num_threads.restype = None
+    L.mmo_set_num_threads.argtypes = [C.c_int]
     _lib = L
     return L
 
@@ -118,6 +120,11 @@ def _c(a, dt):
 
 def num_threads():
     return int(lib().mmo_num_threads())
+
+
+def set_num_threads(n):
+    """torchrun exports OMP_NUM_THREADS=1; the CPU baseline wants all host threads."""
+    lib().mmo_set_num_threads(int(n))
 
 
 def gll_nodes(order):

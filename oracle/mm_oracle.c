@@ -9,7 +9,7 @@
  * PARITY STATUS
  *   * order-1 HEX8 path (mmo_trilinear_interpolator, mmo_centroid): PINNED against
  *     the reference's own C sources compiled into oracle/_ref (see oracle/build.py
- *     and tests/test_oracle_vs_ref.py) -- bit-for-bit.
+ *     and tests/test_oracle.py) -- bit-for-bit.
  *   * GLL order-n path (Newton inverse map, Lagrange weights): PARITY UNPINNED.
  *     The reference delegates this arithmetic to the closed-source salvus.fem
  *     module (multi_mesh/components/interpolator.py:12,22-57,1337-1347,1370-1386),
@@ -805,6 +805,15 @@ int mmo_hex8_inverse(const double pnt[3], const double *vtx_flat, double sol[3])
     double vtx[8][3];
     memcpy(vtx, vtx_flat, sizeof vtx);
     return hex8_inverse(pnt, vtx, sol);
+}
+
+void mmo_set_num_threads(int n)
+{
+#ifdef _OPENMP
+    if (n > 0) omp_set_num_threads(n);
+#else
+    (void)n;
+#endif
 }
 
 int mmo_num_threads(void)
