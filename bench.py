@@ -42,10 +42,18 @@ WORKLOADS = {
     "small": dict(src=24, tgt=22, order=2, k=20),
     "medium": dict(src=60, tgt=56, order=2, k=20),
     "S2o4": dict(src=60, tgt=50, order=4, k=20),
+    # BASELINE configs[4] / north_star target: 100 M target points, order 4, ~10 M source elements, strong
+    # scaling over the GPUs (source generated on the device; random target points; centroid k-NN form)
+    "S5": dict(src=216, tgt=0, order=4, k=20, npoints=100_000_000, form="centroid", device_gen=True),
+    "S5small": dict(src=48, tgt=0, order=4, k=20, npoints=4_000_000, form="centroid", device_gen=True),
 }
 
 
 def workload_name(w):
+    if w.get("device_gen"):
+        return (f"{w['name']}: source {w['src']}^3 hex order-{w['order']} F=5 (generated on the device), "
+                f"{w['npoints']} uniform random target points split over the GPUs (strong scaling), k={w['k']}, "
+                f"V1 location, {w.get('form', 'gll')} k-NN form")
     return (f"{w['name']}: gll_2_gll, source {w['src']}^3 hex order-{w['order']} F=5, targets = GLL points of a "
             f"non-nested {w['tgt']}^3 order-{w['order']} mesh, k={w['k']}, V1 location, GLL-point k-NN form")
 
@@ -55,6 +63,37 @@ def make_source(w):
 
     nodes = meshgen.box_mesh((w["src"],) * 3, w["order"])
     fields = meshgen.analytic_fields(nodes, NAMES)
+    return nodes, fields
+
+
+def make_source_device(w, dev):
+    """Structured order-n hex mesh and five smooth fields built directly in HBM (torch), same layout and
+    formulas as meshgen.box_mesh / analytic_fields; used for the 10 M-element configuration, which is too
+    large to stage through host numpy in a benchmark."""
+    import torch
+    from multimesh_b200.gll import gll_nodes
+
+    n, order = w["src"], w["order"]
+    z = torch.tensor(gll_nodes(order), dtype=torch.float64, device=dev)
+    m = z.numel()
+    t = 0.5 * (z + 1.0)
+    a = torch.arange(m ** 3, device=dev)
+    loc = [a % m, (a // m) % m, a // (m * m)]
+    e = torch.arange(n ** 3, device=dev)
+    eorg = [e % n, (e // n) % n, e // (n * n)]
+    E, P = n ** 3, m ** 3
+    nodes = torch.empty((E, P, 3), dtype=torch.float64, device=dev)
+    for c in range(3):
+        nodes[:, :, c] = (eorg[c].to(torch.float64)[:, None] + t[loc[c]][None, :]) / n
+    fields = torch.empty((E, len(NAMES), P), dtype=torch.float64, device=dev)
+    x, y, zc = nodes[:, :, 0], nodes[:, :, 1], nodes[:, :, 2]
+    vp = 5000.0 + 800.0 * torch.sin(2 * np.pi * x) * torch.cos(2 * np.pi * y) + 300.0 * zc
+    fields[:, 3, :] = vp
+    fields[:, 4, :] = vp / np.sqrt(3.0)
+    del vp
+    fields[:, 0, :] = 57823.0 + 100.0 * torch.cos(np.pi * (x + y + zc))
+    fields[:, 1, :] = 600.0 - 80.0 * x + 40.0 * y * zc
+    fields[:, 2, :] = 2600.0 + 300.0 * x * y + 150.0 * zc * zc
     return nodes, fields
 
 
@@ -219,23 +258,39 @@ def run_ours(args, w):
     order, k = w["order"], w["k"]
     P = (order + 1) ** 3
     F = len(NAMES)
-    nodes_h, fields_h = make_source(w)
-    pts_h = make_targets(w, rank)
-    E, N = nodes_h.shape[0], pts_h.shape[0]
+    device_gen = bool(w.get("device_gen"))
+    gll_form = w.get("form", "gll") == "gll"
+    divisor = P if gll_form else 1
+    if device_gen:
+        nodes, fields = make_source_device(w, dev)
+        from multimesh_b200.parallel import local_slice
+        sl = local_slice(w["npoints"], rank, world)  # strong scaling: this rank's contiguous share
+        g = torch.Generator(device=dev)
+        g.manual_seed(1234 + rank)
+        pts = torch.rand((sl.stop - sl.start, 3), dtype=torch.float64, device=dev, generator=g)
+        nodes_h = fields_h = pts_h = None
+        E, N = nodes.shape[0], pts.shape[0]
+    else:
+        nodes_h, fields_h = make_source(w)
+        pts_h = make_targets(w, rank)
+        E, N = nodes_h.shape[0], pts_h.shape[0]
+        nodes = torch.from_numpy(nodes_h).to(dev)
+        fields = torch.from_numpy(fields_h).to(dev)
+        pts = torch.from_numpy(pts_h).to(dev)
 
     # ---- setup (untimed): source mesh resident, geometry + index built once per source mesh -----
-    nodes = torch.from_numpy(nodes_h).to(dev)
-    fields = torch.from_numpy(fields_h).to(dev)
-    pts = torch.from_numpy(pts_h).to(dev)
     ev = lambda: torch.cuda.Event(enable_timing=True)  # noqa: E731
-    cent, box = ops.element_geometry(nodes)
-    index = ops.GridIndex(nodes.view(E * P, 3))  # first build: includes one-off module loading
+
+    def build_index():
+        c, b = ops.element_geometry(nodes)
+        return c, b, ops.GridIndex(nodes.view(E * P, 3) if gll_form else c)
+
+    cent, box, index = build_index()  # first build: includes one-off module loading
     torch.cuda.synchronize()
     del index
     e0, e1 = ev(), ev()
     e0.record()
-    cent, box = ops.element_geometry(nodes)
-    index = ops.GridIndex(nodes.view(E * P, 3))
+    cent, box, index = build_index()
     e1.record()
     torch.cuda.synchronize()
     build_ms = e0.elapsed_time(e1)  # K0 geometry + index build, amortised per source mesh
@@ -244,7 +299,7 @@ def run_ours(args, w):
     def step():
         """One pass of the hot path: mm_interpolate = spatial sort -> K1 (k-NN, progressive) -> K2 (locate)
         -> K3 (gather); returns values + location."""
-        return ops.interpolate(index, P, nodes, cent, box, fields, pts, k, spec, want_location=True)
+        return ops.interpolate(index, divisor, nodes, cent, box, fields, pts, k, spec, want_location=True)
 
     for _ in range(max(args.warmup, 3)):
         res = step()
@@ -254,10 +309,12 @@ def run_ours(args, w):
     checksum = float(out.sum().item())
     st = torch.bincount(status.to(torch.int64), minlength=9).cpu().tolist()
     # the fused pipeline must agree bit for bit with the three separate kernels
-    cands = index.query_idx(pts, k, divisor=P)
-    e2, x2, s2, _ = ops.locate(nodes, cent, box, pts, cands, spec)
+    nchk = min(N, 2_000_000)
+    cands = index.query_idx(pts[:nchk], k, divisor=divisor)
+    e2, x2, s2, _ = ops.locate(nodes, cent, box, pts[:nchk], cands, spec)
     o2 = ops.interp(fields, e2, x2)
-    assert torch.equal(o2, out) and torch.equal(e2, elem) and torch.equal(x2, xi) and torch.equal(s2, status)
+    assert torch.equal(o2, out[:nchk]) and torch.equal(e2, elem[:nchk]) and torch.equal(x2, xi[:nchk])
+    assert torch.equal(s2, status[:nchk])
     del res, cands, e2, x2, s2, o2
 
     # ---- timed region: EXACTLY K steps; stage boundaries marked with CUDA events recorded on the
@@ -291,42 +348,48 @@ def run_ours(args, w):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         total_ms = float(t.item())
     ms_per_step = total_ms / args.steps
-    value = world * N / (ms_per_step * 1e-3)
+    n_total = w["npoints"] if device_gen else world * N
+    value = n_total / (ms_per_step * 1e-3)
 
-    # ---- e2e: the C-ABI call on HOST buffers (pinned), H2D + index build + K1-K3 + D2H per step --
-    pin = lambda a: torch.from_numpy(a).pin_memory()  # noqa: E731
-    nodes_p, fields_p, pts_p = pin(nodes_h), pin(fields_h), pin(pts_h)
-    vals_p = torch.empty((N, F), dtype=torch.float64).pin_memory()
-    prm = spec.to_c()
-    nf = C.c_int64(0)
-    del elem, xi, status, out
-    torch.cuda.empty_cache()
-    lib.mm_host_release()
+    e2e_value = e2e_s = e2e_checksum = None
+    h2d = d2h = 0
+    e2e_steps = 0
+    if not device_gen:
+        # ---- e2e: the C-ABI call on HOST buffers (pinned), H2D + index build + K1-K3 + D2H per step --
+        pin = lambda a: torch.from_numpy(a).pin_memory()  # noqa: E731
+        nodes_p, fields_p, pts_p = pin(nodes_h), pin(fields_h), pin(pts_h)
+        vals_p = torch.empty((N, F), dtype=torch.float64).pin_memory()
+        prm = spec.to_c()
+        nf = C.c_int64(0)
+        del elem, xi, status, out
+        torch.cuda.empty_cache()
+        lib.mm_host_release()
 
-    def e2e_step():
-        rc = lib.mm_interpolate_host(order, 3, E, C.c_void_p(nodes_p.data_ptr()), F,
-                                     C.c_void_p(fields_p.data_ptr()), N, C.c_void_p(pts_p.data_ptr()), k, 1,
-                                     C.byref(prm), C.c_void_p(vals_p.data_ptr()), None, None, C.byref(nf))
-        _lib.check(rc, "mm_interpolate_host")
+        def e2e_step():
+            rc = lib.mm_interpolate_host(order, 3, E, C.c_void_p(nodes_p.data_ptr()), F,
+                                         C.c_void_p(fields_p.data_ptr()), N, C.c_void_p(pts_p.data_ptr()), k,
+                                         1 if gll_form else 0,
+                                         C.byref(prm), C.c_void_p(vals_p.data_ptr()), None, None, C.byref(nf))
+            _lib.check(rc, "mm_interpolate_host")
 
-    e2e_steps = max(1, min(args.steps, 3))
-    e2e_step()
-    if world > 1:
-        dist.barrier()
-    torch.cuda.synchronize()
-    t0 = time.perf_counter()
-    for _ in range(e2e_steps):
-        e2e_step()  # synchronous: returns after the D2H copy of the values completed
-    torch.cuda.synchronize()
-    e2e_s = (time.perf_counter() - t0) / e2e_steps
-    if world > 1:
-        t = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        e2e_s = float(t.item())
-    e2e_value = world * N / e2e_s
-    e2e_checksum = float(vals_p.sum().item())
-    h2d = int(nodes_h.nbytes + fields_h.nbytes + pts_h.nbytes)
-    d2h = int(N * F * 8 + 8)
+        e2e_steps = max(1, min(args.steps, 3))
+        e2e_step()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for _ in range(e2e_steps):
+            e2e_step()  # synchronous: returns after the D2H copy of the values completed
+        torch.cuda.synchronize()
+        e2e_s = (time.perf_counter() - t0) / e2e_steps
+        if world > 1:
+            t = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            e2e_s = float(t.item())
+        e2e_value = world * N / e2e_s
+        e2e_checksum = float(vals_p.sum().item())
+        h2d = int(nodes_h.nbytes + fields_h.nbytes + pts_h.nbytes)
+        d2h = int(N * F * 8 + 8)
 
     if rank != 0:
         if world > 1:
@@ -371,20 +434,22 @@ def run_ours(args, w):
 
     # ---- CPU baseline, rank 0, N = 1 only -------------------------------------------------------
     cpu = None
-    if world == 1 and not args.no_cpu:
+    if world == 1 and not args.no_cpu and not device_gen:
         crop_src, crop_tgt = (40, 36) if w["src"] >= 40 else (w["src"], w["tgt"] - 2)
         r = cpu_port_run(w, crop_src, crop_tgt, steps=1, warmup=0)
         cpu = {"value": r["value"], "unit": UNIT, "cores": r["cores"], "kind": "port", "sample": r["sample"]}
 
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
-        "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
+        "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True,
+        "scaling": "strong" if device_gen else "weak",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": {"workload": workload_name(w), "points_per_gpu": N, "source_elements": E, "fields": F,
                    "l2": "inputs larger than L2 (source 1.7 GB + targets 0.57 GB per step), no flush"},
         "roofline": roofline, "kernels": kernels, "other_stages": other,
         "cpu_baseline": cpu,
-        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+        "e2e": None if e2e_value is None else {
+                "value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                 "ms_per_step": e2e_s * 1e3, "steps": e2e_steps,
                 "call": "mm_interpolate_host (C-ABI, pinned host buffers; H2D source mesh + targets, index "
                         "build, K1-K3, D2H values every step)"},
