@@ -15,6 +15,8 @@
 // Rounds repeat until every lane is resolved (~1-2 rounds typically).
 //
 // Arithmetic = DESIGN.md section 3 (no FMA, fixed order); mirrors oracle/mm_oracle.c.
+#include <cstdlib>
+
 #include "mm_common.cuh"
 
 namespace {
@@ -78,7 +80,7 @@ __device__ __forceinline__ void eval_map(const mm_gll_table &T, const double *__
             dLz[k] = dL[2][k];
         }
         double X[3] = {0, 0, 0}, Jx[3] = {0, 0, 0}, Jy[3] = {0, 0, 0}, Jz[3] = {0, 0, 0};
-#pragma unroll(M == 5 ? 1 : M)
+#pragma unroll(M >= 3 ? 1 : M)
         for (int k = 0; k < M; ++k) {
             double V[3] = {0, 0, 0}, Dxi[3] = {0, 0, 0}, Deta[3] = {0, 0, 0};
             const double *Xk = Xn + (M * M * k) * 3;
@@ -180,8 +182,8 @@ __device__ __forceinline__ bool accept_xi(const mm_locate_params &prm, const dou
     return ok;
 }
 
-template <int ORDER, int DIM, int WARPS, int SLOTS>
-__global__ void __launch_bounds__(WARPS * 32)
+template <int ORDER, int DIM, int WARPS, int SLOTS, int MINB>
+__global__ void __launch_bounds__(WARPS * 32, MINB)
 locate_kernel(const mm_gll_table T, const mm_locate_params prm, int64_t E,
               const double *__restrict__ nodes, const double *__restrict__ centroid,
               const double *__restrict__ aabb, int64_t N, const double *__restrict__ pts, int k,
@@ -419,7 +421,7 @@ locate_kernel(const mm_gll_table T, const mm_locate_params prm, int64_t E,
     }
 }
 
-template <int ORDER, int DIM, int WARPS, int SLOTS>
+template <int ORDER, int DIM, int WARPS, int SLOTS, int MINB>
 int launch_locate(const mm_locate_params &prm, int64_t E, const double *nodes,
                   const double *centroid, const double *aabb, int64_t N, const double *pts, int k,
                   const int32_t *cands, int32_t *elem, double *xi, uint8_t *status,
@@ -429,7 +431,7 @@ int launch_locate(const mm_locate_params &prm, int64_t E, const double *nodes,
     using tr = elem_traits<ORDER, DIM>;
     mm_gll_table T;
     mm_make_table(ORDER, &T);
-    auto kern = locate_kernel<ORDER, DIM, WARPS, SLOTS>;
+    auto kern = locate_kernel<ORDER, DIM, WARPS, SLOTS, MINB>;
     const size_t smem = (size_t)WARPS * SLOTS * tr::SLOT_BYTES + WARPS * sizeof(uint64_t);
     MM_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int per_sm = 1;
@@ -472,17 +474,18 @@ int mm_locate_impl(int order, int dim, int64_t E, const double *nodes, const dou
                "mm_locate: nodes must be 16-byte aligned");
     MM_REQUIRE(!params->aabb_prefilter || (centroid && aabb), MM_ERR_INVALID,
                "mm_locate: aabb_prefilter needs centroid and aabb (mm_element_geometry)");
-#define MM_LOC(O, D, W)                                                                          \
+    // kernel configuration <order, dim, warps per CTA, shared slots per warp, min CTAs per SM>
+#define MM_LOC(O, D, W, S, B)                                                                    \
     if (order == O && dim == D)                                                                  \
-        return launch_locate<O, D, W, 8>(*params, E, nodes, centroid, aabb, N, pts, k, cands, elem, \
-                                      xi, status, num_failed, unresolved_list, unresolved_count,  \
-                                      stream);
-    MM_LOC(1, 2, 4)
-    MM_LOC(2, 2, 4)
-    MM_LOC(4, 2, 4)
-    MM_LOC(1, 3, 4)
-    MM_LOC(2, 3, 4)
-    MM_LOC(4, 3, 2)
+        return launch_locate<O, D, W, S, B>(*params, E, nodes, centroid, aabb, N, pts, k, cands,  \
+                                            elem, xi, status, num_failed, unresolved_list,       \
+                                            unresolved_count, stream);
+    MM_LOC(1, 2, 4, 8, 1)
+    MM_LOC(2, 2, 4, 8, 1)
+    MM_LOC(4, 2, 4, 8, 1)
+    MM_LOC(1, 3, 4, 8, 1)
+    MM_LOC(2, 3, 4, 8, 4)  // 128 registers, 16 warps per SM: measured best (profiles/)
+    MM_LOC(4, 3, 2, 8, 1)
 #undef MM_LOC
     mm_set_error("mm_locate: unsupported order/dim");
     return MM_ERR_UNSUPPORTED;
