@@ -46,6 +46,10 @@ int mm_locate_impl(int order, int dim, int64_t E, const double *nodes, const dou
                    int64_t *num_failed, bool zero_num_failed, int32_t *unresolved_list,
                    int64_t *unresolved_count, void *stream);
 size_t mm_index_sort_scratch_bytes(const mm_index_t *ix);
+// site table (distinct coordinates) and the site-level first pass of the progressive search
+int mm_index_build_sites(mm_index_t *ix, void *stream);
+int mm_knn_sites(const mm_index_t *ix, int64_t N, const double *pts, int kout, int32_t divisor,
+                 int32_t *idx, void *stream);
 // counting sort of query points by index cell: sorted[i] = pts[perm[i]]
 int mm_index_sort_queries(const mm_index_t *ix, int64_t N, const double *pts, double *sorted,
                           int32_t *perm, void *scratch, void *stream);

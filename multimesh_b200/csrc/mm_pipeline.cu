@@ -11,6 +11,7 @@
 //   4. K3 gathers in sorted order and writes out[perm[n]].
 // Results are identical to mm_knn -> mm_locate -> mm_interp (tests/test_gpu_parity.py).
 #include <algorithm>
+#include <cstdlib>
 #include <vector>
 
 #include "mm_common.cuh"
@@ -168,7 +169,14 @@ extern "C" int mm_interpolate(const mm_index_t *index, int32_t divisor, int orde
 
     mark(1);
     // 2. first pass: k1 nearest candidates, prefix mode (unless k1 == k: complete semantics)
-    MM_TRY(mm_knn(index, N, sorted, k1, divisor, cands1, nullptr, stream));
+    const bool site_pass = divisor > 1 && k1 < k && !getenv("MM_NO_SITES");
+    if (site_pass) {
+        // GLL-point form: shared nodes are stored up to 8 times; search over distinct coordinates
+        MM_TRY(mm_index_build_sites(const_cast<mm_index_t *>(index), stream));  // once per index
+        MM_TRY(mm_knn_sites(index, N, sorted, k1, divisor, cands1, stream));
+    } else {
+        MM_TRY(mm_knn(index, N, sorted, k1, divisor, cands1, nullptr, stream));
+    }
     mark(2);
     mm_locate_params p1 = *params;
     p1.reserved = (k1 < k) ? 1 : 0;
