@@ -445,7 +445,8 @@ def run_ours(args, w):
         "scaling": "strong" if device_gen else "weak",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": {"workload": workload_name(w), "points_per_gpu": N, "source_elements": E, "fields": F,
-                   "l2": "inputs larger than L2 (source 1.7 GB + targets 0.57 GB per step), no flush"},
+                   "l2": f"inputs larger than L2: source {(nodes.numel() + fields.numel()) * 8 / 1e9:.2f} GB + targets "
+                         f"{pts.numel() * 8 / 1e9:.2f} GB read per step, no flush"},
         "roofline": roofline, "kernels": kernels, "other_stages": other,
         "cpu_baseline": cpu,
         "e2e": None if e2e_value is None else {
