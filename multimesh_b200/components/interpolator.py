@@ -66,6 +66,16 @@ class _Source:
     def locate(self, pts, cands, spec):
         return ops.locate(self.nodes, self.centroid, self.aabb, pts, cands, spec)
 
+    def find(self, pts, k, spec, form="centroid", fields=None):
+        """Fused k-NN -> locate (-> gather when `fields` [E,F,P] is given): the mm_interpolate
+        pipeline (spatially sorted points, progressive search).  Same results as
+        candidates() + locate() (+ ops.interp).  -> (values or None, elem, xi, status, nfail)"""
+        index, div = (self.gll_index(), self.P) if form == "gll" else (self.centroid_index(), 1)
+        f = None if fields is None else _dev_f64(fields, self.device)
+        out, elem, xi, status, nfail = ops.interpolate(index, div, self.nodes, self.centroid, self.aabb, f,
+                                                        pts, k, spec)
+        return (out if fields is not None else None), elem, xi, status, nfail
+
 
 def _raise_if_hard(status, ignore_hard_elements):
     if not ignore_hard_elements and bool((status == ops._lib.ST_FB_NAN_MAGIC).any().item()):
@@ -241,11 +251,10 @@ def query_model(coordinates, model, nelem_to_search, model_path, coordinates_pat
     xyz = utils.latlondepth_to_xyz(latlondepth=coordinates)
     src = _Source(original_points)
     pts = _dev_f64(xyz, src.device)
-    cands = src.candidates(pts, nelem_to_search, form="gll")
-    elem, xi, status, _ = src.locate(pts, cands, ops.V1())
+    vals, elem, xi, status, _ = src.find(pts, nelem_to_search, ops.V1(), form="gll", fields=original_data)
     _raise_if_hard(status, False)  # ignore_hard_elements=False (:128)
     print("Interpolation done, need to organize the results")
-    return _gather(src, original_data, elem, xi).cpu().numpy()
+    return vals.cpu().numpy()
 
 
 def interpolate_to_points(mesh, points, params_to_interp, make_spherical=False):
@@ -264,14 +273,13 @@ def interpolate_to_points(mesh, points, params_to_interp, make_spherical=False):
     src = _Source(gll_points)
     print("Retrieving interpolation weights")
     pts = _dev_f64(points, src.device)
-    cands = src.candidates(pts, 25)
-    elem, xi, _, nfail = src.locate(pts, cands, ops.V2())
+    vals, elem, xi, _, nfail = src.find(pts, 25, ops.V2(), fields=_stack_fields(mesh, params_to_interp))
     num_failed = int(nfail.item())
     if num_failed > 0:
         print(num_failed, "points could not find an enclosing element. These points will be set to zero. "
               "Please check your domain or the interpolation tuning parameters")
     print("Interpolating fields...")
-    return _gather(src, _stack_fields(mesh, params_to_interp), elem, xi).cpu().numpy()
+    return vals.cpu().numpy()
 
 
 def _layer_setup(from_gll, to_gll, layers, parameters, make_spherical):
@@ -363,8 +371,7 @@ def _gll_2_gll_layered_impl(from_gll, to_gll, layers, nelem_to_search, parameter
             # one index per layer over that layer's centroids => layer-local element ids (:363-373)
             src = _Source(original_mesh.points[original_mask[k]])
             pts = _dev_f64(unique_new_points[k][0], src.device)
-            cands = src.candidates(pts, nelem_to_search)
-            elem, xi, _, _ = src.locate(pts, cands, spec)
+            _, elem, xi, _, _ = src.find(pts, nelem_to_search, spec)
             located[k] = {"elem": elem, "xi": xi}
         if stored_array is not None:
             _save_interp_info(
@@ -444,8 +451,9 @@ def gll_2_gll(from_gll, to_gll, nelem_to_search=20, parameters="ISO", from_model
         if element is None:
             print("Now we start interpolating")
             pts = _dev_f64(unique_new_points, src.device)
-            cands = src.candidates(pts, nelem_to_search, form="gll")
-            elem, xi, status, nfail = src.locate(pts, cands, ops.V1())  # ignore_hard_elements=True (:781)
+            # V1, ignore_hard_elements=True (:781)
+            vals, elem, xi, status, nfail = src.find(pts, nelem_to_search, ops.V1(), form="gll",
+                                                     fields=original_data)
             print("Interpolation done, Need to organize the results and write to file")
             num_failed = int(nfail.item())
             if num_failed > 0:
@@ -459,7 +467,6 @@ def gll_2_gll(from_gll, to_gll, nelem_to_search=20, parameters="ISO", from_model
                         allow_pickle=True)
                 np.save(os.path.join(stored_array, "coeffs.npy"),
                         np.broadcast_to(w.T[None], (len(parameters),) + w.T.shape).copy(), allow_pickle=True)
-            vals = _gather(src, original_data, elem, xi)
         else:
             vals = _gather_cached(src.device, original_data, element, np.ascontiguousarray(coeffs[0].T))
         # [N_unique, F] -> all GLL nodes -> [E_t, F, P_t]  (:822-826)
@@ -520,9 +527,8 @@ def gll_2_exodus(gll_model, exodus_model, gll_order=4, dimensions=3, nelem_to_se
     exodus = exodus_model if isinstance(exodus_model, Exodus) else Exodus(exodus_model, mode="a")
     print("Querying the KDTree")
     pts = _dev_f64(exodus.points[:, :dimensions], src.device)
-    cands = src.candidates(pts, nelem_to_search)
-    elem, xi, _, _ = src.locate(pts, cands, ops.V1())
-    values = _gather(src, gll_data, elem, xi).cpu().numpy()
+    values, elem, xi, _, _ = src.find(pts, nelem_to_search, ops.V1(), fields=gll_data)
+    values = values.cpu().numpy()
     for i, param in enumerate(parameters):
         exodus.attach_field(param, np.zeros_like(values[:, i]))
         exodus.attach_field(param, values[:, i])
