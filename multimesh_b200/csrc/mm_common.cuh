@@ -45,6 +45,10 @@ int mm_locate_impl(int order, int dim, int64_t E, const double *nodes, const dou
                    const mm_locate_params *params, int32_t *elem, double *xi, uint8_t *status,
                    int64_t *num_failed, bool zero_num_failed, int32_t *unresolved_list,
                    int64_t *unresolved_count, void *stream);
+int mm_interp_fused(int order, int dim, int64_t E, int F, const double *fields, int64_t N,
+                    const int32_t *elem_s, const double *xi_s, const uint8_t *status_s,
+                    const int32_t *perm, double *out, int32_t *elem_u, double *xi_u,
+                    uint8_t *status_u, void *stream);
 size_t mm_index_sort_scratch_bytes(const mm_index_t *ix);
 // site table (distinct coordinates) and the site-level first pass of the progressive search
 int mm_index_build_sites(mm_index_t *ix, void *stream);

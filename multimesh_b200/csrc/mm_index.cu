@@ -31,7 +31,7 @@ struct mm_index {
     // (x, y, z, id), so that points with identical coordinates -- GLL nodes shared by up to 8
     // elements -- are contiguous; a "site" is one distinct coordinate
     int64_t nsites = 0;
-    int32_t *site_rec = nullptr;         // [nsites + 1] first record of each site
+    double4 *site_recs = nullptr;        // [nsites + 1] {x, y, z, first record of the site}
     int32_t *site_cell_start = nullptr;  // [ncells + 1] first site of each cell
 };
 
@@ -344,7 +344,7 @@ struct reg_list {
     }
 };
 
-template <class List>
+template <bool POS_ID, class List>
 __device__ __forceinline__ void scan_range(List &L, const double4 *__restrict__ recs, int32_t lo,
                                            int32_t hi, double px, double py, double pz,
                                            bool three_d)
@@ -365,19 +365,29 @@ __device__ __forceinline__ void scan_range(List &L, const double4 *__restrict__ 
             double dz = pz - czw.x;
             s = s + dz * dz;
         }
-        L.insert(s, (int32_t)__double_as_longlong(czw.y));
+        L.insert(s, POS_ID ? j : (int32_t)__double_as_longlong(czw.y));
     }
 }
 
-template <class List>
+// SITES = false: `recs` are the point records, the result is the k nearest point ids.
+// SITES = true (first pass of the progressive search, GLL-point form): `recs` / `cell_start` are
+// the site table -- one record per DISTINCT coordinate (shared GLL nodes are stored up to 8
+// times), so the search needs 3-4x fewer distance evaluations and insertions.  The 4 nearest
+// sites are found; the k-NN list over the points starts with all copies of site 1 (ids
+// ascending), then all copies of site 2, ... as long as the site distances are strictly
+// increasing; that prefix is written (up to k entries, idx / divisor, -1 padded).  At the first
+// exact tie between site distances the prefix stops (copies of tied sites interleave by id) and
+// the caller's full search handles the point.
+template <class List, bool SITES>
 __global__ void __launch_bounds__(KNN_BLOCK)
 knn_kernel(grid_t g, int64_t N, const double *__restrict__ pts, int k, int32_t divisor,
            const double4 *__restrict__ recs, const int32_t *__restrict__ cell_start,
-           int32_t *__restrict__ out_idx, double *__restrict__ out_d2)
+           int32_t *__restrict__ out_idx, double *__restrict__ out_d2,
+           const double4 *__restrict__ point_recs)
 {
     extern __shared__ __align__(16) unsigned char smem[];
     List L;
-    L.init(smem, k);
+    L.init(smem, SITES ? 4 : k);
 
     const bool three_d = g.dim == 3;
     const double h = g.cell;
@@ -429,16 +439,16 @@ knn_kernel(grid_t g, int64_t N, const double *__restrict__ pts, int k, int32_t d
                     }
                     const int64_t base = (int64_t)g.n[0] * (yy + (int64_t)g.n[1] * zz);
                     if (zedge || abs(yy - ci[1]) == r) {
-                        scan_range(L, recs, cell_start[base + xa], cell_start[base + xb + 1], px,
-                                   py, pz, three_d);
+                        scan_range<SITES>(L, recs, cell_start[base + xa], cell_start[base + xb + 1], px,
+                                          py, pz, three_d);
                     } else {  // interior row of the shell: only its two end cells are new
                         const int x0 = ci[0] - r, x1 = ci[0] + r;
                         if (x0 >= xa && x0 <= xb)
-                            scan_range(L, recs, cell_start[base + x0], cell_start[base + x0 + 1],
-                                       px, py, pz, three_d);
+                            scan_range<SITES>(L, recs, cell_start[base + x0], cell_start[base + x0 + 1],
+                                              px, py, pz, three_d);
                         if (r > 0 && x1 >= xa && x1 <= xb)
-                            scan_range(L, recs, cell_start[base + x1], cell_start[base + x1 + 1],
-                                       px, py, pz, three_d);
+                            scan_range<SITES>(L, recs, cell_start[base + x1], cell_start[base + x1 + 1],
+                                              px, py, pz, three_d);
                     }
                 }
             }
@@ -460,7 +470,24 @@ knn_kernel(grid_t g, int64_t N, const double *__restrict__ pts, int k, int32_t d
             bound = fmax(bound - margin, 0.0);
             if (L.full() && L.worst() < bound * bound) break;
         }
-        L.write(out_idx + n * k, out_d2 ? out_d2 + n * k : nullptr, divisor);
+        if constexpr (SITES) {
+            // expand: copies of site j continue the prefix only while d2[j] < d2[j+1] strictly
+            int32_t *o = out_idx + n * k;
+            int c = 0;
+#pragma unroll
+            for (int j = 0; j < 3; ++j) {
+                const bool have = L.d2[j] < INFINITY;
+                const bool strict = L.d2[j] < L.d2[j + 1];  // slot j+1 is +inf without such a site
+                if (!(have && strict)) break;
+                const int32_t r0 = (int32_t)__double_as_longlong(recs[L.id[j]].w);
+                const int32_t r1 = (int32_t)__double_as_longlong(recs[L.id[j] + 1].w);
+                for (int32_t t = r0; t < r1 && c < k; ++t)
+                    o[c++] = (int32_t)__double_as_longlong(point_recs[t].w) / divisor;
+            }
+            for (; c < k; ++c) o[c] = -1;
+        } else {
+            L.write(out_idx + n * k, out_d2 ? out_d2 + n * k : nullptr, divisor);
+        }
     }
 }
 
@@ -525,138 +552,31 @@ site_sort_kernel(int64_t ncells, const int32_t *__restrict__ cell_start, double4
 __global__ void __launch_bounds__(128)
 site_fill_kernel(int64_t ncells, const int32_t *__restrict__ cell_start,
                  const double4 *__restrict__ recs, const int32_t *__restrict__ site_cell_start,
-                 int32_t *__restrict__ site_rec, int64_t nsites, int32_t M)
+                 double4 *__restrict__ site_recs, int64_t nsites, int32_t M)
 {
     for (int64_t c = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; c < ncells;
          c += (int64_t)gridDim.x * blockDim.x) {
         const int32_t lo = cell_start[c], hi = cell_start[c + 1];
         int32_t s = site_cell_start[c];
         for (int32_t i = lo; i < hi; ++i) {
+            const double4 b = recs[i];
             bool head = i == lo;
             if (!head) {
-                const double4 a = recs[i - 1], b = recs[i];
+                const double4 a = recs[i - 1];
                 head = a.x != b.x || a.y != b.y || a.z != b.z;
             }
-            if (head) site_rec[s++] = i;
-        }
-        if (c == ncells - 1) site_rec[nsites] = M;
-    }
-}
-
-// Site-level first pass of the progressive search (GLL-point form).  For every query: the 4
-// nearest SITES (distinct coordinates) -- 3-4x fewer candidates and insertions than over the
-// points.  The k-NN list over the points starts with all copies of site 1 (ids ascending), then
-// all copies of site 2, ... as long as the site distances are strictly increasing; that prefix is
-// written (up to kout entries, idx / divisor).  At the first exact tie between site distances the
-// prefix stops (entries of tied sites interleave by id); the caller's full search handles what is
-// left.  Entries beyond the prefix are -1.
-__global__ void __launch_bounds__(KNN_BLOCK)
-knn_sites_kernel(grid_t g, int64_t N, const double *__restrict__ pts, int kout, int32_t divisor,
-                 const double4 *__restrict__ recs, const int32_t *__restrict__ site_rec,
-                 const int32_t *__restrict__ site_cell_start, int32_t *__restrict__ out_idx)
-{
-    reg_list<4> L;
-    L.init(nullptr, 4);
-    const bool three_d = g.dim == 3;
-    const double h = g.cell;
-    const double margin = h * 1e-6;
-    for (int64_t n = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; n < N;
-         n += (int64_t)gridDim.x * blockDim.x) {
-        const double px = pts[n * g.dim + 0], py = pts[n * g.dim + 1];
-        const double pz = three_d ? pts[n * g.dim + 2] : 0.0;
-        const double p[3] = {px, py, pz};
-        int ci[3];
-        ci[0] = cell_coord(g, px, 0);
-        ci[1] = cell_coord(g, py, 1);
-        ci[2] = three_d ? cell_coord(g, pz, 2) : 0;
-        L.reset();
-        for (int r = 0;; ++r) {
-            const int zlo = max(ci[2] - r, 0), zhi = min(ci[2] + r, g.n[2] - 1);
-            const int ylo = max(ci[1] - r, 0), yhi = min(ci[1] + r, g.n[1] - 1);
-            const int xlo = max(ci[0] - r, 0), xhi = min(ci[0] + r, g.n[0] - 1);
-            const int nz = three_d ? 2 * r + 1 : 1;
-            for (int iz = 0; iz < nz; ++iz) {
-                const int zz = ci[2] + ((iz & 1) ? -((iz + 1) >> 1) : ((iz + 1) >> 1));
-                if (zz < zlo || zz > zhi) continue;
-                double gz = 0.0;
-                if (three_d) {
-                    double zl = g.origin[2] + zz * h, zh = zl + h;
-                    gz = fmax(fmax(zl - pz, pz - zh) - margin, 0.0);
-                }
-                const bool zedge = three_d && (abs(zz - ci[2]) == r);
-                for (int iy = 0; iy < 2 * r + 1; ++iy) {
-                    const int yy = ci[1] + ((iy & 1) ? -((iy + 1) >> 1) : ((iy + 1) >> 1));
-                    if (yy < ylo || yy > yhi) continue;
-                    double yl = g.origin[1] + yy * h, yh = yl + h;
-                    double gy = fmax(fmax(yl - py, py - yh) - margin, 0.0);
-                    const double g2 = gy * gy + gz * gz;
-                    int xa = xlo, xb = xhi;
-                    if (L.full()) {
-                        const double w2 = L.worst() - g2;
-                        if (w2 < 0.0) continue;
-                        const double wx = sqrt(w2) + margin;
-                        xa = max(xa, cell_coord(g, px - wx, 0));
-                        xb = min(xb, cell_coord(g, px + wx, 0));
-                        if (xa > xb) continue;
-                    }
-                    const int64_t base = (int64_t)g.n[0] * (yy + (int64_t)g.n[1] * zz);
-                    const bool edge = zedge || abs(yy - ci[1]) == r;
-                    const int x0 = ci[0] - r, x1 = ci[0] + r;
-                    for (int part = 0; part < 2; ++part) {
-                        int ca, cb;  // cell range [ca, cb] of this part
-                        if (edge) {
-                            if (part) break;
-                            ca = xa;
-                            cb = xb;
-                        } else {
-                            const int xc = part ? x1 : x0;
-                            if ((part && r == 0) || xc < xa || xc > xb) continue;
-                            ca = cb = xc;
-                        }
-                        const int32_t s0 = site_cell_start[base + ca], s1 = site_cell_start[base + cb + 1];
-                        for (int32_t sidx = s0; sidx < s1; ++sidx) {
-                            const double2 *q = reinterpret_cast<const double2 *>(&recs[site_rec[sidx]]);
-                            const double2 xy = __ldg(q), zw = __ldg(q + 1);
-                            double dx = px - xy.x, dy = py - xy.y;
-                            double d2 = dx * dx + dy * dy;
-                            if (three_d) {
-                                double dz = pz - zw.x;
-                                d2 = d2 + dz * dz;
-                            }
-                            L.insert(d2, sidx);
-                        }
-                    }
-                }
+            if (head) {
+                double4 r = b;
+                r.w = __longlong_as_double((long long)i);
+                site_recs[s++] = r;
             }
-            double bound = INFINITY;
-            bool remaining = false;
-            for (int c = 0; c < g.dim; ++c) {
-                if (ci[c] - r > 0) {
-                    remaining = true;
-                    bound = fmin(bound, p[c] - (g.origin[c] + (ci[c] - r) * h));
-                }
-                if (ci[c] + r < g.n[c] - 1) {
-                    remaining = true;
-                    bound = fmin(bound, (g.origin[c] + (ci[c] + r + 1) * h) - p[c]);
-                }
-            }
-            if (!remaining) break;
-            bound = fmax(bound - margin, 0.0);
-            if (L.full() && L.worst() < bound * bound) break;
         }
-        // expand: copies of site j are a valid continuation only while d2[j] < d2[j+1] strictly
-        int32_t *o = out_idx + n * kout;
-        int c = 0;
-#pragma unroll
-        for (int j = 0; j < 3; ++j) {
-            const bool have = L.d2[j] < INFINITY;
-            const bool strict = L.d2[j] < L.d2[j + 1];  // slot j+1 = +inf when there is no such site
-            if (!(have && strict)) break;
-            const int32_t r0 = site_rec[L.id[j]], r1 = site_rec[L.id[j] + 1];
-            for (int32_t t = r0; t < r1 && c < kout; ++t)
-                o[c++] = (int32_t)__double_as_longlong(recs[t].w) / divisor;
+        if (c == ncells - 1) {
+            double4 r;
+            r.x = r.y = r.z = 0.0;
+            r.w = __longlong_as_double((long long)M);
+            site_recs[nsites] = r;
         }
-        for (; c < kout; ++c) o[c] = -1;
     }
 }
 
@@ -701,7 +621,7 @@ extern "C" int mm_index_destroy(mm_index_t *ix)
     if (!ix) return MM_OK;
     if (ix->recs) cudaFreeAsync(ix->recs, nullptr);
     if (ix->cell_start) cudaFreeAsync(ix->cell_start, nullptr);
-    if (ix->site_rec) cudaFreeAsync(ix->site_rec, nullptr);
+    if (ix->site_recs) cudaFreeAsync(ix->site_recs, nullptr);
     if (ix->site_cell_start) cudaFreeAsync(ix->site_cell_start, nullptr);
     delete ix;
     return MM_OK;
@@ -899,18 +819,18 @@ extern "C" int mm_knn(const mm_index_t *ix, int64_t N, const double *pts, int k,
     grid_t g = grid_of(ix);
     cudaStream_t st = (cudaStream_t)stream;
     if (k <= 4) {
-        knn_kernel<reg_list<4>><<<launch_blocks(N, KNN_BLOCK, 8), KNN_BLOCK, 0, st>>>(
-            g, N, pts, k, divisor, ix->recs, ix->cell_start, idx, d2);
+        knn_kernel<reg_list<4>, false><<<launch_blocks(N, KNN_BLOCK, 8), KNN_BLOCK, 0, st>>>(
+            g, N, pts, k, divisor, ix->recs, ix->cell_start, idx, d2, nullptr);
     } else if (k <= 8) {
-        knn_kernel<reg_list<8>><<<launch_blocks(N, KNN_BLOCK, 8), KNN_BLOCK, 0, st>>>(
-            g, N, pts, k, divisor, ix->recs, ix->cell_start, idx, d2);
+        knn_kernel<reg_list<8>, false><<<launch_blocks(N, KNN_BLOCK, 8), KNN_BLOCK, 0, st>>>(
+            g, N, pts, k, divisor, ix->recs, ix->cell_start, idx, d2, nullptr);
     } else {
         size_t smem = (size_t)k * KNN_BLOCK * (sizeof(double) + sizeof(int32_t));
-        MM_CUDA(cudaFuncSetAttribute(knn_kernel<smem_list>,
+        MM_CUDA(cudaFuncSetAttribute(knn_kernel<smem_list, false>,
                                      cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         int per_sm = (int)std::max<size_t>(1, std::min<size_t>(8, (200 * 1024) / smem));
-        knn_kernel<smem_list><<<launch_blocks(N, KNN_BLOCK, per_sm), KNN_BLOCK, smem, st>>>(
-            g, N, pts, k, divisor, ix->recs, ix->cell_start, idx, d2);
+        knn_kernel<smem_list, false><<<launch_blocks(N, KNN_BLOCK, per_sm), KNN_BLOCK, smem, st>>>(
+            g, N, pts, k, divisor, ix->recs, ix->cell_start, idx, d2, nullptr);
     }
     MM_CUDA(cudaGetLastError());
     return MM_OK;
@@ -957,7 +877,7 @@ int mm_index_sort_queries(const mm_index_t *ix, int64_t N, const double *pts, do
 int mm_index_build_sites(mm_index_t *ix, void *stream_)
 {
     cudaStream_t stream = (cudaStream_t)stream_;
-    if (ix->site_rec || ix->M == 0) return MM_OK;
+    if (ix->site_recs || ix->M == 0) return MM_OK;
     int32_t *per_cell = nullptr, *tile_sums = nullptr;
     const int64_t ntiles = (ix->ncells + SCAN_TILE - 1) / SCAN_TILE;
     MM_CUDA(pool_alloc((void **)&per_cell, sizeof(int32_t) * (size_t)(ix->ncells + 1), stream));
@@ -973,23 +893,23 @@ int mm_index_build_sites(mm_index_t *ix, void *stream_)
     MM_CUDA(cudaMemcpyAsync(&ns, ix->site_cell_start + ix->ncells, sizeof(int32_t), cudaMemcpyDeviceToHost, stream));
     MM_CUDA(cudaStreamSynchronize(stream));
     ix->nsites = ns;
-    MM_CUDA(pool_alloc((void **)&ix->site_rec, sizeof(int32_t) * (size_t)(ns + 1), stream));
+    MM_CUDA(pool_alloc((void **)&ix->site_recs, sizeof(double4) * (size_t)(ns + 1), stream));
     site_fill_kernel<<<launch_blocks(ix->ncells, 128, 16), 128, 0, stream>>>(
-        ix->ncells, ix->cell_start, ix->recs, ix->site_cell_start, ix->site_rec, ns, (int32_t)ix->M);
+        ix->ncells, ix->cell_start, ix->recs, ix->site_cell_start, ix->site_recs, ns, (int32_t)ix->M);
     MM_CUDA(cudaGetLastError());
     cudaFreeAsync(per_cell, stream);
     cudaFreeAsync(tile_sums, stream);
-    ix->bytes += sizeof(int32_t) * (size_t)(ix->ncells + 1 + ns + 1);
+    ix->bytes += sizeof(int32_t) * (size_t)(ix->ncells + 1) + sizeof(double4) * (size_t)(ns + 1);
     return MM_OK;
 }
 
 int mm_knn_sites(const mm_index_t *ix, int64_t N, const double *pts, int kout, int32_t divisor,
                  int32_t *idx, void *stream)
 {
-    MM_REQUIRE(ix && ix->site_rec, MM_ERR_INVALID, "mm_knn_sites: site table not built");
+    MM_REQUIRE(ix && ix->site_recs, MM_ERR_INVALID, "mm_knn_sites: site table not built");
     if (N == 0) return MM_OK;
-    knn_sites_kernel<<<launch_blocks(N, KNN_BLOCK, 8), KNN_BLOCK, 0, (cudaStream_t)stream>>>(
-        grid_of(ix), N, pts, kout, divisor, ix->recs, ix->site_rec, ix->site_cell_start, idx);
+    knn_kernel<reg_list<4>, true><<<launch_blocks(N, KNN_BLOCK, 8), KNN_BLOCK, 0, (cudaStream_t)stream>>>(
+        grid_of(ix), N, pts, kout, divisor, ix->site_recs, ix->site_cell_start, idx, nullptr, ix->recs);
     MM_CUDA(cudaGetLastError());
     return MM_OK;
 }

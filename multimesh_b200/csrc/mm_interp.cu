@@ -254,7 +254,9 @@ __global__ void __launch_bounds__(INTERP_MAX_WARPS * 32)
 interp_coherent_kernel(const mm_gll_table T, const coh_cfg cfg, int64_t E,
                        const double *__restrict__ fields, int64_t N,
                        const int32_t *__restrict__ elem, const double *__restrict__ xi,
-                       const int32_t *__restrict__ perm, double *__restrict__ out)
+                       const int32_t *__restrict__ perm, double *__restrict__ out,
+                       const uint8_t *__restrict__ status, int32_t *__restrict__ elem_u,
+                       double *__restrict__ xi_u, uint8_t *__restrict__ status_u)
 {
     constexpr int M = ORDER + 1;
     constexpr int P = DIM == 2 ? M * M : M * M * M;
@@ -353,9 +355,23 @@ interp_coherent_kernel(const mm_gll_table T, const coh_cfg cfg, int64_t E,
         const int s = (int)(q % cfg.stages);
         if (cc.b != last_b) {  // new batch: Lagrange values of this lane's point
             last_b = cc.b;
+            double x[DIM];
+            if (cc.n < N) {
+#pragma unroll
+                for (int ax = 0; ax < DIM; ++ax) x[ax] = xi[cc.n * DIM + ax];
+                if (elem_u) {  // fused un-permute of the location outputs (mm_interpolate)
+                    const int64_t t = perm ? (int64_t)perm[cc.n] : cc.n;
+                    elem_u[t] = cc.e;
+                    if (status_u) status_u[t] = status[cc.n];
+                    if (xi_u) {
+#pragma unroll
+                        for (int ax = 0; ax < DIM; ++ax) xi_u[t * DIM + ax] = x[ax];
+                    }
+                }
+            }
             if (cc.e >= 0) {
 #pragma unroll
-                for (int ax = 0; ax < DIM; ++ax) lagrange_values<ORDER>(T, xi[cc.n * DIM + ax], L[ax]);
+                for (int ax = 0; ax < DIM; ++ax) lagrange_values<ORDER>(T, x[ax], L[ax]);
             }
         }
         mbar_wait(&bars[s], (uint32_t)((q / cfg.stages) & 1));
@@ -379,7 +395,9 @@ interp_coherent_kernel(const mm_gll_table T, const coh_cfg cfg, int64_t E,
 
 template <int ORDER, int DIM>
 int launch_interp_coherent(int64_t E, int F, const double *fields, int64_t N, const int32_t *elem,
-                           const double *xi, const int32_t *perm, double *out, cudaStream_t stream)
+                           const double *xi, const int32_t *perm, double *out, cudaStream_t stream,
+                           const uint8_t *status = nullptr, int32_t *elem_u = nullptr,
+                           double *xi_u = nullptr, uint8_t *status_u = nullptr)
 {
     constexpr int M = ORDER + 1;
     constexpr int P = DIM == 2 ? M * M : M * M * M;
@@ -418,7 +436,8 @@ int launch_interp_coherent(int64_t E, int F, const double *fields, int64_t N, co
     int64_t need = (nbatch + cfg.warps - 1) / cfg.warps;
     if (grid > need) grid = need;
     if (grid < 1) grid = 1;
-    kern<<<(int)grid, cfg.warps * 32, smem, stream>>>(T, cfg, E, fields, N, elem, xi, perm, out);
+    kern<<<(int)grid, cfg.warps * 32, smem, stream>>>(T, cfg, E, fields, N, elem, xi, perm, out, status,
+                                                      elem_u, xi_u, status_u);
     MM_CUDA(cudaGetLastError());
     return MM_OK;
 }
@@ -566,4 +585,22 @@ extern "C" int mm_gather_coeffs(int P, int64_t E, int F, const double *fields, i
         P, E, F, fields, N, elem, coeffs, out);
     MM_CUDA(cudaGetLastError());
     return MM_OK;
+}
+
+// internal: K3 of the fused pipeline -- gather in sorted order + un-permuted location outputs
+int mm_interp_fused(int order, int dim, int64_t E, int F, const double *fields, int64_t N,
+                    const int32_t *elem_s, const double *xi_s, const uint8_t *status_s,
+                    const int32_t *perm, double *out, int32_t *elem_u, double *xi_u,
+                    uint8_t *status_u, void *stream_)
+{
+    cudaStream_t stream = (cudaStream_t)stream_;
+    MM_REQUIRE(((uintptr_t)fields & 15) == 0, MM_ERR_INVALID, "mm_interpolate: fields must be 16-byte aligned");
+#define MM_INTF(O, D)                                                                             \
+    if (order == O && dim == D)                                                                   \
+        return launch_interp_coherent<O, D>(E, F, fields, N, elem_s, xi_s, perm, out, stream,     \
+                                            status_s, elem_u, xi_u, status_u);
+    MM_INTF(1, 2) MM_INTF(2, 2) MM_INTF(4, 2) MM_INTF(1, 3) MM_INTF(2, 3) MM_INTF(4, 3)
+#undef MM_INTF
+    mm_set_error("mm_interpolate: unsupported order/dim");
+    return MM_ERR_UNSUPPORTED;
 }

@@ -213,13 +213,17 @@ extern "C" int mm_interpolate(const mm_index_t *index, int32_t divisor, int orde
         MM_CUDA(cudaMemcpyAsync(num_failed, counters + 1, sizeof(int64_t), cudaMemcpyDeviceToDevice, stream));
 
     mark(4);
-    // 4. gather in sorted order, written back through the permutation
+    // 4. gather in sorted order, written back through the permutation; the kernel also writes the
+    //    un-permuted elem / xi / status when they are requested (needs elem)
+    bool unpermuted = false;
     if (fields) {
         MM_REQUIRE(out, MM_ERR_INVALID, "mm_interpolate: null out");
-        MM_TRY(mm_interp_perm(order, dim, E, F, fields, N, elem_s, xi_s, perm, out, stream));
+        MM_TRY(mm_interp_fused(order, dim, E, F, fields, N, elem_s, xi_s, status_s, perm, out, elem, xi,
+                               status, stream));
+        unpermuted = elem != nullptr;
     }
     mark(5);
-    if (elem || xi || status) {
+    if (!unpermuted && (elem || xi || status)) {
         unpermute_kernel<<<blocks_for(N), 256, 0, stream>>>(dim, N, perm, elem_s, xi_s, status_s,
                                                             elem, xi, status);
         MM_CUDA(cudaGetLastError());
