@@ -432,10 +432,12 @@ knn_kernel(grid_t g, int64_t N, const double *__restrict__ pts, int k, int32_t d
                         // inside a row only the cells that the k-th-neighbour ball reaches can
                         const double w2 = L.worst() - g2;
                         if (w2 < 0.0) continue;
-                        const double wx = sqrt(w2) + margin;
-                        xa = max(xa, cell_coord(g, px - wx, 0));
-                        xb = min(xb, cell_coord(g, px + wx, 0));
-                        if (xa > xb) continue;
+                        if (!SITES || r > 1) {  // site rows are short: the x restriction costs more
+                            const double wx = sqrt(w2) + margin;
+                            xa = max(xa, cell_coord(g, px - wx, 0));
+                            xb = min(xb, cell_coord(g, px + wx, 0));
+                            if (xa > xb) continue;
+                        }
                     }
                     const int64_t base = (int64_t)g.n[0] * (yy + (int64_t)g.n[1] * zz);
                     if (zedge || abs(yy - ci[1]) == r) {
