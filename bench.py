@@ -283,14 +283,15 @@ def run_ours(args, w):
 
     def build_index():
         c, b = ops.element_geometry(nodes)
-        return c, b, ops.GridIndex(nodes.view(E * P, 3) if gll_form else c)
+        pre = ops.element_presolve(nodes)
+        return c, b, pre, ops.GridIndex(nodes.view(E * P, 3) if gll_form else c)
 
-    cent, box, index = build_index()  # first build: includes one-off module loading
+    cent, box, presolve, index = build_index()  # first build: includes one-off module loading
     torch.cuda.synchronize()
     del index
     e0, e1 = ev(), ev()
     e0.record()
-    cent, box, index = build_index()
+    cent, box, presolve, index = build_index()
     e1.record()
     torch.cuda.synchronize()
     build_ms = e0.elapsed_time(e1)  # K0 geometry + index build, amortised per source mesh
@@ -299,7 +300,8 @@ def run_ours(args, w):
     def step():
         """One pass of the hot path: mm_interpolate = spatial sort -> K1 (k-NN, progressive) -> K2 (locate)
         -> K3 (gather); returns values + location."""
-        return ops.interpolate(index, divisor, nodes, cent, box, fields, pts, k, spec, want_location=True)
+        return ops.interpolate(index, divisor, nodes, cent, box, fields, pts, k, spec, want_location=True,
+                               presolve=presolve)
 
     for _ in range(max(args.warmup, 3)):
         res = step()
@@ -311,7 +313,7 @@ def run_ours(args, w):
     # the fused pipeline must agree bit for bit with the three separate kernels
     nchk = min(N, 2_000_000)
     cands = index.query_idx(pts[:nchk], k, divisor=divisor)
-    e2, x2, s2, _ = ops.locate(nodes, cent, box, pts[:nchk], cands, spec)
+    e2, x2, s2, _ = ops.locate(nodes, cent, box, pts[:nchk], cands, spec, presolve=presolve)
     o2 = ops.interp(fields, e2, x2)
     assert torch.equal(o2, out[:nchk]) and torch.equal(e2, elem[:nchk]) and torch.equal(x2, xi[:nchk])
     assert torch.equal(s2, status[:nchk])

@@ -51,6 +51,14 @@ const char *mm_last_error(void);
 int mm_element_geometry(int order, int dim, int64_t E, const double *nodes, double *centroid,
                         double *aabb, void *stream);
 
+/* Affine pre-solve per element (optional accelerator of K2): presolve [E][dim + dim*dim] f64 =
+ * { x(xi=0)[dim], inverse Jacobian at xi=0 [dim][dim] }.  K2 then starts Newton at
+ * xi0 = Jinv0 (p - x0) -- the first Newton step with point-independent quantities -- so an exactly
+ * affine element needs one map evaluation instead of two.  Converged xi agree with the xi0 = 0
+ * start to roundoff (1e-16); the CPU oracle implements the same start. */
+int mm_element_presolve(int order, int dim, int64_t E, const double *nodes, double *presolve,
+                        void *stream);
+
 /* In-place x <- x * r_earth * z_node_1D / |x| for |x| > 0.
  * Replaces: map_to_sphere (components/interpolator.py:1125-1144). nodes [n][3], radius_1d [n]. */
 int mm_map_to_sphere(int64_t n, double *nodes, const double *radius_1d, double r_earth,
@@ -121,12 +129,14 @@ typedef struct {
 /*   nodes    [E][P][dim]   source control nodes
  *   centroid [E][dim]      from mm_element_geometry (needed when aabb_prefilter)
  *   aabb     [E][2][dim]   from mm_element_geometry (needed when aabb_prefilter)
+ *   presolve [E][dim+dim*dim] from mm_element_presolve, or NULL (Newton starts at xi = 0)
  *   pts      [N][dim]
  *   cands    [N][k] int32  candidate element ids in neighbour order; negatives are skipped
  *   elem     [N] int32 (out), xi [N][dim] f64 (out), status [N] u8 (out, may be NULL)
  *   num_failed : device int64 (out, may be NULL) = number of points with elem = -1 */
 int mm_locate(int order, int dim, int64_t E, const double *nodes, const double *centroid,
-              const double *aabb, int64_t N, const double *pts, int k, const int32_t *cands,
+              const double *aabb, const double *presolve, int64_t N, const double *pts, int k,
+              const int32_t *cands,
               const mm_locate_params *params, int32_t *elem, double *xi, uint8_t *status,
               int64_t *num_failed, void *stream);
 
@@ -195,7 +205,8 @@ int mm_gather_nodal(int F, int64_t npoints_mesh, const double *param, int64_t N,
  * ---------------------------------------------------------------------------------------- */
 size_t mm_interpolate_workspace_bytes(const mm_index_t *index, int dim, int64_t N, int k);
 int mm_interpolate(const mm_index_t *index, int32_t divisor, int order, int dim, int64_t E,
-                   const double *nodes, const double *centroid, const double *aabb, int F,
+                   const double *nodes, const double *centroid, const double *aabb,
+                   const double *presolve /* may be NULL */, int F,
                    const double *fields, int64_t N, const double *pts, int k,
                    const mm_locate_params *params, double *out, int32_t *elem, double *xi,
                    uint8_t *status, int64_t *num_failed, void *workspace, size_t workspace_bytes,

@@ -50,12 +50,13 @@ _SIGNATURES = {
     "mm_index_destroy": (_int, [_vp]),
     "mm_index_info": (_int, [_vp, C.POINTER(_i64 * 8), C.POINTER(C.c_double)]),
     "mm_knn": (_int, [_vp, _i64, _vp, _int, C.c_int32, _vp, _vp, _vp]),
-    "mm_locate": (_int, [_int, _int, _i64, _vp, _vp, _vp, _i64, _vp, _int, _vp,
+    "mm_element_presolve": (_int, [_int, _int, _i64, _vp, _vp, _vp]),
+    "mm_locate": (_int, [_int, _int, _i64, _vp, _vp, _vp, _vp, _i64, _vp, _int, _vp,
                          C.POINTER(LocateParams), _vp, _vp, _vp, _vp, _vp]),
     "mm_interp": (_int, [_int, _int, _i64, _int, _vp, _i64, _vp, _vp, _vp, _vp]),
     "mm_interp_perm": (_int, [_int, _int, _i64, _int, _vp, _i64, _vp, _vp, _vp, _vp, _vp]),
     "mm_interpolate_workspace_bytes": (C.c_size_t, [_vp, _int, _i64, _int]),
-    "mm_interpolate": (_int, [_vp, C.c_int32, _int, _int, _i64, _vp, _vp, _vp, _int, _vp, _i64, _vp, _int,
+    "mm_interpolate": (_int, [_vp, C.c_int32, _int, _int, _i64, _vp, _vp, _vp, _vp, _int, _vp, _i64, _vp, _int,
                               C.POINTER(LocateParams), _vp, _vp, _vp, _vp, _vp, _vp, C.c_size_t, _vp]),
     "mm_coeffs": (_int, [_int, _int, _i64, _vp, _vp, _vp, _vp]),
     "mm_gather_coeffs": (_int, [_int, _i64, _int, _vp, _i64, _vp, _vp, _vp, _vp]),

@@ -45,6 +45,7 @@ class _Source:
         self.E, self.P, self.dim = self.nodes.shape
         self.order = order_from_npoints(self.P, self.dim)
         self.centroid, self.aabb = ops.element_geometry(self.nodes)
+        self.presolve = ops.element_presolve(self.nodes)
         self._cent_index = None
         self._gll_index = None
 
@@ -64,7 +65,7 @@ class _Source:
         return self.centroid_index().query_idx(pts, k)
 
     def locate(self, pts, cands, spec):
-        return ops.locate(self.nodes, self.centroid, self.aabb, pts, cands, spec)
+        return ops.locate(self.nodes, self.centroid, self.aabb, pts, cands, spec, presolve=self.presolve)
 
     def find(self, pts, k, spec, form="centroid", fields=None):
         """Fused k-NN -> locate (-> gather when `fields` [E,F,P] is given): the mm_interpolate
@@ -73,7 +74,7 @@ class _Source:
         index, div = (self.gll_index(), self.P) if form == "gll" else (self.centroid_index(), 1)
         f = None if fields is None else _dev_f64(fields, self.device)
         out, elem, xi, status, nfail = ops.interpolate(index, div, self.nodes, self.centroid, self.aabb, f,
-                                                        pts, k, spec)
+                                                        pts, k, spec, presolve=self.presolve)
         return (out if fields is not None else None), elem, xi, status, nfail
 
 

@@ -41,7 +41,8 @@ int mm_num_sms();                 // SM count of the current device
 
 // internal (C++) entry points shared between translation units
 int mm_locate_impl(int order, int dim, int64_t E, const double *nodes, const double *centroid,
-                   const double *aabb, int64_t N, const double *pts, int k, const int32_t *cands,
+                   const double *aabb, const double *presolve, int64_t N, const double *pts, int k,
+                   const int32_t *cands,
                    const mm_locate_params *params, int32_t *elem, double *xi, uint8_t *status,
                    int64_t *num_failed, bool zero_num_failed, int32_t *unresolved_list,
                    int64_t *unresolved_count, void *stream);

@@ -4,6 +4,7 @@
 // what makes it bit-equal to np.mean(points, axis=1) (salvus_mesh_reader.py:99-100) and to the
 // reference's centroid.c:15-24; a tree reduction would not be.
 #include "mm_common.cuh"
+#include "mm_newton.cuh"
 
 namespace {
 
@@ -69,6 +70,49 @@ map_to_sphere_kernel(int64_t n, double *__restrict__ nodes, const double *__rest
     }
 }
 
+// affine pre-solve per element: pre[e] = {x(0), Jinv(0)} on the unshifted nodes (thread per element)
+template <int ORDER, int DIM>
+__global__ void __launch_bounds__(128)
+presolve_kernel(const mm_gll_table T, int64_t E, const double *__restrict__ nodes,
+                double *__restrict__ pre)
+{
+    constexpr int M = ORDER + 1;
+    constexpr int P = DIM == 2 ? M * M : M * M * M;
+    constexpr int W = DIM + DIM * DIM;
+    for (int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; e < E;
+         e += (int64_t)gridDim.x * blockDim.x) {
+        double zero[DIM], xi0[DIM], x[DIM], J[DIM][DIM];
+#pragma unroll
+        for (int c = 0; c < DIM; ++c) zero[c] = xi0[c] = 0.0;
+        eval_map<ORDER, DIM>(T, nodes + e * (int64_t)(P * DIM), zero, xi0, x, J);
+        double *o = pre + e * W;
+#pragma unroll
+        for (int c = 0; c < DIM; ++c) o[c] = x[c];
+        double *I = o + DIM;
+        if constexpr (DIM == 2) {
+            double det = J[0][0] * J[1][1] - J[0][1] * J[1][0];
+            I[0] = J[1][1] / det;
+            I[1] = (-J[0][1]) / det;
+            I[2] = (-J[1][0]) / det;
+            I[3] = J[0][0] / det;
+        } else {
+            double C00 = J[1][1] * J[2][2] - J[1][2] * J[2][1];
+            double C01 = J[1][2] * J[2][0] - J[1][0] * J[2][2];
+            double C02 = J[1][0] * J[2][1] - J[1][1] * J[2][0];
+            double C10 = J[0][2] * J[2][1] - J[0][1] * J[2][2];
+            double C11 = J[0][0] * J[2][2] - J[0][2] * J[2][0];
+            double C12 = J[0][1] * J[2][0] - J[0][0] * J[2][1];
+            double C20 = J[0][1] * J[1][2] - J[0][2] * J[1][1];
+            double C21 = J[0][2] * J[1][0] - J[0][0] * J[1][2];
+            double C22 = J[0][0] * J[1][1] - J[0][1] * J[1][0];
+            double det = (J[0][0] * C00 + J[0][1] * C01) + J[0][2] * C02;
+            I[0] = C00 / det; I[1] = C10 / det; I[2] = C20 / det;
+            I[3] = C01 / det; I[4] = C11 / det; I[5] = C21 / det;
+            I[6] = C02 / det; I[7] = C12 / det; I[8] = C22 / det;
+        }
+    }
+}
+
 int grid_for(int64_t work, int block)
 {
     int sms = mm_num_sms();
@@ -115,4 +159,26 @@ extern "C" int mm_map_to_sphere(int64_t n, double *nodes, const double *radius_1
                                                                              r_earth);
     MM_CUDA(cudaGetLastError());
     return MM_OK;
+}
+
+extern "C" int mm_element_presolve(int order, int dim, int64_t E, const double *nodes,
+                                   double *presolve, void *stream)
+{
+    MM_REQUIRE(mm_valid_order(order), MM_ERR_INVALID, "mm_element_presolve: order %d", order);
+    MM_REQUIRE(dim == 2 || dim == 3, MM_ERR_INVALID, "mm_element_presolve: dim %d", dim);
+    if (E == 0) return MM_OK;
+    MM_REQUIRE(E > 0 && nodes && presolve, MM_ERR_INVALID, "mm_element_presolve: arguments");
+    mm_gll_table T;
+    mm_make_table(order, &T);
+#define MM_PRE(O, D)                                                                          \
+    if (order == O && dim == D) {                                                             \
+        presolve_kernel<O, D><<<grid_for(E, 128), 128, 0, (cudaStream_t)stream>>>(T, E, nodes, \
+                                                                                 presolve);   \
+        MM_CUDA(cudaGetLastError());                                                          \
+        return MM_OK;                                                                         \
+    }
+    MM_PRE(1, 2) MM_PRE(2, 2) MM_PRE(4, 2) MM_PRE(1, 3) MM_PRE(2, 3) MM_PRE(4, 3)
+#undef MM_PRE
+    mm_set_error("mm_element_presolve: unsupported order/dim");
+    return MM_ERR_UNSUPPORTED;
 }

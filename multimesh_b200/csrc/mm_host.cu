@@ -35,10 +35,10 @@ struct host_pool {
     int device = -1;
     cudaStream_t main = nullptr, copy = nullptr;
     cudaEvent_t copied = nullptr;
-    buf_t nodes, fields, pts, cent, aabb, elem, xi, out, nf, ws;
+    buf_t nodes, fields, pts, cent, aabb, pre, elem, xi, out, nf, ws;
     void release()
     {
-        for (buf_t *b : {&nodes, &fields, &pts, &cent, &aabb, &elem, &xi, &out, &nf, &ws}) b->release();
+        for (buf_t *b : {&nodes, &fields, &pts, &cent, &aabb, &pre, &elem, &xi, &out, &nf, &ws}) b->release();
         if (copied) cudaEventDestroy(copied);
         if (main) cudaStreamDestroy(main);
         if (copy) cudaStreamDestroy(copy);
@@ -98,6 +98,7 @@ extern "C" int mm_interpolate_host(int order, int dim, int64_t E, const double *
     MM_CUDA(pl.pts.ensure(sizeof(double) * N * dim));
     MM_CUDA(pl.cent.ensure(sizeof(double) * E * dim));
     MM_CUDA(pl.aabb.ensure(sizeof(double) * E * 2 * dim));
+    MM_CUDA(pl.pre.ensure(sizeof(double) * E * (dim + dim * dim)));
     MM_CUDA(pl.out.ensure(sizeof(double) * N * F));
     MM_CUDA(pl.nf.ensure(sizeof(int64_t)));
     if (elem) MM_CUDA(pl.elem.ensure(sizeof(int32_t) * N));
@@ -110,6 +111,7 @@ extern "C" int mm_interpolate_host(int order, int dim, int64_t E, const double *
     MM_CUDA(cudaEventRecord(pl.copied, pl.copy));
     MM_TRY(mm_element_geometry(order, dim, E, pl.nodes.as<double>(), pl.cent.as<double>(),
                                pl.aabb.as<double>(), pl.main));
+    MM_TRY(mm_element_presolve(order, dim, E, pl.nodes.as<double>(), pl.pre.as<double>(), pl.main));
     index_holder ih;
     if (gll_points_form)
         MM_TRY(mm_index_create(&ih.ix, dim, E * P, pl.nodes.as<double>(), pl.main));
@@ -119,7 +121,8 @@ extern "C" int mm_interpolate_host(int order, int dim, int64_t E, const double *
     MM_CUDA(pl.ws.ensure(ws_bytes));
     MM_CUDA(cudaStreamWaitEvent(pl.main, pl.copied, 0));
     MM_TRY(mm_interpolate(ih.ix, gll_points_form ? P : 1, order, dim, E, pl.nodes.as<double>(),
-                          pl.cent.as<double>(), pl.aabb.as<double>(), F, pl.fields.as<double>(), N,
+                          pl.cent.as<double>(), pl.aabb.as<double>(), pl.pre.as<double>(), F,
+                          pl.fields.as<double>(), N,
                           pl.pts.as<double>(), k, params, pl.out.as<double>(),
                           elem ? pl.elem.as<int32_t>() : nullptr, xi ? pl.xi.as<double>() : nullptr,
                           nullptr, pl.nf.as<int64_t>(), pl.ws.p, pl.ws.cap, pl.main));

@@ -18,6 +18,7 @@
 #include <cstdlib>
 
 #include "mm_common.cuh"
+#include "mm_newton.cuh"
 
 namespace {
 
@@ -31,144 +32,6 @@ struct elem_traits {
     static constexpr int COPY_BYTES = MISALIGNED ? BYTES + 8 : BYTES;
     static constexpr int SLOT_BYTES = ((COPY_BYTES + 15) / 16) * 16;
 };
-
-// x[c] = sum_a w_a Y_a[c],  J[c][s] = sum_a dw_a/dxi_s Y_a[c]; i innermost, then j, then k.
-template <int ORDER, int DIM>
-__device__ __forceinline__ void eval_map(const mm_gll_table &T, const double *__restrict__ Xn,
-                                         const double (&p)[DIM], const double (&xi)[DIM],
-                                         double (&x)[DIM], double (&J)[DIM][DIM])
-{
-    constexpr int M = ORDER + 1;
-    double L[DIM][M], dL[DIM][M];
-#pragma unroll
-    for (int ax = 0; ax < DIM; ++ax) lagrange_values_derivs<ORDER>(T, xi[ax], L[ax], dL[ax]);
-
-    if constexpr (DIM == 2) {
-        double V[2] = {0, 0}, Dxi[2] = {0, 0}, Deta[2] = {0, 0};
-#pragma unroll
-        for (int j = 0; j < M; ++j) {
-            double a[2] = {0, 0}, b[2] = {0, 0};
-#pragma unroll
-            for (int i = 0; i < M; ++i) {
-#pragma unroll
-                for (int c = 0; c < 2; ++c) {
-                    double y = Xn[(i + M * j) * 2 + c] - p[c];
-                    a[c] = a[c] + L[0][i] * y;
-                    b[c] = b[c] + dL[0][i] * y;
-                }
-            }
-#pragma unroll
-            for (int c = 0; c < 2; ++c) {
-                V[c] = V[c] + L[1][j] * a[c];
-                Deta[c] = Deta[c] + dL[1][j] * a[c];
-                Dxi[c] = Dxi[c] + L[1][j] * b[c];
-            }
-        }
-#pragma unroll
-        for (int c = 0; c < 2; ++c) {
-            x[c] = V[c];
-            J[c][0] = Dxi[c];
-            J[c][1] = Deta[c];
-        }
-    } else {
-        // the z-direction values are indexed by the k loop; for order 4 that loop stays rolled
-        // (keeps the live register set and the code size down), so they live in their own arrays
-        double Lz[M], dLz[M];
-#pragma unroll
-        for (int k = 0; k < M; ++k) {
-            Lz[k] = L[2][k];
-            dLz[k] = dL[2][k];
-        }
-        double X[3] = {0, 0, 0}, Jx[3] = {0, 0, 0}, Jy[3] = {0, 0, 0}, Jz[3] = {0, 0, 0};
-#pragma unroll(M >= 3 ? 1 : M)
-        for (int k = 0; k < M; ++k) {
-            double V[3] = {0, 0, 0}, Dxi[3] = {0, 0, 0}, Deta[3] = {0, 0, 0};
-            const double *Xk = Xn + (M * M * k) * 3;
-#pragma unroll
-            for (int j = 0; j < M; ++j) {
-                double a[3] = {0, 0, 0}, b[3] = {0, 0, 0};
-#pragma unroll
-                for (int i = 0; i < M; ++i) {
-#pragma unroll
-                    for (int c = 0; c < 3; ++c) {
-                        double y = Xk[(i + M * j) * 3 + c] - p[c];
-                        a[c] = a[c] + L[0][i] * y;
-                        b[c] = b[c] + dL[0][i] * y;
-                    }
-                }
-#pragma unroll
-                for (int c = 0; c < 3; ++c) {
-                    V[c] = V[c] + L[1][j] * a[c];
-                    Deta[c] = Deta[c] + dL[1][j] * a[c];
-                    Dxi[c] = Dxi[c] + L[1][j] * b[c];
-                }
-            }
-            const double lz = Lz[k], dlz = dLz[k];
-#pragma unroll
-            for (int c = 0; c < 3; ++c) {
-                X[c] = X[c] + lz * V[c];
-                Jz[c] = Jz[c] + dlz * V[c];
-                Jx[c] = Jx[c] + lz * Dxi[c];
-                Jy[c] = Jy[c] + lz * Deta[c];
-            }
-        }
-#pragma unroll
-        for (int c = 0; c < 3; ++c) {
-            x[c] = X[c];
-            J[c][0] = Jx[c];
-            J[c][1] = Jy[c];
-            J[c][2] = Jz[c];
-        }
-    }
-}
-
-// Newton from xi = 0 on the point-shifted nodes Y = X - p; true when max|delta| <= 1e-13.
-template <int ORDER, int DIM>
-__device__ __forceinline__ bool newton_inverse(const mm_gll_table &T,
-                                               const double *__restrict__ X,
-                                               const double (&p)[DIM], double (&xi)[DIM])
-{
-#pragma unroll
-    for (int c = 0; c < DIM; ++c) xi[c] = 0.0;
-#pragma unroll 1
-    for (int it = 0; it < MM_NEWTON_MAXIT; ++it) {
-        double x[DIM], J[DIM][DIM], delta[DIM];
-        eval_map<ORDER, DIM>(T, X, p, xi, x, J);
-        if constexpr (DIM == 2) {
-            double r0 = -x[0], r1 = -x[1];
-            double det = J[0][0] * J[1][1] - J[0][1] * J[1][0];
-            delta[0] = (J[1][1] * r0 - J[0][1] * r1) / det;
-            delta[1] = (J[0][0] * r1 - J[1][0] * r0) / det;
-        } else {
-            double r0 = -x[0], r1 = -x[1], r2 = -x[2];
-            double C00 = J[1][1] * J[2][2] - J[1][2] * J[2][1];
-            double C01 = J[1][2] * J[2][0] - J[1][0] * J[2][2];
-            double C02 = J[1][0] * J[2][1] - J[1][1] * J[2][0];
-            double C10 = J[0][2] * J[2][1] - J[0][1] * J[2][2];
-            double C11 = J[0][0] * J[2][2] - J[0][2] * J[2][0];
-            double C12 = J[0][1] * J[2][0] - J[0][0] * J[2][1];
-            double C20 = J[0][1] * J[1][2] - J[0][2] * J[1][1];
-            double C21 = J[0][2] * J[1][0] - J[0][0] * J[1][2];
-            double C22 = J[0][0] * J[1][1] - J[0][1] * J[1][0];
-            double det = (J[0][0] * C00 + J[0][1] * C01) + J[0][2] * C02;
-            delta[0] = ((C00 * r0 + C10 * r1) + C20 * r2) / det;
-            delta[1] = ((C01 * r0 + C11 * r1) + C21 * r2) / det;
-            delta[2] = ((C02 * r0 + C12 * r1) + C22 * r2) / det;
-        }
-        double dmax = 0.0;
-        bool bad = false;
-#pragma unroll
-        for (int c = 0; c < DIM; ++c) {
-            double ad = fabs(delta[c]);
-            if (!(ad <= MM_NEWTON_DIVERGE)) bad = true;
-            if (ad > dmax) dmax = ad;
-            xi[c] = xi[c] + delta[c];
-        }
-        if (bad) return false;
-        if (dmax <= MM_NEWTON_TOL) return true;
-    }
-    return false;
-}
 
 template <int DIM>
 __device__ __forceinline__ bool accept_xi(const mm_locate_params &prm, const double (&xi)[DIM])
@@ -186,7 +49,8 @@ template <int ORDER, int DIM, int WARPS, int SLOTS, int MINB>
 __global__ void __launch_bounds__(WARPS * 32, MINB)
 locate_kernel(const mm_gll_table T, const mm_locate_params prm, int64_t E,
               const double *__restrict__ nodes, const double *__restrict__ centroid,
-              const double *__restrict__ aabb, int64_t N, const double *__restrict__ pts, int k,
+              const double *__restrict__ aabb, const double *__restrict__ presolve, int64_t N,
+              const double *__restrict__ pts, int k,
               const int32_t *__restrict__ cands, int32_t *__restrict__ elem_out,
               double *__restrict__ xi_out, uint8_t *__restrict__ status_out,
               unsigned long long *__restrict__ num_failed, int32_t *__restrict__ unresolved_list,
@@ -355,7 +219,8 @@ locate_kernel(const mm_gll_table T, const mm_locate_params prm, int64_t E,
             __syncwarp();  // plain-load tail path: make the leader's stores visible to its group
             if (served) {
                 double x[DIM];
-                const bool ok = newton_inverse<ORDER, DIM>(T, X, p, x);
+                const bool ok = newton_inverse<ORDER, DIM>(
+                    T, X, p, presolve ? presolve + (int64_t)e * (DIM + DIM * DIM) : nullptr, x);
                 if (fb_newton) {  // V1: nearest-centre element, interpolator.py:1460-1473
                     bool big = false;
 #pragma unroll
@@ -423,7 +288,8 @@ locate_kernel(const mm_gll_table T, const mm_locate_params prm, int64_t E,
 
 template <int ORDER, int DIM, int WARPS, int SLOTS, int MINB>
 int launch_locate(const mm_locate_params &prm, int64_t E, const double *nodes,
-                  const double *centroid, const double *aabb, int64_t N, const double *pts, int k,
+                  const double *centroid, const double *aabb, const double *presolve, int64_t N,
+                  const double *pts, int k,
                   const int32_t *cands, int32_t *elem, double *xi, uint8_t *status,
                   int64_t *num_failed, int32_t *unresolved_list, int64_t *unresolved_count,
                   cudaStream_t stream)
@@ -442,7 +308,7 @@ int launch_locate(const mm_locate_params &prm, int64_t E, const double *nodes,
     int64_t grid = (int64_t)sms * per_sm;  // persistent: resident CTAs loop over point batches
     if (grid > batches) grid = batches;
     if (grid < 1) grid = 1;
-    kern<<<(int)grid, WARPS * 32, smem, stream>>>(T, prm, E, nodes, centroid, aabb, N, pts, k,
+    kern<<<(int)grid, WARPS * 32, smem, stream>>>(T, prm, E, nodes, centroid, aabb, presolve, N, pts, k,
                                                   cands, elem, xi, status,
                                                   reinterpret_cast<unsigned long long *>(num_failed),
                                                   unresolved_list,
@@ -454,7 +320,8 @@ int launch_locate(const mm_locate_params &prm, int64_t E, const double *nodes,
 }  // namespace
 
 int mm_locate_impl(int order, int dim, int64_t E, const double *nodes, const double *centroid,
-                   const double *aabb, int64_t N, const double *pts, int k, const int32_t *cands,
+                   const double *aabb, const double *presolve, int64_t N, const double *pts, int k,
+                   const int32_t *cands,
                    const mm_locate_params *params, int32_t *elem, double *xi, uint8_t *status,
                    int64_t *num_failed, bool zero_num_failed, int32_t *unresolved_list,
                    int64_t *unresolved_count, void *stream_)
@@ -477,7 +344,8 @@ int mm_locate_impl(int order, int dim, int64_t E, const double *nodes, const dou
     // kernel configuration <order, dim, warps per CTA, shared slots per warp, min CTAs per SM>
 #define MM_LOC(O, D, W, S, B)                                                                    \
     if (order == O && dim == D)                                                                  \
-        return launch_locate<O, D, W, S, B>(*params, E, nodes, centroid, aabb, N, pts, k, cands,  \
+        return launch_locate<O, D, W, S, B>(*params, E, nodes, centroid, aabb, presolve, N, pts, k,  \
+                                            cands,                                                \
                                             elem, xi, status, num_failed, unresolved_list,       \
                                             unresolved_count, stream);
     MM_LOC(1, 2, 4, 8, 1)
@@ -492,14 +360,15 @@ int mm_locate_impl(int order, int dim, int64_t E, const double *nodes, const dou
 }
 
 extern "C" int mm_locate(int order, int dim, int64_t E, const double *nodes,
-                         const double *centroid, const double *aabb, int64_t N, const double *pts,
-                         int k, const int32_t *cands, const mm_locate_params *params,
+                         const double *centroid, const double *aabb, const double *presolve,
+                         int64_t N, const double *pts, int k, const int32_t *cands,
+                         const mm_locate_params *params,
                          int32_t *elem, double *xi, uint8_t *status, int64_t *num_failed,
                          void *stream)
 {
     MM_REQUIRE(params, MM_ERR_INVALID, "mm_locate: null params");
     mm_locate_params prm = *params;
     prm.reserved = 0;  // the partial (progressive first pass) mode is internal to mm_interpolate
-    return mm_locate_impl(order, dim, E, nodes, centroid, aabb, N, pts, k, cands, &prm, elem, xi,
+    return mm_locate_impl(order, dim, E, nodes, centroid, aabb, presolve, N, pts, k, cands, &prm, elem, xi,
                           status, num_failed, true, nullptr, nullptr, stream);
 }

@@ -128,7 +128,8 @@ extern "C" size_t mm_interpolate_workspace_bytes(const mm_index_t *index, int di
 
 extern "C" int mm_interpolate(const mm_index_t *index, int32_t divisor, int order, int dim,
                               int64_t E, const double *nodes, const double *centroid,
-                              const double *aabb, int F, const double *fields, int64_t N,
+                              const double *aabb, const double *presolve, int F,
+                              const double *fields, int64_t N,
                               const double *pts, int k, const mm_locate_params *params,
                               double *out, int32_t *elem, double *xi, uint8_t *status,
                               int64_t *num_failed, void *workspace, size_t workspace_bytes,
@@ -180,7 +181,7 @@ extern "C" int mm_interpolate(const mm_index_t *index, int32_t divisor, int orde
     mark(2);
     mm_locate_params p1 = *params;
     p1.reserved = (k1 < k) ? 1 : 0;
-    MM_TRY(mm_locate_impl(order, dim, E, nodes, centroid, aabb, N, sorted, k1, cands1, &p1, elem_s,
+    MM_TRY(mm_locate_impl(order, dim, E, nodes, centroid, aabb, presolve, N, sorted, k1, cands1, &p1, elem_s,
                           xi_s, status_s, counters + 1, false, (k1 < k) ? list : nullptr,
                           (k1 < k) ? counters : nullptr, stream));
 
@@ -201,7 +202,7 @@ extern "C" int mm_interpolate(const mm_index_t *index, int32_t divisor, int orde
             const int64_t nb = std::min<int64_t>(CHUNK_B, n_un - at);
             gather_points_kernel<<<blocks_for(nb), 256, 0, stream>>>(dim, nb, list + at, sorted, b_pts);
             MM_TRY(mm_knn(index, nb, b_pts, k, divisor, b_cands, nullptr, stream));
-            MM_TRY(mm_locate_impl(order, dim, E, nodes, centroid, aabb, nb, b_pts, k, b_cands, &p2,
+            MM_TRY(mm_locate_impl(order, dim, E, nodes, centroid, aabb, presolve, nb, b_pts, k, b_cands, &p2,
                                   b_elem, b_xi, b_status, counters + 1, false, nullptr, nullptr,
                                   stream));
             scatter_results_kernel<<<blocks_for(nb), 256, 0, stream>>>(

@@ -24,7 +24,7 @@ from .gll import SUPPORTED_ORDERS
 __all__ = [
     "LocateSpec", "V1", "V2", "V3", "V4", "V5", "GridIndex", "element_geometry", "locate", "interp",
     "coeffs", "gather_coeffs", "trilinear", "centroid_conn", "gather_nodal", "map_to_sphere_",
-    "interpolate",
+    "interpolate", "element_presolve",
 ]
 
 
@@ -128,6 +128,20 @@ def element_geometry(nodes: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor]:
     return cent, box
 
 
+@torch.library.custom_op("multimesh::element_presolve", mutates_args=())
+def element_presolve(nodes: torch.Tensor) -> torch.Tensor:
+    """nodes [E,P,d] -> presolve [E, d + d*d] = (x(xi=0), inverse Jacobian at xi=0): the affine
+    pre-solve that lets K2 start Newton one step ahead (computed once per source mesh)."""
+    nodes = _need_cuda(nodes, "nodes", torch.float64)
+    E, P, d = nodes.shape
+    order = _order_dim(P, d)
+    with torch.cuda.device(nodes.device):
+        pre = torch.empty((E, d + d * d), dtype=torch.float64, device=nodes.device)
+        check(load_lib().mm_element_presolve(order, d, E, _ptr(nodes), _ptr(pre), _stream()),
+              "mm_element_presolve")
+    return pre
+
+
 def map_to_sphere_(points: torch.Tensor, radius_1d: torch.Tensor, r_earth: float = 6371000.0):
     """In place; points [..., 3], radius_1d [...] (interpolator.py:1125-1144)."""
     p = _need_cuda(points, "points", torch.float64)
@@ -214,8 +228,8 @@ class GridIndex:
 # K2
 # ----------------------------------------------------------------------------------------------
 @torch.library.custom_op("multimesh::locate", mutates_args=())
-def _locate_op(nodes: torch.Tensor, centroid: torch.Tensor, aabb: torch.Tensor, pts: torch.Tensor,
-               cands: torch.Tensor, aabb_prefilter: bool, tol: float, strict: bool, fallback: int,
+def _locate_op(nodes: torch.Tensor, centroid: torch.Tensor, aabb: torch.Tensor, presolve: torch.Tensor,
+               pts: torch.Tensor, cands: torch.Tensor, aabb_prefilter: bool, tol: float, strict: bool, fallback: int,
                snap_clip: float, m0: float, m1: float, m2: float
                ) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor, torch.Tensor]:
     nodes = _need_cuda(nodes, "nodes", torch.float64)
@@ -223,6 +237,7 @@ def _locate_op(nodes: torch.Tensor, centroid: torch.Tensor, aabb: torch.Tensor, 
     cands = _need_cuda(cands, "cands", torch.int32)
     centroid = _need_cuda(centroid, "centroid", torch.float64)
     aabb = _need_cuda(aabb, "aabb", torch.float64)
+    pre = _need_cuda(presolve, "presolve", torch.float64) if presolve.numel() else None
     E, P, d = nodes.shape
     order = _order_dim(P, d)
     N, k = cands.shape
@@ -235,15 +250,21 @@ def _locate_op(nodes: torch.Tensor, centroid: torch.Tensor, aabb: torch.Tensor, 
         xi = torch.empty((N, d), dtype=torch.float64, device=dev)
         status = torch.empty((N,), dtype=torch.uint8, device=dev)
         nfail = torch.zeros((1,), dtype=torch.int64, device=dev)
-        check(load_lib().mm_locate(order, d, E, _ptr(nodes), _ptr(centroid), _ptr(aabb), N,
+        check(load_lib().mm_locate(order, d, E, _ptr(nodes), _ptr(centroid), _ptr(aabb), _ptr(pre), N,
                                    _ptr(pts), k, _ptr(cands), C.byref(prm), _ptr(elem), _ptr(xi),
                                    _ptr(status), _ptr(nfail), _stream()), "mm_locate")
     return elem, xi, status, nfail
 
 
-def locate(nodes, centroid, aabb, pts, cands, spec: LocateSpec):
-    """-> (elem [N] i32, xi [N,d] f64, status [N] u8, num_failed [1] i64 on device)."""
-    return _locate_op(nodes, centroid, aabb, pts, cands, spec.aabb_prefilter, spec.tol,
+def _no_tensor(like):
+    return torch.empty((0,), dtype=torch.float64, device=like.device)
+
+
+def locate(nodes, centroid, aabb, pts, cands, spec: LocateSpec, presolve=None):
+    """-> (elem [N] i32, xi [N,d] f64, status [N] u8, num_failed [1] i64 on device).
+    `presolve` (element_presolve) makes Newton start from the affine pre-solve instead of xi = 0."""
+    return _locate_op(nodes, centroid, aabb, _no_tensor(nodes) if presolve is None else presolve, pts, cands,
+                      spec.aabb_prefilter, spec.tol,
                       spec.strict, spec.fallback, spec.snap_clip, *spec.magic_xi)
 
 
@@ -367,7 +388,7 @@ def gather_nodal(param: torch.Tensor, enclosing: torch.Tensor, weights: torch.Te
 # ----------------------------------------------------------------------------------------------
 @torch.library.custom_op("multimesh::interpolate", mutates_args=())
 def _interpolate_op(handle: int, divisor: int, nodes: torch.Tensor, centroid: torch.Tensor,
-                    aabb: torch.Tensor, fields: torch.Tensor, pts: torch.Tensor, k: int,
+                    aabb: torch.Tensor, presolve: torch.Tensor, fields: torch.Tensor, pts: torch.Tensor, k: int,
                     aabb_prefilter: bool, tol: float, strict: bool, fallback: int, snap_clip: float,
                     m0: float, m1: float, m2: float, want_location: bool
                     ) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor, torch.Tensor, torch.Tensor]:
@@ -375,6 +396,7 @@ def _interpolate_op(handle: int, divisor: int, nodes: torch.Tensor, centroid: to
     centroid = _need_cuda(centroid, "centroid", torch.float64)
     aabb = _need_cuda(aabb, "aabb", torch.float64)
     pts = _need_cuda(pts, "pts", torch.float64)
+    pre = _need_cuda(presolve, "presolve", torch.float64) if presolve.numel() else None
     E, P, d = nodes.shape
     order = _order_dim(P, d)
     N = pts.shape[0]
@@ -402,7 +424,7 @@ def _interpolate_op(handle: int, divisor: int, nodes: torch.Tensor, centroid: to
             xi = torch.empty((0, d), dtype=torch.float64, device=dev)
             status = torch.empty((0,), dtype=torch.uint8, device=dev)
         check(lib.mm_interpolate(C.c_void_p(handle), divisor, order, d, E, _ptr(nodes), _ptr(centroid),
-                                 _ptr(aabb), F, _ptr(fields) if have_fields else None, N, _ptr(pts), k,
+                                 _ptr(aabb), _ptr(pre), F, _ptr(fields) if have_fields else None, N, _ptr(pts), k,
                                  C.byref(prm), _ptr(out) if have_fields else None,
                                  _ptr(elem) if want_location else None, _ptr(xi) if want_location else None,
                                  _ptr(status) if want_location else None, _ptr(nfail), _ptr(ws),
@@ -411,12 +433,13 @@ def _interpolate_op(handle: int, divisor: int, nodes: torch.Tensor, centroid: to
 
 
 def interpolate(index: "GridIndex", divisor: int, nodes, centroid, aabb, fields, pts, k: int,
-                spec: LocateSpec, want_location: bool = True):
+                spec: LocateSpec, want_location: bool = True, presolve=None):
     """Fused k-NN -> locate -> gather.  `fields` may be None (locate only).
     -> (out [N,F], elem [N], xi [N,d], status [N], num_failed [1]); identical to running
     GridIndex.query_idx, locate and interp one after the other."""
     if fields is None:
         fields = torch.empty((0, 0, 0), dtype=torch.float64, device=nodes.device)
-    return _interpolate_op(index._h, int(divisor), nodes, centroid, aabb, fields, pts, int(k),
+    return _interpolate_op(index._h, int(divisor), nodes, centroid, aabb,
+                           _no_tensor(nodes) if presolve is None else presolve, fields, pts, int(k),
                            spec.aabb_prefilter, spec.tol, spec.strict, spec.fallback, spec.snap_clip,
                            *spec.magic_xi, bool(want_location))

@@ -95,8 +95,12 @@ def lib():
     L.mmo_knn_bruteforce.argtypes = [C.c_longlong, C.c_int, _f64, C.c_longlong, _f64, C.c_int,
                                      _i32, C.c_void_p]
     L.mmo_locate.restype = C.c_longlong
-    L.mmo_locate.argtypes = [C.c_int, C.c_int, C.c_longlong, _f64, _f64, _f64, C.c_longlong, _f64,
-                             C.c_int, _i32, C.POINTER(LocateParams), _i32, _f64, _u8]
+    L.mmo_locate.argtypes = [C.c_int, C.c_int, C.c_longlong, _f64, _f64, _f64, C.c_void_p, C.c_longlong,
+                             _f64, C.c_int, _i32, C.POINTER(LocateParams), _i32, _f64, _u8]
+    L.mmo_presolve.restype = None
+    L.mmo_presolve.argtypes = [C.c_int, C.c_int, C.c_longlong, _f64, _f64]
+    L.mmo_inverse_map_pre.restype = C.c_int
+    L.mmo_inverse_map_pre.argtypes = [C.c_int, C.c_int, _f64, _f64, _f64, _f64, C.POINTER(C.c_int)]
     L.mmo_interp.restype = C.c_int
     L.mmo_interp.argtypes = [C.c_int, C.c_int, C.c_longlong, C.c_int, _f64, C.c_longlong, _i32,
                              _f64, _f64]
@@ -239,7 +243,19 @@ def knn_ckdtree_canonical(data, pts, k, pad=64, workers=-1):
     return out
 
 
-def locate(order, dim, nodes, pts, cands, prm, cent=None, box=None):
+def presolve(nodes):
+    """Affine pre-solve per element: [E, d + d*d] = (x(0), Jinv(0)); K0 output."""
+    nodes = _c(nodes, np.float64)
+    E, P, d = nodes.shape
+    order = round(P ** (1.0 / d)) - 1
+    out = np.zeros((E, d + d * d))
+    lib().mmo_presolve(order, d, E, nodes, out)
+    return out
+
+
+def locate(order, dim, nodes, pts, cands, prm, cent=None, box=None, pre=True):
+    """pre=True: start Newton from the affine pre-solve (what the drivers / pipeline do);
+    pre=False: start from xi = 0; or pass a presolve array."""
     nodes = _c(nodes, np.float64)
     pts = _c(pts, np.float64).reshape(-1, dim)
     cands = _c(cands, np.int32)
@@ -252,7 +268,10 @@ def locate(order, dim, nodes, pts, cands, prm, cent=None, box=None):
     elem = np.zeros(N, dtype=np.int32)
     xi = np.zeros((N, dim))
     status = np.zeros(N, dtype=np.uint8)
-    nfailed = lib().mmo_locate(order, dim, E, nodes, _c(cent, np.float64), _c(box, np.float64), N,
+    if pre is True:
+        pre = presolve(nodes)
+    prep = None if pre is False or pre is None else _c(pre, np.float64).ctypes.data_as(C.c_void_p)
+    nfailed = lib().mmo_locate(order, dim, E, nodes, _c(cent, np.float64), _c(box, np.float64), prep, N,
                                pts, k, cands, C.byref(prm), elem, xi, status)
     assert nfailed >= 0
     return elem, xi, status, int(nfailed)

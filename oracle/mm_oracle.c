@@ -257,6 +257,51 @@ int mmo_forward_map(int order, int dim, const double *nodes, const double *xi, d
 }
 
 /*
+ * Affine pre-solve per element (p-independent, computed once per source mesh, K0):
+ *   pre[e] = { x0[dim], Jinv[dim][dim] },  x0 = x(xi = 0),  Jinv = inverse of J(xi = 0)
+ * evaluated on the UNSHIFTED nodes with the same nested order; Jinv[s][c] = cofactor / det.
+ */
+void mmo_presolve(int order, int dim, long long E, const double *nodes, double *pre)
+{
+    basis_t b;
+    if (!basis_init(&b, order)) return;
+    int P = dim == 2 ? b.m * b.m : b.m * b.m * b.m;
+    int W = dim + dim * dim;
+#pragma omp parallel for schedule(static)
+    for (long long e = 0; e < E; ++e) {
+        double xi0[3] = {0, 0, 0}, x[3], J[3][3];
+        double Y[MMO_MAXM * MMO_MAXM * MMO_MAXM * 3];
+        for (int a = 0; a < P * dim; ++a) Y[a] = nodes[(size_t)e * P * dim + a] - 0.0;
+        eval_map(&b, dim, Y, xi0, x, J);
+        double *o = pre + (size_t)e * W;
+        for (int c = 0; c < dim; ++c) o[c] = x[c];
+        double *I = o + dim;
+        if (dim == 2) {
+            double det = J[0][0] * J[1][1] - J[0][1] * J[1][0];
+            I[0] = J[1][1] / det;
+            I[1] = (-J[0][1]) / det;
+            I[2] = (-J[1][0]) / det;
+            I[3] = J[0][0] / det;
+        } else {
+            double C00 = J[1][1] * J[2][2] - J[1][2] * J[2][1];
+            double C01 = J[1][2] * J[2][0] - J[1][0] * J[2][2];
+            double C02 = J[1][0] * J[2][1] - J[1][1] * J[2][0];
+            double C10 = J[0][2] * J[2][1] - J[0][1] * J[2][2];
+            double C11 = J[0][0] * J[2][2] - J[0][2] * J[2][0];
+            double C12 = J[0][1] * J[2][0] - J[0][0] * J[2][1];
+            double C20 = J[0][1] * J[1][2] - J[0][2] * J[1][1];
+            double C21 = J[0][2] * J[1][0] - J[0][0] * J[1][2];
+            double C22 = J[0][0] * J[1][1] - J[0][1] * J[1][0];
+            double det = (J[0][0] * C00 + J[0][1] * C01) + J[0][2] * C02;
+            /* delta_s = sum_c Jinv[s][c] r_c,  Jinv[s][c] = C[c][s] / det */
+            I[0] = C00 / det; I[1] = C10 / det; I[2] = C20 / det;
+            I[3] = C01 / det; I[4] = C11 / det; I[5] = C21 / det;
+            I[6] = C02 / det; I[7] = C12 / det; I[8] = C22 / det;
+        }
+    }
+}
+
+/*
  * Newton inverse of the isoparametric map.  Structure follows
  * inverseCoordinateTransform (trilinearinterpolator.c:260-305): start at xi = 0,
  * <= 50 iterations, update = J^-1 (p - x(xi)) through an explicit cofactor inverse
@@ -271,7 +316,7 @@ int mmo_forward_map(int order, int dim, const double *nodes, const double *xi, d
  * Returns 1 if converged (xi valid), 0 otherwise.
  */
 static int newton_inverse(const basis_t *b, int dim, const double *nodes, const double *p,
-                          double *xi, int *iters)
+                          const double *pre, double *xi, int *iters)
 {
     double Y[MMO_MAXM * MMO_MAXM * MMO_MAXM * 3];
     int m = b->m;
@@ -279,6 +324,23 @@ static int newton_inverse(const basis_t *b, int dim, const double *nodes, const 
     for (int a = 0; a < P; ++a)
         for (int c = 0; c < dim; ++c) Y[a * dim + c] = nodes[a * dim + c] - p[c];
     for (int c = 0; c < dim; ++c) xi[c] = 0.0;
+    if (pre) {
+        /* affine pre-solve (mmo_presolve): xi0 = Jinv0 (p - x0), the first Newton step from the
+           element centre with p-independent quantities; an exactly affine element then needs one
+           evaluation instead of two.  Falls back to xi0 = 0 when the pre-solve is unusable. */
+        double r[3], g[3];
+        int ok = 1;
+        for (int c = 0; c < dim; ++c) r[c] = p[c] - pre[c];
+        for (int s = 0; s < dim; ++s) {
+            const double *row = pre + dim + s * dim;
+            double v = row[0] * r[0] + row[1] * r[1];
+            if (dim == 3) v = v + row[2] * r[2];
+            g[s] = v;
+            if (!(fabs(v) <= MMO_NEWTON_DIVERGE)) ok = 0;
+        }
+        if (ok)
+            for (int c = 0; c < dim; ++c) xi[c] = g[c];
+    }
     for (int it = 0; it < MMO_NEWTON_MAXIT; ++it) {
         double x[3], J[3][3], delta[3];
         eval_map(b, dim, Y, xi, x, J);
@@ -323,7 +385,15 @@ int mmo_inverse_map(int order, int dim, const double *nodes, const double *p, do
 {
     basis_t b;
     if (!basis_init(&b, order) || (dim != 2 && dim != 3)) return -1;
-    return newton_inverse(&b, dim, nodes, p, xi, iters);
+    return newton_inverse(&b, dim, nodes, p, NULL, xi, iters);
+}
+
+int mmo_inverse_map_pre(int order, int dim, const double *nodes, const double *p, const double *pre,
+                        double *xi, int *iters)
+{
+    basis_t b;
+    if (!basis_init(&b, order) || (dim != 2 && dim != 3)) return -1;
+    return newton_inverse(&b, dim, nodes, p, pre, xi, iters);
 }
 
 /* ------------------------------------------------------------------------------------------
@@ -475,13 +545,15 @@ static int accept_xi(const mmo_locate_params *prm, int dim, const double *xi)
  * Returns the number of points with elem = -1.
  */
 long long mmo_locate(int order, int dim, long long E, const double *nodes, const double *cent,
-                     const double *box, long long N, const double *pts, int k,
+                     const double *box, const double *pre /* may be NULL */, long long N,
+                     const double *pts, int k,
                      const int32_t *cands, const mmo_locate_params *prm, int32_t *elem_out,
                      double *xi_out, uint8_t *status_out)
 {
     basis_t b;
     if (!basis_init(&b, order) || (dim != 2 && dim != 3)) return -1;
     int P = dim == 2 ? b.m * b.m : b.m * b.m * b.m;
+    int W = dim + dim * dim;
     long long nfailed = 0;
     (void)E;
 #pragma omp parallel for schedule(dynamic, 256) reduction(+ : nfailed)
@@ -522,7 +594,8 @@ long long mmo_locate(int order, int dim, long long E, const double *nodes, const
                 if (first_inside < 0) first_inside = e;
             }
             double x[3];
-            int ok = newton_inverse(&b, dim, nodes + (size_t)e * P * dim, p, x, NULL);
+            int ok = newton_inverse(&b, dim, nodes + (size_t)e * P * dim, p,
+                                    pre ? pre + (size_t)e * W : NULL, x, NULL);
             if (!ok) continue; /* "NaN" branch */
             if (prm->fallback == MMO_FB_SNAP || prm->fallback == MMO_FB_MINL1) {
                 double key = 0.0;
@@ -551,7 +624,8 @@ long long mmo_locate(int order, int dim, long long E, const double *nodes, const
                 } else if (near_elem >= 0) {
                     double x[3];
                     elem = near_elem;
-                    int ok = newton_inverse(&b, dim, nodes + (size_t)elem * P * dim, p, x, NULL);
+                    int ok = newton_inverse(&b, dim, nodes + (size_t)elem * P * dim, p,
+                                            pre ? pre + (size_t)elem * W : NULL, x, NULL);
                     int big = 0;
                     if (ok)
                         for (int c = 0; c < dim; ++c)

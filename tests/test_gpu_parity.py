@@ -140,15 +140,19 @@ def _variants(oracle):
     ]
 
 
-def _locate_both(cuda, oracle, nodes, pts, cands, spec, prm):
+def _locate_both(cuda, oracle, nodes, pts, cands, spec, prm, use_pre=True):
+    """use_pre: Newton starts from the affine pre-solve (K0) on both sides; else from xi = 0."""
     from multimesh_b200 import ops
 
     order = round(nodes.shape[1] ** (1.0 / nodes.shape[2])) - 1
     dim = nodes.shape[2]
     tn = _t(nodes, cuda)
     cent, box = ops.element_geometry(tn)
-    elem, xi, status, nfail = ops.locate(tn, cent, box, _t(pts, cuda), _t(cands, cuda), spec)
-    o_elem, o_xi, o_status, o_nfail = oracle.locate(order, dim, nodes, pts, cands, prm)
+    pre = ops.element_presolve(tn) if use_pre else None
+    if use_pre:
+        assert np.array_equal(pre.cpu().numpy(), oracle.presolve(nodes)), "presolve not bit-identical"
+    elem, xi, status, nfail = ops.locate(tn, cent, box, _t(pts, cuda), _t(cands, cuda), spec, presolve=pre)
+    o_elem, o_xi, o_status, o_nfail = oracle.locate(order, dim, nodes, pts, cands, prm, pre=use_pre)
     return (elem.cpu().numpy(), xi.cpu().numpy(), status.cpu().numpy(), int(nfail.item()),
             o_elem, o_xi, o_status, o_nfail)
 
@@ -163,13 +167,26 @@ def test_locate_all_variants(cuda, oracle, order, dim, n, warp):
     # inside points, points outside the mesh (fallbacks), and points exactly on nodes (ties)
     pts = np.concatenate([_targets(rng, dim, 1501, -0.08, 1.08), nodes.reshape(-1, dim)[::5]])
     cands = oracle.knn_bruteforce(oracle.centroids(nodes), pts, 20)
-    for name, spec, prm in _variants(oracle):
-        elem, xi, st, nf, o_elem, o_xi, o_st, o_nf = _locate_both(cuda, oracle, nodes, pts, cands, spec, prm)
-        assert np.array_equal(elem, o_elem), name          # ownership: bit-exact
-        assert np.array_equal(st, o_st), name
-        assert nf == o_nf == int((o_elem < 0).sum()), name
-        assert np.max(np.abs(xi - o_xi), initial=0.0) <= XI_ATOL, name
-        assert np.array_equal(xi, o_xi), f"{name}: xi not bit-identical"
+    ref_xi = {}
+    for use_pre in (True, False):
+        for name, spec, prm in _variants(oracle):
+            elem, xi, st, nf, o_elem, o_xi, o_st, o_nf = _locate_both(cuda, oracle, nodes, pts, cands, spec, prm,
+                                                                      use_pre)
+            assert np.array_equal(elem, o_elem), name          # ownership: bit-exact
+            assert np.array_equal(st, o_st), name
+            assert nf == o_nf == int((o_elem < 0).sum()), name
+            assert np.max(np.abs(xi - o_xi), initial=0.0) <= XI_ATOL, name
+            assert np.array_equal(xi, o_xi), f"{name}: xi not bit-identical"
+            if use_pre:
+                ref_xi[name] = (elem, xi, st)
+            else:
+                # the two Newton starts agree on ownership and to roundoff on xi for every point
+                # accepted in the candidate loop (fallbacks that rank candidates by |xi| may
+                # legitimately flip on roundoff-level ties)
+                acc = (st == 0) & (ref_xi[name][2] == 0)
+                assert acc.sum() > 0.5 * len(st), name
+                assert np.array_equal(ref_xi[name][0][acc], elem[acc]), name
+                assert np.max(np.abs(ref_xi[name][1][acc] - xi[acc]), initial=0.0) <= XI_ATOL, name
     # sanity: most points are accepted by the plain V2 search
     assert (o_elem >= 0).mean() > 0.5
 
@@ -266,7 +283,8 @@ def test_pipeline_polynomial_reproduction(cuda, oracle, order):
     tn = _t(nodes, cuda)
     cent, box = ops.element_geometry(tn)
     cands = ops.GridIndex(cent).query_idx(_t(pts, cuda), 20)
-    elem, xi, st, nf = ops.locate(tn, cent, box, _t(pts, cuda), cands, ops.V1())
+    elem, xi, st, nf = ops.locate(tn, cent, box, _t(pts, cuda), cands, ops.V1(),
+                                  presolve=ops.element_presolve(tn))
     out = ops.interp(_t(fields, cuda), elem, xi).cpu().numpy()[:, 0]
     exact, _ = meshgen.polynomial_field(pts[None, :, :], order, rng) if False else (None, None)
     exact = np.zeros(len(pts))
@@ -288,7 +306,8 @@ def test_pipeline_identity_mesh(cuda, oracle):
     tn = _t(nodes, cuda)
     cent, box = ops.element_geometry(tn)
     cands = ops.GridIndex(cent).query_idx(_t(pts, cuda), 20)
-    elem, xi, st, nf = ops.locate(tn, cent, box, _t(pts, cuda), cands, ops.V1())
+    elem, xi, st, nf = ops.locate(tn, cent, box, _t(pts, cuda), cands, ops.V1(),
+                                  presolve=ops.element_presolve(tn))
     out = ops.interp(_t(fields, cuda), elem, xi).cpu().numpy()
     want = np.swapaxes(fields, 1, 2).reshape(-1, len(names))
     assert np.max(np.abs(out - want) / np.abs(want)) < VAL_RTOL
@@ -422,6 +441,7 @@ def test_fused_pipeline_equals_separate_kernels(cuda, oracle, order, dim, form):
     pts = np.concatenate([_targets(rng, dim, 3001, -0.1, 1.1), nodes.reshape(-1, dim)[::7]])
     tn, tf, tp = _t(nodes, cuda), _t(fields, cuda), _t(pts, cuda)
     cent, box = ops.element_geometry(tn)
+    pre = ops.element_presolve(tn)
     if form == "gll":
         index, div = ops.GridIndex(tn.view(E * P, dim)), P
         data = nodes.reshape(-1, dim)
@@ -431,8 +451,10 @@ def test_fused_pipeline_equals_separate_kernels(cuda, oracle, order, dim, form):
     for k in (20, 6):
         cands = (oracle.knn_bruteforce(data, pts, k) // div).astype(np.int32)
         for name, spec, prm in _variants(oracle):
-            out, elem, xi, st, nf = ops.interpolate(index, div, tn, cent, box, tf, tp, k, spec)
-            o_elem, o_xi, o_st, o_nf = oracle.locate(order, dim, nodes, pts, cands, prm)
+            use_pre = name not in ("V3", "V5")  # exercise both Newton starts
+            out, elem, xi, st, nf = ops.interpolate(index, div, tn, cent, box, tf, tp, k, spec,
+                                                    presolve=pre if use_pre else None)
+            o_elem, o_xi, o_st, o_nf = oracle.locate(order, dim, nodes, pts, cands, prm, pre=use_pre)
             assert np.array_equal(elem.cpu().numpy(), o_elem), (name, k)
             assert np.array_equal(st.cpu().numpy(), o_st), (name, k)
             assert np.array_equal(xi.cpu().numpy(), o_xi), (name, k)
