@@ -65,7 +65,7 @@ def test_argument_validation_without_device(lib):
     prm = _lib.LocateParams()
     rc = lib.mm_interp(3, 3, 1, 1, None, 1, None, None, None, None)  # order 3 unsupported
     assert rc == -1 and b"order" in lib.mm_last_error()
-    rc = lib.mm_locate(2, 5, 1, None, None, None, 1, None, 20, None, C.byref(prm), None, None, None, None, None)
+    rc = lib.mm_locate(2, 5, 1, None, None, None, None, 1, None, 20, None, C.byref(prm), None, None, None, None, None)
     assert rc == -1 and b"dim" in lib.mm_last_error()
     h = C.c_void_p()
     rc = lib.mm_index_create(C.byref(h), 7, 10, None, None)
