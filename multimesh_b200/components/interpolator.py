@@ -283,7 +283,25 @@ def interpolate_to_points(mesh, points, params_to_interp, make_spherical=False):
     return vals.cpu().numpy()
 
 
-def _layer_setup(from_gll, to_gll, layers, parameters, make_spherical):
+def _all_points(points, layers=None, mesh=None):
+    """Stand-in for utils.get_unique_points when the de-duplicated point list itself is not
+    needed (no stored interpolation matrices): every GLL node is interpolated directly -- the
+    result of a point is a pure function of the point, so duplicates simply get identical values --
+    which on the GPU is cheaper than the lexicographic np.unique of 1e7-1e8 rows."""
+    if mesh is None:
+        allp = points.reshape(points.shape[0] * points.shape[1], points.shape[2])
+        return allp, np.arange(allp.shape[0])
+    layers, _ = utils._assess_layers(mesh=mesh, layers=layers)
+    mask, _ = utils._create_mask(mesh=mesh, layers=layers)
+    out = {}
+    for layer in layers:
+        nodes = mesh.get_element_nodes()[mask[str(layer)]]
+        allp = nodes.reshape(nodes.shape[0] * nodes.shape[1], nodes.shape[2])
+        out[str(layer)] = (allp, np.arange(allp.shape[0]))
+    return out, mask, layers
+
+
+def _layer_setup(from_gll, to_gll, layers, parameters, make_spherical, dedup=True):
     print("Initialization stage")
     original_mesh = _as_salvus_mesh(from_gll)
     if make_spherical:
@@ -294,7 +312,10 @@ def _layer_setup(from_gll, to_gll, layers, parameters, make_spherical):
     new_mesh = _as_salvus_mesh(to_gll)
     if make_spherical:
         map_to_sphere(new_mesh)
-    unique_new_points, mask, layers = utils.get_unique_points(points=new_mesh, mesh=True, layers=layers)
+    if dedup:
+        unique_new_points, mask, layers = utils.get_unique_points(points=new_mesh, mesh=True, layers=layers)
+    else:
+        unique_new_points, mask, layers = _all_points(None, layers=layers, mesh=new_mesh)
     parameters = utils.pick_parameters(parameters)
     return original_mesh, original_mask, new_mesh, unique_new_points, mask, layers, parameters
 
@@ -358,7 +379,8 @@ def _layered_write_back(original_mesh, original_mask, new_mesh, unique_new_point
 def _gll_2_gll_layered_impl(from_gll, to_gll, layers, nelem_to_search, parameters, stored_array, make_spherical,
                             spec):
     (original_mesh, original_mask, new_mesh, unique_new_points, mask, layers,
-     parameters) = _layer_setup(from_gll, to_gll, layers, parameters, make_spherical)
+     parameters) = _layer_setup(from_gll, to_gll, layers, parameters, make_spherical,
+                                dedup=stored_array is not None)
     order = original_mesh.shape_order
     keys = list(unique_new_points.keys())
     cached = _load_interp_info(stored_array, keys)
@@ -448,7 +470,10 @@ def gll_2_gll(from_gll, to_gll, nelem_to_search=20, parameters="ISO", from_model
             assert not np.isnan(coeffs).any(), "Stored coeffs matrix has NaNs"
             print("Matrix was already stored. Will use that one")
 
-        unique_new_points, recon = utils.get_unique_points(points=new_points)
+        if stored_array:  # the stored matrices are defined on the unique points (:744, :797-810)
+            unique_new_points, recon = utils.get_unique_points(points=new_points)
+        else:
+            unique_new_points, recon = _all_points(new_points)
         if element is None:
             print("Now we start interpolating")
             pts = _dev_f64(unique_new_points, src.device)
