@@ -133,7 +133,7 @@ class ClockSampler:
         try:
             self.p = subprocess.Popen(
                 ["nvidia-smi", f"--id={self.gpu}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                 "-lms", "100"], stdout=self.f, stderr=subprocess.DEVNULL)
+                 "-lms", "20"], stdout=self.f, stderr=subprocess.DEVNULL)
         except Exception:
             self.p = None
 
@@ -430,9 +430,11 @@ def run_ours(args, w):
                 "unit": "GB/s", "frac": kernels[dom]["frac"], "traffic": kernels[dom]["traffic"],
                 "peak_source": peak_src, "graded_kernel_K3": kernels["K3_interp"],
                 "note": "achieved = SURVEY 8d no-reuse algorithmic bytes x points of one launch / CUDA-event "
-                        "duration of that kernel inside the timed step; K2/K3 serve most bytes from L2/shared "
-                        "memory (points are processed in spatial order, one copy per distinct element per warp), "
-                        "so their algorithmic rate may exceed the HBM peak -- `traffic` is the DRAM bytes ncu saw"}
+                        "duration of that kernel inside the timed step. K1 (k-NN) moves only 56 algorithmic B/point "
+                        "and is instruction-issue bound (69 % issue-active, ncu), so its HBM fraction is small by "
+                        "construction; K2/K3 serve most bytes from L2/shared memory (points are processed in spatial "
+                        "order, one copy per distinct element per warp) and are fp64-pipe bound (52-61 % active), so "
+                        "their algorithmic rate may exceed the HBM peak -- `traffic` is the DRAM bytes ncu saw"}
 
     # ---- CPU baseline, rank 0, N = 1 only -------------------------------------------------------
     cpu = None

@@ -46,6 +46,12 @@ int mm_locate_impl(int order, int dim, int64_t E, const double *nodes, const dou
                    const mm_locate_params *params, int32_t *elem, double *xi, uint8_t *status,
                    int64_t *num_failed, bool zero_num_failed, int32_t *unresolved_list,
                    int64_t *unresolved_count, void *stream);
+int mm_interpolate_impl(const mm_index_t *index, int32_t divisor, int order, int dim, int64_t E,
+                        const double *nodes, const double *centroid, const double *aabb,
+                        const double *presolve, int F, const double *fields, int64_t N,
+                        const double *pts, int k, const mm_locate_params *params, double *out,
+                        int32_t *elem, double *xi, uint8_t *status, int64_t *num_failed,
+                        void *workspace, size_t workspace_bytes, void *stream, void *fields_ready);
 int mm_interp_fused(int order, int dim, int64_t E, int F, const double *fields, int64_t N,
                     const int32_t *elem_s, const double *xi_s, const uint8_t *status_s,
                     const int32_t *perm, double *out, int32_t *elem_u, double *xi_u,

@@ -34,15 +34,16 @@ struct buf_t {
 struct host_pool {
     int device = -1;
     cudaStream_t main = nullptr, copy = nullptr;
-    cudaEvent_t copied = nullptr;
+    cudaEvent_t copied = nullptr, fields_copied = nullptr;
     buf_t nodes, fields, pts, cent, aabb, pre, elem, xi, out, nf, ws;
     void release()
     {
         for (buf_t *b : {&nodes, &fields, &pts, &cent, &aabb, &pre, &elem, &xi, &out, &nf, &ws}) b->release();
         if (copied) cudaEventDestroy(copied);
+        if (fields_copied) cudaEventDestroy(fields_copied);
         if (main) cudaStreamDestroy(main);
         if (copy) cudaStreamDestroy(copy);
-        copied = nullptr;
+        copied = fields_copied = nullptr;
         main = copy = nullptr;
         device = -1;
     }
@@ -91,6 +92,7 @@ extern "C" int mm_interpolate_host(int order, int dim, int64_t E, const double *
         MM_CUDA(cudaStreamCreateWithFlags(&pl.main, cudaStreamNonBlocking));
         MM_CUDA(cudaStreamCreateWithFlags(&pl.copy, cudaStreamNonBlocking));
         MM_CUDA(cudaEventCreateWithFlags(&pl.copied, cudaEventDisableTiming));
+        MM_CUDA(cudaEventCreateWithFlags(&pl.fields_copied, cudaEventDisableTiming));
         pl.device = dev;
     }
     MM_CUDA(pl.nodes.ensure(sizeof(double) * E * P * dim));
@@ -107,8 +109,9 @@ extern "C" int mm_interpolate_host(int order, int dim, int64_t E, const double *
     // main stream: nodes -> geometry -> index;   copy stream: target points, field blocks
     MM_CUDA(cudaMemcpyAsync(pl.nodes.p, nodes, sizeof(double) * E * P * dim, cudaMemcpyHostToDevice, pl.main));
     MM_CUDA(cudaMemcpyAsync(pl.pts.p, pts, sizeof(double) * N * dim, cudaMemcpyHostToDevice, pl.copy));
+    MM_CUDA(cudaEventRecord(pl.copied, pl.copy));  // target points on the device
     MM_CUDA(cudaMemcpyAsync(pl.fields.p, fields, sizeof(double) * E * F * P, cudaMemcpyHostToDevice, pl.copy));
-    MM_CUDA(cudaEventRecord(pl.copied, pl.copy));
+    MM_CUDA(cudaEventRecord(pl.fields_copied, pl.copy));  // only K3 needs the fields
     MM_TRY(mm_element_geometry(order, dim, E, pl.nodes.as<double>(), pl.cent.as<double>(),
                                pl.aabb.as<double>(), pl.main));
     MM_TRY(mm_element_presolve(order, dim, E, pl.nodes.as<double>(), pl.pre.as<double>(), pl.main));
@@ -120,12 +123,12 @@ extern "C" int mm_interpolate_host(int order, int dim, int64_t E, const double *
     const size_t ws_bytes = mm_interpolate_workspace_bytes(ih.ix, dim, N, k);
     MM_CUDA(pl.ws.ensure(ws_bytes));
     MM_CUDA(cudaStreamWaitEvent(pl.main, pl.copied, 0));
-    MM_TRY(mm_interpolate(ih.ix, gll_points_form ? P : 1, order, dim, E, pl.nodes.as<double>(),
+    MM_TRY(mm_interpolate_impl(ih.ix, gll_points_form ? P : 1, order, dim, E, pl.nodes.as<double>(),
                           pl.cent.as<double>(), pl.aabb.as<double>(), pl.pre.as<double>(), F,
                           pl.fields.as<double>(), N,
                           pl.pts.as<double>(), k, params, pl.out.as<double>(),
                           elem ? pl.elem.as<int32_t>() : nullptr, xi ? pl.xi.as<double>() : nullptr,
-                          nullptr, pl.nf.as<int64_t>(), pl.ws.p, pl.ws.cap, pl.main));
+                          nullptr, pl.nf.as<int64_t>(), pl.ws.p, pl.ws.cap, pl.main, pl.fields_copied));
     MM_CUDA(cudaMemcpyAsync(values, pl.out.p, sizeof(double) * N * F, cudaMemcpyDeviceToHost, pl.main));
     if (elem) MM_CUDA(cudaMemcpyAsync(elem, pl.elem.p, sizeof(int32_t) * N, cudaMemcpyDeviceToHost, pl.main));
     if (xi) MM_CUDA(cudaMemcpyAsync(xi, pl.xi.p, sizeof(double) * N * dim, cudaMemcpyDeviceToHost, pl.main));

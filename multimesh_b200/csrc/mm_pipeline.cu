@@ -126,14 +126,14 @@ extern "C" size_t mm_interpolate_workspace_bytes(const mm_index_t *index, int di
     return make_layout(index, dim, N, k).total;
 }
 
-extern "C" int mm_interpolate(const mm_index_t *index, int32_t divisor, int order, int dim,
-                              int64_t E, const double *nodes, const double *centroid,
-                              const double *aabb, const double *presolve, int F,
-                              const double *fields, int64_t N,
-                              const double *pts, int k, const mm_locate_params *params,
-                              double *out, int32_t *elem, double *xi, uint8_t *status,
-                              int64_t *num_failed, void *workspace, size_t workspace_bytes,
-                              void *stream_)
+// fields_ready: optional event the stream waits on right before K3 (the host entry point copies
+// the field blocks on a second stream while K1/K2 run)
+int mm_interpolate_impl(const mm_index_t *index, int32_t divisor, int order, int dim, int64_t E,
+                        const double *nodes, const double *centroid, const double *aabb,
+                        const double *presolve, int F, const double *fields, int64_t N,
+                        const double *pts, int k, const mm_locate_params *params, double *out,
+                        int32_t *elem, double *xi, uint8_t *status, int64_t *num_failed,
+                        void *workspace, size_t workspace_bytes, void *stream_, void *fields_ready)
 {
     cudaStream_t stream = (cudaStream_t)stream_;
     MM_REQUIRE(index && params, MM_ERR_INVALID, "mm_interpolate: null index/params");
@@ -219,6 +219,7 @@ extern "C" int mm_interpolate(const mm_index_t *index, int32_t divisor, int orde
     bool unpermuted = false;
     if (fields) {
         MM_REQUIRE(out, MM_ERR_INVALID, "mm_interpolate: null out");
+        if (fields_ready) MM_CUDA(cudaStreamWaitEvent(stream, (cudaEvent_t)fields_ready, 0));
         MM_TRY(mm_interp_fused(order, dim, E, F, fields, N, elem_s, xi_s, status_s, perm, out, elem, xi,
                                status, stream));
         unpermuted = elem != nullptr;
@@ -231,6 +232,19 @@ extern "C" int mm_interpolate(const mm_index_t *index, int32_t divisor, int orde
     }
     mark(6);
     return MM_OK;
+}
+
+extern "C" int mm_interpolate(const mm_index_t *index, int32_t divisor, int order, int dim,
+                              int64_t E, const double *nodes, const double *centroid,
+                              const double *aabb, const double *presolve, int F,
+                              const double *fields, int64_t N, const double *pts, int k,
+                              const mm_locate_params *params, double *out, int32_t *elem,
+                              double *xi, uint8_t *status, int64_t *num_failed, void *workspace,
+                              size_t workspace_bytes, void *stream)
+{
+    return mm_interpolate_impl(index, divisor, order, dim, E, nodes, centroid, aabb, presolve, F, fields,
+                               N, pts, k, params, out, elem, xi, status, num_failed, workspace,
+                               workspace_bytes, stream, nullptr);
 }
 
 extern "C" int mm_profile_create(mm_profile_t **out, int max_calls)
