@@ -51,10 +51,11 @@ const char *mm_last_error(void);
 int mm_element_geometry(int order, int dim, int64_t E, const double *nodes, double *centroid,
                         double *aabb, void *stream);
 
-/* Affine pre-solve per element (optional accelerator of K2): presolve [E][dim + dim*dim] f64 =
- * { x(xi=0)[dim], inverse Jacobian at xi=0 [dim][dim] }.  K2 then starts Newton at
- * xi0 = Jinv0 (p - x0) -- the first Newton step with point-independent quantities -- so an exactly
- * affine element needs one map evaluation instead of two.  Converged xi agree with the xi0 = 0
+/* Affine pre-solve per element (optional accelerator of K2): presolve [E][2*dim + dim*dim] f64 =
+ * { ref[dim] = first control node, x(xi=0) - ref [dim], inverse Jacobian at xi=0 [dim][dim] }, the
+ * last two evaluated on ref-shifted nodes.  K2 then starts Newton at xi0 = Jinv0 ((p - ref) - x0)
+ * -- the first Newton step with point-independent quantities -- so an exactly affine element needs
+ * one map evaluation instead of two.  Converged xi agree with the xi0 = 0
  * start to roundoff (1e-16); the CPU oracle implements the same start. */
 int mm_element_presolve(int order, int dim, int64_t E, const double *nodes, double *presolve,
                         void *stream);
@@ -129,7 +130,7 @@ typedef struct {
 /*   nodes    [E][P][dim]   source control nodes
  *   centroid [E][dim]      from mm_element_geometry (needed when aabb_prefilter)
  *   aabb     [E][2][dim]   from mm_element_geometry (needed when aabb_prefilter)
- *   presolve [E][dim+dim*dim] from mm_element_presolve, or NULL (Newton starts at xi = 0)
+ *   presolve [E][2*dim+dim*dim] from mm_element_presolve, or NULL (Newton starts at xi = 0)
  *   pts      [N][dim]
  *   cands    [N][k] int32  candidate element ids in neighbour order; negatives are skipped
  *   elem     [N] int32 (out), xi [N][dim] f64 (out), status [N] u8 (out, may be NULL)

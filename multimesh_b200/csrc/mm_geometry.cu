@@ -70,7 +70,8 @@ map_to_sphere_kernel(int64_t n, double *__restrict__ nodes, const double *__rest
     }
 }
 
-// affine pre-solve per element: pre[e] = {x(0), Jinv(0)} on the unshifted nodes (thread per element)
+// affine pre-solve per element: pre[e] = {ref, x(0) - ref, Jinv(0)}, ref = first node, evaluated on
+// the ref-shifted nodes (thread per element)
 template <int ORDER, int DIM>
 __global__ void __launch_bounds__(128)
 presolve_kernel(const mm_gll_table T, int64_t E, const double *__restrict__ nodes,
@@ -78,17 +79,24 @@ presolve_kernel(const mm_gll_table T, int64_t E, const double *__restrict__ node
 {
     constexpr int M = ORDER + 1;
     constexpr int P = DIM == 2 ? M * M : M * M * M;
-    constexpr int W = DIM + DIM * DIM;
+    constexpr int W = 2 * DIM + DIM * DIM;
     for (int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; e < E;
          e += (int64_t)gridDim.x * blockDim.x) {
-        double zero[DIM], xi0[DIM], x[DIM], J[DIM][DIM];
+        const double *X = nodes + e * (int64_t)(P * DIM);
+        double ref[DIM], xi0[DIM], x[DIM], J[DIM][DIM];
 #pragma unroll
-        for (int c = 0; c < DIM; ++c) zero[c] = xi0[c] = 0.0;
-        eval_map<ORDER, DIM>(T, nodes + e * (int64_t)(P * DIM), zero, xi0, x, J);
+        for (int c = 0; c < DIM; ++c) {
+            ref[c] = X[c];
+            xi0[c] = 0.0;
+        }
+        eval_map<ORDER, DIM>(T, X, ref, xi0, x, J);
         double *o = pre + e * W;
 #pragma unroll
-        for (int c = 0; c < DIM; ++c) o[c] = x[c];
-        double *I = o + DIM;
+        for (int c = 0; c < DIM; ++c) {
+            o[c] = ref[c];
+            o[DIM + c] = x[c];
+        }
+        double *I = o + 2 * DIM;
         if constexpr (DIM == 2) {
             double det = J[0][0] * J[1][1] - J[0][1] * J[1][0];
             I[0] = J[1][1] / det;

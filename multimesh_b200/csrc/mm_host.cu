@@ -100,7 +100,7 @@ extern "C" int mm_interpolate_host(int order, int dim, int64_t E, const double *
     MM_CUDA(pl.pts.ensure(sizeof(double) * N * dim));
     MM_CUDA(pl.cent.ensure(sizeof(double) * E * dim));
     MM_CUDA(pl.aabb.ensure(sizeof(double) * E * 2 * dim));
-    MM_CUDA(pl.pre.ensure(sizeof(double) * E * (dim + dim * dim)));
+    MM_CUDA(pl.pre.ensure(sizeof(double) * E * (2 * dim + dim * dim)));
     MM_CUDA(pl.out.ensure(sizeof(double) * N * F));
     MM_CUDA(pl.nf.ensure(sizeof(int64_t)));
     if (elem) MM_CUDA(pl.elem.ensure(sizeof(int32_t) * N));

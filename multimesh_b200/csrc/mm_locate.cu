@@ -220,7 +220,7 @@ locate_kernel(const mm_gll_table T, const mm_locate_params prm, int64_t E,
             if (served) {
                 double x[DIM];
                 const bool ok = newton_inverse<ORDER, DIM>(
-                    T, X, p, presolve ? presolve + (int64_t)e * (DIM + DIM * DIM) : nullptr, x);
+                    T, X, p, presolve ? presolve + (int64_t)e * (2 * DIM + DIM * DIM) : nullptr, x);
                 if (fb_newton) {  // V1: nearest-centre element, interpolator.py:1460-1473
                     bool big = false;
 #pragma unroll
@@ -348,6 +348,11 @@ int mm_locate_impl(int order, int dim, int64_t E, const double *nodes, const dou
                                             cands,                                                \
                                             elem, xi, status, num_failed, unresolved_list,       \
                                             unresolved_count, stream);
+    if (const char *v = getenv("MM_LOC_VARIANT")) {  // profiling only
+        if (atoi(v) == 1) { MM_LOC(4, 3, 2, 16, 1) MM_LOC(2, 3, 4, 16, 4) }
+        if (atoi(v) == 2) { MM_LOC(4, 3, 2, 12, 1) MM_LOC(2, 3, 4, 12, 4) }
+        if (atoi(v) == 3) { MM_LOC(4, 3, 3, 12, 1) }
+    }
     MM_LOC(1, 2, 4, 8, 1)
     MM_LOC(2, 2, 4, 8, 1)
     MM_LOC(4, 2, 4, 8, 1)

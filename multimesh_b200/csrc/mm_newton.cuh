@@ -95,9 +95,10 @@ __device__ __forceinline__ void eval_map(const mm_gll_table &T, const double *__
 }
 
 // Newton on the point-shifted nodes Y = X - p; true when max|delta| <= 1e-13.
-// Start: xi0 = Jinv0 (p - x0) from the element's affine pre-solve `pre` = {x0[DIM], Jinv[DIM][DIM]}
-// (K0, mm_element_presolve) -- an exactly affine element then needs one evaluation instead of
-// two -- or xi0 = 0 when `pre` is null or unusable.
+// Start: xi0 = Jinv0 ((p - ref) - x0) from the element's affine pre-solve
+// `pre` = {ref[DIM], x0[DIM], Jinv[DIM][DIM]} (K0, mm_element_presolve; ref = first control node,
+// x0 and Jinv evaluated on ref-shifted nodes) -- an exactly affine element then needs one
+// evaluation instead of two -- or xi0 = 0 when `pre` is null or unusable.
 template <int ORDER, int DIM>
 __device__ __forceinline__ bool newton_inverse(const mm_gll_table &T,
                                                const double *__restrict__ X,
@@ -110,10 +111,10 @@ __device__ __forceinline__ bool newton_inverse(const mm_gll_table &T,
         double r[DIM], g[DIM];
         bool ok = true;
 #pragma unroll
-        for (int c = 0; c < DIM; ++c) r[c] = p[c] - pre[c];
+        for (int c = 0; c < DIM; ++c) r[c] = (p[c] - pre[c]) - pre[DIM + c];
 #pragma unroll
         for (int s = 0; s < DIM; ++s) {
-            const double *row = pre + DIM + s * DIM;
+            const double *row = pre + 2 * DIM + s * DIM;
             double v = row[0] * r[0] + row[1] * r[1];
             if constexpr (DIM == 3) v = v + row[2] * r[2];
             g[s] = v;

@@ -130,13 +130,13 @@ def element_geometry(nodes: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor]:
 
 @torch.library.custom_op("multimesh::element_presolve", mutates_args=())
 def element_presolve(nodes: torch.Tensor) -> torch.Tensor:
-    """nodes [E,P,d] -> presolve [E, d + d*d] = (x(xi=0), inverse Jacobian at xi=0): the affine
-    pre-solve that lets K2 start Newton one step ahead (computed once per source mesh)."""
+    """nodes [E,P,d] -> presolve [E, 2d + d*d] = (first node, x(xi=0) - first node, inverse Jacobian
+    at xi=0): the affine pre-solve that lets K2 start Newton one step ahead (once per source mesh)."""
     nodes = _need_cuda(nodes, "nodes", torch.float64)
     E, P, d = nodes.shape
     order = _order_dim(P, d)
     with torch.cuda.device(nodes.device):
-        pre = torch.empty((E, d + d * d), dtype=torch.float64, device=nodes.device)
+        pre = torch.empty((E, 2 * d + d * d), dtype=torch.float64, device=nodes.device)
         check(load_lib().mm_element_presolve(order, d, E, _ptr(nodes), _ptr(pre), _stream()),
               "mm_element_presolve")
     return pre

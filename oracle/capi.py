@@ -244,11 +244,11 @@ def knn_ckdtree_canonical(data, pts, k, pad=64, workers=-1):
 
 
 def presolve(nodes):
-    """Affine pre-solve per element: [E, d + d*d] = (x(0), Jinv(0)); K0 output."""
+    """Affine pre-solve per element: [E, 2d + d*d] = (ref node, x(0) - ref, Jinv(0)); K0 output."""
     nodes = _c(nodes, np.float64)
     E, P, d = nodes.shape
     order = round(P ** (1.0 / d)) - 1
-    out = np.zeros((E, d + d * d))
+    out = np.zeros((E, 2 * d + d * d))
     lib().mmo_presolve(order, d, E, nodes, out)
     return out
 

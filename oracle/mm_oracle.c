@@ -258,24 +258,33 @@ int mmo_forward_map(int order, int dim, const double *nodes, const double *xi, d
 
 /*
  * Affine pre-solve per element (p-independent, computed once per source mesh, K0):
- *   pre[e] = { x0[dim], Jinv[dim][dim] },  x0 = x(xi = 0),  Jinv = inverse of J(xi = 0)
- * evaluated on the UNSHIFTED nodes with the same nested order; Jinv[s][c] = cofactor / det.
+ *   pre[e] = { ref[dim], x0[dim], Jinv[dim][dim] }
+ *   ref  = the element's first control node (an exact reference point),
+ *   x0   = x(xi = 0) - ref and Jinv = inverse of J(xi = 0), both evaluated on the nodes shifted
+ *          by ref with the same nested order (so roundoff scales with the element size, not with
+ *          the coordinate magnitude); Jinv[s][c] = cofactor / det.
+ * Newton then starts at xi0 = Jinv ((p - ref) - x0).
  */
 void mmo_presolve(int order, int dim, long long E, const double *nodes, double *pre)
 {
     basis_t b;
     if (!basis_init(&b, order)) return;
     int P = dim == 2 ? b.m * b.m : b.m * b.m * b.m;
-    int W = dim + dim * dim;
+    int W = 2 * dim + dim * dim;
 #pragma omp parallel for schedule(static)
     for (long long e = 0; e < E; ++e) {
         double xi0[3] = {0, 0, 0}, x[3], J[3][3];
         double Y[MMO_MAXM * MMO_MAXM * MMO_MAXM * 3];
-        for (int a = 0; a < P * dim; ++a) Y[a] = nodes[(size_t)e * P * dim + a] - 0.0;
+        const double *X = nodes + (size_t)e * P * dim;
+        for (int a = 0; a < P; ++a)
+            for (int c = 0; c < dim; ++c) Y[a * dim + c] = X[a * dim + c] - X[c];
         eval_map(&b, dim, Y, xi0, x, J);
         double *o = pre + (size_t)e * W;
-        for (int c = 0; c < dim; ++c) o[c] = x[c];
-        double *I = o + dim;
+        for (int c = 0; c < dim; ++c) {
+            o[c] = X[c];
+            o[dim + c] = x[c];
+        }
+        double *I = o + 2 * dim;
         if (dim == 2) {
             double det = J[0][0] * J[1][1] - J[0][1] * J[1][0];
             I[0] = J[1][1] / det;
@@ -330,9 +339,9 @@ static int newton_inverse(const basis_t *b, int dim, const double *nodes, const 
            evaluation instead of two.  Falls back to xi0 = 0 when the pre-solve is unusable. */
         double r[3], g[3];
         int ok = 1;
-        for (int c = 0; c < dim; ++c) r[c] = p[c] - pre[c];
+        for (int c = 0; c < dim; ++c) r[c] = (p[c] - pre[c]) - pre[dim + c];
         for (int s = 0; s < dim; ++s) {
-            const double *row = pre + dim + s * dim;
+            const double *row = pre + 2 * dim + s * dim;
             double v = row[0] * r[0] + row[1] * r[1];
             if (dim == 3) v = v + row[2] * r[2];
             g[s] = v;
@@ -553,7 +562,7 @@ long long mmo_locate(int order, int dim, long long E, const double *nodes, const
     basis_t b;
     if (!basis_init(&b, order) || (dim != 2 && dim != 3)) return -1;
     int P = dim == 2 ? b.m * b.m : b.m * b.m * b.m;
-    int W = dim + dim * dim;
+    int W = 2 * dim + dim * dim;
     long long nfailed = 0;
     (void)E;
 #pragma omp parallel for schedule(dynamic, 256) reduction(+ : nfailed)
