@@ -120,7 +120,9 @@ def make_targets(w, rank=0, crop=None):
 # clocks sampling during the timed region
 # ----------------------------------------------------------------------------------------------
 class ClockSampler:
-    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+    """nvidia-smi sampled in the background; samples are time-stamped and only those inside the
+    marked window(s) are used (nvidia-smi needs ~0.1-0.3 s to start, so it is started early)."""
+    Q = ("timestamp,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
          "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
@@ -128,6 +130,7 @@ class ClockSampler:
         self.gpu = gpu_index
         self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
         self.p = None
+        self.windows = []
 
     def start(self):
         try:
@@ -137,11 +140,16 @@ class ClockSampler:
         except Exception:
             self.p = None
 
+    def mark(self, t0, t1, label):
+        self.windows.append((t0, t1, label))
+
     def stop(self):
-        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        import datetime
+
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0, "window": None}
         if self.p is None:
             return out
-        time.sleep(0.15)
+        time.sleep(0.1)
         self.p.terminate()
         try:
             self.p.wait(timeout=5)
@@ -150,19 +158,22 @@ class ClockSampler:
         self.f.flush()
         rows = [r.strip().split(",") for r in open(self.f.name) if r.strip()]
         os.unlink(self.f.name)
-        sm, reasons, smmax = [], set(), None
+        parsed = []
         for r in rows:
             try:
-                sm.append(float(r[1]))
-                smmax = float(r[2])
-                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"),
-                                   r[5:9]):
-                    if v.strip().lower().startswith("active"):
-                        reasons.add(name)
+                ts = datetime.datetime.strptime(r[0].strip(), "%Y/%m/%d %H:%M:%S.%f").timestamp()
+                flags = [name for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown",
+                                                  "sw_power_cap"), r[5:9]) if v.strip().lower().startswith("active")]
+                parsed.append((ts, float(r[1]), float(r[2]), flags))
             except Exception:
                 continue
-        if sm:
-            out.update(sm_mhz=float(np.median(sm)), sm_max_mhz=smmax, reasons=sorted(reasons), samples=len(sm))
+        for (t0, t1, label) in self.windows:  # first window with enough samples wins
+            sel = [q for q in parsed if t0 - 0.02 <= q[0] <= t1 + 0.02]
+            if len(sel) >= 3 or label == self.windows[-1][2]:
+                if sel:
+                    out.update(sm_mhz=float(np.median([q[1] for q in sel])), sm_max_mhz=sel[0][2],
+                               reasons=sorted({f for q in sel for f in q[3]}), samples=len(sel), window=label)
+                break
         return out
 
 
@@ -303,6 +314,8 @@ def run_ours(args, w):
         return ops.interpolate(index, divisor, nodes, cent, box, fields, pts, k, spec, want_location=True,
                                presolve=presolve)
 
+    sampler = ClockSampler(local_rank)
+    sampler.start()
     for _ in range(max(args.warmup, 3)):
         res = step()
     torch.cuda.synchronize()
@@ -323,19 +336,28 @@ def run_ours(args, w):
     # ---- launching stream inside mm_interpolate (mm_profile_*), read after the final sync ----------
     prof = C.c_void_p()
     _lib.check(lib.mm_profile_create(C.byref(prof), args.steps), "mm_profile_create")
-    sampler = ClockSampler(local_rank)
     if world > 1:
         dist.barrier()
     torch.cuda.synchronize()
-    sampler.start()
     t_start, t_end = ev(), ev()
     lib.mm_profile_begin(prof)
+    w0 = time.time()
     t_start.record()
     for s in range(args.steps):
         step()
     t_end.record()
     torch.cuda.synchronize()
+    w1 = time.time()
     lib.mm_profile_end()
+    sampler.mark(w0, w1, "timed region")
+    if w1 - w0 < 0.25:
+        # the timed region is shorter than a few nvidia-smi periods: keep the same load running
+        # (untimed) so that the clock / throttle record has enough samples
+        x0 = time.time()
+        while time.time() - x0 < 0.4:
+            step()
+        torch.cuda.synchronize()
+        sampler.mark(w0, time.time(), "timed region + identical untimed load (region < 0.25 s)")
     if world > 1:
         dist.barrier()
     clocks = sampler.stop()

@@ -33,6 +33,7 @@ struct mm_index {
     int64_t nsites = 0;
     double4 *site_recs = nullptr;        // [nsites + 1] {x, y, z, first record of the site}
     int32_t *site_cell_start = nullptr;  // [ncells + 1] first site of each cell
+    cudaStream_t stream = nullptr;       // stream the buffers were allocated on (stream-ordered pool)
 };
 
 namespace {
@@ -621,10 +622,12 @@ void choose_dims(const double ext[3], int dim, double h, int n[3])
 extern "C" int mm_index_destroy(mm_index_t *ix)
 {
     if (!ix) return MM_OK;
-    if (ix->recs) cudaFreeAsync(ix->recs, nullptr);
-    if (ix->cell_start) cudaFreeAsync(ix->cell_start, nullptr);
-    if (ix->site_recs) cudaFreeAsync(ix->site_recs, nullptr);
-    if (ix->site_cell_start) cudaFreeAsync(ix->site_cell_start, nullptr);
+    // freed on the allocating stream so that the pool can hand the blocks straight back to the
+    // next build on that stream (a cross-stream free makes the pool grow instead)
+    if (ix->recs) cudaFreeAsync(ix->recs, ix->stream);
+    if (ix->cell_start) cudaFreeAsync(ix->cell_start, ix->stream);
+    if (ix->site_recs) cudaFreeAsync(ix->site_recs, ix->stream);
+    if (ix->site_cell_start) cudaFreeAsync(ix->site_cell_start, ix->stream);
     delete ix;
     return MM_OK;
 }
@@ -658,6 +661,7 @@ extern "C" int mm_index_create(mm_index_t **out, int dim, int64_t M, const doubl
     mm_index *ix = new mm_index();
     ix->dim = dim;
     ix->M = M;
+    ix->stream = stream;
     struct guard_t {
         mm_index *p;
         ~guard_t() { if (p) mm_index_destroy(p); }
