@@ -175,6 +175,16 @@ def inverse_map(order, dim, nodes, p):
     return bool(ok == 1), xi, it.value
 
 
+def inverse_map_presolved(order, dim, nodes, p):
+    """One element, Newton started from that element's affine pre-solve (the start mmo_locate uses)."""
+    nodes = _c(nodes, np.float64).reshape(1, -1, dim)
+    pre = presolve(nodes)
+    xi = np.zeros(dim)
+    it = C.c_int(0)
+    ok = lib().mmo_inverse_map_pre(order, dim, nodes, _c(p, np.float64), pre, xi, C.byref(it))
+    return bool(ok == 1), xi
+
+
 def centroids(nodes):
     nodes = _c(nodes, np.float64)
     E, P, d = nodes.shape

@@ -1,0 +1,238 @@
+"""
+Generates tests/golden/glue_*.npz by RUNNING THE REFERENCE'S OWN PYTHON (imported from
+/root/reference through tests/golden/refglue.py) on small seeded meshes:
+
+  glue_v1_*.npz      find_gll_coeffs -> _check_if_inside_element            interpolator.py:1540-1597, 1409-1473
+  glue_v2_*.npz      get_element_weights (tolerance, snap_to_nearest)       interpolator.py:1147-1255
+  glue_v3.npz        get_element_weights_layered                            interpolator.py:1258-1334
+  glue_v4.npz        v2_interpolation_tools.get_element_weights             v2_interpolation_tools.py:71-164
+  glue_v5.npz        scripts/cli.py _check_if_inside_element                cli.py:401-430
+  glue_points.npz    interpolate_to_points (centroid tree, V2, gather)      interpolator.py:931-977
+  glue_gll2gll.npz   gll_2_gll end to end (dedup, GLL-point tree // P, V1, gather, recon, fluid
+                     fix-up) on in-memory files                             interpolator.py:621-852
+
+What these pin: the reference's control flow (candidate order, accept predicates, AABB prefilter,
+fall-backs and their tie-breaks, -1 / zero-weight handling, de-duplication + reconstruction, the
+gather, the fluid/solid fix-up).  What they do NOT pin: the arithmetic inside salvus.fem (closed
+source) and pykdtree's tie order -- both are served by the oracle here, see refglue.py.
+
+Run in the build container:  OMP_NUM_THREADS=1 python tests/golden/make_golden_glue.py
+"""
+import os
+import sys
+
+os.environ.setdefault("OMP_NUM_THREADS", "1")  # the reference forks worker pools; keep libgomp single-threaded
+sys.dont_write_bytecode = True  # /root/reference is read-only
+
+import numpy as np  # noqa: E402
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+sys.path.insert(0, HERE)
+sys.path.insert(0, ROOT)
+
+import refglue  # noqa: E402
+
+interp, v2, ref_utils = refglue.load_reference()
+cli = refglue.load_reference_cli()
+
+from multimesh_b200 import meshgen  # noqa: E402  (after the reference: `multi_mesh` must be the reference's)
+from oracle import capi  # noqa: E402
+
+capi.set_num_threads(1)
+NAMES = ["QKAPPA", "QMU", "RHO", "VP", "VS"]
+SEEDS = {"case_v3": 301, "case_v4": 401, "case_v5": 501, "case_points": 601, "case_gll2gll": 701}
+
+
+def save(name, **kw):
+    path = os.path.join(HERE, name)
+    np.savez_compressed(path, **kw)
+    print(f"{name}: {os.path.getsize(path) / 1024:.0f} KiB")
+
+
+def targets(rng, nodes, n_random, stride, lo=-0.08, hi=1.08):
+    d = nodes.shape[2]
+    return np.concatenate([rng.uniform(lo, hi, (n_random, d)), nodes.reshape(-1, d)[::stride]])
+
+
+def run_v1(nodes, pts, cands):
+    """find_gll_coeffs exactly as gll_2_gll calls it (:790-799): [d,N] points, [k,N] candidates."""
+    N, P, d = len(pts), nodes.shape[1], nodes.shape[2]
+    order = round(P ** (1.0 / d)) - 1
+    element, coeffs = interp.find_gll_coeffs(
+        original_coordinates=nodes, coordinates=np.swapaxes(pts, 0, 1), nearest_elements=np.swapaxes(cands, 0, 1),
+        coeffs=np.zeros((1, P, N)), element=np.zeros(N), dimensions=d, from_gll_order=order,
+        ignore_hard_elements=True)
+    return element.astype(np.int64), np.ascontiguousarray(coeffs[0].T)
+
+
+def case_v1(tag, shape, order, warp, n_random, stride, seed):
+    rng = np.random.default_rng(seed)
+    nodes = meshgen.box_mesh(shape, order, warp=warp)
+    E, P, d = nodes.shape
+    pts = targets(rng, nodes, n_random, stride)
+    k = min(20, E)
+    cen = refglue.CanonicalKDTree(capi.centroids(nodes)).query(pts, k)[1]
+    gll = np.floor(refglue.CanonicalKDTree(nodes.reshape(-1, d)).query(pts, k)[1] / P).astype(int)  # :751-756
+    e1, c1 = run_v1(nodes, pts, cen)
+    e2, c2 = run_v1(nodes, pts, gll)
+    save(f"glue_v1_{tag}.npz", shape=np.array(shape), order=order, warp=warp, points=pts, k=k,
+         cands_centroid=cen.astype(np.int32), cands_gll=gll.astype(np.int32), elem_centroid=e1, coeffs_centroid=c1,
+         elem_gll=e2, coeffs_gll=c2)
+
+
+def case_v2(tag, shape, order, warp, n_random, stride, seed, tolerance):
+    rng = np.random.default_rng(seed)
+    nodes = meshgen.box_mesh(shape, order, warp=warp)
+    pts = targets(rng, nodes, n_random, stride, -0.15, 1.15)
+    tree = refglue.CanonicalKDTree(capi.centroids(nodes))
+    k = min(25, len(nodes))
+    out = {}
+    for snap in (False, True):
+        e, c = interp.get_element_weights(nodes, order, tree, pts, nelem_to_search=k, tolerance=tolerance,
+                                          snap_to_nearest=snap)
+        out[f"elem_snap{int(snap)}"] = np.asarray(e, dtype=np.int64)
+        out[f"coeffs_snap{int(snap)}"] = np.asarray(c, dtype=np.float64)
+    save(f"glue_v2_{tag}.npz", shape=np.array(shape), order=order, warp=warp, points=pts, k=k, tolerance=tolerance,
+         **out)
+
+
+class DuckMesh:
+    """The attributes the reference reads from a salvus UnstructuredMesh on these paths."""
+
+    def __init__(self, nodes, fields, names):
+        E, P, d = nodes.shape
+        self.points_flat = nodes.reshape(E * P, d)
+        self.connectivity = np.arange(E * P).reshape(E, P)
+        self.shape_order = round(P ** (1.0 / d)) - 1
+        self.element_nodal_fields = {n: fields[:, i, :] for i, n in enumerate(names)}
+        self.n_gll_points = P
+        self.points = self.points_flat
+
+    def get_element_centroid(self):
+        return np.mean(self.points[self.connectivity], axis=1)
+
+
+def case_v3(seed):
+    rng = np.random.default_rng(seed)
+    nodes = meshgen.box_mesh((4, 4, 6), 2, warp=0.03)
+    cz = capi.centroids(nodes)[:, 2]
+    layer_of = np.where(cz < 0.34, 2, np.where(cz < 0.67, 1, 0))
+    pts = targets(rng, nodes, 700, 9, -0.05, 1.05)
+    new_coordinates, nearest, mask = {}, {}, {}
+    for lay in (0, 1, 2):
+        m = layer_of == lay
+        lo, hi = {2: (-1, 0.34), 1: (0.30, 0.70), 0: (0.64, 2)}[lay]  # overlapping bands: some points miss their layer
+        sel = (pts[:, 2] >= lo) & (pts[:, 2] <= hi)
+        mask[str(lay)] = m
+        new_coordinates[str(lay)] = (pts[sel],)
+        nearest[str(lay)] = refglue.CanonicalKDTree(capi.centroids(nodes[m])).query(pts[sel], 20)[1]
+
+    class M:  # get_element_weights_layered indexes original_mesh.points[original_mask[layer]] (:1277)
+        points = nodes
+
+    elems, coeffs = interp.get_element_weights_layered(new_coordinates, nearest, M, mask, dimensions=3,
+                                                       from_gll_order=2)
+    out = {"shape": np.array((4, 4, 6)), "order": 2, "warp": 0.03, "layer_of": layer_of}
+    for lay in ("0", "1", "2"):
+        out[f"points_{lay}"] = new_coordinates[lay][0]
+        out[f"cands_{lay}"] = nearest[lay].astype(np.int32)
+        out[f"elem_{lay}"] = np.asarray(elems[lay], dtype=np.int64)
+        out[f"coeffs_{lay}"] = np.asarray(coeffs[lay], dtype=np.float64)
+    save("glue_v3.npz", **out)
+
+
+def case_v4(seed):
+    rng = np.random.default_rng(seed)
+    nodes = meshgen.box_mesh((5, 5, 4), 2, warp=0.03)
+    pts = targets(rng, nodes, 800, 11, -0.12, 1.12)
+    tree = refglue.CanonicalKDTree(capi.centroids(nodes))
+    e, c = v2.get_element_weights(nodes, tree, pts)
+    save("glue_v4.npz", shape=np.array((5, 5, 4)), order=2, warp=0.03, points=pts, k=25,
+         elem=np.asarray(e, dtype=np.int64), coeffs=np.asarray(c, dtype=np.float64))
+
+
+def case_v5(seed):
+    import contextlib
+    import io
+
+    rng = np.random.default_rng(seed)
+    nodes = meshgen.box_mesh((3, 3, 3), 4, warp=0.02)
+    out = {}
+    # k = 20: far candidates of outside points do not converge -> the reference accepts their NaN xi (cli.py:421,
+    # `not any(nan > 1.02)`); k = 3: every candidate converges, so the min-sum|xi| fall-back (:424-428) is reached.
+    for k, lo, hi in ((20, -0.1, 1.1), (3, -0.04, 1.04)):
+        pts = targets(rng, nodes, 300, 31, lo, hi)
+        cands = refglue.CanonicalKDTree(capi.centroids(nodes)).query(pts, k)[1]
+        elem = np.zeros(len(pts), dtype=np.int64)
+        xi = np.zeros((len(pts), 3))
+        with contextlib.redirect_stdout(io.StringIO()):
+            for i, p in enumerate(pts):
+                elem[i], xi[i] = cli._check_if_inside_element(nodes, cands[i], p)
+        out.update({f"points_k{k}": pts, f"cands_k{k}": cands.astype(np.int32), f"elem_k{k}": elem, f"xi_k{k}": xi})
+    save("glue_v5.npz", shape=np.array((3, 3, 3)), order=4, warp=0.02, **out)
+
+
+def case_points(seed):
+    rng = np.random.default_rng(seed)
+    nodes = meshgen.box_mesh((5, 4, 6), 2, warp=0.03)
+    fields = meshgen.analytic_fields(nodes, NAMES)
+    pts = targets(rng, nodes, 900, 13, -0.1, 1.1)
+    vals = interp.interpolate_to_points(DuckMesh(nodes, fields, NAMES), pts, NAMES)
+    save("glue_points.npz", shape=np.array((5, 4, 6)), order=2, warp=0.03, points=pts, names=np.array(NAMES),
+         values=vals)
+
+
+def case_gll2gll(seed):
+    rng = np.random.default_rng(seed)
+    src = meshgen.box_mesh((5, 4, 6), 2, warp=0.03)
+    tgt = meshgen.box_mesh((4, 5, 5), 2, warp=0.02)
+    fields = meshgen.analytic_fields(src, NAMES)
+    # a block of the source with VS == 0 (a "fluid" region) so the fake-fluid fix-up (:829-841) has work to do
+    cx = capi.centroids(src)[:, 0]
+    fields[cx < 0.25, NAMES.index("VS"), :] = 0.0
+    old = rng.uniform(1.0, 2.0, (tgt.shape[0], len(NAMES), tgt.shape[1]))
+    fluid = (capi.centroids(tgt)[:, 2] > 0.85).astype(np.float64)
+    edata = np.stack([fluid, np.arange(len(tgt), dtype=np.float64)], axis=1)
+    refglue.write_gll_file("from.h5", src, fields, NAMES)
+    refglue.write_gll_file("to.h5", tgt, old, NAMES, element_data=edata, element_labels=["fluid", "layer"])
+    # interpolator.py:814 indexes with the float `element` array find_gll_coeffs hands back (IndexError on every
+    # numpy >= 1.12 unless points failed and :803 cast it); apply that same cast so the driver can run.
+    original = interp.find_gll_coeffs
+
+    def find_gll_coeffs_int(**kw):
+        element, coeffs = original(**kw)
+        return element.astype(int), coeffs
+
+    interp.find_gll_coeffs = find_gll_coeffs_int
+    try:
+        interp.gll_2_gll("from.h5", "to.h5", nelem_to_search=20)
+    finally:
+        interp.find_gll_coeffs = original
+    out = refglue.FILES["to.h5"]["MODEL/data"].array
+    label = refglue.FILES["to.h5"]["MODEL/data"].dims[1].label
+    save("glue_gll2gll.npz", src_shape=np.array((5, 4, 6)), src_warp=0.03, tgt_shape=np.array((4, 5, 5)),
+         tgt_warp=0.02, order=2, names=np.array(NAMES), source_fields=fields, target_old=old, fluid=fluid,
+         values=out, label=np.array(label))
+
+
+def main():
+    if len(sys.argv) > 1:  # regenerate selected cases only, e.g. `make_golden_glue.py case_v5`
+        for name in sys.argv[1:]:
+            globals()[name](SEEDS[name])
+        return
+    case_v1("o2", (5, 4, 6), 2, 0.03, 500, 7, 101)
+    case_v1("o4", (3, 3, 2), 4, 0.02, 250, 23, 102)
+    case_v1("2d", (6, 5), 4, 0.03, 400, 5, 103)
+    case_v2("o2", (5, 4, 6), 2, 0.03, 700, 11, 201, 1.05)
+    case_v2("o4", (3, 2, 3), 4, 0.02, 250, 29, 202, 1.01)
+    case_v3(301)
+    case_v4(401)
+    case_v5(501)
+    case_points(601)
+    case_gll2gll(701)
+    print("reference calls served by the oracle arithmetic:", refglue.CALLS)
+
+
+if __name__ == "__main__":
+    main()
