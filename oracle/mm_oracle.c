@@ -18,6 +18,11 @@
  *     the published mathematics (tensor-product GLL Lagrange basis, Newton on the
  *     order-n isoparametric map) anchored on the reference's call sites, with a
  *     documented canonical operation order so that CPU and GPU agree bit for bit.
+ *   * location logic around that arithmetic (candidate loops V1-V5, fall-backs, layer
+ *     masks, de-duplication, gathers, fix-ups): PINNED against the reference's own Python,
+ *     run in the build container with salvus.fem's two functions served by this file
+ *     (tests/golden/make_golden_glue.py -> tests/golden/glue_*.npz, checked by
+ *     tests/test_golden_glue.py).
  *
  * CANONICAL ARITHMETIC (shared spec with the CUDA kernels)
  *   - all arithmetic IEEE-754 binary64, one rounding per operation, NO fused

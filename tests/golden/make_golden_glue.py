@@ -38,10 +38,12 @@ cli = refglue.load_reference_cli()
 
 from multimesh_b200 import meshgen  # noqa: E402  (after the reference: `multi_mesh` must be the reference's)
 from oracle import capi  # noqa: E402
+import glue_inputs  # noqa: E402
 
 capi.set_num_threads(1)
 NAMES = ["QKAPPA", "QMU", "RHO", "VP", "VS"]
-SEEDS = {"case_v3": 301, "case_v4": 401, "case_v5": 501, "case_points": 601, "case_gll2gll": 701}
+SEEDS = {"case_v3": 301, "case_v4": 401, "case_v5": 501, "case_points": 601, "case_gll2gll": 701, "case_layered": 801,
+         "case_query_model": 901, "case_exodus": 1001}
 
 
 def save(name, **kw):
@@ -216,6 +218,100 @@ def case_gll2gll(seed):
          values=out, label=np.array(label))
 
 
+def shell_files(order, seed, layers=None):
+    pair = glue_inputs.shell_pair(order, seed, layers)
+    for key, (coords, data, ed) in pair.items():
+        refglue.write_gll_file(f"shell_{key}.h5", coords, data, NAMES + ["z_node_1D"], element_data=ed,
+                               element_labels=["fluid", "layer"], global_strings={"moho_idx": "2"})
+
+
+STRIDE = {"layered": 1, "layered_o4": 5, "multi": 2, "multi_two": 2, "points_layered": 2}
+
+
+def case_layered(seed):
+    """gll_2_gll_layered (V1 per layer, :288-439), gll_2_gll_layered_multi (:442-618),
+    gll_2_gll_layered_multi_two (V2 snap, k=30, :980-1082), interpolate_to_points_layered (V3, :855-928)."""
+    import contextlib
+    import io
+
+    res = {}
+    runs = [("layered", 2, lambda: interp.gll_2_gll_layered("shell_from.h5", "shell_to.h5", layers=[1, 2, 3],
+                                                              parameters="ISO")),
+            ("layered_o4", 4, lambda: interp.gll_2_gll_layered("shell_from.h5", "shell_to.h5", layers="nocore",
+                                                                 parameters="ISO")),
+            ("multi", 2, lambda: interp.gll_2_gll_layered_multi("shell_from.h5", "shell_to.h5", layers=[1, 2, 3],
+                                                                 parameters=NAMES, threads=3)),
+            ("multi_two", 2, lambda: interp.gll_2_gll_layered_multi_two("shell_from.h5", "shell_to.h5",
+                                                                         layers=[1, 2, 3], parameters=NAMES)),
+            ("points_layered", 2, lambda: interp.interpolate_to_points_layered("shell_from.h5", "shell_to.h5", NAMES,
+                                                                                layers=[1, 2, 3]))]
+    for tag, order, run in runs:
+        shell_files(order, seed, glue_inputs.CORE_LAYERS if tag == "layered_o4" else None)
+        with contextlib.redirect_stdout(io.StringIO()):
+            run()
+        vals = refglue.FILES["shell_to.h5"]["MODEL/data"].array[:, :5, :]
+        res[f"{tag}_values"] = vals[::STRIDE[tag]].copy()  # every STRIDE-th target element (fixture size)
+        res[f"{tag}_order"] = order
+        res[f"{tag}_stride"] = STRIDE[tag]
+    save("glue_layered.npz", seed=seed, **res)
+
+
+def case_query_model(seed):
+    rng = np.random.default_rng(seed)
+    nodes = meshgen.box_mesh((5, 5, 5), 2, lo=[6.0e6, -2e5, -2e5], hi=[6.371e6, 2e5, 2e5], warp=0.01)
+    data = meshgen.analytic_fields(nodes, NAMES)
+    refglue.write_gll_file("model.h5", nodes, data, NAMES)
+    lld = np.stack([rng.uniform(-1.5, 1.5, 300), rng.uniform(-1.5, 1.5, 300), rng.uniform(1e3, 3.5e5, 300)], axis=1)
+    vals = interp.query_model(lld, "model.h5", 20, "MODEL/data", "MODEL/coordinates")
+    save("glue_query_model.npz", latlondepth=lld, values=vals)
+
+
+def case_exodus(seed):
+    """exodus_2_gll (reference Python + the reference's own compiled C, :142-224) and gll_2_exodus (V1, :227-285)."""
+    import contextlib
+    import io
+
+    from oracle import build as oracle_build
+
+    oracle_build.build_ref()
+    refglue.load_reference_exodus(interp)
+    names = ["VP", "VS", "RHO"]
+    points, conn = meshgen.hex8_mesh((8, 7, 6), warp=0.02)
+    nodal = {"VP": 2.0 + points[:, 0] + 2 * points[:, 1] + 3 * points[:, 2],
+             "VS": np.sin(points[:, 0]) * np.cos(points[:, 1]) + 2.0, "RHO": 2600 + 300 * points[:, 2] ** 2}
+    refglue.write_exodus_file("mesh.e", points, conn, nodal)
+    gll = meshgen.box_mesh((3, 3, 2), 4, lo=[0.04] * 3, hi=[0.95] * 3, warp=0.01)
+    f = refglue.write_gll_file("gll.h5", gll, np.zeros((len(gll), 3, 125)), names)
+    f["MODEL/data"].attrs["DIMENSION_LABELS"] = [b"element", ("[ " + " | ".join(names) + " ]").encode(), b"point"]
+    with contextlib.redirect_stdout(io.StringIO()):
+        interp.exodus_2_gll("mesh.e", "gll.h5", gll_order=4, parameters=names)
+    on_gll = refglue.FILES["gll.h5"]["MODEL/data"].array.copy()
+    # back onto exodus nodes inside the GLL mesh.  create_dimension_labels (utils.py:159-168) only sets the
+    # dimension-scale labels; real h5py then serves them through attrs["DIMENSION_LABELS"], the fake does not:
+    ds = refglue.FILES["gll.h5"]["MODEL/data"]
+    ds.attrs["DIMENSION_LABELS"] = [b"element", ds.dims[1].label.encode(), b"point"]
+    inside = np.all((points > 0.07) & (points < 0.92), axis=1)
+    refglue.write_exodus_file("back.e", points[inside], np.zeros((0, 8), dtype=np.int64),
+                              {n: np.zeros(int(inside.sum())) for n in names})
+    # gll_2_exodus calls _check_if_inside_element with four arguments (:274-276) although it takes five (:1409-1411):
+    # TypeError as shipped.  Supply the missing `ignore_hard_elements` with the value its other call sites use (True).
+    original = interp._check_if_inside_element
+
+    def with_default(gll_model, nearest_elements, point, dimension, ignore_hard_elements=True):
+        return original(gll_model, nearest_elements, point, dimension, ignore_hard_elements)
+
+    interp._check_if_inside_element = with_default
+    try:
+        with contextlib.redirect_stdout(io.StringIO()):
+            interp.gll_2_exodus("gll.h5", "back.e", gll_order=4)
+    finally:
+        interp._check_if_inside_element = original
+    back = np.stack([refglue.EXO["back.e"]["nodal"][n] for n in names], axis=1)
+    save("glue_exodus.npz", hex_shape=np.array((8, 7, 6)), hex_warp=0.02, gll_shape=np.array((3, 3, 2)),
+         gll_lo=0.04, gll_hi=0.95, gll_warp=0.01, names=np.array(names), on_gll=on_gll, inside=inside, back=back,
+         label=np.array(ds.dims[1].label))
+
+
 def main():
     if len(sys.argv) > 1:  # regenerate selected cases only, e.g. `make_golden_glue.py case_v5`
         for name in sys.argv[1:]:
@@ -231,6 +327,9 @@ def main():
     case_v5(501)
     case_points(601)
     case_gll2gll(701)
+    case_layered(801)
+    case_query_model(901)
+    case_exodus(1001)
     print("reference calls served by the oracle arithmetic:", refglue.CALLS)
 
 

@@ -15,7 +15,18 @@ Stand-ins (what is and is not pinned by the fixtures made with them):
   pykdtree.kdtree.KDTree    absent.  Exact k-NN served by the oracle's canonical brute force
                             ((d2, index) order; pykdtree's own tie order is unspecified).
   h5py                      absent.  A small in-memory File/Dataset model (paths -> numpy arrays).
-  pyexodus, xarray, geographiclib, salvus.mesh, salvus.flow: empty placeholders (never called).
+  pyexodus                  absent.  A small in-memory `exodus` file model (coords, 1-based connectivity,
+                            nodal variables) -- enough for the reference's own io/exodus.py reader.
+  multi_mesh*.so            the reference's C library: the reference's own helpers.load_lib() loads the
+                            build of its C sources made by oracle/build.py (oracle/_ref), LIB_DIR pointed there.
+                            The exodus drivers therefore run WITHOUT any oracle arithmetic: exodus_2_gll is
+                            reference Python + reference C end to end.
+  names the reference left undefined: interpolator.py:6-7 and io/exodus.py:4-6 comment out the imports of
+                            `load_lib`, `Exodus` and the module-level `lib`, and utils.py:200 uses `KDTree`
+                            without importing it, so exodus_2_gll / gll_2_exodus / load_exodus /
+                            Exodus.get_element_centroid raise NameError as shipped; load_reference_exodus()
+                            binds exactly those four names (the first three to the reference's own objects).
+  xarray, geographiclib, salvus.mesh, salvus.flow: empty placeholders (never called).
   numpy                     the reference predates numpy 1.24; `np.int` is aliased to int for the
                             duration of the calls.
 """
@@ -48,7 +59,7 @@ class FakeDataset:
         return self.array.shape
 
     def __getitem__(self, key):
-        return self.array[key]
+        return np.array(self.array[key])  # h5py hands out copies, never views of the file
 
     def __setitem__(self, key, value):
         self.array[key] = value
@@ -96,9 +107,13 @@ class FakeFile:
         return self.store.keys()
 
 
-def write_gll_file(name, coordinates, data, params, element_data=None, element_labels=None):
+def write_gll_file(name, coordinates, data, params, element_data=None, element_labels=None, global_strings=None):
     """Populate an in-memory Salvus-style GLL file: MODEL/coordinates [E,P,d], MODEL/data [E,F,P]."""
     f = FakeFile(name, "w")
+    f.store.clear()
+    grp = f.create_dataset("MODEL", data=np.zeros(()))
+    for key, val in (global_strings or {}).items():
+        grp.attrs[key] = np.bytes_(val)
     f.create_dataset("MODEL/coordinates", data=np.array(coordinates, dtype=np.float64))
     ds = f.create_dataset("MODEL/data", data=np.array(data, dtype=np.float64))
     label = "[ " + " | ".join(params) + " ]"
@@ -173,6 +188,56 @@ class CanonicalKDTree:
         return np.sqrt(d2), idx.astype(np.int64)
 
 
+# ------------------------------------------------------------------------------------------------
+# in-memory pyexodus
+# ------------------------------------------------------------------------------------------------
+EXO = {}  # filename -> dict(points [n,3], connectivity0 [E,8] 0-based, nodal {name: values})
+
+
+def write_exodus_file(name, points, connectivity0, nodal):
+    EXO[str(name)] = dict(points=np.array(points, dtype=np.float64),
+                          connectivity0=np.array(connectivity0, dtype=np.int64),
+                          nodal={k: np.array(v, dtype=np.float64) for k, v in nodal.items()}, names=list(nodal))
+
+
+class FakeExodusFile:
+    def __init__(self, filename, mode="r"):
+        self.f = EXO[str(filename)]
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        return False
+
+    @property
+    def num_dims(self):
+        return self.f["points"].shape[1]
+
+    def get_elem_connectivity(self, id=1):
+        c = self.f["connectivity0"]
+        return c + 1, c.shape[0], c.shape[1]  # exodus is 1-based
+
+    def get_element_variable_names(self):
+        return []
+
+    def get_coords(self):
+        p = self.f["points"]
+        return tuple(p[:, c].copy() for c in range(p.shape[1]))
+
+    def get_node_variable_names(self):
+        return list(self.f["names"])
+
+    def get_node_variable_values(self, name, step):
+        return self.f["nodal"][name].copy()
+
+    def put_node_variable_name(self, name, index):
+        assert self.f["names"][index - 1] == name
+
+    def put_node_variable_values(self, name, step, values):
+        self.f["nodal"][name] = np.array(values, dtype=np.float64)
+
+
 def _module(name, **attrs):
     m = types.ModuleType(name)
     m.__dict__.update(attrs)
@@ -197,7 +262,7 @@ def install_stubs():
     kd = _module("pykdtree.kdtree", KDTree=CanonicalKDTree)
     _module("pykdtree", kdtree=kd)
     _module("h5py", File=FakeFile)
-    _module("pyexodus", exodus=type("exodus", (), {}))
+    _module("pyexodus", exodus=FakeExodusFile)
     _module("xarray", Dataset=type("Dataset", (), {}), DataArray=type("DataArray", (), {}))
     gl = _module("geographiclib.geodesic", Geodesic=type("Geodesic", (), {}))
     _module("geographiclib", geodesic=gl)
@@ -232,3 +297,19 @@ def load_reference_cli():
         sys.path.remove(REFERENCE)
     assert cli.__file__.startswith(REFERENCE)
     return cli
+
+
+def load_reference_exodus(interp):
+    """Bind the three names the reference left undefined (see the header) to the reference's own objects and
+    point its load_lib() at the build of its own C sources."""
+    root = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    helpers = sys.modules["multi_mesh.helpers"]
+    exo = sys.modules["multi_mesh.io.exodus"]
+    assert helpers.__file__.startswith(REFERENCE) and exo.__file__.startswith(REFERENCE)
+    helpers.LIB_DIR = os.path.join(root, "oracle", "_ref")
+    lib = helpers.load_lib()
+    exo.lib = lib
+    interp.load_lib = helpers.load_lib
+    interp.Exodus = exo.Exodus
+    sys.modules["multi_mesh.utils"].KDTree = CanonicalKDTree  # utils.py:200 uses KDTree without importing it
+    return lib

@@ -315,3 +315,158 @@ def test_cuda_gll_2_gll_driver(cuda, tmp_path):
         got = st.read("MODEL/data")
         assert st.labels("MODEL/data") == NAMES
     check_gll2gll_values(got, g)
+
+
+# ------------------------------------------------------------------------------------------------
+# layered drivers + query_model (reference drivers run end to end on in-memory files)
+# ------------------------------------------------------------------------------------------------
+import sys  # noqa: E402
+
+sys.path.insert(0, GOLD)
+import glue_inputs  # noqa: E402
+
+LAYERED = {  # tag: (order, layers, source layers spec, location variant, k, elements outside the layers)
+    "layered": (2, [1, 2, 3], None, ("V1", {}), 20, "zero"),
+    "layered_o4": (4, [3, 2, 1], glue_inputs.CORE_LAYERS, ("V1", {}), 20, "zero"),  # "nocore" resolves to 3,2,1
+    "multi": (2, [1, 2, 3], None, ("V1", {}), 20, "keep"),
+    "multi_two": (2, [1, 2, 3], None, ("V2", {"tolerance": 1.05, "snap_to_nearest": True}), 30, "keep"),
+    "points_layered": (2, [1, 2, 3], None, ("V3", {}), 20, "zero"),
+}
+
+
+def layered_expected(be, tag):
+    """The layered workflow (interpolator.py:363-427) assembled from back-end pieces."""
+    order, layers, core, (variant, kw), k, outside = LAYERED[tag]
+    g = load("glue_layered.npz")
+    pair = glue_inputs.shell_pair(order, int(g["seed"]), core)
+    (sc, sd, se), (tc, td, te) = pair["from"], pair["to"]
+    out = np.zeros_like(td[:, :5, :]) if outside == "zero" else td[:, :5, :].copy()
+    for lay in layers:
+        ms, mt = se[:, 1] == lay, te[:, 1] == lay
+        nodes = np.ascontiguousarray(sc[ms])
+        tl = tc[mt]
+        uniq, inv = np.unique(tl.reshape(-1, 3), return_inverse=True, axis=0)
+        cands = be.knn(be.centroids(nodes), uniq, k)
+        elem, xi = be.locate(nodes, uniq, cands, be.spec(variant, **kw))
+        vals = be.interp(nodes, np.ascontiguousarray(sd[ms][:, :5, :]), elem, xi)  # elem -1 -> 0
+        out[mt] = vals[inv.reshape(-1)].reshape(tl.shape[0], tl.shape[1], 5).swapaxes(1, 2)
+    return out, g
+
+
+def compare_layered(got, g, tag):
+    want = g[f"{tag}_values"]
+    got = got[:: int(g[f"{tag}_stride"])]
+    assert got.shape == want.shape
+    nz = want != 0
+    assert np.array_equal(nz, got != 0)
+    assert np.max(np.abs(got[nz] - want[nz]) / np.abs(want[nz])) <= REL
+
+
+@pytest.mark.parametrize("tag", list(LAYERED))
+def test_oracle_layered_drivers(oracle, tag):
+    got, g = layered_expected(OracleBackend(oracle), tag)
+    compare_layered(got, g, tag)
+
+
+def test_oracle_query_model(oracle):
+    g = load("glue_query_model.npz")
+    nodes = meshgen.box_mesh((5, 5, 5), 2, lo=[6.0e6, -2e5, -2e5], hi=[6.371e6, 2e5, 2e5], warp=0.01)
+    data = meshgen.analytic_fields(nodes, NAMES)
+    xyz = utils.latlondepth_to_xyz(g["latlondepth"])
+    cands = oracle.knn_bruteforce(nodes.reshape(-1, 3), xyz, 20) // 27
+    elem, xi, _, _ = oracle.locate(2, 3, nodes, xyz, cands.astype(np.int32), oracle.V1())
+    vals = oracle.interp(2, 3, data, elem, xi)
+    assert np.max(np.abs(vals - g["values"]) / np.abs(g["values"])) <= REL
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("tag", list(LAYERED))
+def test_cuda_layered_drivers(cuda, tag):
+    """multi_mesh.api drivers on the meshes the reference's drivers were run on."""
+    import multi_mesh.api as api
+    from multi_mesh.components import interpolator as itp
+    from multimesh_b200.components.salvus_mesh_reader import SalvusMesh
+
+    order, layers, core, _, _, _ = LAYERED[tag]
+    g = load("glue_layered.npz")
+    pair = glue_inputs.shell_pair(order, int(g["seed"]), core)
+    names = NAMES + ["z_node_1D"]
+    src, tgt = (SalvusMesh.from_arrays(c, d, names, e, ["fluid", "layer"], {"moho_idx": "2"})
+                for c, d, e in (pair["from"], pair["to"]))
+    if tag == "layered":
+        api.gll_2_gll_layered(src, tgt, layers=[1, 2, 3], parameters="ISO")
+    elif tag == "layered_o4":
+        api.gll_2_gll_layered(src, tgt, layers="nocore", parameters="ISO")
+    elif tag == "multi":
+        api.gll_2_gll_layered_multi(src, tgt, layers=[1, 2, 3], parameters=NAMES, threads=3)
+    elif tag == "multi_two":
+        api.gll_2_gll_layered_multi_two(src, tgt, layers=[1, 2, 3], parameters=NAMES)
+    else:
+        itp.interpolate_to_points_layered(src, tgt, NAMES, layers=[1, 2, 3])
+    got = np.stack([tgt.element_nodal_fields[p] for p in NAMES], axis=1)
+    compare_layered(got, g, tag)
+
+
+@pytest.mark.gpu
+def test_cuda_query_model(cuda, tmp_path):
+    import multi_mesh.api as api
+    from multimesh_b200.io.store import write_gll_model
+
+    g = load("glue_query_model.npz")
+    nodes = meshgen.box_mesh((5, 5, 5), 2, lo=[6.0e6, -2e5, -2e5], hi=[6.371e6, 2e5, 2e5], warp=0.01)
+    path = str(tmp_path / "m.npz")
+    write_gll_model(path, nodes, meshgen.analytic_fields(nodes, NAMES), NAMES)
+    vals = api.query_model(g["latlondepth"], path)
+    assert np.max(np.abs(vals - g["values"]) / np.abs(g["values"])) <= REL
+
+
+# ------------------------------------------------------------------------------------------------
+# exodus drivers: exodus_2_gll is reference Python + the reference's own compiled C (no oracle arithmetic at all)
+# ------------------------------------------------------------------------------------------------
+def exodus_inputs():
+    g = load("glue_exodus.npz")
+    points, conn = meshgen.hex8_mesh(tuple(int(v) for v in g["hex_shape"]), warp=float(g["hex_warp"]))
+    nodal = {"VP": 2.0 + points[:, 0] + 2 * points[:, 1] + 3 * points[:, 2],
+             "VS": np.sin(points[:, 0]) * np.cos(points[:, 1]) + 2.0, "RHO": 2600 + 300 * points[:, 2] ** 2}
+    gll = meshgen.box_mesh(tuple(int(v) for v in g["gll_shape"]), 4, lo=[float(g["gll_lo"])] * 3,
+                           hi=[float(g["gll_hi"])] * 3, warp=float(g["gll_warp"]))
+    return g, points, conn, nodal, gll, [str(n) for n in g["names"]]
+
+
+def test_oracle_exodus_drivers(oracle):
+    g, points, conn, nodal, gll, names = exodus_inputs()
+    connC = np.ascontiguousarray(conn[:, np.argsort([0, 3, 2, 1, 4, 5, 6, 7])])
+    q = gll.reshape(-1, 3)
+    nn = oracle.knn_bruteforce(oracle.centroid_conn(conn, points), q, 20).astype(np.int64)
+    nf, enc, w = oracle.trilinear_interpolator(20, nn, connC, points, q)
+    assert nf == 0
+    param = np.stack([nodal[n] for n in names])
+    on_gll = np.sum(param[:, enc] * w, axis=2).reshape(3, len(gll), 125).swapaxes(0, 1)
+    assert np.array_equal(on_gll, g["on_gll"])  # same gather expression as interpolator.py:219-224 -> bit-equal
+    inside = g["inside"]
+    cands = oracle.knn_bruteforce(oracle.centroids(gll), points[inside], 20)
+    e, x, _, _ = oracle.locate(4, 3, gll, points[inside], cands, oracle.V1())
+    back = oracle.interp(4, 3, on_gll, e, x)
+    assert np.max(np.abs(back - g["back"]) / np.abs(g["back"])) <= REL
+
+
+@pytest.mark.gpu
+def test_cuda_exodus_drivers(cuda, tmp_path):
+    import multi_mesh.api as api
+    from multimesh_b200.io.exodus import Exodus
+    from multimesh_b200.io.store import open_store, write_gll_model
+
+    g, points, conn, nodal, gll, names = exodus_inputs()
+    path = str(tmp_path / "gll.npz")
+    write_gll_model(path, gll, np.zeros((len(gll), 3, 125)), names)
+    api.exodus_2_gll(Exodus.from_arrays(points, conn, nodal), path, gll_order=4, parameters=names)
+    with open_store(path, "r") as st:
+        on_gll = st.read("MODEL/data")
+        assert st.labels("MODEL/data") == names
+    assert np.max(np.abs(on_gll - g["on_gll"]) / np.abs(g["on_gll"])) <= REL
+    inside = g["inside"]
+    ex2 = Exodus.from_arrays(points[inside], np.zeros((0, 8), dtype=np.int64),
+                             {n: np.zeros(int(inside.sum())) for n in names})
+    api.gll_2_exodus(path, ex2, gll_order=4)
+    back = np.stack([ex2.get_nodal_field(n) for n in names], axis=1)
+    assert np.max(np.abs(back - g["back"]) / np.abs(g["back"])) <= REL
