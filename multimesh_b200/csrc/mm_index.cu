@@ -345,6 +345,13 @@ struct reg_list {
     }
 };
 
+// distance from coordinate x to the grid's extent along axis c (0 inside), shrunk by the margin
+__device__ __forceinline__ double box_gap(const grid_t &g, double x, int c, double margin)
+{
+    const double lo = g.origin[c], hi = g.origin[c] + g.n[c] * g.cell;
+    return fmax(fmax(lo - x, x - hi) - margin, 0.0);
+}
+
 template <bool POS_ID, class List>
 __device__ __forceinline__ void scan_range(List &L, const double4 *__restrict__ recs, int32_t lo,
                                            int32_t hi, double px, double py, double pz,
@@ -380,11 +387,11 @@ __device__ __forceinline__ void scan_range(List &L, const double4 *__restrict__ 
 // exact tie between site distances the prefix stops (copies of tied sites interleave by id) and
 // the caller's full search handles the point.
 template <class List, bool SITES>
-__global__ void __launch_bounds__(KNN_BLOCK)
-knn_kernel(grid_t g, int64_t N, const double *__restrict__ pts, int k, int32_t divisor,
-           const double4 *__restrict__ recs, const int32_t *__restrict__ cell_start,
-           int32_t *__restrict__ out_idx, double *__restrict__ out_d2,
-           const double4 *__restrict__ point_recs)
+__device__ __forceinline__ void
+knn_body(const grid_t &g, int64_t N, const double *__restrict__ pts, int k, int32_t divisor,
+         const double4 *__restrict__ recs, const int32_t *__restrict__ cell_start,
+         int32_t *__restrict__ out_idx, double *__restrict__ out_d2,
+         const double4 *__restrict__ point_recs)
 {
     extern __shared__ __align__(16) unsigned char smem[];
     List L;
@@ -404,6 +411,16 @@ knn_kernel(grid_t g, int64_t N, const double *__restrict__ pts, int k, int32_t d
         ci[1] = cell_coord(g, py, 1);
         ci[2] = three_d ? cell_coord(g, pz, 2) : 0;
         L.reset();
+        // squared distance from the query to the grid's bounding box (0 for queries inside it): every
+        // indexed point is at least that far away, which tightens the termination bound for targets
+        // that lie outside the source mesh
+        double out2 = 0.0;
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+            if (c >= g.dim) break;
+            const double o = box_gap(g, p[c], c, margin);
+            out2 += o * o;
+        }
 
         for (int r = 0;; ++r) {
             const int zlo = max(ci[2] - r, 0), zhi = min(ci[2] + r, g.n[2] - 1);
@@ -459,7 +476,9 @@ knn_kernel(grid_t g, int64_t N, const double *__restrict__ pts, int k, int32_t d
             // distance to p is at least the gap to the nearest block face that has cells beyond it
             double bound = INFINITY;
             bool remaining = false;
-            for (int c = 0; c < g.dim; ++c) {
+#pragma unroll
+            for (int c = 0; c < 3; ++c) {
+                if (c >= g.dim) break;
                 if (ci[c] - r > 0) {
                     remaining = true;
                     bound = fmin(bound, p[c] - (g.origin[c] + (ci[c] - r) * h));
@@ -470,8 +489,29 @@ knn_kernel(grid_t g, int64_t N, const double *__restrict__ pts, int k, int32_t d
                 }
             }
             if (!remaining) break;
+            if (!L.full()) continue;
             bound = fmax(bound - margin, 0.0);
-            if (L.full() && L.worst() < bound * bound) break;
+            if (L.worst() < bound * bound) break;
+            if (out2 > 0.0) {
+                // query outside the grid's box: a point beyond the face of axis c is also at least
+                // the out-of-box distance away along the other axes
+                double bound2 = INFINITY;
+#pragma unroll
+                for (int c = 0; c < 3; ++c) {
+                    if (c >= g.dim) break;
+                    const double o = box_gap(g, p[c], c, margin);
+                    const double other = out2 - o * o;
+                    if (ci[c] - r > 0) {
+                        const double gap = fmax(p[c] - (g.origin[c] + (ci[c] - r) * h) - margin, 0.0);
+                        bound2 = fmin(bound2, gap * gap + other);
+                    }
+                    if (ci[c] + r < g.n[c] - 1) {
+                        const double gap = fmax((g.origin[c] + (ci[c] + r + 1) * h) - p[c] - margin, 0.0);
+                        bound2 = fmin(bound2, gap * gap + other);
+                    }
+                }
+                if (L.worst() < bound2) break;
+            }
         }
         if constexpr (SITES) {
             // expand: copies of site j continue the prefix only while d2[j] < d2[j+1] strictly
@@ -492,6 +532,25 @@ knn_kernel(grid_t g, int64_t N, const double *__restrict__ pts, int k, int32_t d
             L.write(out_idx + n * k, out_d2 ? out_d2 + n * k : nullptr, divisor);
         }
     }
+}
+
+template <class List>
+__global__ void __launch_bounds__(KNN_BLOCK)
+knn_kernel(grid_t g, int64_t N, const double *__restrict__ pts, int k, int32_t divisor,
+           const double4 *__restrict__ recs, const int32_t *__restrict__ cell_start,
+           int32_t *__restrict__ out_idx, double *__restrict__ out_d2)
+{
+    knn_body<List, false>(g, N, pts, k, divisor, recs, cell_start, out_idx, out_d2, nullptr);
+}
+
+// site pass: 64 registers so that 8 blocks of 128 threads stay resident per SM
+__global__ void __launch_bounds__(KNN_BLOCK, 8)
+knn_sites_kernel(grid_t g, int64_t N, const double *__restrict__ pts, int k, int32_t divisor,
+                 const double4 *__restrict__ site_recs, const int32_t *__restrict__ site_cell_start,
+                 int32_t *__restrict__ out_idx, const double4 *__restrict__ point_recs)
+{
+    knn_body<reg_list<4>, true>(g, N, pts, k, divisor, site_recs, site_cell_start, out_idx, nullptr,
+                                point_recs);
 }
 
 // ---- counting sort of QUERY points by index cell (coherent warps in K1-K3) -----------------------
@@ -825,18 +884,18 @@ extern "C" int mm_knn(const mm_index_t *ix, int64_t N, const double *pts, int k,
     grid_t g = grid_of(ix);
     cudaStream_t st = (cudaStream_t)stream;
     if (k <= 4) {
-        knn_kernel<reg_list<4>, false><<<launch_blocks(N, KNN_BLOCK, 8), KNN_BLOCK, 0, st>>>(
-            g, N, pts, k, divisor, ix->recs, ix->cell_start, idx, d2, nullptr);
+        knn_kernel<reg_list<4>><<<launch_blocks(N, KNN_BLOCK, 8), KNN_BLOCK, 0, st>>>(
+            g, N, pts, k, divisor, ix->recs, ix->cell_start, idx, d2);
     } else if (k <= 8) {
-        knn_kernel<reg_list<8>, false><<<launch_blocks(N, KNN_BLOCK, 8), KNN_BLOCK, 0, st>>>(
-            g, N, pts, k, divisor, ix->recs, ix->cell_start, idx, d2, nullptr);
+        knn_kernel<reg_list<8>><<<launch_blocks(N, KNN_BLOCK, 8), KNN_BLOCK, 0, st>>>(
+            g, N, pts, k, divisor, ix->recs, ix->cell_start, idx, d2);
     } else {
         size_t smem = (size_t)k * KNN_BLOCK * (sizeof(double) + sizeof(int32_t));
-        MM_CUDA(cudaFuncSetAttribute(knn_kernel<smem_list, false>,
+        MM_CUDA(cudaFuncSetAttribute(knn_kernel<smem_list>,
                                      cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         int per_sm = (int)std::max<size_t>(1, std::min<size_t>(8, (200 * 1024) / smem));
-        knn_kernel<smem_list, false><<<launch_blocks(N, KNN_BLOCK, per_sm), KNN_BLOCK, smem, st>>>(
-            g, N, pts, k, divisor, ix->recs, ix->cell_start, idx, d2, nullptr);
+        knn_kernel<smem_list><<<launch_blocks(N, KNN_BLOCK, per_sm), KNN_BLOCK, smem, st>>>(
+            g, N, pts, k, divisor, ix->recs, ix->cell_start, idx, d2);
     }
     MM_CUDA(cudaGetLastError());
     return MM_OK;
@@ -914,8 +973,8 @@ int mm_knn_sites(const mm_index_t *ix, int64_t N, const double *pts, int kout, i
 {
     MM_REQUIRE(ix && ix->site_recs, MM_ERR_INVALID, "mm_knn_sites: site table not built");
     if (N == 0) return MM_OK;
-    knn_kernel<reg_list<4>, true><<<launch_blocks(N, KNN_BLOCK, 8), KNN_BLOCK, 0, (cudaStream_t)stream>>>(
-        grid_of(ix), N, pts, kout, divisor, ix->site_recs, ix->site_cell_start, idx, nullptr, ix->recs);
+    knn_sites_kernel<<<launch_blocks(N, KNN_BLOCK, 8), KNN_BLOCK, 0, (cudaStream_t)stream>>>(
+        grid_of(ix), N, pts, kout, divisor, ix->site_recs, ix->site_cell_start, idx, ix->recs);
     MM_CUDA(cudaGetLastError());
     return MM_OK;
 }

@@ -96,6 +96,40 @@ def test_knn_gll_point_form_duplicates(cuda, oracle):
     assert np.array_equal(got, want)
 
 
+def test_knn_queries_far_outside_the_source(cuda, oracle):
+    """Targets well outside the source's bounding box (a target mesh larger than the source): the ring
+    search must stay exact and must terminate on the out-of-box distance, not after O(distance / cell)^3 rows."""
+    import time
+
+    import torch
+    from multimesh_b200 import ops
+
+    rng = np.random.default_rng(77)
+    nodes = _mesh(2, 3, 12, 0.01)
+    allp = nodes.reshape(-1, 3)
+    far = np.concatenate([rng.uniform(-4.0, 5.0, (1500, 3)),             # up to 4 domain widths away, all octants
+                          np.stack([rng.uniform(-60, 60, 300), rng.uniform(0, 1, 300), rng.uniform(0, 1, 300)], 1),
+                          np.array([[1e6, 0.5, 0.5], [-1e6, -1e6, -1e6], [0.5, 0.5, 1e9]])])
+    for data, div in ((oracle.centroids(nodes), 1), (allp, 27)):
+        ix = ops.GridIndex(_t(data, cuda))
+        for k in (4, 20):
+            got = ix.query_idx(_t(far, cuda), k, divisor=div).cpu().numpy()
+            assert np.array_equal(got, oracle.knn_bruteforce(data, far, k) // div)
+    # the fused pipeline on the same targets (site pass + progressive search) and a timing guard
+    tn = _t(nodes, cuda)
+    cent, box = ops.element_geometry(tn)
+    ix = ops.GridIndex(tn.view(-1, 3))
+    big = _t(np.tile(far, (200, 1)), cuda)  # 360 k far targets
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    out, elem, xi, st, nf = ops.interpolate(ix, 27, tn, cent, box, None, big, 20, ops.V1())
+    torch.cuda.synchronize()
+    assert time.perf_counter() - t0 < 5.0
+    cands = oracle.knn_bruteforce(allp, far, 20) // 27
+    e, x, _, _ = oracle.locate(2, 3, nodes, far, cands.astype(np.int32), oracle.V1())
+    assert np.array_equal(elem[: len(far)].cpu().numpy(), e)
+
+
 def test_knn_edge_cases(cuda, oracle):
     from multimesh_b200 import ops
     import torch
