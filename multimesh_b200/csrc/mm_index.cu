@@ -778,12 +778,16 @@ extern "C" int mm_index_create(mm_index_t **out, int dim, int64_t M, const doubl
                 vol *= ext[c];
             }
         }
-        // 2. cell size: ~2 points per cell by volume, then refine while cells stay crowded and
-        //    halving the cell still separates points (duplicated points never separate)
+        // 2. cell size.  Target: ~1.25 DISTINCT coordinates per cell by volume (measured optimum of the
+        //    ring search on lattice-like and random data, tools/exp_cell.py) -- the GLL-point form
+        //    stores shared nodes 2-8 times and duplicates never separate, so the number of distinct
+        //    coordinates is first estimated as the number of non-empty cells of a probe grid twice as
+        //    fine as "2 points per cell".  Then refine while cells stay crowded and halving the cell
+        //    still separates points (clustered data).
         double h = 1.0;
+        double emax = std::max(ext[0], std::max(ext[1], ext[2]));
         if (nd > 0) {
             h = std::pow(vol * 2.0 / (double)M, 1.0 / nd);
-            double emax = std::max(ext[0], std::max(ext[1], ext[2]));
             if (!(h > 0.0) || !std::isfinite(h)) h = emax;
             h = std::max(h, emax / 4096.0);
         }
@@ -814,24 +818,48 @@ extern "C" int mm_index_create(mm_index_t **out, int dim, int64_t M, const doubl
         };
         while (cells_at(h) > MAX_CELLS) h *= 1.25;
         int64_t nonempty = 0;
-        int rc = evaluate(h, &nonempty);
+        int rc = MM_OK;
+        double distinct = (double)M;  // estimate of the number of distinct coordinates
+        if (nd > 0) {
+            double hp = std::max(0.5 * h, emax / 4096.0);
+            while (cells_at(hp) > MAX_CELLS) hp *= 1.1;
+            int64_t ne = 0;
+            rc = evaluate(hp, &ne);
+            if (rc != MM_OK) return rc;
+            distinct = (double)std::max<int64_t>(ne, 1);
+            double ht = std::pow(vol * 1.25 / distinct, 1.0 / nd);
+            if (ht > 0.0 && std::isfinite(ht)) h = std::min(std::max(ht, emax / 4096.0), emax);
+            while (cells_at(h) > MAX_CELLS) h *= 1.25;
+        }
+        rc = evaluate(h, &nonempty);
         if (rc != MM_OK) return rc;
         for (int it = 0; it < 8 && nd > 0; ++it) {
             if ((double)M / (double)std::max<int64_t>(nonempty, 1) <= 4.0) break;
             double h2 = 0.5 * h;
-            double emax = std::max(ext[0], std::max(ext[1], ext[2]));
             if (h2 < emax / 4096.0) break;  // keep every axis below the per-axis cell cap
             if (cells_at(h2) > MAX_CELLS || cells_at(h2) == cells_at(h)) break;
             int64_t ne2 = 0;
             rc = evaluate(h2, &ne2);
             if (rc != MM_OK) return rc;
-            if ((double)ne2 >= 1.5 * (double)nonempty) {
+            // accept only if the finer grid finds coordinates the probe did not know about (clusters);
+            // merely separating lattice neighbours that the target density keeps together is a loss
+            const bool finds_more = (double)ne2 > 1.25 * distinct;
+            distinct = std::max(distinct, (double)ne2);
+            if (finds_more && (double)ne2 >= 1.5 * (double)nonempty) {
                 h = h2;
                 nonempty = ne2;
             } else {
                 rc = evaluate(h, &nonempty);  // restore the coarser grid
                 if (rc != MM_OK) return rc;
                 break;
+            }
+        }
+        if (const char *e = std::getenv("MM_INDEX_CELL_SCALE")) {  // tuning experiments only
+            double sc = std::atof(e);
+            if (sc > 0.0 && sc != 1.0 && nd > 0 && cells_at(h * sc) <= MAX_CELLS) {
+                h *= sc;
+                rc = evaluate(h, &nonempty);
+                if (rc != MM_OK) return rc;
             }
         }
         ix->nonempty = nonempty;
