@@ -59,6 +59,9 @@ cudaError_t pool_alloc(void **p, size_t bytes, cudaStream_t st)
 
 constexpr int64_t MAX_CELLS = (int64_t)1 << 26;
 constexpr int KNN_BLOCK = 128;
+#ifndef MM_KNN_MERGED
+#define MM_KNN_MERGED 1
+#endif
 
 struct grid_t {
     double origin[3];
@@ -422,13 +425,41 @@ knn_body(const grid_t &g, int64_t N, const double *__restrict__ pts, int k, int3
             out2 += o * o;
         }
 
-        for (int r = 0;; ++r) {
+        // rings 0 and 1 merged: the 3 x 3 block of cell rows around the query's cell, each row ONE
+        // contiguous record range [cx-1, cx+1], own row first, then face, edge neighbours; rows the
+        // current k-th distance cannot reach are skipped.  (With cells of about one distinct coordinate
+        // this is where almost every first-pass query ends.)
+        if (MM_KNN_MERGED) {
+            const int xa = max(ci[0] - 1, 0), xb = min(ci[0] + 1, g.n[0] - 1);
+            const int nrow = three_d ? 9 : 3;
+            for (int it = 0; it < nrow; ++it) {
+                const int dy = (int)((0x22161u >> (2 * it)) & 3u) - 1;   // 0,-1,+1, 0, 0,-1,+1,-1,+1
+                const int dz = (int)((0x28215u >> (2 * it)) & 3u) - 1;   // 0, 0, 0,-1,+1,-1,-1,+1,+1
+                const int yy = ci[1] + dy, zz = ci[2] + dz;
+                if (yy < 0 || yy >= g.n[1] || zz < 0 || zz >= g.n[2]) continue;
+                if (L.full()) {
+                    double yl = g.origin[1] + yy * h, yh = yl + h;
+                    double gy = fmax(fmax(yl - py, py - yh) - margin, 0.0);
+                    double gz = 0.0;
+                    if (three_d) {
+                        double zl = g.origin[2] + zz * h, zh = zl + h;
+                        gz = fmax(fmax(zl - pz, pz - zh) - margin, 0.0);
+                    }
+                    if (L.worst() - (gy * gy + gz * gz) < 0.0) continue;
+                }
+                const int64_t base = (int64_t)g.n[0] * (yy + (int64_t)g.n[1] * zz);
+                scan_range<SITES>(L, recs, cell_start[base + xa], cell_start[base + xb + 1], px, py, pz,
+                                  three_d);
+            }
+        }
+
+        for (int r = MM_KNN_MERGED ? 1 : 0;; ++r) {
             const int zlo = max(ci[2] - r, 0), zhi = min(ci[2] + r, g.n[2] - 1);
             const int ylo = max(ci[1] - r, 0), yhi = min(ci[1] + r, g.n[1] - 1);
             const int xlo = max(ci[0] - r, 0), xhi = min(ci[0] + r, g.n[0] - 1);
             // rows of the shell are visited nearest-first (offsets 0, -1, +1, -2, +2, ...), so the
             // list tightens early and the farther rows are pruned
-            const int nz = three_d ? 2 * r + 1 : 1;
+            const int nz = (MM_KNN_MERGED && r == 1) ? 0 : (three_d ? 2 * r + 1 : 1);  // r = 1: done above
             for (int iz = 0; iz < nz; ++iz) {
                 const int zz = ci[2] + ((iz & 1) ? -((iz + 1) >> 1) : ((iz + 1) >> 1));
                 if (zz < zlo || zz > zhi) continue;
