@@ -180,6 +180,11 @@ __device__ __forceinline__ void bulk_copy_g2s(void *dst_smem, const void *src_gm
         : "memory");
 }
 
+__device__ __forceinline__ void prefetch_l2(const void *ptr)
+{
+    asm volatile("prefetch.global.L2 [%0];" ::"l"(ptr));
+}
+
 // orders generic-proxy accesses to shared memory before later async-proxy (TMA) writes
 __device__ __forceinline__ void fence_proxy_async_smem()
 {

@@ -72,6 +72,13 @@ locate_kernel(const mm_gll_table T, const mm_locate_params prm, int64_t E,
     for (int64_t batch = (int64_t)blockIdx.x * WARPS + warp; batch * 32 < N; batch += warps_total) {
         const int64_t n = batch * 32 + lane;
         bool done = n >= N;
+        {  // the warp's next batch: pull its points and candidate rows towards L2 now
+            const int64_t nn = n + warps_total * 32;
+            if (nn < N) {
+                prefetch_l2(pts + nn * DIM);
+                prefetch_l2(cands + nn * (int64_t)k);
+            }
+        }
         double p[DIM];
 #pragma unroll
         for (int c = 0; c < DIM; ++c) p[c] = done ? 0.0 : pts[n * DIM + c];
@@ -114,6 +121,9 @@ locate_kernel(const mm_gll_table T, const mm_locate_params prm, int64_t E,
                         for (int q = 0; q < DIM; ++q)
                             if (!(p[q] >= lo[q] && p[q] <= hi[q])) inside = false;
                         if (!inside) {
+                            // prefix mode takes no fallback (unresolved points are re-run with the
+                            // full list), so the nearest-centre bookkeeping is not needed there
+                            if (prm.reserved & 1) continue;
                             const double *cc = centroid + (int64_t)c * DIM;
                             double dx = p[0] - cc[0], dy = p[1] - cc[1];
                             double s = dx * dx + dy * dy;
@@ -212,15 +222,18 @@ locate_kernel(const mm_gll_table T, const mm_locate_params prm, int64_t E,
                 double *dst = reinterpret_cast<double *>(slot + shift);
                 for (int q = 0; q < tr::DOUBLES; ++q) dst[q] = src[q];
             }
+            // Newton start value from the element's pre-solve row: needs no nodes, so its loads
+            // overlap the bulk copy instead of queueing behind the barrier wait
+            double x[DIM];
+            if (served)
+                newton_start<DIM>(p, presolve ? presolve + (int64_t)e * (2 * DIM + DIM * DIM) : nullptr, x);
             if (tma_mask) {
                 mbar_wait(bar, phase);
                 phase ^= 1;
             }
             __syncwarp();  // plain-load tail path: make the leader's stores visible to its group
             if (served) {
-                double x[DIM];
-                const bool ok = newton_inverse<ORDER, DIM>(
-                    T, X, p, presolve ? presolve + (int64_t)e * (2 * DIM + DIM * DIM) : nullptr, x);
+                const bool ok = newton_iterate<ORDER, DIM>(T, X, p, x);
                 if (fb_newton) {  // V1: nearest-centre element, interpolator.py:1460-1473
                     bool big = false;
 #pragma unroll

@@ -99,11 +99,9 @@ __device__ __forceinline__ void eval_map(const mm_gll_table &T, const double *__
 // `pre` = {ref[DIM], x0[DIM], Jinv[DIM][DIM]} (K0, mm_element_presolve; ref = first control node,
 // x0 and Jinv evaluated on ref-shifted nodes) -- an exactly affine element then needs one
 // evaluation instead of two -- or xi0 = 0 when `pre` is null or unusable.
-template <int ORDER, int DIM>
-__device__ __forceinline__ bool newton_inverse(const mm_gll_table &T,
-                                               const double *__restrict__ X,
-                                               const double (&p)[DIM],
-                                               const double *__restrict__ pre, double (&xi)[DIM])
+template <int DIM>
+__device__ __forceinline__ void newton_start(const double (&p)[DIM], const double *__restrict__ pre,
+                                             double (&xi)[DIM])
 {
 #pragma unroll
     for (int c = 0; c < DIM; ++c) xi[c] = 0.0;
@@ -125,6 +123,15 @@ __device__ __forceinline__ bool newton_inverse(const mm_gll_table &T,
             for (int c = 0; c < DIM; ++c) xi[c] = g[c];
         }
     }
+}
+
+// Newton iterations from the start value already in xi (newton_start needs only the pre-solve row
+// and the point, so K2 computes it while the element block is still in flight).
+template <int ORDER, int DIM>
+__device__ __forceinline__ bool newton_iterate(const mm_gll_table &T,
+                                               const double *__restrict__ X,
+                                               const double (&p)[DIM], double (&xi)[DIM])
+{
 #pragma unroll 1
     for (int it = 0; it < MM_NEWTON_MAXIT; ++it) {
         double x[DIM], J[DIM][DIM], delta[DIM];
@@ -165,3 +172,13 @@ __device__ __forceinline__ bool newton_inverse(const mm_gll_table &T,
     return false;
 }
 
+
+template <int ORDER, int DIM>
+__device__ __forceinline__ bool newton_inverse(const mm_gll_table &T,
+                                               const double *__restrict__ X,
+                                               const double (&p)[DIM],
+                                               const double *__restrict__ pre, double (&xi)[DIM])
+{
+    newton_start<DIM>(p, pre, xi);
+    return newton_iterate<ORDER, DIM>(T, X, p, xi);
+}
