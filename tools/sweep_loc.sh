@@ -1,9 +1,11 @@
-for v in 0 1 2 3; do
-for wl in medium S5small; do
-MM_LOC_VARIANT=$v timeout -s KILL 100 python bench.py --workload $wl --steps 3 --warmup 3 --no-cpu 2>&1 | python -c "
-import sys,json
-for l in sys.stdin:
-    if l.startswith('{'):
-        d=json.loads(l); print('variant $v $wl', 'step ms', round(d['ms_per_step'],3), 'K2 ms', d['kernels']['K2_locate']['ms'], 'K1', d['kernels']['K1_knn']['ms'], 'K3', d['kernels']['K3_interp']['ms'])
-"
-done; done
+#!/bin/bash
+# K2 launch-configuration variants (MM_LOC_VARIANT, profiling only) on the bench workload
+WL=${WL:-S2}
+for v in ${VARIANTS:-0 4 5 6 7}; do
+  MM_LOC_VARIANT=$v timeout -s KILL 300 python bench.py --workload $WL --steps 5 --warmup 3 --no-cpu > gpurun_out/loc_$v.json 2> gpurun_out/loc_$v.err
+  python - <<PY
+import json
+d=json.loads(open("gpurun_out/loc_$v.json").read().strip().splitlines()[-1])
+print("$WL variant $v", d["ms_per_step"], {k:v["ms"] for k,v in d["kernels"].items()})
+PY
+done
