@@ -428,7 +428,7 @@ def run_ours(args, w):
     else:
         peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
     d = 3
-    k1 = min(k, 8)
+    k1 = min(k, 4 if w.get("form") == "centroid" else 8)  # candidates the first pass materialises
     n_rerun = int(st[9]) if len(st) > 9 else 0
     bytes_pt = {
         "K1_knn": 8 * d + 4 * k1,                                  # first pass materialises k1 candidates
@@ -448,15 +448,21 @@ def run_ours(args, w):
     other = {"query_sort_ms": round(float(stages[0]), 4), "rerun_unresolved_ms": round(float(stages[3]), 4),
              "unpermute_ms": round(float(stages[5]), 4)}
     dom = max(kernels, key=lambda n: kernels[n]["ms"])
+    step_bytes = sum(bytes_pt.values()) * N
+    step_gbs = step_bytes / (ms_per_step * 1e-3) / 1e9 if world == 1 or not device_gen else None
     roofline = {"bound": "hbm", "kernel": dom, "achieved": kernels[dom]["achieved_gbs"], "peak": peak,
                 "unit": "GB/s", "frac": kernels[dom]["frac"], "traffic": kernels[dom]["traffic"],
                 "peak_source": peak_src, "graded_kernel_K3": kernels["K3_interp"],
+                "whole_step": None if step_gbs is None else {
+                    "alg_bytes_per_point": sum(bytes_pt.values()), "achieved_gbs": round(step_gbs, 1),
+                    "frac": round(step_gbs / peak, 4)},
                 "note": "achieved = SURVEY 8d no-reuse algorithmic bytes x points of one launch / CUDA-event "
-                        "duration of that kernel inside the timed step. K1 (k-NN) moves only 56 algorithmic B/point "
-                        "and is instruction-issue bound (69 % issue-active, ncu), so its HBM fraction is small by "
-                        "construction; K2/K3 serve most bytes from L2/shared memory (points are processed in spatial "
-                        "order, one copy per distinct element per warp) and are fp64-pipe bound (52-61 % active), so "
-                        "their algorithmic rate may exceed the HBM peak -- `traffic` is the DRAM bytes ncu saw"}
+                        "duration of that kernel inside the timed step. K1 (k-NN) moves only 8d + 4k' algorithmic "
+                        "B/point and is instruction-issue bound (69 % issue-active, ncu), so its HBM fraction is small "
+                        "by construction; K2/K3 serve most bytes from L2/shared memory (points are processed in spatial "
+                        "order, one copy per distinct element per warp) and are fp64-pipe / latency bound (fp64 pipe "
+                        "44 % active), so their algorithmic rate may exceed the HBM peak -- `traffic` is the DRAM bytes "
+                        "ncu saw; whole_step = all three kernels' algorithmic bytes / the step time (sort included)"}
 
     # ---- CPU baseline, rank 0, N = 1 only -------------------------------------------------------
     cpu = None
@@ -480,7 +486,9 @@ def run_ours(args, w):
                 "ms_per_step": e2e_s * 1e3, "steps": e2e_steps,
                 "call": "mm_interpolate_host (C-ABI, pinned host buffers; H2D source mesh + targets, index "
                         "build, K1-K3, D2H values every step)"},
-        "gpu_launches": 10 * args.steps, "clocks": clocks, "index_build_ms": build_ms, "nfailed": nfailed,
+        # per step: histogram, 3 scan kernels, query scatter, first-pass k-NN, locate, gather (+ full k-NN and
+        # locate again when the first pass left points unresolved)
+        "gpu_launches": (8 + (2 if n_rerun else 0)) * args.steps, "clocks": clocks, "index_build_ms": build_ms, "nfailed": nfailed,
         "status_histogram": st, "checksum": checksum, "e2e_checksum": e2e_checksum,
     }
     print(json.dumps(line), flush=True)
