@@ -356,27 +356,58 @@ __device__ __forceinline__ double box_gap(const grid_t &g, double x, int c, doub
 }
 
 template <bool POS_ID, class List>
+__device__ __forceinline__ void rank_record(List &L, const double2 &cxy, const double2 &czw, int32_t j,
+                                            double px, double py, double pz, bool three_d)
+{
+    double dx = px - cxy.x, dy = py - cxy.y;
+    double s = dx * dx + dy * dy;
+    if (three_d) {
+        double dz = pz - czw.x;
+        s = s + dz * dz;
+    }
+    L.insert(s, POS_ID ? j : (int32_t)__double_as_longlong(czw.y));
+}
+
+// Ranks the records [lo, hi).  The next record is always in flight while the current one is ranked.
+// PINGPONG: the loop is unrolled by two with two register sets, so the prefetched record does not
+// have to be moved into place every iteration (8 register moves per record otherwise); used for
+// the merged ring-0/1 pass, where almost all records are ranked.
+template <bool POS_ID, bool PINGPONG, class List>
 __device__ __forceinline__ void scan_range(List &L, const double4 *__restrict__ recs, int32_t lo,
                                            int32_t hi, double px, double py, double pz,
                                            bool three_d)
 {
     if (lo >= hi) return;
     const double2 *q = reinterpret_cast<const double2 *>(&recs[lo]);  // 2 x LDG.128 per record
-    double2 xy = __ldg(q), zw = __ldg(q + 1);
-    for (int32_t j = lo; j < hi; ++j) {
-        const double2 cxy = xy, czw = zw;
-        if (j + 1 < hi) {  // next record in flight while this one is ranked
-            q += 2;
-            xy = __ldg(q);
-            zw = __ldg(q + 1);
+    if constexpr (PINGPONG) {
+        double2 axy = __ldg(q), azw = __ldg(q + 1), bxy = axy, bzw = azw;
+        int32_t j = lo;
+        while (true) {
+            if (j + 1 < hi) {
+                bxy = __ldg(q + 2);
+                bzw = __ldg(q + 3);
+            }
+            rank_record<POS_ID>(L, axy, azw, j, px, py, pz, three_d);
+            if (++j >= hi) break;
+            if (j + 1 < hi) {
+                axy = __ldg(q + 4);
+                azw = __ldg(q + 5);
+            }
+            q += 4;
+            rank_record<POS_ID>(L, bxy, bzw, j, px, py, pz, three_d);
+            if (++j >= hi) break;
         }
-        double dx = px - cxy.x, dy = py - cxy.y;
-        double s = dx * dx + dy * dy;
-        if (three_d) {
-            double dz = pz - czw.x;
-            s = s + dz * dz;
+    } else {
+        double2 xy = __ldg(q), zw = __ldg(q + 1);
+        for (int32_t j = lo; j < hi; ++j) {
+            const double2 cxy = xy, czw = zw;
+            if (j + 1 < hi) {  // next record in flight while this one is ranked
+                q += 2;
+                xy = __ldg(q);
+                zw = __ldg(q + 1);
+            }
+            rank_record<POS_ID>(L, cxy, czw, j, px, py, pz, three_d);
         }
-        L.insert(s, POS_ID ? j : (int32_t)__double_as_longlong(czw.y));
     }
 }
 
@@ -448,8 +479,8 @@ knn_body(const grid_t &g, int64_t N, const double *__restrict__ pts, int k, int3
                     if (L.worst() - (gy * gy + gz * gz) < 0.0) continue;
                 }
                 const int64_t base = (int64_t)g.n[0] * (yy + (int64_t)g.n[1] * zz);
-                scan_range<SITES>(L, recs, cell_start[base + xa], cell_start[base + xb + 1], px, py, pz,
-                                  three_d);
+                scan_range<SITES, true>(L, recs, cell_start[base + xa], cell_start[base + xb + 1], px, py,
+                                        pz, three_d);
             }
         }
 
@@ -490,15 +521,15 @@ knn_body(const grid_t &g, int64_t N, const double *__restrict__ pts, int k, int3
                     }
                     const int64_t base = (int64_t)g.n[0] * (yy + (int64_t)g.n[1] * zz);
                     if (zedge || abs(yy - ci[1]) == r) {
-                        scan_range<SITES>(L, recs, cell_start[base + xa], cell_start[base + xb + 1], px,
+                        scan_range<SITES, false>(L, recs, cell_start[base + xa], cell_start[base + xb + 1], px,
                                           py, pz, three_d);
                     } else {  // interior row of the shell: only its two end cells are new
                         const int x0 = ci[0] - r, x1 = ci[0] + r;
                         if (x0 >= xa && x0 <= xb)
-                            scan_range<SITES>(L, recs, cell_start[base + x0], cell_start[base + x0 + 1],
+                            scan_range<SITES, false>(L, recs, cell_start[base + x0], cell_start[base + x0 + 1],
                                               px, py, pz, three_d);
                         if (r > 0 && x1 >= xa && x1 <= xb)
-                            scan_range<SITES>(L, recs, cell_start[base + x1], cell_start[base + x1 + 1],
+                            scan_range<SITES, false>(L, recs, cell_start[base + x1], cell_start[base + x1 + 1],
                                               px, py, pz, three_d);
                     }
                 }
