@@ -59,6 +59,28 @@ cudaError_t pool_alloc(void **p, size_t bytes, cudaStream_t st)
 
 constexpr int64_t MAX_CELLS = (int64_t)1 << 26;
 constexpr int KNN_BLOCK = 128;
+
+// idx / divisor for 0 <= idx < 2^31 with a host-computed multiplier (Granlund-Montgomery:
+// M = ceil(2^(31+l) / d), l = ceil(log2 d)); a runtime integer division costs ~20 instructions and K1
+// performs one per candidate written
+struct fast_div {
+    unsigned long long mul = 1;
+    int shift = 0;
+    int32_t d = 1;
+    __host__ explicit fast_div(int32_t divisor = 1) : d(divisor)
+    {
+        if (divisor > 1) {
+            int l = 0;
+            while (((int64_t)1 << l) < divisor) ++l;
+            shift = 31 + l;
+            mul = ((1ull << shift) + (unsigned long long)divisor - 1) / (unsigned long long)divisor;
+        }
+    }
+    __device__ __forceinline__ int32_t operator()(int32_t n) const
+    {
+        return d == 1 ? n : (int32_t)(((unsigned long long)(uint32_t)n * mul) >> shift);
+    }
+};
 #ifndef MM_KNN_MERGED
 #define MM_KNN_MERGED 1
 #endif
@@ -284,11 +306,11 @@ struct smem_list {
             kth_id = I(k - 1);
         }
     }
-    __device__ __forceinline__ void write(int32_t *oi, double *od, int32_t divisor)
+    __device__ __forceinline__ void write(int32_t *oi, double *od, const fast_div &divisor)
     {
         for (int t = 0; t < k; ++t) {
             bool have = t < cnt;
-            oi[t] = have ? I(t) / divisor : -1;
+            oi[t] = have ? divisor(I(t)) : -1;
             if (od) od[t] = have ? D(t) : INFINITY;
         }
     }
@@ -334,14 +356,14 @@ struct reg_list {
             id[0] = ni;
         }
     }
-    __device__ __forceinline__ void write(int32_t *oi, double *od, int32_t divisor)
+    __device__ __forceinline__ void write(int32_t *oi, double *od, const fast_div &divisor)
     {
 #pragma unroll
         for (int j = 0; j < K; ++j) {
             int t = j - (K - k);
             if (t >= 0) {
                 bool have = d2[j] < INFINITY;
-                oi[t] = have ? id[j] / divisor : -1;
+                oi[t] = have ? divisor(id[j]) : -1;
                 if (od) od[t] = have ? d2[j] : INFINITY;
             }
         }
@@ -422,7 +444,7 @@ __device__ __forceinline__ void scan_range(List &L, const double4 *__restrict__ 
 // the caller's full search handles the point.
 template <class List, bool SITES>
 __device__ __forceinline__ void
-knn_body(const grid_t &g, int64_t N, const double *__restrict__ pts, int k, int32_t divisor,
+knn_body(const grid_t &g, int64_t N, const double *__restrict__ pts, int k, const fast_div &divisor,
          const double4 *__restrict__ recs, const int32_t *__restrict__ cell_start,
          int32_t *__restrict__ out_idx, double *__restrict__ out_d2,
          const double4 *__restrict__ point_recs)
@@ -587,7 +609,7 @@ knn_body(const grid_t &g, int64_t N, const double *__restrict__ pts, int k, int3
                 const int32_t r0 = (int32_t)__double_as_longlong(recs[L.id[j]].w);
                 const int32_t r1 = (int32_t)__double_as_longlong(recs[L.id[j] + 1].w);
                 for (int32_t t = r0; t < r1 && c < k; ++t)
-                    o[c++] = (int32_t)__double_as_longlong(point_recs[t].w) / divisor;
+                    o[c++] = divisor((int32_t)__double_as_longlong(point_recs[t].w));
             }
             for (; c < k; ++c) o[c] = -1;
         } else {
@@ -598,7 +620,7 @@ knn_body(const grid_t &g, int64_t N, const double *__restrict__ pts, int k, int3
 
 template <class List>
 __global__ void __launch_bounds__(KNN_BLOCK)
-knn_kernel(grid_t g, int64_t N, const double *__restrict__ pts, int k, int32_t divisor,
+knn_kernel(grid_t g, int64_t N, const double *__restrict__ pts, int k, const fast_div divisor,
            const double4 *__restrict__ recs, const int32_t *__restrict__ cell_start,
            int32_t *__restrict__ out_idx, double *__restrict__ out_d2)
 {
@@ -607,7 +629,7 @@ knn_kernel(grid_t g, int64_t N, const double *__restrict__ pts, int k, int32_t d
 
 // site pass: 64 registers so that 8 blocks of 128 threads stay resident per SM
 __global__ void __launch_bounds__(KNN_BLOCK, 8)
-knn_sites_kernel(grid_t g, int64_t N, const double *__restrict__ pts, int k, int32_t divisor,
+knn_sites_kernel(grid_t g, int64_t N, const double *__restrict__ pts, int k, const fast_div divisor,
                  const double4 *__restrict__ site_recs, const int32_t *__restrict__ site_cell_start,
                  int32_t *__restrict__ out_idx, const double4 *__restrict__ point_recs)
 {
@@ -975,17 +997,17 @@ extern "C" int mm_knn(const mm_index_t *ix, int64_t N, const double *pts, int k,
     cudaStream_t st = (cudaStream_t)stream;
     if (k <= 4) {
         knn_kernel<reg_list<4>><<<launch_blocks(N, KNN_BLOCK, 8), KNN_BLOCK, 0, st>>>(
-            g, N, pts, k, divisor, ix->recs, ix->cell_start, idx, d2);
+            g, N, pts, k, fast_div(divisor), ix->recs, ix->cell_start, idx, d2);
     } else if (k <= 8) {
         knn_kernel<reg_list<8>><<<launch_blocks(N, KNN_BLOCK, 8), KNN_BLOCK, 0, st>>>(
-            g, N, pts, k, divisor, ix->recs, ix->cell_start, idx, d2);
+            g, N, pts, k, fast_div(divisor), ix->recs, ix->cell_start, idx, d2);
     } else {
         size_t smem = (size_t)k * KNN_BLOCK * (sizeof(double) + sizeof(int32_t));
         MM_CUDA(cudaFuncSetAttribute(knn_kernel<smem_list>,
                                      cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         int per_sm = (int)std::max<size_t>(1, std::min<size_t>(8, (200 * 1024) / smem));
         knn_kernel<smem_list><<<launch_blocks(N, KNN_BLOCK, per_sm), KNN_BLOCK, smem, st>>>(
-            g, N, pts, k, divisor, ix->recs, ix->cell_start, idx, d2);
+            g, N, pts, k, fast_div(divisor), ix->recs, ix->cell_start, idx, d2);
     }
     MM_CUDA(cudaGetLastError());
     return MM_OK;
@@ -1064,7 +1086,7 @@ int mm_knn_sites(const mm_index_t *ix, int64_t N, const double *pts, int kout, i
     MM_REQUIRE(ix && ix->site_recs, MM_ERR_INVALID, "mm_knn_sites: site table not built");
     if (N == 0) return MM_OK;
     knn_sites_kernel<<<launch_blocks(N, KNN_BLOCK, 8), KNN_BLOCK, 0, (cudaStream_t)stream>>>(
-        grid_of(ix), N, pts, kout, divisor, ix->site_recs, ix->site_cell_start, idx, ix->recs);
+        grid_of(ix), N, pts, kout, fast_div(divisor), ix->site_recs, ix->site_cell_start, idx, ix->recs);
     MM_CUDA(cudaGetLastError());
     return MM_OK;
 }
