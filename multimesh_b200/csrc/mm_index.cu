@@ -485,12 +485,29 @@ knn_body(const grid_t &g, int64_t N, const double *__restrict__ pts, int k, cons
         if (MM_KNN_MERGED) {
             const int xa = max(ci[0] - 1, 0), xb = min(ci[0] + 1, g.n[0] - 1);
             const int nrow = three_d ? 9 : 3;
-            for (int it = 0; it < nrow; ++it) {
+            // record range of row `it` (empty when the row lies outside the grid); the bounds of the
+            // NEXT row are loaded before the current row is scanned, so their latency is hidden
+            auto row_bounds = [&](int it, int32_t &lo, int32_t &hi) {
                 const int dy = (int)((0x22161u >> (2 * it)) & 3u) - 1;   // 0,-1,+1, 0, 0,-1,+1,-1,+1
                 const int dz = (int)((0x28215u >> (2 * it)) & 3u) - 1;   // 0, 0, 0,-1,+1,-1,-1,+1,+1
                 const int yy = ci[1] + dy, zz = ci[2] + dz;
-                if (yy < 0 || yy >= g.n[1] || zz < 0 || zz >= g.n[2]) continue;
+                lo = hi = 0;
+                if (it < nrow && yy >= 0 && yy < g.n[1] && zz >= 0 && zz < g.n[2]) {
+                    const int base = g.n[0] * (yy + g.n[1] * zz);  // ncells <= MAX_CELLS = 2^26
+                    lo = cell_start[base + xa];
+                    hi = cell_start[base + xb + 1];
+                }
+            };
+            int32_t nlo, nhi;
+            row_bounds(0, nlo, nhi);
+            for (int it = 0; it < nrow; ++it) {
+                const int32_t lo = nlo, hi = nhi;
+                row_bounds(it + 1, nlo, nhi);
+                if (lo >= hi) continue;
                 if (L.full()) {
+                    const int dy = (int)((0x22161u >> (2 * it)) & 3u) - 1;
+                    const int dz = (int)((0x28215u >> (2 * it)) & 3u) - 1;
+                    const int yy = ci[1] + dy, zz = ci[2] + dz;
                     double yl = g.origin[1] + yy * h, yh = yl + h;
                     double gy = fmax(fmax(yl - py, py - yh) - margin, 0.0);
                     double gz = 0.0;
@@ -500,9 +517,7 @@ knn_body(const grid_t &g, int64_t N, const double *__restrict__ pts, int k, cons
                     }
                     if (L.worst() - (gy * gy + gz * gz) < 0.0) continue;
                 }
-                const int64_t base = (int64_t)g.n[0] * (yy + (int64_t)g.n[1] * zz);
-                scan_range<SITES, true>(L, recs, cell_start[base + xa], cell_start[base + xb + 1], px, py,
-                                        pz, three_d);
+                scan_range<SITES, true>(L, recs, lo, hi, px, py, pz, three_d);
             }
         }
 
@@ -541,7 +556,7 @@ knn_body(const grid_t &g, int64_t N, const double *__restrict__ pts, int k, cons
                             if (xa > xb) continue;
                         }
                     }
-                    const int64_t base = (int64_t)g.n[0] * (yy + (int64_t)g.n[1] * zz);
+                    const int base = g.n[0] * (yy + g.n[1] * zz);  // ncells <= MAX_CELLS = 2^26
                     if (zedge || abs(yy - ci[1]) == r) {
                         scan_range<SITES, false>(L, recs, cell_start[base + xa], cell_start[base + xb + 1], px,
                                           py, pz, three_d);
