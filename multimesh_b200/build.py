@@ -3,8 +3,9 @@ Builds the CUDA library IN-TREE for sm_100a:  multimesh_b200/lib/multi_mesh_b200
 
 The name matches the glob `multi_mesh*.so` the reference's loader uses (multi_mesh/helpers.py:33).
 Flags that matter for correctness:
-    -fmad=false                      no FMA contraction on the device   } canonical arithmetic,
-    -Xcompiler -ffp-contract=off     nor in host code                   } DESIGN.md section 3
+    -fmad=false                      no implicit FMA contraction on the device } canonical arithmetic, DESIGN.md
+    -Xcompiler -ffp-contract=off     nor in host code                          } section 3 (the only fused operations
+                                                                                 are the explicit __fma_rn calls)
     (no --use_fast_math; IEEE division and square root are the nvcc defaults for binary64)
 """
 import os
@@ -41,8 +42,8 @@ def _stale(target, deps):
 
 def build(force=False, verbose=False):
     os.makedirs(OBJ_DIR, exist_ok=True)
-    headers = [os.path.join(CSRC, "mm_common.cuh"),
-               os.path.join(HERE, "..", "include", "multimesh_b200.h"), __file__]
+    headers = sorted(os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith(".cuh")) + [
+        os.path.join(HERE, "..", "include", "multimesh_b200.h"), __file__]
     nvcc = _nvcc()
     jobs = []
     for s in SOURCES:

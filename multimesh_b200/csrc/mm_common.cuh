@@ -2,8 +2,10 @@
 //
 // CANONICAL ARITHMETIC: every floating-point operation below is a single
 // IEEE binary64 operation in the order written.  The library is compiled with -fmad=false so the
-// compiler never contracts a*b+c; nothing here may be re-associated.  The CPU oracle
-// (oracle/mm_oracle.c, test infrastructure) restates the same order independently.
+// compiler never contracts a*b+c by itself; the only fused operations are the explicit __fma_rn
+// calls in the two tensor contractions (mm_newton.cuh eval_map, mm_interp.cu contract_field);
+// nothing may be re-associated.  The CPU oracle (oracle/mm_oracle.c, test infrastructure)
+// restates the same order independently, with C fma() at the same places.
 #pragma once
 
 #include <cuda_runtime.h>

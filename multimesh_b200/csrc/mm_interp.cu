@@ -50,8 +50,8 @@ __device__ __forceinline__ double contract_field(const double *__restrict__ v,
         for (int j = 0; j < M; ++j) {
             double t = 0.0;
 #pragma unroll
-            for (int i = 0; i < M; ++i) t = t + L[0][i] * v[i + M * j];
-            u = u + L[1][j] * t;
+            for (int i = 0; i < M; ++i) t = __fma_rn(L[0][i], v[i + M * j], t);
+            u = __fma_rn(L[1][j], t, u);
         }
         return u;
     } else {
@@ -63,10 +63,10 @@ __device__ __forceinline__ double contract_field(const double *__restrict__ v,
             for (int j = 0; j < M; ++j) {
                 double t = 0.0;
 #pragma unroll
-                for (int i = 0; i < M; ++i) t = t + L[0][i] * v[i + M * j + M * M * k];
-                u = u + L[1][j] * t;
+                for (int i = 0; i < M; ++i) t = __fma_rn(L[0][i], v[i + M * j + M * M * k], t);
+                u = __fma_rn(L[1][j], t, u);
             }
-            acc = acc + L[2][k] * u;
+            acc = __fma_rn(L[2][k], u, acc);
         }
         return acc;
     }

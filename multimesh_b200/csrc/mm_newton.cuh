@@ -5,6 +5,9 @@
 #include "mm_common.cuh"
 
 // x[c] = sum_a w_a Y_a[c],  J[c][s] = sum_a dw_a/dxi_s Y_a[c]; i innermost, then j, then k.
+// Every accumulation of the contraction is ONE fused multiply-add, acc <- fma(w, v, acc) (explicit
+// __fma_rn; the build keeps -fmad=false, so nothing else is contracted) -- the oracle uses C fma()
+// at the same places, which is what keeps CPU and GPU bit-identical.
 template <int ORDER, int DIM>
 __device__ __forceinline__ void eval_map(const mm_gll_table &T, const double *__restrict__ Xn,
                                          const double (&p)[DIM], const double (&xi)[DIM],
@@ -25,15 +28,15 @@ __device__ __forceinline__ void eval_map(const mm_gll_table &T, const double *__
 #pragma unroll
                 for (int c = 0; c < 2; ++c) {
                     double y = Xn[(i + M * j) * 2 + c] - p[c];
-                    a[c] = a[c] + L[0][i] * y;
-                    b[c] = b[c] + dL[0][i] * y;
+                    a[c] = __fma_rn(L[0][i], y, a[c]);
+                    b[c] = __fma_rn(dL[0][i], y, b[c]);
                 }
             }
 #pragma unroll
             for (int c = 0; c < 2; ++c) {
-                V[c] = V[c] + L[1][j] * a[c];
-                Deta[c] = Deta[c] + dL[1][j] * a[c];
-                Dxi[c] = Dxi[c] + L[1][j] * b[c];
+                V[c] = __fma_rn(L[1][j], a[c], V[c]);
+                Deta[c] = __fma_rn(dL[1][j], a[c], Deta[c]);
+                Dxi[c] = __fma_rn(L[1][j], b[c], Dxi[c]);
             }
         }
 #pragma unroll
@@ -64,24 +67,24 @@ __device__ __forceinline__ void eval_map(const mm_gll_table &T, const double *__
 #pragma unroll
                     for (int c = 0; c < 3; ++c) {
                         double y = Xk[(i + M * j) * 3 + c] - p[c];
-                        a[c] = a[c] + L[0][i] * y;
-                        b[c] = b[c] + dL[0][i] * y;
+                        a[c] = __fma_rn(L[0][i], y, a[c]);
+                        b[c] = __fma_rn(dL[0][i], y, b[c]);
                     }
                 }
 #pragma unroll
                 for (int c = 0; c < 3; ++c) {
-                    V[c] = V[c] + L[1][j] * a[c];
-                    Deta[c] = Deta[c] + dL[1][j] * a[c];
-                    Dxi[c] = Dxi[c] + L[1][j] * b[c];
+                    V[c] = __fma_rn(L[1][j], a[c], V[c]);
+                    Deta[c] = __fma_rn(dL[1][j], a[c], Deta[c]);
+                    Dxi[c] = __fma_rn(L[1][j], b[c], Dxi[c]);
                 }
             }
             const double lz = Lz[k], dlz = dLz[k];
 #pragma unroll
             for (int c = 0; c < 3; ++c) {
-                X[c] = X[c] + lz * V[c];
-                Jz[c] = Jz[c] + dlz * V[c];
-                Jx[c] = Jx[c] + lz * Dxi[c];
-                Jy[c] = Jy[c] + lz * Deta[c];
+                X[c] = __fma_rn(lz, V[c], X[c]);
+                Jz[c] = __fma_rn(dlz, V[c], Jz[c]);
+                Jx[c] = __fma_rn(lz, Dxi[c], Jx[c]);
+                Jy[c] = __fma_rn(lz, Deta[c], Jy[c]);
             }
         }
 #pragma unroll

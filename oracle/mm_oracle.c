@@ -25,8 +25,11 @@
  *     tests/test_golden_glue.py).
  *
  * CANONICAL ARITHMETIC (shared spec with the CUDA kernels)
- *   - all arithmetic IEEE-754 binary64, one rounding per operation, NO fused
- *     multiply-add anywhere (build with -ffp-contract=off; nvcc with -fmad=false);
+ *   - all arithmetic IEEE-754 binary64; the accumulations of the two tensor contractions
+ *     (eval_map: Newton's x and J; mmo_interp: the gather) are explicit fused multiply-adds,
+ *     acc <- fma(w, v, acc), one rounding each (C fma() here, __fma_rn on the device); every
+ *     other operation is a separate IEEE operation with its own rounding -- the compilers are
+ *     kept from contracting anything themselves (-ffp-contract=off; nvcc -fmad=false);
  *   - node index a = i + m*j + m*m*k, m = order+1, i along xi (fastest);
  *   - sums are evaluated in the loop order written below, never re-associated.
  */
@@ -201,14 +204,14 @@ static void eval_map(const basis_t *b, int dim, const double *Y /*[P][dim]*/, co
             for (int i = 0; i < m; ++i) {
                 const double *y = Y + (size_t)(i + m * j) * 2;
                 for (int c = 0; c < 2; ++c) {
-                    a[c] = a[c] + L[0][i] * y[c];
-                    bb[c] = bb[c] + dL[0][i] * y[c];
+                    a[c] = fma(L[0][i], y[c], a[c]);
+                    bb[c] = fma(dL[0][i], y[c], bb[c]);
                 }
             }
             for (int c = 0; c < 2; ++c) {
-                V[c] = V[c] + L[1][j] * a[c];
-                Deta[c] = Deta[c] + dL[1][j] * a[c];
-                Dxi[c] = Dxi[c] + L[1][j] * bb[c];
+                V[c] = fma(L[1][j], a[c], V[c]);
+                Deta[c] = fma(dL[1][j], a[c], Deta[c]);
+                Dxi[c] = fma(L[1][j], bb[c], Dxi[c]);
             }
         }
         for (int c = 0; c < 2; ++c) {
@@ -226,21 +229,21 @@ static void eval_map(const basis_t *b, int dim, const double *Y /*[P][dim]*/, co
             for (int i = 0; i < m; ++i) {
                 const double *y = Y + (size_t)(i + m * j + m * m * k) * 3;
                 for (int c = 0; c < 3; ++c) {
-                    a[c] = a[c] + L[0][i] * y[c];
-                    bb[c] = bb[c] + dL[0][i] * y[c];
+                    a[c] = fma(L[0][i], y[c], a[c]);
+                    bb[c] = fma(dL[0][i], y[c], bb[c]);
                 }
             }
             for (int c = 0; c < 3; ++c) {
-                V[c] = V[c] + L[1][j] * a[c];
-                Deta[c] = Deta[c] + dL[1][j] * a[c];
-                Dxi[c] = Dxi[c] + L[1][j] * bb[c];
+                V[c] = fma(L[1][j], a[c], V[c]);
+                Deta[c] = fma(dL[1][j], a[c], Deta[c]);
+                Dxi[c] = fma(L[1][j], bb[c], Dxi[c]);
             }
         }
         for (int c = 0; c < 3; ++c) {
-            X[c] = X[c] + L[2][k] * V[c];
-            Jz[c] = Jz[c] + dL[2][k] * V[c];
-            Jx[c] = Jx[c] + L[2][k] * Dxi[c];
-            Jy[c] = Jy[c] + L[2][k] * Deta[c];
+            X[c] = fma(L[2][k], V[c], X[c]);
+            Jz[c] = fma(dL[2][k], V[c], Jz[c]);
+            Jx[c] = fma(L[2][k], Dxi[c], Jx[c]);
+            Jy[c] = fma(L[2][k], Deta[c], Jy[c]);
         }
     }
     for (int c = 0; c < 3; ++c) {
@@ -716,10 +719,10 @@ int mmo_interp(int order, int dim, long long E, int F, const double *fields, lon
                 double u = 0.0;
                 for (int j = 0; j < m; ++j) {
                     double t = 0.0;
-                    for (int i = 0; i < m; ++i) t = t + L[0][i] * v[i + m * j + m * m * k];
-                    u = u + L[1][j] * t;
+                    for (int i = 0; i < m; ++i) t = fma(L[0][i], v[i + m * j + m * m * k], t);
+                    u = fma(L[1][j], t, u);
                 }
-                if (dim == 3) acc = acc + L[2][k] * u;
+                if (dim == 3) acc = fma(L[2][k], u, acc);
                 else acc = u;
             }
             o[f] = acc;
