@@ -458,10 +458,10 @@ def run_ours(args, w):
                     "frac": round(step_gbs / peak, 4)},
                 "note": "achieved = SURVEY 8d no-reuse algorithmic bytes x points of one launch / CUDA-event "
                         "duration of that kernel inside the timed step. K1 (k-NN) moves only 8d + 4k' algorithmic "
-                        "B/point and is instruction-issue bound (69 % issue-active, ncu), so its HBM fraction is small "
+                        "B/point and is instruction-issue / latency bound (64 % issue-active, ncu), so its HBM fraction is small "
                         "by construction; K2/K3 serve most bytes from L2/shared memory (points are processed in spatial "
-                        "order, one copy per distinct element per warp) and are fp64-pipe / latency bound (fp64 pipe "
-                        "44 % active), so their algorithmic rate may exceed the HBM peak -- `traffic` is the DRAM bytes "
+                        "order, one copy per distinct element per warp) and are latency / fp64-pipe bound (fp64 pipe "
+                        "26-37 % active), so their algorithmic rate may exceed the HBM peak -- `traffic` is the DRAM bytes "
                         "ncu saw; whole_step = all three kernels' algorithmic bytes / the step time (sort included)"}
 
     # ---- CPU baseline, rank 0, N = 1 only -------------------------------------------------------
