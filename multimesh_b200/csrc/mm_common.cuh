@@ -65,7 +65,7 @@ int mm_knn_sites(const mm_index_t *ix, int64_t N, const double *pts, int kout, i
                  int32_t *idx, void *stream);
 // counting sort of query points by index cell: sorted[i] = pts[perm[i]]
 int mm_index_sort_queries(const mm_index_t *ix, int64_t N, const double *pts, double *sorted,
-                          int32_t *perm, void *scratch, void *stream);
+                          int32_t *perm, int32_t *rank_tmp, void *scratch, void *stream);
 
 static inline bool mm_valid_order(int order) { return order == 1 || order == 2 || order == 4; }
 static inline int mm_pow(int m, int dim) { return dim == 2 ? m * m : m * m * m; }

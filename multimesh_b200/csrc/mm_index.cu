@@ -653,16 +653,28 @@ knn_sites_kernel(grid_t g, int64_t N, const double *__restrict__ pts, int k, con
 }
 
 // ---- counting sort of QUERY points by index cell (coherent warps in K1-K3) -----------------------
+// pass 1: histogram of the query cells; the value the atomic returns is the query's rank inside its
+// cell, so the placement pass needs no second round of atomics
 __global__ void __launch_bounds__(256)
-query_scatter_kernel(grid_t g, int64_t N, const double *__restrict__ pts,
-                     const int32_t *__restrict__ start, int32_t *__restrict__ cursor,
-                     double *__restrict__ sorted, int32_t *__restrict__ perm)
+query_rank_kernel(grid_t g, int64_t N, const double *__restrict__ pts, int32_t *__restrict__ counts,
+                  int32_t *__restrict__ rank)
+{
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < N;
+         i += (int64_t)gridDim.x * blockDim.x)
+        rank[i] = atomicAdd(&counts[cell_of(g, pts + i * g.dim)], 1);
+}
+
+// pass 2 (after the exclusive scan): query i goes to start[cell] + rank[i]
+__global__ void __launch_bounds__(256)
+query_place_kernel(grid_t g, int64_t N, const double *__restrict__ pts,
+                   const int32_t *__restrict__ start, const int32_t *__restrict__ rank,
+                   double *__restrict__ sorted, int32_t *__restrict__ perm)
 {
     for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < N;
          i += (int64_t)gridDim.x * blockDim.x) {
         const double *p = pts + i * g.dim;
-        int64_t c = cell_of(g, p);
-        int32_t pos = start[c] + atomicAdd(&cursor[c], 1);
+        const int64_t c = cell_of(g, p);
+        const int32_t pos = start[c] + rank[i];
         for (int q = 0; q < g.dim; ++q) sorted[(int64_t)pos * g.dim + q] = p[q];
         perm[pos] = (int32_t)i;
     }
@@ -1041,7 +1053,7 @@ size_t mm_index_sort_scratch_bytes(const mm_index_t *ix)
 }
 
 int mm_index_sort_queries(const mm_index_t *ix, int64_t N, const double *pts, double *sorted,
-                          int32_t *perm, void *scratch, void *stream_)
+                          int32_t *perm, int32_t *rank_tmp, void *scratch, void *stream_)
 {
     cudaStream_t stream = (cudaStream_t)stream_;
     MM_REQUIRE(N < ((int64_t)1 << 31), MM_ERR_INVALID, "mm_interpolate: N=%lld >= 2^31 per call",
@@ -1052,13 +1064,12 @@ int mm_index_sort_queries(const mm_index_t *ix, int64_t N, const double *pts, do
     int32_t *tile_sums = starts + (ix->ncells + 1);
     int64_t ntiles = (ix->ncells + SCAN_TILE - 1) / SCAN_TILE;
     MM_CUDA(cudaMemsetAsync(counts, 0, sizeof(int32_t) * (size_t)(ix->ncells + 1), stream));
-    histogram_kernel<<<launch_blocks(N, 256, 8), 256, 0, stream>>>(g, N, pts, counts);
+    query_rank_kernel<<<launch_blocks(N, 256, 8), 256, 0, stream>>>(g, N, pts, counts, rank_tmp);
     scan_tile_sums<<<(int)ntiles, SCAN_BLOCK, 0, stream>>>(ix->ncells, counts, tile_sums);
     scan_tile_offsets<<<1, 1024, 0, stream>>>(ntiles, tile_sums);
     scan_apply<<<(int)ntiles, SCAN_BLOCK, 0, stream>>>(ix->ncells, counts, tile_sums, starts);
-    MM_CUDA(cudaMemsetAsync(counts, 0, sizeof(int32_t) * (size_t)(ix->ncells + 1), stream));
-    query_scatter_kernel<<<launch_blocks(N, 256, 8), 256, 0, stream>>>(g, N, pts, starts, counts,
-                                                                       sorted, perm);
+    query_place_kernel<<<launch_blocks(N, 256, 8), 256, 0, stream>>>(g, N, pts, starts, rank_tmp, sorted,
+                                                                     perm);
     MM_CUDA(cudaGetLastError());
     return MM_OK;
 }

@@ -165,7 +165,9 @@ int mm_interpolate_impl(const mm_index_t *index, int32_t divisor, int order, int
     mark(0);
 
     // 1. spatial sort of the target points
-    MM_TRY(mm_index_sort_queries(index, N, pts, sorted, perm, ws + L.sort_scratch, stream));
+    // (the element array is not written before K2: it holds the per-cell ranks of the sort meanwhile)
+    MM_TRY(mm_index_sort_queries(index, N, pts, sorted, perm, reinterpret_cast<int32_t *>(ws + L.elem),
+                                 ws + L.sort_scratch, stream));
     MM_CUDA(cudaMemsetAsync(counters, 0, 64, stream));
 
     mark(1);
