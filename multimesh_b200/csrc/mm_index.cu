@@ -96,7 +96,8 @@ __device__ __forceinline__ int cell_coord(const grid_t &g, double x, int c)
 {
     double f = floor((x - g.origin[c]) * g.inv_cell);
     double hi = (double)(g.n[c] - 1);
-    f = f < 0.0 ? 0.0 : (f > hi ? hi : f);  // NaN maps to hi; clamping keeps monotonicity
+    if (!(f >= 0.0)) f = 0.0;  // negative or NaN (the conversion of a NaN to int is not a valid cell)
+    if (f > hi) f = hi;        // clamping keeps monotonicity
     return (int)f;
 }
 
@@ -462,6 +463,15 @@ knn_body(const grid_t &g, int64_t N, const double *__restrict__ pts, int k, cons
         const double px = pts[n * g.dim + 0], py = pts[n * g.dim + 1];
         const double pz = three_d ? pts[n * g.dim + 2] : 0.0;
         const double p[3] = {px, py, pz};
+        if (!(isfinite(px) && isfinite(py) && isfinite(pz))) {
+            // a NaN / infinite query has no nearest neighbours (every comparison is false); without this
+            // guard it would walk the whole grid before reporting the same thing
+            for (int t = 0; t < k; ++t) {
+                out_idx[n * k + t] = -1;
+                if (out_d2) out_d2[n * k + t] = INFINITY;
+            }
+            continue;
+        }
         int ci[3];
         ci[0] = cell_coord(g, px, 0);
         ci[1] = cell_coord(g, py, 1);

@@ -130,6 +130,42 @@ def test_knn_queries_far_outside_the_source(cuda, oracle):
     assert np.array_equal(elem[: len(far)].cpu().numpy(), e)
 
 
+def test_non_finite_queries_fail_fast(cuda, oracle):
+    """NaN / infinite target coordinates: no neighbours, the point is reported as failed (elem -1, zero row),
+    and the other points of the batch are unaffected -- without a walk over the whole grid."""
+    import time
+
+    import torch
+    from multimesh_b200 import ops
+
+    nodes = _mesh(2, 3, 20, 0.01)
+    fields = meshgen.analytic_fields(nodes, ["VP", "VS"])
+    rng = np.random.default_rng(3)
+    pts = rng.random((4000, 3))
+    bad = np.arange(0, 4000, 97)
+    pts[bad[0::3], 0] = np.nan
+    pts[bad[1::3], 1] = np.inf
+    pts[bad[2::3], 2] = -np.inf
+    tn, tf = _t(nodes, cuda), _t(fields, cuda)
+    cent, box = ops.element_geometry(tn)
+    for data, div in ((tn.view(-1, 3), 27), (cent, 1)):
+        ix = ops.GridIndex(data)
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        idx = ix.query_idx(_t(pts, cuda), 20, divisor=div)
+        out, elem, xi, st, nf = ops.interpolate(ix, div, tn, cent, box, tf, _t(pts, cuda), 20, ops.V2())
+        torch.cuda.synchronize()
+        assert time.perf_counter() - t0 < 2.0
+        idx, elem, out = idx.cpu().numpy(), elem.cpu().numpy(), out.cpu().numpy()
+        assert (idx[bad] == -1).all() and (elem[bad] == -1).all() and (out[bad] == 0).all()
+        assert int(nf.item()) == len(bad)
+        good = np.setdiff1d(np.arange(4000), bad)
+        want = oracle.knn_bruteforce(data.cpu().numpy(), pts[good], 20) // div
+        assert np.array_equal(idx[good], want)
+        e, x, _, _ = oracle.locate(2, 3, nodes, pts[good], want.astype(np.int32), oracle.V2())
+        assert np.array_equal(elem[good], e)
+
+
 def test_knn_edge_cases(cuda, oracle):
     from multimesh_b200 import ops
     import torch
