@@ -463,9 +463,10 @@ knn_body(const grid_t &g, int64_t N, const double *__restrict__ pts, int k, cons
         const double px = pts[n * g.dim + 0], py = pts[n * g.dim + 1];
         const double pz = three_d ? pts[n * g.dim + 2] : 0.0;
         const double p[3] = {px, py, pz};
-        if (!(isfinite(px) && isfinite(py) && isfinite(pz))) {
-            // a NaN / infinite query has no nearest neighbours (every comparison is false); without this
-            // guard it would walk the whole grid before reporting the same thing
+        if (!(fabs(px) <= 1e150 && fabs(py) <= 1e150 && fabs(pz) <= 1e150)) {
+            // a NaN / infinite query (or one so far away that its squared distances overflow) has no
+            // nearest neighbours: every comparison is false; without this guard it would walk the whole
+            // grid before reporting the same thing
             for (int t = 0; t < k; ++t) {
                 out_idx[n * k + t] = -1;
                 if (out_d2) out_d2[n * k + t] = INFINITY;

@@ -39,6 +39,9 @@ __host__ __device__ inline int chunk_copy_bytes(int nf, int P, int odd_p)
     return odd_p ? ((b + 8 + 15) / 16) * 16 : b;
 }
 
+// element ids come from the caller: anything outside [0, E) is treated like -1 (failed point, zero row)
+__device__ __forceinline__ int32_t valid_elem(int32_t e, int64_t E) { return (e >= 0 && e < E) ? e : -1; }
+
 template <int ORDER, int DIM>
 __device__ __forceinline__ double contract_field(const double *__restrict__ v,
                                                  const double (&L)[DIM][ORDER + 1])
@@ -108,7 +111,7 @@ interp_kernel(const mm_gll_table T, const interp_cfg cfg, int64_t E,
         const int bytes = chunk_copy_bytes(nf, P, cfg.odd_p);
         const int s = (int)(q % cfg.stages);
         const int64_t n = b * 32 + lane;
-        const int32_t e = n < N ? elem[n] : -1;
+        const int32_t e = n < N ? valid_elem(elem[n], E) : -1;
         int shift = 0;
         bool use_tma = false;
         int64_t off = 0;
@@ -152,7 +155,7 @@ interp_kernel(const mm_gll_table T, const interp_cfg cfg, int64_t E,
         const int bytes = chunk_copy_bytes(nf, P, cfg.odd_p);
         const int s = (int)(q % cfg.stages);
         const int64_t n = b * 32 + lane;
-        const int32_t e = n < N ? elem[n] : -1;
+        const int32_t e = n < N ? valid_elem(elem[n], E) : -1;
         int shift = 0;
         bool use_tma = false;
         if (e >= 0) {
@@ -278,7 +281,7 @@ interp_coherent_kernel(const mm_gll_table T, const coh_cfg cfg, int64_t E,
     using cur_t = coh_cursor<ORDER, DIM>;
     auto load_batch = [&](cur_t &k) {  // group the lanes of batch k.b by element
         k.n = k.b * 32 + lane;
-        k.e = (k.b < nbatch && k.n < N) ? elem[k.n] : -1;
+        k.e = (k.b < nbatch && k.n < N) ? valid_elem(elem[k.n], E) : -1;
         const unsigned same = __match_any_sync(0xffffffffu, k.e);
         const int leader = __ffs(same) - 1;
         const unsigned leaders = __ballot_sync(0xffffffffu, lane == leader && k.e >= 0);
@@ -490,7 +493,7 @@ gather_coeffs_kernel(int P, int64_t E, int F, const double *__restrict__ fields,
          t += (int64_t)gridDim.x * blockDim.x) {
         int64_t n = t / F;
         int f = (int)(t - n * F);
-        int32_t e = elem[n];
+        int32_t e = valid_elem(elem[n], E);
         double acc = 0.0;
         if (e >= 0) {
             const double *v = fields + ((int64_t)e * F + f) * P;

@@ -109,7 +109,7 @@ locate_kernel(const mm_gll_table T, const mm_locate_params prm, int64_t E,
                 while (t < k) {
                     int32_t c = cl[t];
                     ++t;
-                    if (c < 0) continue;
+                    if (c < 0 || c >= E) continue;  // padding (-1) or an id the caller got wrong
                     bool dup = false;
                     for (int u = 0; u < t - 1; ++u) dup = dup || (cl[u] == c);
                     if (dup) continue;

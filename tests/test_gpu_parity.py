@@ -166,6 +166,43 @@ def test_non_finite_queries_fail_fast(cuda, oracle):
         assert np.array_equal(elem[good], e)
 
 
+def test_out_of_range_ids_are_treated_as_missing(cuda, oracle):
+    """Candidate / element ids come from the caller through the C-ABI: ids outside [0, E) must behave like the
+    -1 padding (skipped candidate, zero row), never read outside the arrays."""
+    import torch
+    from multimesh_b200 import ops
+
+    nodes = _mesh(2, 3, 5, 0.02)
+    E = nodes.shape[0]
+    fields = meshgen.analytic_fields(nodes, ["VP", "VS", "RHO"])
+    rng = np.random.default_rng(8)
+    pts = rng.random((2000, 3))
+    cands = oracle.knn_bruteforce(oracle.centroids(nodes), pts, 20).astype(np.int32)
+    broken = cands.copy()
+    broken[::3, 0] = E + 7          # first candidate replaced by garbage
+    broken[1::3, 1] = 2**31 - 1
+    clean = cands.copy()
+    clean[::3, 0] = -1
+    clean[1::3, 1] = -1
+    tn, tf = _t(nodes, cuda), _t(fields, cuda)
+    cent, box = ops.element_geometry(tn)
+    for spec in (ops.V1(), ops.V2(snap_to_nearest=True)):
+        e1, x1, s1, n1 = ops.locate(tn, cent, box, _t(pts, cuda), _t(broken, cuda), spec)
+        e2, x2, s2, n2 = ops.locate(tn, cent, box, _t(pts, cuda), _t(clean, cuda), spec)
+        assert torch.equal(e1, e2) and torch.equal(x1, x2) and torch.equal(s1, s2)
+    elem = e2.clone()
+    elem[::5] = E            # out of range -> zero row
+    elem[1::5] = -3
+    out = ops.interp(tf, elem, x2).cpu().numpy()
+    ref = elem.clone()
+    ref[::5] = -1
+    ref[1::5] = -1
+    assert np.array_equal(out, ops.interp(tf, ref, x2).cpu().numpy())
+    assert (out[::5] == 0).all() and (out[1::5] == 0).all() and (out[2::5] != 0).all()
+    perm = torch.randperm(len(pts), device=cuda).to(torch.int32)
+    assert torch.equal(ops.interp_perm(tf, elem, x2, perm)[perm.long()], torch.from_numpy(out).to(cuda))
+
+
 def test_knn_edge_cases(cuda, oracle):
     from multimesh_b200 import ops
     import torch
