@@ -140,6 +140,7 @@ trilinear_kernel(int64_t k, int64_t npoints, const int64_t *__restrict__ nearest
         int64_t best = -1, hit = -1;
         for (int64_t j = 0; j < k && hit < 0; ++j) {
             int64_t e = nearest[i * k + j];
+            if (e < 0) continue;  // -1 padding of a k-NN list longer than the mesh (the C twin has no such case)
             load_vtx(conn, nodes, e, vtx);
             if (hex8_check_hull(pnt, vtx, sol)) {
                 double maxerr = 0.0;
