@@ -43,7 +43,8 @@ int mm_num_sms();                 // SM count of the current device
 
 // internal (C++) entry points shared between translation units
 int mm_locate_impl(int order, int dim, int64_t E, const double *nodes, const double *centroid,
-                   const double *aabb, const double *presolve, int64_t N, const double *pts, int k,
+                   const double *aabb, const double *presolve, int64_t N, const double *pts,
+                   int pts_stride /* doubles between consecutive points */, int k,
                    const int32_t *cands,
                    const mm_locate_params *params, int32_t *elem, double *xi, uint8_t *status,
                    int64_t *num_failed, bool zero_num_failed, int32_t *unresolved_list,
@@ -56,16 +57,21 @@ int mm_interpolate_impl(const mm_index_t *index, int32_t divisor, int order, int
                         void *workspace, size_t workspace_bytes, void *stream, void *fields_ready);
 int mm_interp_fused(int order, int dim, int64_t E, int F, const double *fields, int64_t N,
                     const int32_t *elem_s, const double *xi_s, const uint8_t *status_s,
-                    const int32_t *perm, double *out, int32_t *elem_u, double *xi_u,
+                    const int32_t *perm, int perm_stride, double *out, int32_t *elem_u, double *xi_u,
                     uint8_t *status_u, void *stream);
 size_t mm_index_sort_scratch_bytes(const mm_index_t *ix);
 // site table (distinct coordinates) and the site-level first pass of the progressive search
 int mm_index_build_sites(mm_index_t *ix, void *stream);
-int mm_knn_sites(const mm_index_t *ix, int64_t N, const double *pts, int kout, int32_t divisor,
-                 int32_t *idx, void *stream);
-// counting sort of query points by index cell: sorted[i] = pts[perm[i]]
-int mm_index_sort_queries(const mm_index_t *ix, int64_t N, const double *pts, double *sorted,
-                          int32_t *perm, int32_t *rank_tmp, void *scratch, void *stream);
+int mm_knn_sites(const mm_index_t *ix, int64_t N, const double *pts, int pts_stride, int kout,
+                 int32_t divisor, int32_t *idx, void *stream);
+// mm_knn with a stride (in doubles) between consecutive query points
+int mm_knn_strided(const mm_index_t *ix, int64_t N, const double *pts, int pts_stride, int k,
+                   int32_t divisor, int32_t *idx, double *d2, void *stream);
+// counting sort of query points by index cell into 32-byte records {x, y, z (0 in 2-D), original
+// index in the low 32 bits of the fourth lane}: one aligned full-sector store per point
+constexpr int MM_QREC = 4;  // doubles per sorted-query record
+int mm_index_sort_queries(const mm_index_t *ix, int64_t N, const double *pts, double *sorted_rec,
+                          int32_t *rank_tmp, void *scratch, void *stream);
 
 static inline bool mm_valid_order(int order) { return order == 1 || order == 2 || order == 4; }
 static inline int mm_pow(int m, int dim) { return dim == 2 ? m * m : m * m * m; }

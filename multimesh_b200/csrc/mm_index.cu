@@ -445,7 +445,8 @@ __device__ __forceinline__ void scan_range(List &L, const double4 *__restrict__ 
 // the caller's full search handles the point.
 template <class List, bool SITES>
 __device__ __forceinline__ void
-knn_body(const grid_t &g, int64_t N, const double *__restrict__ pts, int k, const fast_div &divisor,
+knn_body(const grid_t &g, int64_t N, const double *__restrict__ pts, int pstride, int k,
+         const fast_div &divisor,
          const double4 *__restrict__ recs, const int32_t *__restrict__ cell_start,
          int32_t *__restrict__ out_idx, double *__restrict__ out_d2,
          const double4 *__restrict__ point_recs)
@@ -460,8 +461,8 @@ knn_body(const grid_t &g, int64_t N, const double *__restrict__ pts, int k, cons
 
     for (int64_t n = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; n < N;
          n += (int64_t)gridDim.x * blockDim.x) {
-        const double px = pts[n * g.dim + 0], py = pts[n * g.dim + 1];
-        const double pz = three_d ? pts[n * g.dim + 2] : 0.0;
+        const double px = pts[n * pstride + 0], py = pts[n * pstride + 1];
+        const double pz = three_d ? pts[n * pstride + 2] : 0.0;
         const double p[3] = {px, py, pz};
         if (!(fabs(px) <= 1e150 && fabs(py) <= 1e150 && fabs(pz) <= 1e150)) {
             // a NaN / infinite query (or one so far away that its squared distances overflow) has no
@@ -646,20 +647,22 @@ knn_body(const grid_t &g, int64_t N, const double *__restrict__ pts, int k, cons
 
 template <class List>
 __global__ void __launch_bounds__(KNN_BLOCK)
-knn_kernel(grid_t g, int64_t N, const double *__restrict__ pts, int k, const fast_div divisor,
+knn_kernel(grid_t g, int64_t N, const double *__restrict__ pts, int pstride, int k,
+           const fast_div divisor,
            const double4 *__restrict__ recs, const int32_t *__restrict__ cell_start,
            int32_t *__restrict__ out_idx, double *__restrict__ out_d2)
 {
-    knn_body<List, false>(g, N, pts, k, divisor, recs, cell_start, out_idx, out_d2, nullptr);
+    knn_body<List, false>(g, N, pts, pstride, k, divisor, recs, cell_start, out_idx, out_d2, nullptr);
 }
 
 // site pass: 64 registers so that 8 blocks of 128 threads stay resident per SM
 __global__ void __launch_bounds__(KNN_BLOCK, 8)
-knn_sites_kernel(grid_t g, int64_t N, const double *__restrict__ pts, int k, const fast_div divisor,
+knn_sites_kernel(grid_t g, int64_t N, const double *__restrict__ pts, int pstride, int k,
+                 const fast_div divisor,
                  const double4 *__restrict__ site_recs, const int32_t *__restrict__ site_cell_start,
                  int32_t *__restrict__ out_idx, const double4 *__restrict__ point_recs)
 {
-    knn_body<reg_list<4>, true>(g, N, pts, k, divisor, site_recs, site_cell_start, out_idx, nullptr,
+    knn_body<reg_list<4>, true>(g, N, pts, pstride, k, divisor, site_recs, site_cell_start, out_idx, nullptr,
                                 point_recs);
 }
 
@@ -675,19 +678,25 @@ query_rank_kernel(grid_t g, int64_t N, const double *__restrict__ pts, int32_t *
         rank[i] = atomicAdd(&counts[cell_of(g, pts + i * g.dim)], 1);
 }
 
-// pass 2 (after the exclusive scan): query i goes to start[cell] + rank[i]
+// pass 2 (after the exclusive scan): query i goes to record start[cell] + rank[i].  A record is 32
+// bytes {x, y, z (0 in 2-D), i in the low 32 bits of the fourth lane} written with one aligned
+// 32-byte store: a scattered 24-byte row plus a scattered 4-byte permutation entry would be two
+// partial-sector writes per point
 __global__ void __launch_bounds__(256)
 query_place_kernel(grid_t g, int64_t N, const double *__restrict__ pts,
                    const int32_t *__restrict__ start, const int32_t *__restrict__ rank,
-                   double *__restrict__ sorted, int32_t *__restrict__ perm)
+                   double *__restrict__ sorted_rec)
 {
     for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < N;
          i += (int64_t)gridDim.x * blockDim.x) {
         const double *p = pts + i * g.dim;
         const int64_t c = cell_of(g, p);
-        const int32_t pos = start[c] + rank[i];
-        for (int q = 0; q < g.dim; ++q) sorted[(int64_t)pos * g.dim + q] = p[q];
-        perm[pos] = (int32_t)i;
+        const int64_t pos = (int64_t)start[c] + rank[i];
+        const double z = g.dim == 3 ? p[2] : 0.0;
+        const double w = __longlong_as_double((long long)i);
+        asm volatile("st.global.v4.f64 [%0], {%1, %2, %3, %4};" ::"l"(sorted_rec + pos * MM_QREC),
+                     "d"(p[0]), "d"(p[1]), "d"(z), "d"(w)
+                     : "memory");
     }
 }
 
@@ -1026,6 +1035,13 @@ extern "C" int mm_knn(const mm_index_t *ix, int64_t N, const double *pts, int k,
                       int32_t *idx, double *d2, void *stream)
 {
     MM_REQUIRE(ix, MM_ERR_INVALID, "mm_knn: null index");
+    return mm_knn_strided(ix, N, pts, ix->dim, k, divisor, idx, d2, stream);
+}
+
+int mm_knn_strided(const mm_index_t *ix, int64_t N, const double *pts, int pts_stride, int k,
+                   int32_t divisor, int32_t *idx, double *d2, void *stream)
+{
+    MM_REQUIRE(ix, MM_ERR_INVALID, "mm_knn: null index");
     MM_REQUIRE(k >= 1 && k <= 64, MM_ERR_INVALID, "mm_knn: k=%d outside [1, 64]", k);
     MM_REQUIRE(divisor >= 1, MM_ERR_INVALID, "mm_knn: divisor %d", (int)divisor);
     MM_REQUIRE(N >= 0, MM_ERR_INVALID, "mm_knn: N");
@@ -1035,17 +1051,17 @@ extern "C" int mm_knn(const mm_index_t *ix, int64_t N, const double *pts, int k,
     cudaStream_t st = (cudaStream_t)stream;
     if (k <= 4) {
         knn_kernel<reg_list<4>><<<launch_blocks(N, KNN_BLOCK, 8), KNN_BLOCK, 0, st>>>(
-            g, N, pts, k, fast_div(divisor), ix->recs, ix->cell_start, idx, d2);
+            g, N, pts, pts_stride, k, fast_div(divisor), ix->recs, ix->cell_start, idx, d2);
     } else if (k <= 8) {
         knn_kernel<reg_list<8>><<<launch_blocks(N, KNN_BLOCK, 8), KNN_BLOCK, 0, st>>>(
-            g, N, pts, k, fast_div(divisor), ix->recs, ix->cell_start, idx, d2);
+            g, N, pts, pts_stride, k, fast_div(divisor), ix->recs, ix->cell_start, idx, d2);
     } else {
         size_t smem = (size_t)k * KNN_BLOCK * (sizeof(double) + sizeof(int32_t));
         MM_CUDA(cudaFuncSetAttribute(knn_kernel<smem_list>,
                                      cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         int per_sm = (int)std::max<size_t>(1, std::min<size_t>(8, (200 * 1024) / smem));
         knn_kernel<smem_list><<<launch_blocks(N, KNN_BLOCK, per_sm), KNN_BLOCK, smem, st>>>(
-            g, N, pts, k, fast_div(divisor), ix->recs, ix->cell_start, idx, d2);
+            g, N, pts, pts_stride, k, fast_div(divisor), ix->recs, ix->cell_start, idx, d2);
     }
     MM_CUDA(cudaGetLastError());
     return MM_OK;
@@ -1054,7 +1070,8 @@ extern "C" int mm_knn(const mm_index_t *ix, int64_t N, const double *pts, int k,
 // ------------------------------------------------------------------------------------------------
 // internal: counting sort of query points by the index's cell id.  The order inside a cell depends
 // on atomics and is NOT deterministic; results of the pipeline do not depend on it (every point's
-// result is a pure function of the point) and are written back through `perm`.
+// result is a pure function of the point) and are written back through the index stored in the
+// records.
 // scratch layout: counts[ncells + 1] | starts[ncells + 1] | tile_sums[ntiles]
 // ------------------------------------------------------------------------------------------------
 size_t mm_index_sort_scratch_bytes(const mm_index_t *ix)
@@ -1063,12 +1080,13 @@ size_t mm_index_sort_scratch_bytes(const mm_index_t *ix)
     return sizeof(int32_t) * (size_t)(2 * (ix->ncells + 1) + ntiles + 4);
 }
 
-int mm_index_sort_queries(const mm_index_t *ix, int64_t N, const double *pts, double *sorted,
-                          int32_t *perm, int32_t *rank_tmp, void *scratch, void *stream_)
+int mm_index_sort_queries(const mm_index_t *ix, int64_t N, const double *pts, double *sorted_rec,
+                          int32_t *rank_tmp, void *scratch, void *stream_)
 {
     cudaStream_t stream = (cudaStream_t)stream_;
     MM_REQUIRE(N < ((int64_t)1 << 31), MM_ERR_INVALID, "mm_interpolate: N=%lld >= 2^31 per call",
                (long long)N);
+    MM_REQUIRE(((uintptr_t)sorted_rec & 31) == 0, MM_ERR_INVALID, "mm_interpolate: workspace alignment");
     grid_t g = grid_of(ix);
     int32_t *counts = static_cast<int32_t *>(scratch);
     int32_t *starts = counts + (ix->ncells + 1);
@@ -1079,8 +1097,8 @@ int mm_index_sort_queries(const mm_index_t *ix, int64_t N, const double *pts, do
     scan_tile_sums<<<(int)ntiles, SCAN_BLOCK, 0, stream>>>(ix->ncells, counts, tile_sums);
     scan_tile_offsets<<<1, 1024, 0, stream>>>(ntiles, tile_sums);
     scan_apply<<<(int)ntiles, SCAN_BLOCK, 0, stream>>>(ix->ncells, counts, tile_sums, starts);
-    query_place_kernel<<<launch_blocks(N, 256, 8), 256, 0, stream>>>(g, N, pts, starts, rank_tmp, sorted,
-                                                                     perm);
+    query_place_kernel<<<launch_blocks(N, 256, 8), 256, 0, stream>>>(g, N, pts, starts, rank_tmp,
+                                                                     sorted_rec);
     MM_CUDA(cudaGetLastError());
     return MM_OK;
 }
@@ -1117,13 +1135,14 @@ int mm_index_build_sites(mm_index_t *ix, void *stream_)
     return MM_OK;
 }
 
-int mm_knn_sites(const mm_index_t *ix, int64_t N, const double *pts, int kout, int32_t divisor,
-                 int32_t *idx, void *stream)
+int mm_knn_sites(const mm_index_t *ix, int64_t N, const double *pts, int pts_stride, int kout,
+                 int32_t divisor, int32_t *idx, void *stream)
 {
     MM_REQUIRE(ix && ix->site_recs, MM_ERR_INVALID, "mm_knn_sites: site table not built");
     if (N == 0) return MM_OK;
     knn_sites_kernel<<<launch_blocks(N, KNN_BLOCK, 8), KNN_BLOCK, 0, (cudaStream_t)stream>>>(
-        grid_of(ix), N, pts, kout, fast_div(divisor), ix->site_recs, ix->site_cell_start, idx, ix->recs);
+        grid_of(ix), N, pts, pts_stride, kout, fast_div(divisor), ix->site_recs, ix->site_cell_start, idx,
+        ix->recs);
     MM_CUDA(cudaGetLastError());
     return MM_OK;
 }

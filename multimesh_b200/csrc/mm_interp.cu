@@ -240,6 +240,8 @@ int launch_interp(int64_t E, int F, const double *fields, int64_t N, const int32
 // ================================================================================================
 struct coh_cfg {
     int F, FC, chunks, stages, slots, slot_bytes, odd_p, warps;
+    int perm_stride;  // in int32 units: 1 for a plain permutation array, 8 when the permutation lives in
+                      // the .w lane of the pipeline's 32-byte sorted-query records
 };
 
 template <int ORDER, int DIM>
@@ -363,7 +365,7 @@ interp_coherent_kernel(const mm_gll_table T, const coh_cfg cfg, int64_t E,
 #pragma unroll
                 for (int ax = 0; ax < DIM; ++ax) x[ax] = xi[cc.n * DIM + ax];
                 if (elem_u) {  // fused un-permute of the location outputs (mm_interpolate)
-                    const int64_t t = perm ? (int64_t)perm[cc.n] : cc.n;
+                    const int64_t t = perm ? (int64_t)perm[cc.n * cfg.perm_stride] : cc.n;
                     elem_u[t] = cc.e;
                     if (status_u) status_u[t] = status[cc.n];
                     if (xi_u) {
@@ -385,11 +387,11 @@ interp_coherent_kernel(const mm_gll_table T, const coh_cfg cfg, int64_t E,
                 const int shift = cfg.odd_p ? (int)(off & 8) : 0;
                 const double *v = reinterpret_cast<const double *>(
                     wbase + s * stage_bytes + (size_t)slot_id * cfg.slot_bytes + shift);
-                double *o = out + (perm ? (int64_t)perm[cc.n] : cc.n) * cfg.F + f0;
+                double *o = out + (perm ? (int64_t)perm[cc.n * cfg.perm_stride] : cc.n) * cfg.F + f0;
                 for (int f = 0; f < nf; ++f) o[f] = contract_field<ORDER, DIM>(v + f * P, L);
             }
         } else if (cc.n < N && cc.b < nbatch && cc.r == 0) {
-            double *o = out + (perm ? (int64_t)perm[cc.n] : cc.n) * cfg.F + f0;
+            double *o = out + (perm ? (int64_t)perm[cc.n * cfg.perm_stride] : cc.n) * cfg.F + f0;
             for (int f = 0; f < nf; ++f) o[f] = 0.0;  // failed point: zero row
         }
         advance(cc);
@@ -400,7 +402,7 @@ template <int ORDER, int DIM>
 int launch_interp_coherent(int64_t E, int F, const double *fields, int64_t N, const int32_t *elem,
                            const double *xi, const int32_t *perm, double *out, cudaStream_t stream,
                            const uint8_t *status = nullptr, int32_t *elem_u = nullptr,
-                           double *xi_u = nullptr, uint8_t *status_u = nullptr)
+                           double *xi_u = nullptr, uint8_t *status_u = nullptr, int perm_stride = 1)
 {
     constexpr int M = ORDER + 1;
     constexpr int P = DIM == 2 ? M * M : M * M * M;
@@ -408,6 +410,7 @@ int launch_interp_coherent(int64_t E, int F, const double *fields, int64_t N, co
     mm_make_table(ORDER, &T);
     coh_cfg cfg;
     cfg.F = F;
+    cfg.perm_stride = perm_stride;
     cfg.odd_p = P % 2;
     // slots of about 1 KB (whole block at order <= 2 / F = 5, one field at order 4), 4 slots x 2
     // stages per warp, 8 warps per CTA: measured best on B200 (profiles/r1_*), ~3 CTAs per SM
@@ -593,7 +596,7 @@ extern "C" int mm_gather_coeffs(int P, int64_t E, int F, const double *fields, i
 // internal: K3 of the fused pipeline -- gather in sorted order + un-permuted location outputs
 int mm_interp_fused(int order, int dim, int64_t E, int F, const double *fields, int64_t N,
                     const int32_t *elem_s, const double *xi_s, const uint8_t *status_s,
-                    const int32_t *perm, double *out, int32_t *elem_u, double *xi_u,
+                    const int32_t *perm, int perm_stride, double *out, int32_t *elem_u, double *xi_u,
                     uint8_t *status_u, void *stream_)
 {
     cudaStream_t stream = (cudaStream_t)stream_;
@@ -601,7 +604,7 @@ int mm_interp_fused(int order, int dim, int64_t E, int F, const double *fields, 
 #define MM_INTF(O, D)                                                                             \
     if (order == O && dim == D)                                                                   \
         return launch_interp_coherent<O, D>(E, F, fields, N, elem_s, xi_s, perm, out, stream,     \
-                                            status_s, elem_u, xi_u, status_u);
+                                            status_s, elem_u, xi_u, status_u, perm_stride);
     MM_INTF(1, 2) MM_INTF(2, 2) MM_INTF(4, 2) MM_INTF(1, 3) MM_INTF(2, 3) MM_INTF(4, 3)
 #undef MM_INTF
     mm_set_error("mm_interpolate: unsupported order/dim");

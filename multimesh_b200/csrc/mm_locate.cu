@@ -50,7 +50,7 @@ __global__ void __launch_bounds__(WARPS * 32, MINB)
 locate_kernel(const mm_gll_table T, const mm_locate_params prm, int64_t E,
               const double *__restrict__ nodes, const double *__restrict__ centroid,
               const double *__restrict__ aabb, const double *__restrict__ presolve, int64_t N,
-              const double *__restrict__ pts, int k,
+              const double *__restrict__ pts, int pstride, int k,
               const int32_t *__restrict__ cands, int32_t *__restrict__ elem_out,
               double *__restrict__ xi_out, uint8_t *__restrict__ status_out,
               unsigned long long *__restrict__ num_failed, int32_t *__restrict__ unresolved_list,
@@ -75,13 +75,13 @@ locate_kernel(const mm_gll_table T, const mm_locate_params prm, int64_t E,
         {  // the warp's next batch: pull its points and candidate rows towards L2 now
             const int64_t nn = n + warps_total * 32;
             if (nn < N) {
-                prefetch_l2(pts + nn * DIM);
+                prefetch_l2(pts + nn * pstride);
                 prefetch_l2(cands + nn * (int64_t)k);
             }
         }
         double p[DIM];
 #pragma unroll
-        for (int c = 0; c < DIM; ++c) p[c] = done ? 0.0 : pts[n * DIM + c];
+        for (int c = 0; c < DIM; ++c) p[c] = done ? 0.0 : pts[n * pstride + c];
         const int32_t *cl = cands + (done ? 0 : n * (int64_t)k);
         int t = 0;
         int32_t r_elem = -1;
@@ -302,7 +302,7 @@ locate_kernel(const mm_gll_table T, const mm_locate_params prm, int64_t E,
 template <int ORDER, int DIM, int WARPS, int SLOTS, int MINB>
 int launch_locate(const mm_locate_params &prm, int64_t E, const double *nodes,
                   const double *centroid, const double *aabb, const double *presolve, int64_t N,
-                  const double *pts, int k,
+                  const double *pts, int pstride, int k,
                   const int32_t *cands, int32_t *elem, double *xi, uint8_t *status,
                   int64_t *num_failed, int32_t *unresolved_list, int64_t *unresolved_count,
                   cudaStream_t stream)
@@ -321,7 +321,7 @@ int launch_locate(const mm_locate_params &prm, int64_t E, const double *nodes,
     int64_t grid = (int64_t)sms * per_sm;  // persistent: resident CTAs loop over point batches
     if (grid > batches) grid = batches;
     if (grid < 1) grid = 1;
-    kern<<<(int)grid, WARPS * 32, smem, stream>>>(T, prm, E, nodes, centroid, aabb, presolve, N, pts, k,
+    kern<<<(int)grid, WARPS * 32, smem, stream>>>(T, prm, E, nodes, centroid, aabb, presolve, N, pts, pstride, k,
                                                   cands, elem, xi, status,
                                                   reinterpret_cast<unsigned long long *>(num_failed),
                                                   unresolved_list,
@@ -333,7 +333,8 @@ int launch_locate(const mm_locate_params &prm, int64_t E, const double *nodes,
 }  // namespace
 
 int mm_locate_impl(int order, int dim, int64_t E, const double *nodes, const double *centroid,
-                   const double *aabb, const double *presolve, int64_t N, const double *pts, int k,
+                   const double *aabb, const double *presolve, int64_t N, const double *pts,
+                   int pts_stride, int k,
                    const int32_t *cands,
                    const mm_locate_params *params, int32_t *elem, double *xi, uint8_t *status,
                    int64_t *num_failed, bool zero_num_failed, int32_t *unresolved_list,
@@ -357,7 +358,8 @@ int mm_locate_impl(int order, int dim, int64_t E, const double *nodes, const dou
     // kernel configuration <order, dim, warps per CTA, shared slots per warp, min CTAs per SM>
 #define MM_LOC(O, D, W, S, B)                                                                    \
     if (order == O && dim == D)                                                                  \
-        return launch_locate<O, D, W, S, B>(*params, E, nodes, centroid, aabb, presolve, N, pts, k,  \
+        return launch_locate<O, D, W, S, B>(*params, E, nodes, centroid, aabb, presolve, N, pts,     \
+                                            pts_stride, k,                                        \
                                             cands,                                                \
                                             elem, xi, status, num_failed, unresolved_list,       \
                                             unresolved_count, stream);
@@ -387,6 +389,6 @@ extern "C" int mm_locate(int order, int dim, int64_t E, const double *nodes,
     MM_REQUIRE(params, MM_ERR_INVALID, "mm_locate: null params");
     mm_locate_params prm = *params;
     prm.reserved = 0;  // the partial (progressive first pass) mode is internal to mm_interpolate
-    return mm_locate_impl(order, dim, E, nodes, centroid, aabb, presolve, N, pts, k, cands, &prm, elem, xi,
+    return mm_locate_impl(order, dim, E, nodes, centroid, aabb, presolve, N, pts, dim, k, cands, &prm, elem, xi,
                           status, num_failed, true, nullptr, nullptr, stream);
 }

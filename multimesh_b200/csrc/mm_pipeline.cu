@@ -45,8 +45,8 @@ ws_layout make_layout(const mm_index_t *ix, int dim, int64_t N, int k)
     size_t o = 0;
     auto take = [&](size_t bytes) { size_t at = o; o += align_up(bytes); return at; };
     const int k1 = std::min(k, 8);  // sized for the larger first pass
-    L.sorted = take(sizeof(double) * N * dim);
-    L.perm = take(sizeof(int32_t) * N);
+    L.sorted = take(sizeof(double) * N * MM_QREC);  // 32-byte records {x, y, z, original index}
+    L.perm = 0;
     L.cands1 = take(sizeof(int32_t) * N * k1);
     L.elem = take(sizeof(int32_t) * N);
     L.xi = take(sizeof(double) * N * dim);
@@ -70,7 +70,7 @@ gather_points_kernel(int dim, int64_t n, const int32_t *__restrict__ list,
 {
     for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n;
          i += (int64_t)gridDim.x * blockDim.x)
-        for (int c = 0; c < dim; ++c) out[i * dim + c] = pts[(int64_t)list[i] * dim + c];
+        for (int c = 0; c < dim; ++c) out[i * dim + c] = pts[(int64_t)list[i] * MM_QREC + c];  // from the records
 }
 
 __global__ void __launch_bounds__(256)
@@ -89,14 +89,14 @@ scatter_results_kernel(int dim, int64_t n, const int32_t *__restrict__ list,
 }
 
 __global__ void __launch_bounds__(256)
-unpermute_kernel(int dim, int64_t n, const int32_t *__restrict__ perm,
+unpermute_kernel(int dim, int64_t n, const int32_t *__restrict__ perm, int perm_stride,
                  const int32_t *__restrict__ elem_s, const double *__restrict__ xi_s,
                  const uint8_t *__restrict__ status_s, int32_t *__restrict__ elem,
                  double *__restrict__ xi, uint8_t *__restrict__ status)
 {
     for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n;
          i += (int64_t)gridDim.x * blockDim.x) {
-        const int64_t t = perm[i];
+        const int64_t t = perm[i * perm_stride];
         if (elem) elem[t] = elem_s[i];
         if (status) status[t] = status_s[i];
         if (xi)
@@ -147,7 +147,9 @@ int mm_interpolate_impl(const mm_index_t *index, int32_t divisor, int order, int
     MM_REQUIRE(((uintptr_t)workspace & 255) == 0, MM_ERR_INVALID, "mm_interpolate: workspace must be 256-byte aligned");
     unsigned char *ws = static_cast<unsigned char *>(workspace);
     double *sorted = reinterpret_cast<double *>(ws + L.sorted);
-    int32_t *perm = reinterpret_cast<int32_t *>(ws + L.perm);
+    // the permutation is the low word of the fourth lane of every record
+    const int32_t *perm = reinterpret_cast<const int32_t *>(sorted + 3);
+    constexpr int PERM_STRIDE = MM_QREC * 2;
     int32_t *cands1 = reinterpret_cast<int32_t *>(ws + L.cands1);
     int32_t *elem_s = reinterpret_cast<int32_t *>(ws + L.elem);
     double *xi_s = reinterpret_cast<double *>(ws + L.xi);
@@ -166,7 +168,7 @@ int mm_interpolate_impl(const mm_index_t *index, int32_t divisor, int order, int
 
     // 1. spatial sort of the target points
     // (the element array is not written before K2: it holds the per-cell ranks of the sort meanwhile)
-    MM_TRY(mm_index_sort_queries(index, N, pts, sorted, perm, reinterpret_cast<int32_t *>(ws + L.elem),
+    MM_TRY(mm_index_sort_queries(index, N, pts, sorted, reinterpret_cast<int32_t *>(ws + L.elem),
                                  ws + L.sort_scratch, stream));
     MM_CUDA(cudaMemsetAsync(counters, 0, 64, stream));
 
@@ -176,14 +178,14 @@ int mm_interpolate_impl(const mm_index_t *index, int32_t divisor, int order, int
     if (site_pass) {
         // GLL-point form: shared nodes are stored up to 8 times; search over distinct coordinates
         MM_TRY(mm_index_build_sites(const_cast<mm_index_t *>(index), stream));  // once per index
-        MM_TRY(mm_knn_sites(index, N, sorted, k1, divisor, cands1, stream));
+        MM_TRY(mm_knn_sites(index, N, sorted, MM_QREC, k1, divisor, cands1, stream));
     } else {
-        MM_TRY(mm_knn(index, N, sorted, k1, divisor, cands1, nullptr, stream));
+        MM_TRY(mm_knn_strided(index, N, sorted, MM_QREC, k1, divisor, cands1, nullptr, stream));
     }
     mark(2);
     mm_locate_params p1 = *params;
     p1.reserved = (k1 < k) ? 1 : 0;
-    MM_TRY(mm_locate_impl(order, dim, E, nodes, centroid, aabb, presolve, N, sorted, k1, cands1, &p1, elem_s,
+    MM_TRY(mm_locate_impl(order, dim, E, nodes, centroid, aabb, presolve, N, sorted, MM_QREC, k1, cands1, &p1, elem_s,
                           xi_s, status_s, counters + 1, false, (k1 < k) ? list : nullptr,
                           (k1 < k) ? counters : nullptr, stream));
 
@@ -204,7 +206,7 @@ int mm_interpolate_impl(const mm_index_t *index, int32_t divisor, int order, int
             const int64_t nb = std::min<int64_t>(CHUNK_B, n_un - at);
             gather_points_kernel<<<blocks_for(nb), 256, 0, stream>>>(dim, nb, list + at, sorted, b_pts);
             MM_TRY(mm_knn(index, nb, b_pts, k, divisor, b_cands, nullptr, stream));
-            MM_TRY(mm_locate_impl(order, dim, E, nodes, centroid, aabb, presolve, nb, b_pts, k, b_cands, &p2,
+            MM_TRY(mm_locate_impl(order, dim, E, nodes, centroid, aabb, presolve, nb, b_pts, dim, k, b_cands, &p2,
                                   b_elem, b_xi, b_status, counters + 1, false, nullptr, nullptr,
                                   stream));
             scatter_results_kernel<<<blocks_for(nb), 256, 0, stream>>>(
@@ -222,13 +224,13 @@ int mm_interpolate_impl(const mm_index_t *index, int32_t divisor, int order, int
     if (fields) {
         MM_REQUIRE(out, MM_ERR_INVALID, "mm_interpolate: null out");
         if (fields_ready) MM_CUDA(cudaStreamWaitEvent(stream, (cudaEvent_t)fields_ready, 0));
-        MM_TRY(mm_interp_fused(order, dim, E, F, fields, N, elem_s, xi_s, status_s, perm, out, elem, xi,
+        MM_TRY(mm_interp_fused(order, dim, E, F, fields, N, elem_s, xi_s, status_s, perm, PERM_STRIDE, out, elem, xi,
                                status, stream));
         unpermuted = elem != nullptr;
     }
     mark(5);
     if (!unpermuted && (elem || xi || status)) {
-        unpermute_kernel<<<blocks_for(N), 256, 0, stream>>>(dim, N, perm, elem_s, xi_s, status_s,
+        unpermute_kernel<<<blocks_for(N), 256, 0, stream>>>(dim, N, perm, PERM_STRIDE, elem_s, xi_s, status_s,
                                                             elem, xi, status);
         MM_CUDA(cudaGetLastError());
     }
