@@ -52,7 +52,7 @@ WORKLOADS = {
 def workload_name(w):
     if w.get("device_gen"):
         return (f"{w['name']}: source {w['src']}^3 hex order-{w['order']} F=5 (generated on the device), "
-                f"{w['npoints']} uniform random target points split over the GPUs (strong scaling), k={w['k']}, "
+                f"{w['npoints']} uniform random target points partitioned over the GPUs into equal-count x-slabs (strong scaling), k={w['k']}, "
                 f"V1 location, {w.get('form', 'gll')} k-NN form")
     return (f"{w['name']}: gll_2_gll, source {w['src']}^3 hex order-{w['order']} F=5, targets = GLL points of a "
             f"non-nested {w['tgt']}^3 order-{w['order']} mesh, k={w['k']}, V1 location, GLL-point k-NN form")
@@ -275,10 +275,15 @@ def run_ours(args, w):
     if device_gen:
         nodes, fields = make_source_device(w, dev)
         from multimesh_b200.parallel import local_slice
-        sl = local_slice(w["npoints"], rank, world)  # strong scaling: this rank's contiguous share
+        # strong scaling: the uniform cloud of w["npoints"] points is partitioned into `world` equal-count slabs
+        # along x (multimesh_b200.parallel "slab" partition; a random index-range partition would leave every
+        # rank with all source elements at 1/world of the point density).  Each rank generates its own slab.
+        sl = local_slice(w["npoints"], rank, world)
         g = torch.Generator(device=dev)
         g.manual_seed(1234 + rank)
         pts = torch.rand((sl.stop - sl.start, 3), dtype=torch.float64, device=dev, generator=g)
+        if world > 1 and os.environ.get("MM_BENCH_PARTITION", "slab") == "slab":
+            pts[:, 0] = (pts[:, 0] + rank) / world
         nodes_h = fields_h = pts_h = None
         E, N = nodes.shape[0], pts.shape[0]
     else:

@@ -34,13 +34,22 @@ def _worker(rank, world, port, tmpdir):
         return torch.from_numpy(oracle.interp(2, 3, fields, elem, xi)), torch.from_numpy(elem)
 
     (vals, elem), gathered = interpolate_sharded(compute, pts, gather_to=0)
+    (vals2, elem2), gathered2 = interpolate_sharded(compute, pts, gather_to=0, partition="slab")
+    from multimesh_b200.parallel import slab_partition
+    sets = slab_partition(pts, world)
+    assert sorted(np.concatenate(sets).tolist()) == list(range(len(pts)))      # a partition ...
+    assert abs(len(sets[0]) - len(sets[1])) <= 1                                 # ... of equal counts ...
+    ax = int(np.argmax(pts.max(axis=0) - pts.min(axis=0)))
+    assert pts[sets[0], ax].max() <= pts[sets[1], ax].min()                      # ... into slabs along the longest axis
+    assert vals2.shape[0] == len(sets[rank])
     if rank == 0:
         full_vals, _ = compute(pts)
         assert gathered.shape == full_vals.shape
         assert torch.equal(gathered, full_vals), "sharded result is not bit-identical"
+        assert torch.equal(gathered2, full_vals), "slab-sharded result is not bit-identical"
         open(os.path.join(tmpdir, "ok"), "w").write("ok")
     else:
-        assert gathered is None
+        assert gathered is None and gathered2 is None
     dist.barrier()
     dist.destroy_process_group()
 
