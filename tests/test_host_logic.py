@@ -108,6 +108,34 @@ def test_shard_bounds():
         assert sum(local_slice(n, r, w).stop - local_slice(n, r, w).start for r in range(w)) == n
 
 
+def test_slab_partition():
+    """Equal-count slabs along the longest axis; a partition of all indices; deterministic; edge cases."""
+    from multimesh_b200.parallel import slab_partition
+
+    rng = np.random.default_rng(0)
+    pts = rng.random((10_001, 3)) * np.array([1.0, 5.0, 2.0])  # longest extent: y
+    for world in (1, 2, 3, 8):
+        sets = slab_partition(pts, world)
+        assert len(sets) == world
+        allidx = np.concatenate(sets)
+        assert np.array_equal(np.sort(allidx), np.arange(len(pts)))
+        sizes = [len(s) for s in sets]
+        assert max(sizes) - min(sizes) <= 1
+        for a, b in zip(sets[:-1], sets[1:]):
+            assert pts[a, 1].max() <= pts[b, 1].min()
+        again = slab_partition(pts.copy(), world)
+        assert all(np.array_equal(a, b) for a, b in zip(sets, again))
+    # explicit axis, more ranks than points, no points, ties on the cut stay together
+    assert pts[slab_partition(pts, 2, axis=0)[0], 0].max() <= pts[slab_partition(pts, 2, axis=0)[1], 0].min()
+    few = slab_partition(pts[:3], 8)
+    assert sum(len(s) for s in few) == 3 and len(few) == 8
+    assert [len(s) for s in slab_partition(pts[:0], 4)] == [0, 0, 0, 0]
+    tied = np.zeros((100, 3))
+    tied[:, 0] = np.repeat([0.0, 1.0], 50)
+    t = slab_partition(tied, 2)
+    assert np.array_equal(np.sort(np.concatenate(t)), np.arange(100)) and {len(t[0]), len(t[1])} == {50}
+
+
 def test_meshgen_shapes_and_shell_radii():
     c = meshgen.box_mesh((3, 2), 4, lo=[0, 0], hi=[3, 2])
     assert c.shape == (6, 25, 2) and c.min() == 0 and c[..., 0].max() == 3
