@@ -124,7 +124,7 @@ def test_knn_queries_far_outside_the_source(cuda, oracle):
     t0 = time.perf_counter()
     out, elem, xi, st, nf = ops.interpolate(ix, 27, tn, cent, box, None, big, 20, ops.V1())
     torch.cuda.synchronize()
-    assert time.perf_counter() - t0 < 20.0  # generous: the unbounded search took minutes
+    assert time.perf_counter() - t0 < 20.0  # generous bound; the point is that it does not scale with the distance
     cands = oracle.knn_bruteforce(allp, far, 20) // 27
     e, x, _, _ = oracle.locate(2, 3, nodes, far, cands.astype(np.int32), oracle.V1())
     assert np.array_equal(elem[: len(far)].cpu().numpy(), e)
@@ -155,7 +155,7 @@ def test_non_finite_queries_fail_fast(cuda, oracle):
         idx = ix.query_idx(_t(pts, cuda), 20, divisor=div)
         out, elem, xi, st, nf = ops.interpolate(ix, div, tn, cent, box, tf, _t(pts, cuda), 20, ops.V2())
         torch.cuda.synchronize()
-        assert time.perf_counter() - t0 < 10.0  # generous: includes first-use set-up; a grid walk would take minutes
+        assert time.perf_counter() - t0 < 10.0  # generous bound (first-use set-up included)
         idx, elem, out = idx.cpu().numpy(), elem.cpu().numpy(), out.cpu().numpy()
         assert (idx[bad] == -1).all() and (elem[bad] == -1).all() and (out[bad] == 0).all()
         assert int(nf.item()) == len(bad)
