@@ -8,6 +8,7 @@ Generates tests/golden/glue_*.npz by RUNNING THE REFERENCE'S OWN PYTHON (importe
   glue_v4.npz        v2_interpolation_tools.get_element_weights             v2_interpolation_tools.py:71-164
   glue_v5.npz        scripts/cli.py _check_if_inside_element                cli.py:401-430
   glue_points.npz    interpolate_to_points (centroid tree, V2, gather)      interpolator.py:931-977
+  glue_gll2gll_2d.npz  the same driver on 2-D order-4 quads (BASELINE config 1's shape)
   glue_gll2gll.npz   gll_2_gll end to end (dedup, GLL-point tree // P, V1, gather, recon, fluid
                      fix-up) on in-memory files                             interpolator.py:621-852
 
@@ -43,7 +44,8 @@ import glue_inputs  # noqa: E402
 capi.set_num_threads(1)
 NAMES = ["QKAPPA", "QMU", "RHO", "VP", "VS"]
 SEEDS = {"case_v3": 301, "case_v4": 401, "case_v5": 501, "case_points": 601, "case_gll2gll": 701, "case_layered": 801,
-         "case_query_model": 901, "case_exodus": 1001}
+         "case_query_model": 901, "case_exodus": 1001,
+         "case_gll2gll_2d": 1101}
 
 
 def save(name, **kw):
@@ -218,6 +220,37 @@ def case_gll2gll(seed):
          values=out, label=np.array(label))
 
 
+def case_gll2gll_2d(seed):
+    """gll_2_gll on 2-D quads (BASELINE config 1; the reference's 2-D dispatch exists for order 4 only, :50-53)."""
+    import contextlib
+    import io
+
+    rng = np.random.default_rng(seed)
+    names = ["RHO", "VP", "VS"]
+    src = meshgen.box_mesh((7, 6), 4, warp=0.02)
+    tgt = meshgen.box_mesh((5, 6), 4, lo=[0.01, 0.02], hi=[0.98, 0.97], warp=0.01)
+    fields = meshgen.analytic_fields(src, names)
+    old = rng.uniform(1.0, 2.0, (tgt.shape[0], len(names), tgt.shape[1]))
+    fluid = np.zeros(len(tgt))
+    edata = np.stack([fluid, np.ones(len(tgt))], axis=1)
+    refglue.write_gll_file("from2d.h5", src, fields, names)
+    refglue.write_gll_file("to2d.h5", tgt, old, names, element_data=edata, element_labels=["fluid", "layer"])
+    original = interp.find_gll_coeffs
+
+    def find_gll_coeffs_int(**kw):  # same float-index bridge as case_gll2gll
+        element, coeffs = original(**kw)
+        return element.astype(int), coeffs
+
+    interp.find_gll_coeffs = find_gll_coeffs_int
+    try:
+        with contextlib.redirect_stdout(io.StringIO()):
+            interp.gll_2_gll("from2d.h5", "to2d.h5", nelem_to_search=20)
+    finally:
+        interp.find_gll_coeffs = original
+    save("glue_gll2gll_2d.npz", src_shape=np.array((7, 6)), src_warp=0.02, tgt_shape=np.array((5, 6)), tgt_warp=0.01,
+         order=4, names=np.array(names), values=refglue.FILES["to2d.h5"]["MODEL/data"].array)
+
+
 def shell_files(order, seed, layers=None):
     pair = glue_inputs.shell_pair(order, seed, layers)
     for key, (coords, data, ed) in pair.items():
@@ -330,6 +363,7 @@ def main():
     case_layered(801)
     case_query_model(901)
     case_exodus(1001)
+    case_gll2gll_2d(1101)
     print("reference calls served by the oracle arithmetic:", refglue.CALLS)
 
 

@@ -470,3 +470,23 @@ def test_cuda_exodus_drivers(cuda, tmp_path):
     api.gll_2_exodus(path, ex2, gll_order=4)
     back = np.stack([ex2.get_nodal_field(n) for n in names], axis=1)
     assert np.max(np.abs(back - g["back"]) / np.abs(g["back"])) <= REL
+
+
+def test_oracle_gll_2_gll_driver_2d(oracle):
+    """The reference's gll_2_gll on 2-D order-4 quads (BASELINE config 1's shape; the only 2-D order the reference
+    dispatches, interpolator.py:50-53), replayed with oracle pieces."""
+    g = load("glue_gll2gll_2d.npz")
+    names = [str(n) for n in g["names"]]
+    src = meshgen.box_mesh(tuple(int(v) for v in g["src_shape"]), 4, warp=float(g["src_warp"]))
+    tgt = meshgen.box_mesh(tuple(int(v) for v in g["tgt_shape"]), 4, lo=[0.01, 0.02], hi=[0.98, 0.97],
+                           warp=float(g["tgt_warp"]))
+    fields = meshgen.analytic_fields(src, names)
+    E, P, d = src.shape
+    uniq, recon = utils.get_unique_points(tgt)
+    cands = oracle.knn_bruteforce(src.reshape(-1, d), uniq, 20) // P
+    elem, xi, _, _ = oracle.locate(4, d, src, uniq, cands.astype(np.int32), oracle.V1())
+    vals = oracle.interp(4, d, fields, elem, xi)
+    out = vals[recon].reshape(tgt.shape[0], tgt.shape[1], len(names)).swapaxes(1, 2)
+    want = g["values"]
+    assert out.shape == want.shape
+    assert np.max(np.abs(out - want) / np.abs(want)) <= REL
