@@ -82,6 +82,12 @@ int mm_index_destroy(mm_index_t *index);
 /* info[0]=M, info[1]=dim, info[2..4]=cells per axis, info[5]=non-empty cells, info[6]=bytes held */
 int mm_index_info(const mm_index_t *index, int64_t info[8], double *cell_size);
 
+/* Optional: build the index's SITE TABLE (one record per distinct coordinate).  The GLL-point form stores
+ * every node shared between elements up to 8 times; with the table the first pass of mm_interpolate
+ * searches distinct coordinates only (3-4x fewer distance evaluations).  Mutates the index: call it once
+ * after mm_index_create, before the index is shared between threads / streams.  Synchronises the stream. */
+int mm_index_prepare_sites(mm_index_t *index, void *stream);
+
 /* idx [N][k] int32 (out): neighbour ids divided (integer division) by `divisor`
  *   divisor = 1: plain ids;  divisor = P: the reference's GLL-point form `idx // P`
  *   (components/interpolator.py:116-118, 754-756).  Missing neighbours (k > M) are -1.
@@ -197,7 +203,9 @@ int mm_gather_nodal(int F, int64_t npoints_mesh, const double *param, int64_t N,
  *     results are written back through the permutation;
  *   - the search is progressive: a first pass with the min(k, 8) nearest candidates resolves
  *     most points (any prefix of the canonical k-NN list is the k'-NN list); only points whose
- *     prefix is exhausted are re-run with all k candidates and the variant's fallback.
+ *     prefix is exhausted are re-run with all k candidates and the variant's fallback;
+ *   - the call is STREAM-ORDERED: it never synchronises with the host (the number of points to re-run
+ *     stays on the device), so it can be captured in a CUDA graph.  0 <= N < 2^31 per call.
  *   index    : over element centroids (divisor = 1) or over all GLL points (divisor = P)
  *   fields   : [E][F][P], may be NULL (locate only; out ignored)
  *   out      : [N][F];  elem [N], xi [N][dim], status [N]: optional (NULL to skip)
@@ -242,7 +250,9 @@ long long int triLinearInterpolator(long long int nelem_to_search, long long int
 /* ------------------------------------------------------------------------------------------
  * End-to-end convenience over HOST buffers (the call the e2e benchmark times):
  * H2D of the source mesh and targets, index build over centroids (gll_points_form = 0) or over
- * all GLL points (gll_points_form = 1, the gll_2_gll form), k-NN, locate, gather, D2H.
+ * all GLL points (gll_points_form = 1, the gll_2_gll form), k-NN, locate, gather, D2H
+ * (= mm_source_create_host + mm_source_interpolate_host + mm_source_destroy, with the field upload
+ * overlapping the index build; any N).
  *   values [N][F] f64 (out, host), elem [N] int32 (out, host, may be NULL),
  *   xi [N][dim] (out, host, may be NULL).  Returns MM_OK or an error; *num_failed (host).
  * ---------------------------------------------------------------------------------------- */
@@ -250,9 +260,51 @@ int mm_interpolate_host(int order, int dim, int64_t E, const double *nodes, int 
                         const double *fields, int64_t N, const double *pts, int k,
                         int gll_points_form, const mm_locate_params *params, double *values,
                         int32_t *elem, double *xi, int64_t *num_failed);
-/* mm_interpolate_host keeps its device buffers and two streams in a per-thread pool between calls
- * (repeated interpolations re-use them); this releases the pool. */
+/* All device memory behind mm_interpolate_host / mm_source_* / mm_index_* comes from a stream-ordered pool
+ * PRIVATE to this library (the device's default pool is never reconfigured); freed blocks stay cached for
+ * the next call.  mm_pool_trim() (alias mm_host_release) returns the cached blocks to the driver. */
 int mm_host_release(void);
+int mm_pool_trim(void);
+
+/* ------------------------------------------------------------------------------------------
+ * Resident source mesh.  The reference re-reads the source model and rebuilds its KD-tree in every call
+ * (components/interpolator.py:660-760, 288-373); its users interpolate between a fixed mesh pair many
+ * times (sum of gradients, model updates).  The handle keeps nodes, fields, centroid/AABB, affine
+ * pre-solve and the spatial index (+ site table in the GLL-point form) in HBM; a call then moves only
+ * target points in and values out.
+ *   mm_source_create_host   : nodes [E][P][dim], fields [E][F][P] (F may be 0 / fields NULL) on the HOST
+ *                             (pinned memory makes the upload asynchronous); copies them to the device
+ *   mm_source_create_device : the same from DEVICE arrays, which are BORROWED (caller keeps them alive,
+ *                             16-byte aligned); work already enqueued on `stream` (e.g. an NCCL broadcast
+ *                             of the mesh from the loading rank) is ordered before the build
+ *   mm_source_set_fields_host: replace the fields (new model on the same geometry), host-owned sources
+ *   mm_source_interpolate   : device pointers, one mm_interpolate on the caller's stream (stream-ordered,
+ *                             no host synchronisation unless the internal workspace has to grow)
+ *   mm_source_interpolate_host: HOST pointers; the points are cut into chunks (default 2 M points,
+ *                             MM_HOST_CHUNK overrides) and pipelined over three streams -- H2D of chunk
+ *                             i+1, K1-K3 of chunk i, D2H of chunk i-1 -- so both PCIe directions and the SMs
+ *                             work concurrently.  Any N (chunks are < 2^31 points each).  values/elem/xi:
+ *                             any may be NULL (not all).  Returns after the last byte has arrived.
+ * Results are identical to mm_interpolate for every chunking (each point is a pure function of the source).
+ * gll_points_form: 0 = index over element centroids, 1 = over all GLL points (`idx // P`, gll_2_gll).
+ * info: E, P, dim, F, order, gll_points_form, bytes resident, device.
+ * A handle is bound to the device that was current at creation; not thread-safe (one call at a time).
+ * ---------------------------------------------------------------------------------------- */
+typedef struct mm_source mm_source_t;
+int mm_source_create_host(mm_source_t **out, int order, int dim, int64_t E, const double *nodes, int F,
+                          const double *fields, int gll_points_form);
+int mm_source_create_device(mm_source_t **out, int order, int dim, int64_t E, const double *nodes, int F,
+                            const double *fields, int gll_points_form, void *stream);
+int mm_source_set_fields_host(mm_source_t *src, int F, const double *fields);
+int mm_source_destroy(mm_source_t *src);
+int mm_source_info(const mm_source_t *src, int64_t info[8]);
+const mm_index_t *mm_source_index(const mm_source_t *src);
+int mm_source_interpolate(mm_source_t *src, int64_t N, const double *pts, int k,
+                          const mm_locate_params *params, double *out, int32_t *elem, double *xi,
+                          uint8_t *status, int64_t *num_failed, void *stream);
+int mm_source_interpolate_host(mm_source_t *src, int64_t N, const double *pts, int k,
+                               const mm_locate_params *params, double *values, int32_t *elem, double *xi,
+                               int64_t *num_failed);
 
 #ifdef __cplusplus
 }

@@ -66,6 +66,17 @@ _SIGNATURES = {
     "mm_interpolate_host": (_int, [_int, _int, _i64, _vp, _int, _vp, _i64, _vp, _int, _int,
                                    C.POINTER(LocateParams), _vp, _vp, _vp, C.POINTER(_i64)]),
     "mm_host_release": (_int, []),
+    "mm_pool_trim": (_int, []),
+    "mm_index_prepare_sites": (_int, [_vp, _vp]),
+    "mm_source_create_host": (_int, [C.POINTER(_vp), _int, _int, _i64, _vp, _int, _vp, _int]),
+    "mm_source_create_device": (_int, [C.POINTER(_vp), _int, _int, _i64, _vp, _int, _vp, _int, _vp]),
+    "mm_source_set_fields_host": (_int, [_vp, _int, _vp]),
+    "mm_source_destroy": (_int, [_vp]),
+    "mm_source_info": (_int, [_vp, C.POINTER(_i64 * 8)]),
+    "mm_source_index": (_vp, [_vp]),
+    "mm_source_interpolate": (_int, [_vp, _i64, _vp, _int, C.POINTER(LocateParams), _vp, _vp, _vp, _vp, _vp, _vp]),
+    "mm_source_interpolate_host": (_int, [_vp, _i64, _vp, _int, C.POINTER(LocateParams), _vp, _vp, _vp,
+                                          C.POINTER(_i64)]),
     "mm_profile_create": (_int, [C.POINTER(_vp), _int]),
     "mm_profile_destroy": (_int, [_vp]),
     "mm_profile_begin": (_int, [_vp]),

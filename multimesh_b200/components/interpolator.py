@@ -354,10 +354,17 @@ def _save_interp_info(stored_array, coeffs, elements):
             st.write(f"elements/{k}", np.asarray(v))
 
 
-def _layered_write_back(original_mesh, original_mask, new_mesh, unique_new_points, mask, parameters, located):
-    """values[inverse] -> reshape -> new_field[mask] per parameter, then attach (:415-427)."""
+def _layered_write_back(original_mesh, original_mask, new_mesh, unique_new_points, mask, parameters, located,
+                        keep_outside=False):
+    """values[inverse] -> reshape -> new_field[mask] per parameter, then attach (:415-427).
+    Elements outside the requested layers are zeroed by gll_2_gll_layered (:416) and
+    interpolate_to_points_layered (:913) and KEEP their values in gll_2_gll_layered_multi (:607) and
+    gll_2_gll_layered_multi_two (:1070) -- `keep_outside`."""
     dev = _device()
-    new_fields = {p: np.zeros_like(new_mesh.element_nodal_fields[p]) for p in parameters}
+    if keep_outside:
+        new_fields = {p: np.array(new_mesh.element_nodal_fields[p], dtype=np.float64, copy=True) for p in parameters}
+    else:
+        new_fields = {p: np.zeros_like(new_mesh.element_nodal_fields[p]) for p in parameters}
     num_failed = 0
     for layer, loc in located.items():
         fields = _stack_fields(original_mesh, parameters, original_mask[layer])
@@ -377,7 +384,7 @@ def _layered_write_back(original_mesh, original_mask, new_mesh, unique_new_point
 
 
 def _gll_2_gll_layered_impl(from_gll, to_gll, layers, nelem_to_search, parameters, stored_array, make_spherical,
-                            spec):
+                            spec, keep_outside=False):
     (original_mesh, original_mask, new_mesh, unique_new_points, mask, layers,
      parameters) = _layer_setup(from_gll, to_gll, layers, parameters, make_spherical,
                                 dedup=stored_array is not None)
@@ -402,7 +409,7 @@ def _gll_2_gll_layered_impl(from_gll, to_gll, layers, nelem_to_search, parameter
                 {k: ops.coeffs(v["elem"], v["xi"], order).cpu().numpy() for k, v in located.items()},
                 {k: v["elem"].cpu().numpy().astype(int) for k, v in located.items()})
     num_failed = _layered_write_back(original_mesh, original_mask, new_mesh, unique_new_points, mask,
-                                     parameters, located)
+                                     parameters, located, keep_outside=keep_outside)
     if num_failed > 0:
         print(f"{num_failed} points could not be interpolated")
     return new_mesh
@@ -421,14 +428,14 @@ def gll_2_gll_layered_multi(from_gll, to_gll, layers, nelem_to_search: int = 20,
     """Same as gll_2_gll_layered; the reference parallelises over layers with a process pool
     (:442-618) -- `threads` is accepted and ignored, the layers run back to back on the GPU."""
     return _gll_2_gll_layered_impl(from_gll, to_gll, layers, nelem_to_search, parameters, stored_array,
-                                   make_spherical, ops.V1())
+                                   make_spherical, ops.V1(), keep_outside=True)
 
 
 def gll_2_gll_layered_multi_two(from_gll, to_gll, layers, nelem_to_search: int = 30, parameters="all",
                                 stored_array=None, make_spherical: bool = False, tolerance: float = 1.05):
     """Layered interpolation with V2 location and snap_to_nearest=True (:980-1082)."""
     return _gll_2_gll_layered_impl(from_gll, to_gll, layers, nelem_to_search, parameters, stored_array,
-                                   make_spherical, ops.V2(tolerance, True))
+                                   make_spherical, ops.V2(tolerance, True), keep_outside=True)
 
 
 def interpolate_to_points_layered(from_mesh, to_mesh, parameters, layers="nocore", make_spherical=False,

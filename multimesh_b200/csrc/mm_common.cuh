@@ -40,6 +40,10 @@ int mm_cuda_fail(cudaError_t e, const char *what, const char *file, int line);
     } while (0)
 
 int mm_num_sms();                 // SM count of the current device
+// stream-ordered allocation from the library's own per-device pool (mm_core.cu); never touches the
+// device's default pool, which belongs to the host process
+cudaError_t mm_pool_alloc(void **p, size_t bytes, cudaStream_t st);
+void mm_pool_free(void *p, cudaStream_t st);
 
 // internal (C++) entry points shared between translation units
 int mm_locate_impl(int order, int dim, int64_t E, const double *nodes, const double *centroid,
@@ -48,7 +52,7 @@ int mm_locate_impl(int order, int dim, int64_t E, const double *nodes, const dou
                    const int32_t *cands,
                    const mm_locate_params *params, int32_t *elem, double *xi, uint8_t *status,
                    int64_t *num_failed, bool zero_num_failed, int32_t *unresolved_list,
-                   int64_t *unresolved_count, void *stream);
+                   int64_t *unresolved_count, void *stream, const int64_t *n_dev = nullptr, int64_t n_off = 0);
 int mm_interpolate_impl(const mm_index_t *index, int32_t divisor, int order, int dim, int64_t E,
                         const double *nodes, const double *centroid, const double *aabb,
                         const double *presolve, int F, const double *fields, int64_t N,
@@ -60,13 +64,17 @@ int mm_interp_fused(int order, int dim, int64_t E, int F, const double *fields, 
                     const int32_t *perm, int perm_stride, double *out, int32_t *elem_u, double *xi_u,
                     uint8_t *status_u, void *stream);
 size_t mm_index_sort_scratch_bytes(const mm_index_t *ix);
-// site table (distinct coordinates) and the site-level first pass of the progressive search
-int mm_index_build_sites(mm_index_t *ix, void *stream);
+// site table (distinct coordinates; built by the public mm_index_prepare_sites) and the site-level first
+// pass of the progressive search
+bool mm_index_has_sites(const mm_index_t *ix);
 int mm_knn_sites(const mm_index_t *ix, int64_t N, const double *pts, int pts_stride, int kout,
                  int32_t divisor, int32_t *idx, void *stream);
 // mm_knn with a stride (in doubles) between consecutive query points
+// n_dev (optional, device): the kernel processes points [0, min(N, *n_dev - n_off)) -- for work lists whose
+// length is only known on the device (no host synchronisation)
 int mm_knn_strided(const mm_index_t *ix, int64_t N, const double *pts, int pts_stride, int k,
-                   int32_t divisor, int32_t *idx, double *d2, void *stream);
+                   int32_t divisor, int32_t *idx, double *d2, void *stream, const int64_t *n_dev = nullptr,
+                   int64_t n_off = 0);
 // counting sort of query points by index cell into 32-byte records {x, y, z (0 in 2-D), original
 // index in the low 32 bits of the fourth lane}: one aligned full-sector store per point
 constexpr int MM_QREC = 4;  // doubles per sorted-query record

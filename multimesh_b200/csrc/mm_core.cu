@@ -1,6 +1,7 @@
 // mm_core.cu -- error reporting, device queries, host-side GLL tables.
 #include <cstdarg>
 #include <cstdio>
+#include <mutex>
 
 #include "mm_common.cuh"
 
@@ -19,6 +20,59 @@ int mm_cuda_fail(cudaError_t e, const char *what, const char *file, int line)
     mm_set_error("CUDA error %d (%s) in `%s` at %s:%d", (int)e, cudaGetErrorString(e), what, file,
                  line);
     return MM_ERR_CUDA;
+}
+
+// ---- library-owned stream-ordered memory pool, one per device ------------------------------------
+// Index builds allocate and free a few buffers per call; a pool that keeps freed blocks avoids paying
+// cudaMalloc/cudaFree every time.  The pool is PRIVATE to this library: the device's default pool --
+// shared with the host process (e.g. torch) -- is never reconfigured.  mm_pool_trim() hands the cached
+// blocks back to the driver.
+namespace {
+constexpr int MM_MAX_DEVICES = 64;
+std::mutex g_pool_mutex;
+cudaMemPool_t g_pools[MM_MAX_DEVICES] = {};
+}  // namespace
+
+cudaError_t mm_pool_alloc(void **p, size_t bytes, cudaStream_t st)
+{
+    int dev = 0;
+    cudaError_t rc = cudaGetDevice(&dev);
+    if (rc != cudaSuccess) return rc;
+    if (dev < 0 || dev >= MM_MAX_DEVICES) return cudaErrorInvalidDevice;
+    cudaMemPool_t pool;
+    {
+        std::lock_guard<std::mutex> lock(g_pool_mutex);
+        if (!g_pools[dev]) {
+            cudaMemPoolProps props = {};
+            props.allocType = cudaMemAllocationTypePinned;
+            props.handleTypes = cudaMemHandleTypeNone;
+            props.location.type = cudaMemLocationTypeDevice;
+            props.location.id = dev;
+            rc = cudaMemPoolCreate(&g_pools[dev], &props);
+            if (rc != cudaSuccess) return rc;
+            uint64_t keep = UINT64_MAX;  // freed blocks stay in OUR pool until mm_pool_trim()
+            cudaMemPoolSetAttribute(g_pools[dev], cudaMemPoolAttrReleaseThreshold, &keep);
+        }
+        pool = g_pools[dev];
+    }
+    return cudaMallocFromPoolAsync(p, bytes ? bytes : 16, pool, st);
+}
+
+void mm_pool_free(void *p, cudaStream_t st)
+{
+    if (p) cudaFreeAsync(p, st);
+}
+
+extern "C" int mm_pool_trim(void)
+{
+    int dev = 0;
+    MM_CUDA(cudaGetDevice(&dev));
+    std::lock_guard<std::mutex> lock(g_pool_mutex);
+    if (dev >= 0 && dev < MM_MAX_DEVICES && g_pools[dev]) {
+        MM_CUDA(cudaDeviceSynchronize());
+        MM_CUDA(cudaMemPoolTrimTo(g_pools[dev], 0));
+    }
+    return MM_OK;
 }
 
 int mm_num_sms()

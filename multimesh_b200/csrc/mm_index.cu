@@ -38,24 +38,7 @@ struct mm_index {
 
 namespace {
 
-// stream-ordered allocation from the device's default memory pool; the pool is told to keep freed
-// memory, so rebuilding an index for every call (as the reference rebuilds its KD-tree) does not
-// pay cudaMalloc/cudaFree each time
-cudaError_t pool_alloc(void **p, size_t bytes, cudaStream_t st)
-{
-    static thread_local int configured_dev = -1;
-    int dev = 0;
-    cudaGetDevice(&dev);
-    if (configured_dev != dev) {
-        cudaMemPool_t pool;
-        if (cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
-            uint64_t keep = UINT64_MAX;
-            cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
-        }
-        configured_dev = dev;
-    }
-    return cudaMallocAsync(p, bytes ? bytes : 16, st);
-}
+inline cudaError_t pool_alloc(void **p, size_t bytes, cudaStream_t st) { return mm_pool_alloc(p, bytes, st); }
 
 constexpr int64_t MAX_CELLS = (int64_t)1 << 26;
 constexpr int KNN_BLOCK = 128;
@@ -449,9 +432,13 @@ knn_body(const grid_t &g, int64_t N, const double *__restrict__ pts, int pstride
          const fast_div &divisor,
          const double4 *__restrict__ recs, const int32_t *__restrict__ cell_start,
          int32_t *__restrict__ out_idx, double *__restrict__ out_d2,
-         const double4 *__restrict__ point_recs)
+         const double4 *__restrict__ point_recs, const long long *__restrict__ n_dev, int64_t n_off)
 {
     extern __shared__ __align__(16) unsigned char smem[];
+    if (n_dev) {  // point count known only on the device (re-run of the unresolved points): [n_off, *n_dev)
+        const long long have = *n_dev - n_off;
+        N = have < 0 ? 0 : (have < N ? have : N);
+    }
     List L;
     L.init(smem, SITES ? 4 : k);
 
@@ -650,9 +637,10 @@ __global__ void __launch_bounds__(KNN_BLOCK)
 knn_kernel(grid_t g, int64_t N, const double *__restrict__ pts, int pstride, int k,
            const fast_div divisor,
            const double4 *__restrict__ recs, const int32_t *__restrict__ cell_start,
-           int32_t *__restrict__ out_idx, double *__restrict__ out_d2)
+           int32_t *__restrict__ out_idx, double *__restrict__ out_d2,
+           const long long *__restrict__ n_dev, int64_t n_off)
 {
-    knn_body<List, false>(g, N, pts, pstride, k, divisor, recs, cell_start, out_idx, out_d2, nullptr);
+    knn_body<List, false>(g, N, pts, pstride, k, divisor, recs, cell_start, out_idx, out_d2, nullptr, n_dev, n_off);
 }
 
 // site pass: 64 registers so that 8 blocks of 128 threads stay resident per SM
@@ -663,7 +651,7 @@ knn_sites_kernel(grid_t g, int64_t N, const double *__restrict__ pts, int pstrid
                  int32_t *__restrict__ out_idx, const double4 *__restrict__ point_recs)
 {
     knn_body<reg_list<4>, true>(g, N, pts, pstride, k, divisor, site_recs, site_cell_start, out_idx, nullptr,
-                                point_recs);
+                                point_recs, nullptr, 0);
 }
 
 // ---- counting sort of QUERY points by index cell (coherent warps in K1-K3) -----------------------
@@ -1035,12 +1023,14 @@ extern "C" int mm_knn(const mm_index_t *ix, int64_t N, const double *pts, int k,
                       int32_t *idx, double *d2, void *stream)
 {
     MM_REQUIRE(ix, MM_ERR_INVALID, "mm_knn: null index");
-    return mm_knn_strided(ix, N, pts, ix->dim, k, divisor, idx, d2, stream);
+    return mm_knn_strided(ix, N, pts, ix->dim, k, divisor, idx, d2, stream, nullptr, 0);
 }
 
 int mm_knn_strided(const mm_index_t *ix, int64_t N, const double *pts, int pts_stride, int k,
-                   int32_t divisor, int32_t *idx, double *d2, void *stream)
+                   int32_t divisor, int32_t *idx, double *d2, void *stream, const int64_t *n_dev_,
+                   int64_t n_off)
 {
+    const long long *n_dev = reinterpret_cast<const long long *>(n_dev_);
     MM_REQUIRE(ix, MM_ERR_INVALID, "mm_knn: null index");
     MM_REQUIRE(k >= 1 && k <= 64, MM_ERR_INVALID, "mm_knn: k=%d outside [1, 64]", k);
     MM_REQUIRE(divisor >= 1, MM_ERR_INVALID, "mm_knn: divisor %d", (int)divisor);
@@ -1051,17 +1041,17 @@ int mm_knn_strided(const mm_index_t *ix, int64_t N, const double *pts, int pts_s
     cudaStream_t st = (cudaStream_t)stream;
     if (k <= 4) {
         knn_kernel<reg_list<4>><<<launch_blocks(N, KNN_BLOCK, 8), KNN_BLOCK, 0, st>>>(
-            g, N, pts, pts_stride, k, fast_div(divisor), ix->recs, ix->cell_start, idx, d2);
+            g, N, pts, pts_stride, k, fast_div(divisor), ix->recs, ix->cell_start, idx, d2, n_dev, n_off);
     } else if (k <= 8) {
         knn_kernel<reg_list<8>><<<launch_blocks(N, KNN_BLOCK, 8), KNN_BLOCK, 0, st>>>(
-            g, N, pts, pts_stride, k, fast_div(divisor), ix->recs, ix->cell_start, idx, d2);
+            g, N, pts, pts_stride, k, fast_div(divisor), ix->recs, ix->cell_start, idx, d2, n_dev, n_off);
     } else {
         size_t smem = (size_t)k * KNN_BLOCK * (sizeof(double) + sizeof(int32_t));
         MM_CUDA(cudaFuncSetAttribute(knn_kernel<smem_list>,
                                      cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         int per_sm = (int)std::max<size_t>(1, std::min<size_t>(8, (200 * 1024) / smem));
         knn_kernel<smem_list><<<launch_blocks(N, KNN_BLOCK, per_sm), KNN_BLOCK, smem, st>>>(
-            g, N, pts, pts_stride, k, fast_div(divisor), ix->recs, ix->cell_start, idx, d2);
+            g, N, pts, pts_stride, k, fast_div(divisor), ix->recs, ix->cell_start, idx, d2, n_dev, n_off);
     }
     MM_CUDA(cudaGetLastError());
     return MM_OK;
@@ -1106,9 +1096,10 @@ int mm_index_sort_queries(const mm_index_t *ix, int64_t N, const double *pts, do
 // ------------------------------------------------------------------------------------------------
 // internal: site table and the site-level first pass (see knn_sites_kernel)
 // ------------------------------------------------------------------------------------------------
-int mm_index_build_sites(mm_index_t *ix, void *stream_)
+extern "C" int mm_index_prepare_sites(mm_index_t *ix, void *stream_)
 {
     cudaStream_t stream = (cudaStream_t)stream_;
+    MM_REQUIRE(ix, MM_ERR_INVALID, "mm_index_prepare_sites: null index");
     if (ix->site_recs || ix->M == 0) return MM_OK;
     int32_t *per_cell = nullptr, *tile_sums = nullptr;
     const int64_t ntiles = (ix->ncells + SCAN_TILE - 1) / SCAN_TILE;
@@ -1132,8 +1123,11 @@ int mm_index_build_sites(mm_index_t *ix, void *stream_)
     cudaFreeAsync(per_cell, stream);
     cudaFreeAsync(tile_sums, stream);
     ix->bytes += sizeof(int32_t) * (size_t)(ix->ncells + 1) + sizeof(double4) * (size_t)(ns + 1);
+    MM_CUDA(cudaStreamSynchronize(stream));  // the table is complete when this returns: any stream may use it
     return MM_OK;
 }
+
+bool mm_index_has_sites(const mm_index_t *ix) { return ix && ix->site_recs != nullptr; }
 
 int mm_knn_sites(const mm_index_t *ix, int64_t N, const double *pts, int pts_stride, int kout,
                  int32_t divisor, int32_t *idx, void *stream)

@@ -14,7 +14,8 @@
 //   4. accept test / best tracking; lanes that run out of candidates take the variant's fallback.
 // Rounds repeat until every lane is resolved (~1-2 rounds typically).
 //
-// Arithmetic = DESIGN.md section 3 (no FMA, fixed order); mirrors oracle/mm_oracle.c.
+// Arithmetic = DESIGN.md section 3 (fixed order; the only fused operations are the explicit __fma_rn of the
+// map contraction, mm_newton.cuh); restated independently by oracle/mm_oracle.c.
 #include <cstdlib>
 
 #include "mm_common.cuh"
@@ -54,9 +55,14 @@ locate_kernel(const mm_gll_table T, const mm_locate_params prm, int64_t E,
               const int32_t *__restrict__ cands, int32_t *__restrict__ elem_out,
               double *__restrict__ xi_out, uint8_t *__restrict__ status_out,
               unsigned long long *__restrict__ num_failed, int32_t *__restrict__ unresolved_list,
-              unsigned long long *__restrict__ unresolved_count)
+              unsigned long long *__restrict__ unresolved_count, const long long *__restrict__ n_dev,
+              int64_t n_off)
 {
     using tr = elem_traits<ORDER, DIM>;
+    if (n_dev) {  // point count known only on the device: [n_off, *n_dev)
+        const long long have = *n_dev - n_off;
+        N = have < 0 ? 0 : (have < N ? have : N);
+    }
     extern __shared__ __align__(128) unsigned char smem[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     unsigned char *wslots = smem + (size_t)warp * SLOTS * tr::SLOT_BYTES;
@@ -90,6 +96,7 @@ locate_kernel(const mm_gll_table T, const mm_locate_params prm, int64_t E,
 #pragma unroll
         for (int c = 0; c < DIM; ++c) r_xi[c] = 0.0;
         int32_t first_inside = -1, near_elem = -1, best_elem = -1;
+        bool first_inside_nan = false;  // V1: Newton failed on the first AABB hit (the reference re-inverts it, :1460)
         double near_dist = INFINITY;
         double best_key = prm.fallback == MM_FB_SNAP ? 10e9 : INFINITY;
         double best_xi[DIM];
@@ -152,7 +159,7 @@ locate_kernel(const mm_gll_table T, const mm_locate_params prm, int64_t E,
                     } else if (prm.fallback == MM_FB_MAGIC) {
                         if (first_inside >= 0) {
                             r_elem = first_inside;
-                            r_status = MM_ST_FB_INSIDE_MAGIC;
+                            r_status = first_inside_nan ? MM_ST_FB_NAN_MAGIC : MM_ST_FB_INSIDE_MAGIC;
 #pragma unroll
                             for (int c = 0; c < DIM; ++c) r_xi[c] = prm.magic_xi[c];
                         } else if (near_elem >= 0) {
@@ -245,7 +252,9 @@ locate_kernel(const mm_gll_table T, const mm_locate_params prm, int64_t E,
                     for (int c = 0; c < DIM; ++c)
                         r_xi[c] = (r_status == MM_ST_FB_NEAR_OK) ? x[c] : prm.magic_xi[c];
                     done = true;
-                } else if (ok) {
+                } else if (!ok) {
+                    if (e == first_inside) first_inside_nan = true;
+                } else {
                     if (prm.fallback == MM_FB_SNAP || prm.fallback == MM_FB_MINL1) {
                         double key = 0.0;
 #pragma unroll
@@ -305,7 +314,7 @@ int launch_locate(const mm_locate_params &prm, int64_t E, const double *nodes,
                   const double *pts, int pstride, int k,
                   const int32_t *cands, int32_t *elem, double *xi, uint8_t *status,
                   int64_t *num_failed, int32_t *unresolved_list, int64_t *unresolved_count,
-                  cudaStream_t stream)
+                  cudaStream_t stream, const int64_t *n_dev, int64_t n_off)
 {
     using tr = elem_traits<ORDER, DIM>;
     mm_gll_table T;
@@ -325,7 +334,8 @@ int launch_locate(const mm_locate_params &prm, int64_t E, const double *nodes,
                                                   cands, elem, xi, status,
                                                   reinterpret_cast<unsigned long long *>(num_failed),
                                                   unresolved_list,
-                                                  reinterpret_cast<unsigned long long *>(unresolved_count));
+                                                  reinterpret_cast<unsigned long long *>(unresolved_count),
+                                                  reinterpret_cast<const long long *>(n_dev), n_off);
     MM_CUDA(cudaGetLastError());
     return MM_OK;
 }
@@ -338,7 +348,7 @@ int mm_locate_impl(int order, int dim, int64_t E, const double *nodes, const dou
                    const int32_t *cands,
                    const mm_locate_params *params, int32_t *elem, double *xi, uint8_t *status,
                    int64_t *num_failed, bool zero_num_failed, int32_t *unresolved_list,
-                   int64_t *unresolved_count, void *stream_)
+                   int64_t *unresolved_count, void *stream_, const int64_t *n_dev, int64_t n_off)
 {
     cudaStream_t stream = (cudaStream_t)stream_;
     MM_REQUIRE(mm_valid_order(order), MM_ERR_INVALID, "mm_locate: order %d (supported 1, 2, 4)", order);
@@ -362,7 +372,7 @@ int mm_locate_impl(int order, int dim, int64_t E, const double *nodes, const dou
                                             pts_stride, k,                                        \
                                             cands,                                                \
                                             elem, xi, status, num_failed, unresolved_list,       \
-                                            unresolved_count, stream);
+                                            unresolved_count, stream, n_dev, n_off);
     if (const char *v = getenv("MM_LOC_VARIANT")) {  // profiling only
         if (atoi(v) == 1) { MM_LOC(4, 3, 2, 16, 1) MM_LOC(2, 3, 4, 16, 4) }
         if (atoi(v) == 2) { MM_LOC(4, 3, 2, 12, 1) MM_LOC(2, 3, 4, 12, 4) }

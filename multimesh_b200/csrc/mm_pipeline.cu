@@ -7,7 +7,9 @@
 //      exactly what the full list would have decided, because any prefix of the canonical k-NN
 //      list IS the k1-NN list; points that exhaust the prefix are appended to a work list;
 //   3. the work list (typically a few per cent) is re-run in chunks with all k candidates and
-//      the variant's complete fallback logic, and scattered back;
+//      the variant's complete fallback logic, and scattered back; its length stays on the device
+//      (the re-run kernels read it there), so the whole call is stream-ordered: no host
+//      synchronisation, capturable in a CUDA graph;
 //   4. K3 gathers in sorted order and writes out[perm[n]].
 // Results are identical to mm_knn -> mm_locate -> mm_interp (tests/test_gpu_parity.py).
 #include <algorithm>
@@ -26,7 +28,16 @@ static thread_local mm_profile *g_profile = nullptr;
 
 namespace {
 
-constexpr int64_t CHUNK_B = 1 << 20;  // points per re-run chunk
+// points per re-run chunk: the number of unresolved points is only known on the device, so the host
+// enqueues ceil(N / chunk) <= 8 rounds and the kernels of a round that has nothing to do exit at once
+inline int64_t rerun_chunk(int64_t N)
+{
+    if (const char *e = getenv("MM_RERUN_CHUNK")) {  // tests: force several rounds on small inputs
+        const long long v = atoll(e);
+        if (v > 0) return v;
+    }
+    return std::max<int64_t>((int64_t)1 << 20, (N + 7) / 8);
+}
 
 inline size_t align_up(size_t x) { return (x + 255) & ~(size_t)255; }
 
@@ -54,7 +65,7 @@ ws_layout make_layout(const mm_index_t *ix, int dim, int64_t N, int k)
     L.list = take(sizeof(int32_t) * N);
     L.counters = take(64);
     L.sort_scratch = take(mm_index_sort_scratch_bytes(ix));
-    const int64_t cb = std::min<int64_t>(N, CHUNK_B);
+    const int64_t cb = std::min<int64_t>(N, rerun_chunk(N));
     L.b_pts = take(sizeof(double) * cb * dim);
     L.b_cands = take(sizeof(int32_t) * cb * k);
     L.b_elem = take(sizeof(int32_t) * cb);
@@ -65,20 +76,29 @@ ws_layout make_layout(const mm_index_t *ix, int dim, int64_t N, int k)
 }
 
 __global__ void __launch_bounds__(256)
-gather_points_kernel(int dim, int64_t n, const int32_t *__restrict__ list,
-                     const double *__restrict__ pts, double *__restrict__ out)
+gather_points_kernel(int dim, int64_t n, const long long *__restrict__ n_dev, int64_t n_off,
+                     const int32_t *__restrict__ list, const double *__restrict__ pts, double *__restrict__ out)
 {
+    {
+        const long long have = *n_dev - n_off;
+        n = have < 0 ? 0 : (have < n ? have : n);
+    }
     for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n;
          i += (int64_t)gridDim.x * blockDim.x)
         for (int c = 0; c < dim; ++c) out[i * dim + c] = pts[(int64_t)list[i] * MM_QREC + c];  // from the records
 }
 
 __global__ void __launch_bounds__(256)
-scatter_results_kernel(int dim, int64_t n, const int32_t *__restrict__ list,
+scatter_results_kernel(int dim, int64_t n, const long long *__restrict__ n_dev, int64_t n_off,
+                       const int32_t *__restrict__ list,
                        const int32_t *__restrict__ elem_b, const double *__restrict__ xi_b,
                        const uint8_t *__restrict__ status_b, int32_t *__restrict__ elem,
                        double *__restrict__ xi, uint8_t *__restrict__ status)
 {
+    {
+        const long long have = *n_dev - n_off;
+        n = have < 0 ? 0 : (have < n ? have : n);
+    }
     for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n;
          i += (int64_t)gridDim.x * blockDim.x) {
         const int64_t t = list[i];
@@ -138,7 +158,10 @@ int mm_interpolate_impl(const mm_index_t *index, int32_t divisor, int order, int
     cudaStream_t stream = (cudaStream_t)stream_;
     MM_REQUIRE(index && params, MM_ERR_INVALID, "mm_interpolate: null index/params");
     MM_REQUIRE(k >= 1 && k <= 64, MM_ERR_INVALID, "mm_interpolate: k=%d outside [1, 64]", k);
-    MM_REQUIRE(N >= 0, MM_ERR_INVALID, "mm_interpolate: N");
+    MM_REQUIRE(N >= 0 && N <= (int64_t)INT32_MAX, MM_ERR_INVALID,
+               "mm_interpolate: N=%lld outside [0, 2^31): the permutation and the work lists are int32 -- split "
+               "the target points into several calls", (long long)N);
+    MM_REQUIRE(E >= 0 && E <= (int64_t)INT32_MAX, MM_ERR_INVALID, "mm_interpolate: E=%lld", (long long)E);
     if (num_failed) MM_CUDA(cudaMemsetAsync(num_failed, 0, sizeof(int64_t), stream));
     if (N == 0) return MM_OK;
     const ws_layout L = make_layout(index, dim, N, k);
@@ -174,10 +197,10 @@ int mm_interpolate_impl(const mm_index_t *index, int32_t divisor, int order, int
 
     mark(1);
     // 2. first pass: k1 nearest candidates, prefix mode (unless k1 == k: complete semantics)
-    const bool site_pass = divisor > 1 && k1 < k && !getenv("MM_NO_SITES");
+    // GLL-point form: shared nodes are stored up to 8 times; search over distinct coordinates when the
+    // index has a site table (mm_index_prepare_sites)
+    const bool site_pass = divisor > 1 && k1 < k && mm_index_has_sites(index) && !getenv("MM_NO_SITES");
     if (site_pass) {
-        // GLL-point form: shared nodes are stored up to 8 times; search over distinct coordinates
-        MM_TRY(mm_index_build_sites(const_cast<mm_index_t *>(index), stream));  // once per index
         MM_TRY(mm_knn_sites(index, N, sorted, MM_QREC, k1, divisor, cands1, stream));
     } else {
         MM_TRY(mm_knn_strided(index, N, sorted, MM_QREC, k1, divisor, cands1, nullptr, stream));
@@ -190,11 +213,9 @@ int mm_interpolate_impl(const mm_index_t *index, int32_t divisor, int order, int
                           (k1 < k) ? counters : nullptr, stream));
 
     mark(3);
-    // 3. re-run the unresolved points with the full candidate list
+    // 3. re-run the unresolved points with the full candidate list.  Their number lives in counters[0] on the
+    //    device; every kernel of a round reads it there and processes list[at, min(at + cb, count))
     if (k1 < k) {
-        int64_t n_un = 0;
-        MM_CUDA(cudaMemcpyAsync(&n_un, counters, sizeof(int64_t), cudaMemcpyDeviceToHost, stream));
-        MM_CUDA(cudaStreamSynchronize(stream));
         mm_locate_params p2 = *params;
         p2.reserved = 0;
         double *b_pts = reinterpret_cast<double *>(ws + L.b_pts);
@@ -202,15 +223,17 @@ int mm_interpolate_impl(const mm_index_t *index, int32_t divisor, int order, int
         int32_t *b_elem = reinterpret_cast<int32_t *>(ws + L.b_elem);
         double *b_xi = reinterpret_cast<double *>(ws + L.b_xi);
         uint8_t *b_status = ws + L.b_status;
-        for (int64_t at = 0; at < n_un; at += CHUNK_B) {
-            const int64_t nb = std::min<int64_t>(CHUNK_B, n_un - at);
-            gather_points_kernel<<<blocks_for(nb), 256, 0, stream>>>(dim, nb, list + at, sorted, b_pts);
-            MM_TRY(mm_knn(index, nb, b_pts, k, divisor, b_cands, nullptr, stream));
+        const long long *n_un = reinterpret_cast<const long long *>(counters);
+        const int64_t cb = std::min<int64_t>(N, rerun_chunk(N));
+        for (int64_t at = 0; at < N; at += cb) {
+            const int64_t nb = std::min<int64_t>(cb, N - at);
+            gather_points_kernel<<<blocks_for(nb), 256, 0, stream>>>(dim, nb, n_un, at, list + at, sorted, b_pts);
+            MM_TRY(mm_knn_strided(index, nb, b_pts, dim, k, divisor, b_cands, nullptr, stream, counters, at));
             MM_TRY(mm_locate_impl(order, dim, E, nodes, centroid, aabb, presolve, nb, b_pts, dim, k, b_cands, &p2,
-                                  b_elem, b_xi, b_status, counters + 1, false, nullptr, nullptr,
-                                  stream));
+                                  b_elem, b_xi, b_status, counters + 1, false, nullptr, nullptr, stream, counters,
+                                  at));
             scatter_results_kernel<<<blocks_for(nb), 256, 0, stream>>>(
-                dim, nb, list + at, b_elem, b_xi, b_status, elem_s, xi_s, status_s);
+                dim, nb, n_un, at, list + at, b_elem, b_xi, b_status, elem_s, xi_s, status_s);
             MM_CUDA(cudaGetLastError());
         }
     }

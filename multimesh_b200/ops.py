@@ -24,7 +24,7 @@ from .gll import SUPPORTED_ORDERS
 __all__ = [
     "LocateSpec", "V1", "V2", "V3", "V4", "V5", "GridIndex", "element_geometry", "locate", "interp",
     "coeffs", "gather_coeffs", "trilinear", "centroid_conn", "gather_nodal", "map_to_sphere_",
-    "interpolate", "element_presolve",
+    "interpolate", "element_presolve", "ResidentSource",
 ]
 
 
@@ -89,7 +89,9 @@ def _ptr(t):
     return C.c_void_p(0 if t is None else t.data_ptr())
 
 
-def _need_cuda(t: torch.Tensor, name: str, dtype=None) -> torch.Tensor:
+def _need_cuda(t: torch.Tensor, name: str, dtype=None, align16: bool = False) -> torch.Tensor:
+    """Validates an operand; never copies.  A mis-strided or mis-aligned operand is an error, not a hidden
+    `.contiguous()` / `.clone()` -- at BASELINE config 3 that would silently duplicate an 80 GB mesh."""
     if not isinstance(t, torch.Tensor):
         raise TypeError(f"{name}: expected a torch.Tensor, got {type(t)}")
     if not t.is_cuda:
@@ -98,9 +100,11 @@ def _need_cuda(t: torch.Tensor, name: str, dtype=None) -> torch.Tensor:
     if dtype is not None and t.dtype != dtype:
         raise TypeError(f"{name}: expected dtype {dtype}, got {t.dtype}")
     if not t.is_contiguous():
-        t = t.contiguous()
-    if t.data_ptr() % 16 != 0:  # bulk-async copies need 16-byte aligned bases
-        t = t.clone()
+        raise ValueError(f"{name}: tensor of shape {tuple(t.shape)} with strides {t.stride()} is not contiguous; "
+                         "pass a contiguous tensor (multimesh_b200 does not copy operands behind the caller's back)")
+    if align16 and t.numel() and t.data_ptr() % 16 != 0:  # bulk-async copies need 16-byte aligned bases
+        raise ValueError(f"{name}: data pointer {t.data_ptr():#x} is not 16-byte aligned (slice of a larger "
+                         "tensor?); element blocks are fetched with bulk-async copies that need it")
     return t
 
 
@@ -117,7 +121,7 @@ def _order_dim(P: int, dim: int) -> int:
 @torch.library.custom_op("multimesh::element_geometry", mutates_args=())
 def element_geometry(nodes: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor]:
     """nodes [E,P,d] -> (centroid [E,d], aabb [E,2,d])."""
-    nodes = _need_cuda(nodes, "nodes", torch.float64)
+    nodes = _need_cuda(nodes, "nodes", torch.float64, align16=True)
     E, P, d = nodes.shape
     order = _order_dim(P, d)
     with torch.cuda.device(nodes.device):
@@ -132,7 +136,7 @@ def element_geometry(nodes: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor]:
 def element_presolve(nodes: torch.Tensor) -> torch.Tensor:
     """nodes [E,P,d] -> presolve [E, 2d + d*d] = (first node, x(xi=0) - first node, inverse Jacobian
     at xi=0): the affine pre-solve that lets K2 start Newton one step ahead (once per source mesh)."""
-    nodes = _need_cuda(nodes, "nodes", torch.float64)
+    nodes = _need_cuda(nodes, "nodes", torch.float64, align16=True)
     E, P, d = nodes.shape
     order = _order_dim(P, d)
     with torch.cuda.device(nodes.device):
@@ -185,6 +189,16 @@ class GridIndex:
             check(load_lib().mm_index_create(C.byref(h), self.dim, self.n, _ptr(data), _stream()),
                   "mm_index_create")
         self._h = h.value
+        self._sites = False
+
+    def prepare_sites(self):
+        """Builds the site table (distinct coordinates) once; used by `interpolate` in the GLL-point form
+        (mm_index_prepare_sites).  Mutates the index: not to be raced with queries on other streams."""
+        if not self._sites:
+            with torch.cuda.device(self.device):
+                check(load_lib().mm_index_prepare_sites(C.c_void_p(self._h), _stream()), "mm_index_prepare_sites")
+            self._sites = True
+        return self
 
     def info(self):
         arr = (C.c_int64 * 8)()
@@ -232,7 +246,7 @@ def _locate_op(nodes: torch.Tensor, centroid: torch.Tensor, aabb: torch.Tensor, 
                pts: torch.Tensor, cands: torch.Tensor, aabb_prefilter: bool, tol: float, strict: bool, fallback: int,
                snap_clip: float, m0: float, m1: float, m2: float
                ) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor, torch.Tensor]:
-    nodes = _need_cuda(nodes, "nodes", torch.float64)
+    nodes = _need_cuda(nodes, "nodes", torch.float64, align16=True)
     pts = _need_cuda(pts, "pts", torch.float64)
     cands = _need_cuda(cands, "cands", torch.int32)
     centroid = _need_cuda(centroid, "centroid", torch.float64)
@@ -274,7 +288,7 @@ def locate(nodes, centroid, aabb, pts, cands, spec: LocateSpec, presolve=None):
 @torch.library.custom_op("multimesh::interp", mutates_args=())
 def interp(fields: torch.Tensor, elem: torch.Tensor, xi: torch.Tensor) -> torch.Tensor:
     """fields [E,F,P], elem [N] i32, xi [N,d] -> out [N,F]."""
-    fields = _need_cuda(fields, "fields", torch.float64)
+    fields = _need_cuda(fields, "fields", torch.float64, align16=True)
     elem = _need_cuda(elem, "elem", torch.int32)
     xi = _need_cuda(xi, "xi", torch.float64)
     E, F, P = fields.shape
@@ -290,7 +304,7 @@ def interp(fields: torch.Tensor, elem: torch.Tensor, xi: torch.Tensor) -> torch.
 def interp_perm(fields: torch.Tensor, elem: torch.Tensor, xi: torch.Tensor, perm) -> torch.Tensor:
     """K3, coherent variant (mm_interp_perm): row n of the result goes to out[perm[n]] (perm may be
     None).  Meant for spatially sorted points; correct for any order."""
-    fields = _need_cuda(fields, "fields", torch.float64)
+    fields = _need_cuda(fields, "fields", torch.float64, align16=True)
     elem = _need_cuda(elem, "elem", torch.int32)
     xi = _need_cuda(xi, "xi", torch.float64)
     if perm is not None:
@@ -321,7 +335,7 @@ def coeffs(elem: torch.Tensor, xi: torch.Tensor, order: int) -> torch.Tensor:
 
 def gather_coeffs(fields: torch.Tensor, elem: torch.Tensor, coeff: torch.Tensor) -> torch.Tensor:
     """Cached-matrix gather: out[n,f] = sum_a fields[elem_n,f,a] * coeff[n,a]."""
-    fields = _need_cuda(fields, "fields", torch.float64)
+    fields = _need_cuda(fields, "fields", torch.float64, align16=True)
     elem = _need_cuda(elem, "elem", torch.int32)
     coeff = _need_cuda(coeff, "coeffs", torch.float64)
     E, F, P = fields.shape
@@ -344,7 +358,7 @@ def trilinear(nearest: torch.Tensor, connectivity: torch.Tensor, nodes: torch.Te
     weights [N,8]); failed points keep zero weights / zero node ids."""
     nearest = _need_cuda(nearest, "nearest", torch.int64)
     connectivity = _need_cuda(connectivity, "connectivity", torch.int64)
-    nodes = _need_cuda(nodes, "nodes", torch.float64)
+    nodes = _need_cuda(nodes, "nodes", torch.float64, align16=True)
     points = _need_cuda(points, "points", torch.float64)
     N, k = nearest.shape
     dev = points.device
@@ -386,13 +400,13 @@ def gather_nodal(param: torch.Tensor, enclosing: torch.Tensor, weights: torch.Te
 # ----------------------------------------------------------------------------------------------
 # fused pipeline K1 -> K2 -> K3 (mm_interpolate): spatially sorted points, progressive search
 # ----------------------------------------------------------------------------------------------
-@torch.library.custom_op("multimesh::interpolate", mutates_args=())
+@torch.library.custom_op("multimesh::interpolate", mutates_args=("out_buf",))
 def _interpolate_op(handle: int, divisor: int, nodes: torch.Tensor, centroid: torch.Tensor,
                     aabb: torch.Tensor, presolve: torch.Tensor, fields: torch.Tensor, pts: torch.Tensor, k: int,
                     aabb_prefilter: bool, tol: float, strict: bool, fallback: int, snap_clip: float,
-                    m0: float, m1: float, m2: float, want_location: bool
+                    m0: float, m1: float, m2: float, want_location: bool, out_buf: torch.Tensor
                     ) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor, torch.Tensor, torch.Tensor]:
-    nodes = _need_cuda(nodes, "nodes", torch.float64)
+    nodes = _need_cuda(nodes, "nodes", torch.float64, align16=True)
     centroid = _need_cuda(centroid, "centroid", torch.float64)
     aabb = _need_cuda(aabb, "aabb", torch.float64)
     pts = _need_cuda(pts, "pts", torch.float64)
@@ -402,7 +416,7 @@ def _interpolate_op(handle: int, divisor: int, nodes: torch.Tensor, centroid: to
     N = pts.shape[0]
     have_fields = fields.numel() > 0
     if have_fields:
-        fields = _need_cuda(fields, "fields", torch.float64)
+        fields = _need_cuda(fields, "fields", torch.float64, align16=True)
         F = fields.shape[1]
         assert fields.shape[0] == E and fields.shape[2] == P
     else:
@@ -413,7 +427,13 @@ def _interpolate_op(handle: int, divisor: int, nodes: torch.Tensor, centroid: to
     with torch.cuda.device(dev):
         nbytes = lib.mm_interpolate_workspace_bytes(C.c_void_p(handle), d, N, k)
         ws = torch.empty((max(int(nbytes), 256),), dtype=torch.uint8, device=dev)
-        out = torch.empty((N, F) if have_fields else (0, 0), dtype=torch.float64, device=dev)
+        if have_fields and out_buf.numel():
+            # the caller's buffer (e.g. this rank's rows of the gather buffer): K3 writes straight into it
+            out = _need_cuda(out_buf, "out", torch.float64)
+            if tuple(out.shape) != (N, F):
+                raise ValueError(f"out must be [{N}, {F}], got {tuple(out.shape)}")
+        else:
+            out = torch.empty((N, F) if have_fields else (0, 0), dtype=torch.float64, device=dev)
         nfail = torch.zeros((1,), dtype=torch.int64, device=dev)
         if want_location:
             elem = torch.empty((N,), dtype=torch.int32, device=dev)
@@ -429,17 +449,108 @@ def _interpolate_op(handle: int, divisor: int, nodes: torch.Tensor, centroid: to
                                  _ptr(elem) if want_location else None, _ptr(xi) if want_location else None,
                                  _ptr(status) if want_location else None, _ptr(nfail), _ptr(ws),
                                  ws.numel(), _stream()), "mm_interpolate")
+    if have_fields and out_buf.numel():
+        out = torch.empty((0, 0), dtype=torch.float64, device=dev)  # results are in out_buf (an op may not return an input)
     return out, elem, xi, status, nfail
 
 
 def interpolate(index: "GridIndex", divisor: int, nodes, centroid, aabb, fields, pts, k: int,
-                spec: LocateSpec, want_location: bool = True, presolve=None):
+                spec: LocateSpec, want_location: bool = True, presolve=None, out=None):
     """Fused k-NN -> locate -> gather.  `fields` may be None (locate only).
     -> (out [N,F], elem [N], xi [N,d], status [N], num_failed [1]); identical to running
-    GridIndex.query_idx, locate and interp one after the other."""
+    GridIndex.query_idx, locate and interp one after the other.  Stream-ordered (no host sync).
+    `out`: optional [N,F] buffer the gather writes into (e.g. this rank's slice of a gather buffer)."""
     if fields is None:
         fields = torch.empty((0, 0, 0), dtype=torch.float64, device=nodes.device)
-    return _interpolate_op(index._h, int(divisor), nodes, centroid, aabb,
-                           _no_tensor(nodes) if presolve is None else presolve, fields, pts, int(k),
-                           spec.aabb_prefilter, spec.tol, spec.strict, spec.fallback, spec.snap_clip,
-                           *spec.magic_xi, bool(want_location))
+    if divisor > 1:
+        index.prepare_sites()
+    res = _interpolate_op(index._h, int(divisor), nodes, centroid, aabb,
+                          _no_tensor(nodes) if presolve is None else presolve, fields, pts, int(k),
+                          spec.aabb_prefilter, spec.tol, spec.strict, spec.fallback, spec.snap_clip,
+                          *spec.magic_xi, bool(want_location), _no_tensor(nodes) if out is None else out)
+    if out is not None and fields.numel():
+        return (out,) + tuple(res[1:])
+    return res
+
+
+class ResidentSource:
+    """A source mesh resident in HBM (mm_source_*): nodes, fields, geometry, pre-solve and the spatial index
+    are uploaded / built once; `interpolate_host` then moves only target points in and values out, chunked
+    over three streams so that both PCIe directions and the kernels overlap.  Host (numpy / pinned torch CPU)
+    arrays in and out -- the host-buffer twin of `interpolate`."""
+
+    def __init__(self, nodes, fields=None, form: str = "centroid", device=None):
+        import numpy as np
+
+        self._np = np
+        self._h = None
+        nodes = self._host(nodes)
+        E, P, d = nodes.shape
+        order = _order_dim(P, d)
+        F = 0
+        if fields is not None:
+            fields = self._host(fields)
+            assert fields.shape[0] == E and fields.shape[2] == P
+            F = fields.shape[1]
+        self.E, self.P, self.dim, self.F, self.order = E, P, d, F, order
+        self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+        h = C.c_void_p()
+        with torch.cuda.device(self.device):
+            check(load_lib().mm_source_create_host(C.byref(h), order, d, E, self._p(nodes), F,
+                                                   self._p(fields) if F else None, 1 if form == "gll" else 0),
+                  "mm_source_create_host")
+        self._h = h.value
+
+    def _host(self, a):
+        if isinstance(a, torch.Tensor):
+            if a.is_cuda or a.dtype != torch.float64 or not a.is_contiguous():
+                raise ValueError("ResidentSource: host arrays must be contiguous float64 CPU tensors / numpy arrays")
+            return a
+        return self._np.ascontiguousarray(a, dtype=self._np.float64)
+
+    @staticmethod
+    def _p(a):
+        if a is None:
+            return None
+        return C.c_void_p(a.data_ptr() if isinstance(a, torch.Tensor) else a.ctypes.data)
+
+    def set_fields(self, fields):
+        fields = self._host(fields)
+        assert fields.shape[0] == self.E and fields.shape[2] == self.P
+        check(load_lib().mm_source_set_fields_host(C.c_void_p(self._h), fields.shape[1], self._p(fields)),
+              "mm_source_set_fields_host")
+        self.F = fields.shape[1]
+
+    def info(self):
+        arr = (C.c_int64 * 8)()
+        check(load_lib().mm_source_info(C.c_void_p(self._h), C.byref(arr)), "mm_source_info")
+        return {"E": arr[0], "P": arr[1], "dim": arr[2], "F": arr[3], "order": arr[4], "gll_points_form": arr[5],
+                "resident_bytes": arr[6], "device": arr[7]}
+
+    def interpolate_host(self, pts, k: int, spec: LocateSpec, values=None, want_location: bool = False):
+        """pts [N,d] host -> (values [N,F], elem [N] | None, xi [N,d] | None, num_failed).  `values` may be a
+        preallocated (ideally pinned) host buffer."""
+        np = self._np
+        pts = self._host(pts)
+        N = pts.shape[0]
+        if values is None:
+            values = np.empty((N, self.F), dtype=np.float64)
+        elem = np.empty((N,), dtype=np.int32) if want_location else None
+        xi = np.empty((N, self.dim), dtype=np.float64) if want_location else None
+        prm = spec.to_c()
+        nf = C.c_int64(0)
+        check(load_lib().mm_source_interpolate_host(C.c_void_p(self._h), N, self._p(pts), int(k), C.byref(prm),
+                                                    self._p(values), self._p(elem), self._p(xi), C.byref(nf)),
+              "mm_source_interpolate_host")
+        return values, elem, xi, int(nf.value)
+
+    def close(self):
+        if getattr(self, "_h", None):
+            load_lib().mm_source_destroy(C.c_void_p(self._h))
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

@@ -4,9 +4,15 @@ Multi-GPU partitioning of the target points.
 The path shards by independent units: every target point's result is a pure function of
 (point, source mesh).  The source mesh and its index are replicated on every GPU, the target
 points are split into `world` shards, one process per GPU (torchrun).  There is NO collective
-inside the compute path; the only communication is the optional final gather of the [N/G, F]
-results onto one rank (NCCL on GPUs; gloo in the CPU tests of this host logic).
-Results are bit-identical for every G because no arithmetic depends on the partition.
+inside the compute path.  Communication happens only
+  * at set-up, optionally: `broadcast_source` ships the source mesh from the rank that loaded it to the
+    others over NVLink (NCCL broadcast) instead of every rank pulling its own copy over PCIe;
+  * at the end, optionally: `gather_rows` / `gather_indexed` collect the [N/G, F] results on ONE rank
+    with grouped point-to-point transfers (ncclSend/ncclRecv via `batch_isend_irecv`) straight into
+    the rows of the full result -- the destination's own shard is computed in place (`out_buffer`), so
+    there is no padding, no all-gather to ranks that do not want the data and no concatenation copy.
+Results are bit-identical for every G because no arithmetic depends on the partition (gloo tests on CPU,
+torchrun test on GPUs).
 
 Two partitions:
   "contiguous"  index ranges -- right for target sets that are already spatially ordered (the GLL
@@ -14,10 +20,10 @@ Two partitions:
   "slab"        equal-count slabs along the longest axis -- for unordered point clouds.  A rank then
                 touches 1/G of the source elements with the full point density instead of all of them
                 at 1/G of the density (each element block is fetched once per warp that needs it, so
-                sparse points re-fetch more): 100 M random points on 8 GPUs, 25.6 ms -> see
-                profiles/README.md.
+                sparse points re-fetch more): 100 M random points on 8 GPUs, 14.7 vs 25.6 ms
+                (profiles/README.md).
 """
-from typing import Callable, Optional, Tuple
+from typing import Callable, List, Optional, Sequence, Tuple
 
 import numpy as np
 import torch
@@ -37,30 +43,56 @@ def local_slice(n: int, rank: int, world: int) -> slice:
     return slice(int(b[rank]), int(b[rank + 1]))
 
 
-def gather_rows(local: torch.Tensor, n_total: int, dst: int = 0, group=None) -> Optional[torch.Tensor]:
-    """Gather row-shards (split with `shard_bounds`) onto rank `dst`; other ranks get None.
-    Shards are padded to the largest shard so one all_gather_into_tensor / gather suffices."""
-    world = dist.get_world_size(group)
-    rank = dist.get_rank(group)
-    b = shard_bounds(n_total, world)
-    width = int((b[1:] - b[:-1]).max())
-    assert local.shape[0] == int(b[rank + 1] - b[rank]), "shard size does not match shard_bounds"
-    pad = torch.zeros((width,) + tuple(local.shape[1:]), dtype=local.dtype, device=local.device)
-    pad[: local.shape[0]] = local
-    if dist.get_backend(group) == "nccl":
-        # NCCL: all_gather into one registered buffer (uniform NVSwitch bandwidth); dst slices it
-        out = torch.empty((world * width,) + tuple(local.shape[1:]), dtype=local.dtype, device=local.device)
-        dist.all_gather_into_tensor(out, pad, group=group)
-        chunks = list(out.split(width)) if rank == dst else None
-    else:
-        chunks = [torch.empty_like(pad) for _ in range(world)] if rank == dst else None
-        dist.gather(pad, chunks, dst=dst, group=group)
+def _world(group=None) -> Tuple[int, int]:
+    if dist.is_available() and dist.is_initialized():
+        return dist.get_world_size(group), dist.get_rank(group)
+    return 1, 0
+
+
+def _global_rank(r: int, group=None) -> int:
+    return r if group is None else dist.get_global_rank(group, r)
+
+
+def gather_buffer(n_total: int, tail_shape: Sequence[int], dtype, device, rank: int, dst: int,
+                  bounds: np.ndarray) -> Tuple[Optional[torch.Tensor], Optional[torch.Tensor]]:
+    """(full, mine): on `dst` the full [n_total, ...] result and the view of this rank's rows inside it -- hand
+    `mine` to the gather kernel (`ops.interpolate(..., out=mine)`) so that no copy of the local shard is ever
+    made; (None, None) on the other ranks, which allocate their own shard."""
     if rank != dst:
-        return None
-    return torch.cat([chunks[r][: int(b[r + 1] - b[r])] for r in range(world)], dim=0)
+        return None, None
+    full = torch.empty((int(n_total),) + tuple(tail_shape), dtype=dtype, device=device)
+    return full, full[int(bounds[rank]): int(bounds[rank + 1])]
 
 
-def slab_partition(points: np.ndarray, world: int, axis: Optional[int] = None):
+def gather_rows(local: torch.Tensor, n_total: int, dst: int = 0, group=None,
+                full: Optional[torch.Tensor] = None) -> Optional[torch.Tensor]:
+    """Collect contiguous row-shards (split with `shard_bounds`) on rank `dst`; other ranks get None.
+    Every source rank sends its shard once, `dst` receives each shard directly into its rows of the result.
+    `full`: the buffer from `gather_buffer` when the local shard already lives inside it."""
+    world, rank = _world(group)
+    b = shard_bounds(n_total, world)
+    assert local.shape[0] == int(b[rank + 1] - b[rank]), "shard size does not match shard_bounds"
+    if world == 1:
+        return local if full is None else full
+    ops = []
+    if rank == dst:
+        if full is None:
+            full = torch.empty((int(n_total),) + tuple(local.shape[1:]), dtype=local.dtype, device=local.device)
+        mine = full[int(b[rank]): int(b[rank + 1])]
+        if mine.data_ptr() != local.data_ptr():
+            mine.copy_(local)
+        for r in range(world):
+            if r != dst and b[r + 1] > b[r]:
+                ops.append(dist.P2POp(dist.irecv, full[int(b[r]): int(b[r + 1])], _global_rank(r, group), group))
+    elif local.shape[0] > 0:
+        ops.append(dist.P2POp(dist.isend, local.contiguous(), _global_rank(dst, group), group))
+    if ops:
+        for req in dist.batch_isend_irecv(ops):
+            req.wait()
+    return full if rank == dst else None
+
+
+def slab_partition(points: np.ndarray, world: int, axis: Optional[int] = None) -> List[np.ndarray]:
     """Index sets of `world` equal-count slabs along `axis` (default: the longest extent).  Deterministic:
     every rank computes the same sets from the same array.  Ties on a slab boundary stay together."""
     x = np.asarray(points)
@@ -74,28 +106,55 @@ def slab_partition(points: np.ndarray, world: int, axis: Optional[int] = None):
 
 
 def gather_indexed(local: torch.Tensor, index_sets, dst: int = 0, group=None) -> Optional[torch.Tensor]:
-    """Gather shards of arbitrary sizes onto rank `dst` and place shard r at rows index_sets[r]."""
-    world = dist.get_world_size(group)
-    rank = dist.get_rank(group)
-    n_total = int(sum(len(ix) for ix in index_sets))
-    width = max(1, max(len(ix) for ix in index_sets))
-    assert local.shape[0] == len(index_sets[rank]), "shard size does not match its index set"
-    pad = torch.zeros((width,) + tuple(local.shape[1:]), dtype=local.dtype, device=local.device)
-    pad[: local.shape[0]] = local
-    if dist.get_backend(group) == "nccl":
-        out = torch.empty((world * width,) + tuple(local.shape[1:]), dtype=local.dtype, device=local.device)
-        dist.all_gather_into_tensor(out, pad, group=group)
-        chunks = list(out.split(width)) if rank == dst else None
-    else:
-        chunks = [torch.empty_like(pad) for _ in range(world)] if rank == dst else None
-        dist.gather(pad, chunks, dst=dst, group=group)
+    """Collect shards of arbitrary sizes on rank `dst` and place shard r at rows index_sets[r]: received in
+    shard order into one staging buffer, then ONE device scatter through the concatenated index."""
+    world, rank = _world(group)
+    sizes = [len(ix) for ix in index_sets]
+    n_total = int(sum(sizes))
+    assert local.shape[0] == sizes[rank], "shard size does not match its index set"
+    b = np.concatenate([[0], np.cumsum(sizes)])
+    staged = None
+    ops = []
+    if rank == dst:
+        staged = torch.empty((n_total,) + tuple(local.shape[1:]), dtype=local.dtype, device=local.device)
+        staged[int(b[rank]): int(b[rank + 1])].copy_(local)
+        for r in range(world):
+            if r != dst and sizes[r] > 0:
+                ops.append(dist.P2POp(dist.irecv, staged[int(b[r]): int(b[r + 1])], _global_rank(r, group), group))
+    elif local.shape[0] > 0 and world > 1:
+        ops.append(dist.P2POp(dist.isend, local.contiguous(), _global_rank(dst, group), group))
+    if ops:
+        for req in dist.batch_isend_irecv(ops):
+            req.wait()
     if rank != dst:
         return None
-    full = torch.empty((n_total,) + tuple(local.shape[1:]), dtype=local.dtype, device=local.device)
-    for r in range(world):
-        ix = torch.from_numpy(np.asarray(index_sets[r], dtype=np.int64)).to(local.device)
-        full[ix] = chunks[r][: len(index_sets[r])]
+    order = torch.from_numpy(np.concatenate([np.asarray(ix, dtype=np.int64) for ix in index_sets])).to(local.device)
+    full = torch.empty_like(staged)
+    full.index_copy_(0, order, staged)
     return full
+
+
+def broadcast_source(arrays: Sequence[Optional[np.ndarray]], device, src: int = 0, group=None) -> List[torch.Tensor]:
+    """Source-mesh arrays (nodes, fields, ...) resident on `device` of EVERY rank while only rank `src` holds them
+    on the host: `src` uploads once over PCIe, the other ranks receive over NVLink (NCCL broadcast) -- instead of
+    G uploads of the same gigabytes through the host's PCIe/memory system.  `arrays` on the other ranks may be
+    None; shapes travel first in a small object broadcast."""
+    world, rank = _world(group)
+    if world == 1:
+        return [torch.from_numpy(np.ascontiguousarray(a, dtype=np.float64)).to(device) for a in arrays]
+    meta = [None]
+    if rank == src:
+        meta = [[(tuple(a.shape), str(a.dtype)) for a in arrays]]
+    dist.broadcast_object_list(meta, src=_global_rank(src, group), group=group)
+    out = []
+    for i, (shape, dtype) in enumerate(meta[0]):
+        if rank == src:
+            t = torch.from_numpy(np.ascontiguousarray(arrays[i])).to(device, non_blocking=True)
+        else:
+            t = torch.empty(shape, dtype=getattr(torch, dtype), device=device)
+        dist.broadcast(t, src=_global_rank(src, group), group=group)
+        out.append(t)
+    return out
 
 
 def interpolate_sharded(compute: Callable[[np.ndarray], Tuple[torch.Tensor, ...]], points: np.ndarray,
@@ -103,10 +162,7 @@ def interpolate_sharded(compute: Callable[[np.ndarray], Tuple[torch.Tensor, ...]
     """Run `compute(points_shard)` on this rank's shard of `points` (see the module docstring for the two
     partitions) and optionally gather the first returned tensor (the values), in the original point order,
     onto rank `gather_to`.  Returns (local_outputs, gathered_values_or_None)."""
-    if dist.is_available() and dist.is_initialized():
-        world, rank = dist.get_world_size(group), dist.get_rank(group)
-    else:
-        world, rank = 1, 0
+    world, rank = _world(group)
     if partition == "contiguous":
         sl = local_slice(points.shape[0], rank, world)
         outs = compute(points[sl])

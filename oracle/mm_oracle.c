@@ -583,6 +583,7 @@ long long mmo_locate(int order, int dim, long long E, const double *nodes, const
         int accepted = 0;
         /* fallback trackers */
         int32_t first_inside = -1;            /* V1 */
+        int first_inside_nan = 0;             /* V1: Newton failed on it (:1460-1467 re-inverts and raises) */
         int32_t near_elem = -1;               /* V1: min distance to centroid, first occurrence */
         double near_dist = INFINITY;
         int32_t best_elem = -1;               /* V2: smallest max|xi|; V5: smallest sum|xi| */
@@ -613,7 +614,10 @@ long long mmo_locate(int order, int dim, long long E, const double *nodes, const
             double x[3];
             int ok = newton_inverse(&b, dim, nodes + (size_t)e * P * dim, p,
                                     pre ? pre + (size_t)e * W : NULL, x, NULL);
-            if (!ok) continue; /* "NaN" branch */
+            if (!ok) { /* "NaN" branch */
+                if (e == first_inside) first_inside_nan = 1;
+                continue;
+            }
             if (prm->fallback == MMO_FB_SNAP || prm->fallback == MMO_FB_MINL1) {
                 double key = 0.0;
                 for (int c = 0; c < dim; ++c) {
@@ -635,8 +639,10 @@ long long mmo_locate(int order, int dim, long long E, const double *nodes, const
             switch (prm->fallback) {
             case MMO_FB_MAGIC: /* interpolator.py:1448-1473 */
                 if (first_inside >= 0) {
-                    /* the re-inversion repeats a result already rejected above */
-                    elem = first_inside; status = MMO_ST_FB_INSIDE_MAGIC;
+                    /* the re-inversion (:1460) repeats a result already rejected above: either NaN -- the
+                     * reference raises unless ignore_hard_elements -- or some |xi| > 1.04; magic xi either way */
+                    elem = first_inside;
+                    status = first_inside_nan ? MMO_ST_FB_NAN_MAGIC : MMO_ST_FB_INSIDE_MAGIC;
                     for (int c = 0; c < dim; ++c) xi[c] = prm->magic_xi[c];
                 } else if (near_elem >= 0) {
                     double x[3];

@@ -258,7 +258,9 @@ def shell_files(order, seed, layers=None):
                                element_labels=["fluid", "layer"], global_strings={"moho_idx": "2"})
 
 
-STRIDE = {"layered": 1, "layered_o4": 5, "multi": 2, "multi_two": 2, "points_layered": 2}
+STRIDE = {"layered": 1, "layered_o4": 5, "multi": 2, "multi_two": 2, "points_layered": 2, "multi_subset": 1,
+          "multi_two_nocore": 1}
+CORE_MESH = ("layered_o4", "multi_subset", "multi_two_nocore")  # cases run on the mesh that has a fluid core layer
 
 
 def case_layered(seed):
@@ -277,9 +279,15 @@ def case_layered(seed):
             ("multi_two", 2, lambda: interp.gll_2_gll_layered_multi_two("shell_from.h5", "shell_to.h5",
                                                                          layers=[1, 2, 3], parameters=NAMES)),
             ("points_layered", 2, lambda: interp.interpolate_to_points_layered("shell_from.h5", "shell_to.h5", NAMES,
-                                                                                layers=[1, 2, 3]))]
+                                                                                layers=[1, 2, 3])),
+            # layer SUBSETS on the mesh with a core: the multi drivers start from the target's existing fields
+            # (:607, :1070), so elements outside the requested layers must keep their values
+            ("multi_subset", 2, lambda: interp.gll_2_gll_layered_multi("shell_from.h5", "shell_to.h5", layers=[2, 1],
+                                                                        parameters=NAMES, threads=2)),
+            ("multi_two_nocore", 2, lambda: interp.gll_2_gll_layered_multi_two("shell_from.h5", "shell_to.h5",
+                                                                                layers="nocore", parameters=NAMES))]
     for tag, order, run in runs:
-        shell_files(order, seed, glue_inputs.CORE_LAYERS if tag == "layered_o4" else None)
+        shell_files(order, seed, glue_inputs.CORE_LAYERS if tag in CORE_MESH else None)
         with contextlib.redirect_stdout(io.StringIO()):
             run()
         vals = refglue.FILES["shell_to.h5"]["MODEL/data"].array[:, :5, :]

@@ -331,6 +331,10 @@ LAYERED = {  # tag: (order, layers, source layers spec, location variant, k, ele
     "multi": (2, [1, 2, 3], None, ("V1", {}), 20, "keep"),
     "multi_two": (2, [1, 2, 3], None, ("V2", {"tolerance": 1.05, "snap_to_nearest": True}), 30, "keep"),
     "points_layered": (2, [1, 2, 3], None, ("V3", {}), 20, "zero"),
+    # layer subsets on the mesh with a fluid core: the multi drivers keep everything outside the layers
+    "multi_subset": (2, [2, 1], glue_inputs.CORE_LAYERS, ("V1", {}), 20, "keep"),
+    "multi_two_nocore": (2, [3, 2, 1], glue_inputs.CORE_LAYERS, ("V2", {"tolerance": 1.05, "snap_to_nearest": True}),
+                         30, "keep"),
 }
 
 
@@ -391,6 +395,7 @@ def test_cuda_layered_drivers(cuda, tag):
     g = load("glue_layered.npz")
     pair = glue_inputs.shell_pair(order, int(g["seed"]), core)
     names = NAMES + ["z_node_1D"]
+    old_target = pair["to"][1].copy()
     src, tgt = (SalvusMesh.from_arrays(c, d, names, e, ["fluid", "layer"], {"moho_idx": "2"})
                 for c, d, e in (pair["from"], pair["to"]))
     if tag == "layered":
@@ -401,10 +406,18 @@ def test_cuda_layered_drivers(cuda, tag):
         api.gll_2_gll_layered_multi(src, tgt, layers=[1, 2, 3], parameters=NAMES, threads=3)
     elif tag == "multi_two":
         api.gll_2_gll_layered_multi_two(src, tgt, layers=[1, 2, 3], parameters=NAMES)
+    elif tag == "multi_subset":
+        api.gll_2_gll_layered_multi(src, tgt, layers=[2, 1], parameters=NAMES, threads=2)
+    elif tag == "multi_two_nocore":
+        api.gll_2_gll_layered_multi_two(src, tgt, layers="nocore", parameters=NAMES)
     else:
         itp.interpolate_to_points_layered(src, tgt, NAMES, layers=[1, 2, 3])
     got = np.stack([tgt.element_nodal_fields[p] for p in NAMES], axis=1)
     compare_layered(got, g, tag)
+    if LAYERED[tag][5] == "keep":  # elements outside the requested layers keep the target's old values
+        outside = ~np.isin(pair["to"][2][:, 1], layers)
+        assert np.array_equal(got[outside], old_target[outside][:, :5, :])
+        assert outside.any() == (core is not None)
 
 
 @pytest.mark.gpu
