@@ -3,19 +3,28 @@
 bench.py -- headline benchmark of the mesh-to-mesh interpolation hot path (BASELINE.json metric:
 target GLL points interpolated per second; % of HBM roofline; host CPU path timed beside it).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload S2|small]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+                    [--workload S2|S3|S4|S5|...] [--no-cpu] [--no-north-star]
 
 A step = one pass of the hot path over one batch of target points, all resident in HBM:
-    K1 k-NN over the source GLL points (gll_2_gll form, idx // P)  ->  K2 locate (V1)  ->  K3 gather.
-Workload S2 (BASELINE.json configs[1]): source 100^3 hex elements, order 2, F = 5
-(QKAPPA, QMU, RHO, VP, VS); targets = all 23.9 M GLL points of a non-nested 96^3 order-2 mesh.
-Inputs are far larger than the 126 MB L2 (source 1.7 GB, targets 0.57 GB), so no L2 flush is needed.
-N > 1: one process per GPU (torchrun), source mesh + index replicated, every rank processes its own
-target set of the same size (weak scaling); no data-path collective.
+    spatial sort -> K1 k-NN -> K2 locate -> K3 gather   (one stream-ordered mm_interpolate call)
+Default workload S2 (BASELINE.json configs[1]): source 100^3 hex elements, order 2, F = 5
+(QKAPPA, QMU, RHO, VP, VS); targets = all 23.9 M GLL points of a non-nested 96^3 order-2 mesh; the
+gll_2_gll form (k nearest source GLL points -> idx // P) with V1 location.  Inputs are far larger than the
+126 MB L2 (source 1.7 GB, targets 0.57 GB), so no L2 flush is needed between steps.
+N > 1: one process per GPU (torchrun), source mesh + index replicated, every rank processes its own target
+set of the same size (weak scaling); no data-path collective.
 
-One JSON line is printed by rank 0; see the task contract for the keys.  `--impl reference` times
-the CPU port of the same path (oracle/, test infrastructure: scipy cKDTree + the C oracle with
-OpenMP on all host threads) on a bounded spatial crop of the same workload.
+The same JSON line carries
+  parity_check  the timed run's results compared with the CPU oracle on a sub-block of the workload
+  e2e           the reference-facing C-ABI call on HOST buffers (resident source: targets H2D, K1-K3, values
+                D2H inside the timed region, chunked over three streams) + the cold one-shot call
+  north_star    BASELINE configs[4]: 100 M target points, order 4, 10.1 M-element source, strong scaling over the
+                N GPUs of this run, with and without the NCCL gather of the values onto rank 0
+  cpu_baseline  the CPU port (scipy cKDTree on the FULL source + the C oracle, all host threads) on a bounded
+                sample of the targets;  cpu_baseline_ref_c: the reference's own compiled C (oracle/_ref)
+Other workloads: S3 (cubed-sphere shell, order 4, layered), S4 (exodus <-> GLL round trip), S5 alone.
+`--impl reference` times the CPU port of the same path on the box's host cores.
 """
 import argparse
 import ctypes as C
@@ -46,10 +55,23 @@ WORKLOADS = {
     # scaling over the GPUs (source generated on the device; random target points; centroid k-NN form)
     "S5": dict(src=216, tgt=0, order=4, k=20, npoints=100_000_000, form="centroid", device_gen=True),
     "S5small": dict(src=48, tgt=0, order=4, k=20, npoints=4_000_000, form="centroid", device_gen=True),
+    # BASELINE configs[2]: cubed-sphere shell, order 4, layered (see bench_extra.py)
+    "S3": dict(kind="shell", n_lat=128, rad=(94, 6, 4), tgt_lat=112, tgt_rad=(80, 5, 3), order=4, k=20),
+    "S3small": dict(kind="shell", n_lat=24, rad=(18, 2, 2), tgt_lat=20, tgt_rad=(15, 2, 1), order=4, k=20),
+    # BASELINE configs[3]: exodus (HEX8 nodal) <-> order-4 GLL round trip with gradient fields
+    "S4": dict(kind="exodus", hex=128, gll=40, order=4, k=20),
+    "S4small": dict(kind="exodus", hex=32, gll=10, order=4, k=20),
 }
 
 
 def workload_name(w):
+    if w.get("kind") == "shell":
+        return (f"{w['name']}: layered gll_2_gll on a cubed-sphere shell, order {w['order']}, source n_lat={w['n_lat']} "
+                f"radial {w['rad']} (mantle, lower crust, thin upper crust), target n_lat={w['tgt_lat']} radial "
+                f"{w['tgt_rad']}, per-layer centroid index, k={w['k']}")
+    if w.get("kind") == "exodus":
+        return (f"{w['name']}: exodus_2_gll (HEX8 {w['hex']}^3 nodal -> order-{w['order']} GLL {w['gll']}^3, V6 trilinear) "
+                f"and gll_2_exodus (V1) back, 5 fields + 5 gradient fields")
     if w.get("device_gen"):
         return (f"{w['name']}: source {w['src']}^3 hex order-{w['order']} F=5 (generated on the device), "
                 f"{w['npoints']} uniform random target points partitioned over the GPUs into equal-count x-slabs (strong scaling), k={w['k']}, "
@@ -97,7 +119,7 @@ def make_source_device(w, dev):
     return nodes, fields
 
 
-def make_targets(w, rank=0, crop=None):
+def make_targets(w, rank=0):
     """GLL points of the target mesh.  Ranks > 0 get the same mesh shifted by a fraction of a
     target element so that every rank has distinct points of identical difficulty."""
     from multimesh_b200 import meshgen
@@ -107,13 +129,47 @@ def make_targets(w, rank=0, crop=None):
     shift = (rank % 8) * 0.11 * h
     lo = np.full(3, 0.001 + shift * 0.1)
     hi = np.full(3, 0.999 - shift)
-    if crop is None:
-        pts = meshgen.box_mesh((n,) * 3, w["order"], lo=lo, hi=hi)
-    else:
-        m = crop
-        span = (hi - lo) * (m / n)
-        pts = meshgen.box_mesh((m,) * 3, w["order"], lo=lo, hi=lo + span)
+    pts = meshgen.box_mesh((n,) * 3, w["order"], lo=lo, hi=hi)
     return np.ascontiguousarray(pts.reshape(-1, 3))
+
+
+def bind_to_gpu_numa(gpu_index):
+    """Pin this process to the CPU cores local to its GPU (NVML affinity mask) so that pinned host buffers are
+    first-touched on the GPU's NUMA node: with 8 ranks each moving gigabytes per step over PCIe, remote pages
+    send every byte across the socket interconnect.  Returns the previous affinity (restore for CPU legs)."""
+    prev = os.sched_getaffinity(0)
+    if os.environ.get("MM_BENCH_NO_BIND"):
+        return prev
+    try:
+        import pynvml
+
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(gpu_index)
+        ncpu = os.cpu_count() or 1
+        words = pynvml.nvmlDeviceGetCpuAffinity(h, (ncpu + 63) // 64)
+        cpus = {64 * i + b for i, wd in enumerate(words) for b in range(64) if (wd >> b) & 1}
+        cpus &= prev
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+    except Exception:
+        pass
+    return prev
+
+
+ALL_CPUS = os.sched_getaffinity(0)
+
+
+class full_affinity:
+    """CPU legs (oracle = OpenMP, cKDTree workers) run on ALL host cores: worker threads inherit the mask of the
+    thread that creates them, so the mask is widened before the first oracle call and the GPU-local binding is
+    restored afterwards."""
+
+    def __enter__(self):
+        self.prev = os.sched_getaffinity(0)
+        os.sched_setaffinity(0, ALL_CPUS)
+
+    def __exit__(self, *exc):
+        os.sched_setaffinity(0, self.prev)
 
 
 # ----------------------------------------------------------------------------------------------
@@ -178,77 +234,358 @@ class ClockSampler:
 
 
 # ----------------------------------------------------------------------------------------------
-# CPU port of the path (oracle/ = test infrastructure; allowed here only as the timed baseline)
+# CPU port of the path (oracle/ = test infrastructure; allowed here only as the timed baseline and
+# as the checker of the GPU result)
 # ----------------------------------------------------------------------------------------------
-def cpu_port_run(w, crop_src, crop_tgt, steps=1, warmup=0):
-    """Times the reference's algorithm on the host: cKDTree over the GLL points of a spatial crop
-    of the source mesh (scipy's KD-tree is what the reference's cli.py:66 uses; pykdtree is absent),
-    query k nearest GLL points -> idx // P, V1 location + GLL weights + gather in the C oracle
-    (OpenMP, all host threads)."""
+class CpuPort:
+    """The reference's algorithm on the host, on the FULL source mesh of the workload: cKDTree over all source
+    GLL points (scipy's KD-tree is what the reference's cli.py:66 uses; pykdtree is absent; sliding-midpoint
+    build and leafsize 16 like pykdtree), query k nearest -> idx // P, then V1 location + GLL weights + gather
+    in the C oracle (OpenMP, all host threads).  A step processes a bounded slab of the target points."""
+
+    def __init__(self, w, nodes=None, fields=None):
+        from oracle import capi as oracle
+        from scipy.spatial import cKDTree
+
+        self.oracle = oracle
+        oracle.set_num_threads(len(os.sched_getaffinity(0)))  # torchrun sets OMP_NUM_THREADS=1
+        self.w = w
+        self.order, self.k = w["order"], w["k"]
+        self.P = (self.order + 1) ** 3
+        if nodes is None:
+            nodes, fields = make_source(w)
+        self.nodes, self.fields = nodes, fields
+        t0 = time.perf_counter()
+        self.tree = cKDTree(nodes.reshape(-1, 3), leafsize=16, balanced_tree=False, compact_nodes=False)
+        self.cent = oracle.centroids(nodes)
+        self.box = oracle.aabb(nodes)
+        self.pre = oracle.presolve(nodes)
+        self.build_seconds = time.perf_counter() - t0
+        self.cores = int(oracle.num_threads())
+
+    def step(self, pts):
+        o = self.oracle
+        _, nn = self.tree.query(pts, k=self.k, workers=-1)
+        cands = (nn // self.P).astype(np.int32)
+        elem, xi, _, nfail = o.locate(self.order, 3, self.nodes, pts, cands, o.V1(), cent=self.cent, box=self.box,
+                                      pre=self.pre)
+        vals = o.interp(self.order, 3, self.fields, elem, xi)
+        return vals, elem, nfail
+
+    def run(self, pts_all, sample, steps, warmup):
+        times, nfail, chk = [], 0, 0.0
+        n = len(pts_all)
+        for it in range(warmup + steps):
+            a = (it * sample) % max(1, n - sample + 1)
+            pts = np.ascontiguousarray(pts_all[a:a + sample])
+            t0 = time.perf_counter()
+            vals, elem, nf = self.step(pts)
+            dt = time.perf_counter() - t0
+            if it >= warmup:
+                times.append(dt)
+                nfail += nf
+                chk += float(vals.sum())
+        t = float(np.mean(times))
+        return {"points": int(sample), "seconds_per_step": t, "value": sample / t, "cores": self.cores,
+                "nfailed": int(nfail), "checksum": chk,
+                "sample": (f"FULL source mesh of {self.w['name']} ({self.nodes.shape[0]} elements; cKDTree over all "
+                           f"{self.nodes.shape[0] * self.P} GLL points, build {self.build_seconds:.1f} s excluded like "
+                           f"the GPU index build); each step = a different contiguous slab of {sample} of the "
+                           f"{n} target GLL points")}
+
+
+def cpu_ref_c_baseline(n_hex=128, n_targets=1_000_000):
+    """the reference's OWN compiled C (oracle/_ref = centroid.c +
+    trilinearinterpolator.c, -O3 -fopenmp as setup.py:14 intends) on a HEX8 (order-1, config-4 style) input, k-NN
+    by scipy cKDTree as scripts/cli.py:66, numpy gather as cli.py:98-100.  Newton is serial by construction."""
     from multimesh_b200 import meshgen
     from oracle import capi as oracle
     from scipy.spatial import cKDTree
 
-    oracle.set_num_threads(len(os.sched_getaffinity(0)))  # torchrun sets OMP_NUM_THREADS=1
-    order, k = w["order"], w["k"]
-    P = (order + 1) ** 3
-    frac = crop_src / w["src"]
-    nodes = meshgen.box_mesh((crop_src,) * 3, order, lo=np.zeros(3), hi=np.full(3, frac))
-    fields = meshgen.analytic_fields(nodes, NAMES, scale=np.ones(3))
-    # targets strictly inside the crop
-    h = 1.0 / w["tgt"]
-    lo = np.full(3, 0.001)
-    pts = meshgen.box_mesh((crop_tgt,) * 3, order, lo=lo, hi=lo + crop_tgt * h * 0.998)
-    pts = np.ascontiguousarray(pts.reshape(-1, 3))
-    assert pts.max() < frac
+    if oracle.ref_lib() is None:
+        return None
+    points, conn = meshgen.hex8_mesh((n_hex,) * 3)
+    connC = np.ascontiguousarray(conn[:, np.argsort([0, 3, 2, 1, 4, 5, 6, 7])])  # interpolator.py:186-190
+    q = np.random.default_rng(1234).uniform(0.0, 1.0, size=(n_targets, 3))
+    param = np.stack([2.0 + points[:, 0] + f * points[:, 1] + 3 * points[:, 2] for f in range(5)])
     t0 = time.perf_counter()
-    tree = cKDTree(nodes.reshape(-1, 3))
-    cent = oracle.centroids(nodes)
-    box = oracle.aabb(nodes)
+    cent = oracle.ref_centroid(conn, points)
+    t_cent = time.perf_counter() - t0
+    t0 = time.perf_counter()
+    tree = cKDTree(cent, leafsize=16, balanced_tree=False, compact_nodes=False)
     t_build = time.perf_counter() - t0
-    times = []
-    for it in range(warmup + steps):
-        t0 = time.perf_counter()
-        _, nn = tree.query(pts, k=k, workers=-1)
-        cands = (nn // P).astype(np.int32)
-        elem, xi, _, nfail = oracle.locate(order, 3, nodes, pts, cands, oracle.V1(), cent=cent, box=box)
-        vals = oracle.interp(order, 3, fields, elem, xi)
-        dt = time.perf_counter() - t0
-        if it >= warmup:
-            times.append(dt)
-    t = float(np.mean(times))
-    return {
-        "points": int(len(pts)), "seconds_per_step": t, "build_seconds": t_build,
-        "value": len(pts) / t, "cores": int(oracle.num_threads()), "nfailed": int(nfail),
-        "checksum": float(vals.sum()),
-        "sample": (f"spatial crop of {w['name']}: source {crop_src}^3 of {w['src']}^3 elements, targets = "
-                   f"{len(pts)} GLL points of the {crop_tgt}^3 target elements inside the crop; KD-tree build "
-                   f"({t_build:.1f} s) excluded like the GPU index build"),
-    }
+    t0 = time.perf_counter()
+    _, nn = tree.query(q, k=20, workers=-1)
+    t_knn = time.perf_counter() - t0
+    t0 = time.perf_counter()
+    # the reference printf()s for failed points only; none here
+    nfail, enc, wts = oracle.ref_trilinear_interpolator(20, nn.astype(np.int64), connC, points, q)
+    t_tri = time.perf_counter() - t0
+    t0 = time.perf_counter()
+    vals = np.sum(param[:, enc] * wts, axis=2)
+    t_gather = time.perf_counter() - t0
+    total = t_knn + t_tri + t_gather
+    return {"value": n_targets / total, "unit": UNIT, "cores": len(os.sched_getaffinity(0)), "kind": "reference",
+            "seconds": {"centroid_c": t_cent, "kdtree_build": t_build, "knn": t_knn, "triLinearInterpolator": t_tri,
+                        "numpy_gather": t_gather},
+            "nfailed": int(nfail), "checksum": float(vals.sum()),
+            "sample": (f"oracle/_ref (the reference's centroid.c + trilinearinterpolator.c, gcc -O3 -fopenmp) on a "
+                       f"HEX8 {n_hex}^3 source, {n_targets} uniform random targets, k=20 cKDTree (all threads) + serial "
+                       f"triLinearInterpolator + numpy gather of 5 fields; KD-tree build and centroids excluded")}
 
 
 def run_reference(args, w):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    crop_src, crop_tgt = (40, 36) if w["src"] >= 40 else (w["src"], w["tgt"] - 2)
-    r = cpu_port_run(w, crop_src, crop_tgt, steps=args.steps, warmup=min(args.warmup, 1))
+    if w.get("kind") or w.get("device_gen"):
+        w = dict(WORKLOADS["S2"], name="S2")
+    port = CpuPort(w)
+    pts = make_targets(w, 0)
+    sample = min(len(pts), 1_200_000)
+    r = port.run(pts, sample, steps=args.steps, warmup=args.warmup)
     line = {
         "impl": "reference", "metric": METRIC, "value": r["value"], "unit": UNIT, "n_gpus": args.gpus,
-        "steps": args.steps, "warmup": min(args.warmup, 1), "ms_per_step": r["seconds_per_step"] * 1e3,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": r["seconds_per_step"] * 1e3,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": workload_name(w)},
+        "config": {"workload": workload_name(w), "source_elements": int(port.nodes.shape[0]), "fields": len(NAMES)},
         "cpu_baseline": {"value": r["value"], "unit": UNIT, "cores": r["cores"], "kind": "port",
                          "sample": r["sample"]},
         "e2e": {"value": r["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-        "gpu_launches": 0,
+        "gpu_launches": 0, "nfailed": r["nfailed"],
     }
     print(json.dumps(line), flush=True)
 
 
 # ----------------------------------------------------------------------------------------------
+# parity of the timed GPU result against the CPU oracle
+# ----------------------------------------------------------------------------------------------
+def parity_check(n_src, order, form, k, nodes_d, fields_d, pts_d, elem_d, out_d, block, max_points=150_000):
+    """Compares the GPU results of the TIMED workload with the CPU oracle on a sub-block of it.
+
+    The structured source has element id e = ex + n*(ey + n*ez).  The oracle gets the (b-a)^3 sub-block of source
+    elements [a, b)^3 (nodes / fields copied back from the device: exactly the inputs the kernels saw) and every
+    target point of this rank that lies at least 3 elements inside the block -- far more than the reach of the k
+    nearest neighbours, so the oracle's k-NN over the sub-block equals the k-NN over the whole mesh.  Element ids
+    must be bit-equal (after mapping block-local ids to global ones), values within 1e-10 relative."""
+    import torch
+    from oracle import capi as oracle
+
+    a, b = block
+    nb = b - a
+    P = (order + 1) ** 3
+    ar = torch.arange(a, b, device=nodes_d.device)
+    gid = (ar[None, None, :] + n_src * (ar[None, :, None] + n_src * ar[:, None, None])).reshape(-1)  # ex fastest
+    sub_nodes = nodes_d[gid].cpu().numpy()
+    sub_fields = fields_d[gid].cpu().numpy()
+    lo, hi = (a + 3) / n_src, (b - 3) / n_src
+    inside = ((pts_d > lo) & (pts_d < hi)).all(dim=1).nonzero().reshape(-1)
+    if inside.numel() > max_points:
+        inside = inside[:: (inside.numel() + max_points - 1) // max_points]
+    if inside.numel() == 0:
+        return {"points": 0, "elem_equal": None, "max_rel": None, "note": "no target point of this rank inside the block"}
+    pts = pts_d[inside].cpu().numpy()
+    g_elem = elem_d[inside].cpu().numpy()
+    g_out = out_d[inside].cpu().numpy()
+    t0 = time.perf_counter()
+    if form == "gll":
+        cands = (oracle.knn_ckdtree_canonical(sub_nodes.reshape(-1, 3), pts, k, pad=24) // P).astype(np.int32)
+    else:
+        cands = oracle.knn_ckdtree_canonical(oracle.centroids(sub_nodes), pts, k, pad=12)
+    o_elem, o_xi, _, _ = oracle.locate(order, 3, sub_nodes, pts, cands, oracle.V1())
+    o_out = oracle.interp(order, 3, sub_fields, o_elem, o_xi)
+    lx, ly, lz = o_elem % nb, (o_elem // nb) % nb, o_elem // (nb * nb)
+    o_glob = np.where(o_elem >= 0, (lx + a) + n_src * ((ly + a) + n_src * (lz + a)), -1)
+    elem_equal = bool(np.array_equal(g_elem, o_glob))
+    max_rel = float(np.max(np.abs(g_out - o_out) / np.maximum(np.abs(o_out), 1e-300)))
+    res = {"points": int(len(pts)), "elem_equal": elem_equal, "max_rel": max_rel, "bit_equal_values": bool(np.array_equal(g_out, o_out)),
+           "tolerance_rel": 1e-10, "oracle_seconds": time.perf_counter() - t0,
+           "what": (f"results of the timed run vs the CPU oracle (canonical k-NN via cKDTree over-query + C locate / "
+                    f"gather) on source elements [{a},{b})^3 and the target points at least 3 elements inside")}
+    assert elem_equal, f"parity: element ownership differs from the oracle ({int((g_elem != o_glob).sum())} points)"
+    assert max_rel <= 1e-10, f"parity: values differ from the oracle, max rel {max_rel:.3e}"
+    return res
+
+
+# ----------------------------------------------------------------------------------------------
+# one measured pipeline (spatial sort -> K1 -> K2 -> K3) on resident data
+# ----------------------------------------------------------------------------------------------
+def measure_pipeline(lib, ops, step, steps, warmup, world, dev, sampler=None):
+    """W untimed + EXACTLY `steps` timed calls of `step()`, bracketed by barrier + synchronize, timed with CUDA
+    events on the launching stream; per-stage times from events recorded inside mm_interpolate.  Returns
+    (ms_per_step [max over ranks], stage means [6], last result)."""
+    import torch
+    import torch.distributed as dist
+    from multimesh_b200 import _lib
+
+    for _ in range(max(warmup, 3)):
+        res = step()
+    torch.cuda.synchronize()
+    prof = C.c_void_p()
+    _lib.check(lib.mm_profile_create(C.byref(prof), steps), "mm_profile_create")
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    t_start, t_end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    lib.mm_profile_begin(prof)
+    w0 = time.time()
+    t_start.record()
+    for _ in range(steps):
+        step()
+    t_end.record()
+    torch.cuda.synchronize()
+    w1 = time.time()
+    lib.mm_profile_end()
+    if sampler is not None:
+        sampler.mark(w0, w1, "timed region")
+        if w1 - w0 < 0.25:
+            # the timed region is shorter than a few nvidia-smi periods: keep the same load running
+            # (untimed) so that the clock / throttle record has enough samples
+            x0 = time.time()
+            while time.time() - x0 < 0.4:
+                step()
+            torch.cuda.synchronize()
+            sampler.mark(w0, time.time(), "timed region + identical untimed load (region < 0.25 s)")
+    if world > 1:
+        dist.barrier()
+    total_ms = t_start.elapsed_time(t_end)
+    ncalls = C.c_int(0)
+    stage_ms = (C.c_float * (steps * 6))()
+    _lib.check(lib.mm_profile_read(prof, C.byref(ncalls), stage_ms), "mm_profile_read")
+    lib.mm_profile_destroy(prof)
+    stages = np.array(list(stage_ms), dtype=np.float64).reshape(steps, 6)[: ncalls.value].mean(axis=0)
+    if world > 1:
+        t = torch.tensor([total_ms], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        total_ms = float(t.item())
+    return total_ms / steps, stages, res
+
+
+def launches_per_step(N, rerun):
+    """Kernels of ONE mm_interpolate call: query sort (rank, 3 scan kernels, place), first-pass k-NN, locate,
+    gather; plus 4 kernels per re-run round (gather points, full k-NN, locate, scatter) -- the host enqueues
+    ceil(N / max(2^20, N/4)) rounds because the number of unresolved points stays on the device."""
+    rounds = 0
+    if rerun:
+        chunk = max(1 << 20, (N + 3) // 4)
+        rounds = (N + chunk - 1) // chunk
+    return 8 + 4 * rounds
+
+
+def kernel_report(N, order, F, k, form, stages, peak, traffic_db):
+    d = 3
+    P = (order + 1) ** 3
+    k1 = min(k, 4 if form == "centroid" else 8)  # candidates the first pass materialises
+    bytes_pt = {
+        "K1_knn": 8 * d + 4 * k1,                                  # first pass materialises k1 candidates
+        "K2_locate": 8 * d + 1.0 * (8 * d * P + 16 * d) + (4 + 8 * d),  # c = 1 candidate tested per point
+        "K3_interp": (8 * d + 4) + 8 * F * P + 8 * F,
+    }
+    kernels = {}
+    for name, ms in (("K1_knn", stages[1]), ("K2_locate", stages[2]), ("K3_interp", stages[4])):
+        gbs = bytes_pt[name] * N / (ms * 1e-3) / 1e9
+        kernels[name] = {"ms": round(float(ms), 4), "alg_bytes_per_point": bytes_pt[name],
+                         "achieved_gbs": round(gbs, 1), "frac": round(gbs / peak, 4),
+                         "traffic": traffic_db.get(name)}
+    other = {"query_sort_ms": round(float(stages[0]), 4), "rerun_unresolved_ms": round(float(stages[3]), 4),
+             "unpermute_ms": round(float(stages[5]), 4)}
+    return bytes_pt, kernels, other
+
+
+def hbm_peak():
+    peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(peaks_path):
+        return float(json.load(open(peaks_path))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+# ----------------------------------------------------------------------------------------------
 # our arm
 # ----------------------------------------------------------------------------------------------
+def run_device_gen(args, w, lib, ops, world, rank, dev, with_clocks=True, gather=True):
+    """Strong-scaling configuration (S5 = BASELINE configs[4], the north_star): source generated on the device and
+    replicated, w['npoints'] uniform random targets partitioned over the ranks into equal-count x-slabs, timed
+    without and with the NCCL gather of the [N/G, F] values onto rank 0 (grouped send/recv straight into the rows
+    of the full result; rank 0's K3 writes its own rows in place)."""
+    import torch
+    import torch.distributed as dist
+    from multimesh_b200.parallel import gather_buffer, gather_rows, local_slice, shard_bounds
+
+    order, k = w["order"], w["k"]
+    P, F = (order + 1) ** 3, len(NAMES)
+    form = w.get("form", "gll")
+    gll_form = form == "gll"
+    divisor = P if gll_form else 1
+    nodes, fields = make_source_device(w, dev)
+    E = nodes.shape[0]
+    sl = local_slice(w["npoints"], rank, world)
+    g = torch.Generator(device=dev)
+    g.manual_seed(1234 + rank)
+    pts = torch.rand((sl.stop - sl.start, 3), dtype=torch.float64, device=dev, generator=g)
+    slab = world > 1 and os.environ.get("MM_BENCH_PARTITION", "slab") == "slab"
+    if slab:
+        pts[:, 0] = (pts[:, 0] + rank) / world
+    N = pts.shape[0]
+    t0 = time.perf_counter()
+    cent, box = ops.element_geometry(nodes)
+    presolve = ops.element_presolve(nodes)
+    index = ops.GridIndex(nodes.view(E * P, 3) if gll_form else cent)
+    if gll_form:
+        index.prepare_sites()
+    torch.cuda.synchronize()
+    build_s = time.perf_counter() - t0
+    spec = ops.V1()
+    bounds = shard_bounds(w["npoints"], world)
+    full, mine = gather_buffer(w["npoints"], (F,), torch.float64, dev, rank, 0, bounds) if gather else (None, None)
+    out_local = mine if mine is not None else torch.empty((N, F), dtype=torch.float64, device=dev)
+
+    def step():
+        return ops.interpolate(index, divisor, nodes, cent, box, fields, pts, k, spec, want_location=True,
+                               presolve=presolve, out=out_local)
+
+    def step_gather():
+        r = step()
+        if world > 1:
+            gather_rows(out_local, w["npoints"], dst=0, full=full)
+        return r
+
+    sampler = None
+    if with_clocks:
+        sampler = ClockSampler(dev.index)
+        sampler.start()
+    ms, stages, res = measure_pipeline(lib, ops, step, args.steps, args.warmup, world, dev, sampler)
+    clocks = sampler.stop() if sampler else None
+    _, elem, xi, status, nfail = res
+    st = torch.bincount(status.to(torch.int64), minlength=10).cpu().tolist()
+    nfailed = int(nfail.item())
+    parity = None
+    if rank == 0 and not args.no_parity:
+        a = 3
+        with full_affinity():
+            parity = parity_check(w["src"], order, form, k, nodes, fields, pts, elem, out_local,
+                                  (a, min(w["src"], a + 20)))
+    ms_gather = None
+    if gather and world > 1:
+        ms_gather, _, _ = measure_pipeline(lib, ops, step_gather, args.steps, args.warmup, world, dev, None)
+    checksum = float(out_local.sum().item())
+    peak, _ = hbm_peak()
+    bytes_pt, kernels, other = kernel_report(N, order, F, k, form, stages, peak, {})
+    return {
+        "workload": workload_name(w), "n_gpus": world, "points_total": int(w["npoints"]), "points_per_gpu": int(N),
+        "source_elements": int(E), "source_gb_per_gpu": round((nodes.numel() + fields.numel()) * 8 / 1e9, 1),
+        "partition": "x-slabs" if slab else "index ranges", "ms_per_step": ms,
+        "value": w["npoints"] / (ms * 1e-3), "unit": UNIT,
+        "ms_per_step_with_gather_to_rank0": ms_gather,
+        "value_with_gather": None if ms_gather is None else w["npoints"] / (ms_gather * 1e-3),
+        "gather": None if world == 1 else "grouped ncclSend/ncclRecv (batch_isend_irecv) into the rows of the full "
+                                          "[N, F] result on rank 0; rank 0's K3 writes its own rows in place",
+        "gather_bytes": None if world == 1 else int((w["npoints"] - N) * F * 8),
+        "kernels_rank0": kernels, "other_stages_rank0": other, "index_build_s": build_s, "nfailed_rank0": nfailed,
+        "status_histogram_rank0": st, "checksum_rank0": checksum, "parity_check": parity, "clocks": clocks,
+        "target_north_star": "100 M target points, order 4, end to end < 1 s on 8 GPUs (meshes device-resident)",
+    }, kernels, stages, clocks, nfailed, st, N, E
+
+
 def run_ours(args, w):
     import torch
     import torch.distributed as dist
@@ -262,55 +599,77 @@ def run_ours(args, w):
         raise SystemExit("bench.py: no CUDA device -- the product path has no CPU fallback")
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
+    all_cpus = bind_to_gpu_numa(local_rank)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     lib = _lib.load_lib()
+    peak, peak_src = hbm_peak()
 
+    if w.get("kind"):
+        import bench_extra
+
+        line = bench_extra.run(args, w, lib, ops, world, rank, dev, all_cpus)
+        if rank == 0:
+            print(json.dumps(line), flush=True)
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    if w.get("device_gen"):
+        ns, kernels, stages, clocks, nfailed, st, N, E = run_device_gen(args, w, lib, ops, world, rank, dev)
+        if rank == 0:
+            dom = max(kernels, key=lambda n: kernels[n]["ms"])
+            line = {
+                "metric": METRIC, "value": ns["value"], "unit": UNIT, "n_gpus": world, "steps": args.steps,
+                "warmup": max(args.warmup, 3), "ms_per_step": ns["ms_per_step"], "higher_is_better": True,
+                "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+                "config": {"workload": workload_name(w), "points_per_gpu": N, "source_elements": E, "fields": len(NAMES),
+                           "l2": "inputs larger than L2 (80.6 GB source, 2.4 GB targets), no flush"},
+                "roofline": {"bound": "hbm", "kernel": dom, "achieved": kernels[dom]["achieved_gbs"], "peak": peak,
+                             "unit": "GB/s", "frac": kernels[dom]["frac"], "traffic": None, "peak_source": peak_src},
+                "kernels": kernels, "cpu_baseline": None, "e2e": None, "north_star": ns,
+                "gpu_launches": launches_per_step(N, True) * args.steps, "clocks": clocks, "nfailed": nfailed,
+                "status_histogram": st, "parity_check": ns["parity_check"],
+            }
+            print(json.dumps(line), flush=True)
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    # ------------------------------------------------------------------------------------------
+    # S2-like workload: host-generated meshes, GLL-point form, weak scaling
+    # ------------------------------------------------------------------------------------------
     order, k = w["order"], w["k"]
     P = (order + 1) ** 3
     F = len(NAMES)
-    device_gen = bool(w.get("device_gen"))
-    gll_form = w.get("form", "gll") == "gll"
+    form = w.get("form", "gll")
+    gll_form = form == "gll"
     divisor = P if gll_form else 1
-    if device_gen:
-        nodes, fields = make_source_device(w, dev)
-        from multimesh_b200.parallel import local_slice
-        # strong scaling: the uniform cloud of w["npoints"] points is partitioned into `world` equal-count slabs
-        # along x (multimesh_b200.parallel "slab" partition; a random index-range partition would leave every
-        # rank with all source elements at 1/world of the point density).  Each rank generates its own slab.
-        sl = local_slice(w["npoints"], rank, world)
-        g = torch.Generator(device=dev)
-        g.manual_seed(1234 + rank)
-        pts = torch.rand((sl.stop - sl.start, 3), dtype=torch.float64, device=dev, generator=g)
-        if world > 1 and os.environ.get("MM_BENCH_PARTITION", "slab") == "slab":
-            pts[:, 0] = (pts[:, 0] + rank) / world
-        nodes_h = fields_h = pts_h = None
-        E, N = nodes.shape[0], pts.shape[0]
-    else:
-        nodes_h, fields_h = make_source(w)
-        pts_h = make_targets(w, rank)
-        E, N = nodes_h.shape[0], pts_h.shape[0]
-        nodes = torch.from_numpy(nodes_h).to(dev)
-        fields = torch.from_numpy(fields_h).to(dev)
-        pts = torch.from_numpy(pts_h).to(dev)
+    nodes_h, fields_h = make_source(w)
+    pts_h = make_targets(w, rank)
+    E, N = nodes_h.shape[0], pts_h.shape[0]
+    nodes = torch.from_numpy(nodes_h).to(dev)
+    fields = torch.from_numpy(fields_h).to(dev)
+    pts = torch.from_numpy(pts_h).to(dev)
 
     # ---- setup (untimed): source mesh resident, geometry + index built once per source mesh -----
-    ev = lambda: torch.cuda.Event(enable_timing=True)  # noqa: E731
-
     def build_index():
         c, b = ops.element_geometry(nodes)
         pre = ops.element_presolve(nodes)
-        return c, b, pre, ops.GridIndex(nodes.view(E * P, 3) if gll_form else c)
+        ix = ops.GridIndex(nodes.view(E * P, 3) if gll_form else c)
+        if gll_form:
+            ix.prepare_sites()
+        return c, b, pre, ix
 
     cent, box, presolve, index = build_index()  # first build: includes one-off module loading
     torch.cuda.synchronize()
     del index
-    e0, e1 = ev(), ev()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     cent, box, presolve, index = build_index()
     e1.record()
     torch.cuda.synchronize()
-    build_ms = e0.elapsed_time(e1)  # K0 geometry + index build, amortised per source mesh
+    build_ms = e0.elapsed_time(e1)  # K0 geometry + index build (+ site table), amortised per source mesh
     spec = ops.V1()
 
     def step():
@@ -321,104 +680,98 @@ def run_ours(args, w):
 
     sampler = ClockSampler(local_rank)
     sampler.start()
-    for _ in range(max(args.warmup, 3)):
-        res = step()
-    torch.cuda.synchronize()
+    ms_per_step, stages, res = measure_pipeline(lib, ops, step, args.steps, args.warmup, world, dev, sampler)
+    clocks = sampler.stop()
     out, elem, xi, status, nfail = res
     nfailed = int(nfail.item())
     checksum = float(out.sum().item())
-    st = torch.bincount(status.to(torch.int64), minlength=9).cpu().tolist()
-    # the fused pipeline must agree bit for bit with the three separate kernels
+    st = torch.bincount(status.to(torch.int64), minlength=10).cpu().tolist()
+    value = world * N / (ms_per_step * 1e-3)
+
+    # ---- parity: the timed run's results against the CPU oracle (rank 0) ---------------------------
+    parity = None
+    if rank == 0 and not args.no_parity:
+        a = max(0, min(w["src"] - 24, int(0.3 * w["src"])))
+        with full_affinity():
+            parity = parity_check(w["src"], order, form, k, nodes, fields, pts, elem, out, (a, min(w["src"], a + 24)))
+    # the fused pipeline must also agree bit for bit with the three separate kernels
     nchk = min(N, 2_000_000)
     cands = index.query_idx(pts[:nchk], k, divisor=divisor)
     e2, x2, s2, _ = ops.locate(nodes, cent, box, pts[:nchk], cands, spec, presolve=presolve)
     o2 = ops.interp(fields, e2, x2)
     assert torch.equal(o2, out[:nchk]) and torch.equal(e2, elem[:nchk]) and torch.equal(x2, xi[:nchk])
     assert torch.equal(s2, status[:nchk])
-    del res, cands, e2, x2, s2, o2
+    del res, cands, e2, x2, s2, o2, elem, xi, status, out
+    del index, cent, box, presolve, nodes, fields, pts
+    torch.cuda.empty_cache()
 
-    # ---- timed region: EXACTLY K steps; stage boundaries marked with CUDA events recorded on the
-    # ---- launching stream inside mm_interpolate (mm_profile_*), read after the final sync ----------
-    prof = C.c_void_p()
-    _lib.check(lib.mm_profile_create(C.byref(prof), args.steps), "mm_profile_create")
-    if world > 1:
-        dist.barrier()
-    torch.cuda.synchronize()
-    t_start, t_end = ev(), ev()
-    lib.mm_profile_begin(prof)
-    w0 = time.time()
-    t_start.record()
-    for s in range(args.steps):
-        step()
-    t_end.record()
-    torch.cuda.synchronize()
-    w1 = time.time()
-    lib.mm_profile_end()
-    sampler.mark(w0, w1, "timed region")
-    if w1 - w0 < 0.25:
-        # the timed region is shorter than a few nvidia-smi periods: keep the same load running
-        # (untimed) so that the clock / throttle record has enough samples
-        x0 = time.time()
-        while time.time() - x0 < 0.4:
-            step()
-        torch.cuda.synchronize()
-        sampler.mark(w0, time.time(), "timed region + identical untimed load (region < 0.25 s)")
-    if world > 1:
-        dist.barrier()
-    clocks = sampler.stop()
-    total_ms = t_start.elapsed_time(t_end)
-    ncalls = C.c_int(0)
-    stage_ms = (C.c_float * (args.steps * 6))()
-    _lib.check(lib.mm_profile_read(prof, C.byref(ncalls), stage_ms), "mm_profile_read")
-    lib.mm_profile_destroy(prof)
-    stages = np.array(list(stage_ms), dtype=np.float64).reshape(args.steps, 6)[: ncalls.value].mean(axis=0)
-    if world > 1:
-        t = torch.tensor([total_ms], dtype=torch.float64, device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        total_ms = float(t.item())
-    ms_per_step = total_ms / args.steps
-    n_total = w["npoints"] if device_gen else world * N
-    value = n_total / (ms_per_step * 1e-3)
+    # ---- e2e through the C-ABI on HOST buffers ------------------------------------------------------
+    # (a) resident source (the headline): mm_source_create_host once (like the reference arm's KD-tree build, and
+    #     like the reference arm's source mesh, which sits in host memory before its timed region), then every step
+    #     = mm_source_interpolate_host: targets H2D from pinned memory, K1-K3, values D2H, chunked over 3 streams.
+    # (b) cold one-shot: mm_interpolate_host uploads the source mesh and builds the index inside every step too.
+    pin = lambda a: torch.from_numpy(a).pin_memory()  # noqa: E731
+    nodes_p, fields_p, pts_p = pin(nodes_h), pin(fields_h), pin(pts_h)
+    vals_p = torch.empty((N, F), dtype=torch.float64).pin_memory()
+    prm = spec.to_c()
+    nf = C.c_int64(0)
+    src_h = C.c_void_p()
+    _lib.check(lib.mm_source_create_host(C.byref(src_h), order, 3, E, C.c_void_p(nodes_p.data_ptr()), F,
+                                         C.c_void_p(fields_p.data_ptr()), 1 if gll_form else 0), "mm_source_create_host")
 
-    e2e_value = e2e_s = e2e_checksum = None
-    h2d = d2h = 0
-    e2e_steps = 0
-    if not device_gen:
-        # ---- e2e: the C-ABI call on HOST buffers (pinned), H2D + index build + K1-K3 + D2H per step --
-        pin = lambda a: torch.from_numpy(a).pin_memory()  # noqa: E731
-        nodes_p, fields_p, pts_p = pin(nodes_h), pin(fields_h), pin(pts_h)
-        vals_p = torch.empty((N, F), dtype=torch.float64).pin_memory()
-        prm = spec.to_c()
-        nf = C.c_int64(0)
-        del elem, xi, status, out
-        torch.cuda.empty_cache()
-        lib.mm_host_release()
+    def e2e_step():
+        _lib.check(lib.mm_source_interpolate_host(src_h, N, C.c_void_p(pts_p.data_ptr()), k, C.byref(prm),
+                                                  C.c_void_p(vals_p.data_ptr()), None, None, C.byref(nf)),
+                   "mm_source_interpolate_host")
 
-        def e2e_step():
-            rc = lib.mm_interpolate_host(order, 3, E, C.c_void_p(nodes_p.data_ptr()), F,
-                                         C.c_void_p(fields_p.data_ptr()), N, C.c_void_p(pts_p.data_ptr()), k,
-                                         1 if gll_form else 0,
-                                         C.byref(prm), C.c_void_p(vals_p.data_ptr()), None, None, C.byref(nf))
-            _lib.check(rc, "mm_interpolate_host")
+    def e2e_cold_step():
+        _lib.check(lib.mm_interpolate_host(order, 3, E, C.c_void_p(nodes_p.data_ptr()), F,
+                                           C.c_void_p(fields_p.data_ptr()), N, C.c_void_p(pts_p.data_ptr()), k,
+                                           1 if gll_form else 0, C.byref(prm), C.c_void_p(vals_p.data_ptr()), None,
+                                           None, C.byref(nf)), "mm_interpolate_host")
 
-        e2e_steps = max(1, min(args.steps, 3))
-        e2e_step()
+    def time_host_calls(fn, nsteps, nwarm):
+        for _ in range(nwarm):
+            fn()
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
         t0 = time.perf_counter()
-        for _ in range(e2e_steps):
-            e2e_step()  # synchronous: returns after the D2H copy of the values completed
+        for _ in range(nsteps):
+            fn()  # synchronous: returns after the last D2H byte has arrived
         torch.cuda.synchronize()
-        e2e_s = (time.perf_counter() - t0) / e2e_steps
+        s = (time.perf_counter() - t0) / nsteps
         if world > 1:
-            t = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
+            t = torch.tensor([s], dtype=torch.float64, device=dev)
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            e2e_s = float(t.item())
-        e2e_value = world * N / e2e_s
-        e2e_checksum = float(vals_p.sum().item())
-        h2d = int(nodes_h.nbytes + fields_h.nbytes + pts_h.nbytes)
-        d2h = int(N * F * 8 + 8)
+            s = float(t.item())
+        return s
+
+    e2e_steps = max(1, min(args.steps, 5))
+    e2e_s = time_host_calls(e2e_step, e2e_steps, 2)
+    e2e_checksum = float(vals_p.sum().item())
+    assert int(nf.value) == nfailed
+    lib.mm_source_destroy(src_h)
+    cold_steps = max(1, min(args.steps, 3))
+    cold_s = time_host_calls(e2e_cold_step, cold_steps, 1)
+    cold_checksum = float(vals_p.sum().item())
+    lib.mm_host_release()
+    assert e2e_checksum == cold_checksum, "resident and one-shot host paths disagree"
+    rel = abs(e2e_checksum - checksum) / abs(checksum)
+    assert rel < 1e-12, f"host path and device path disagree: {e2e_checksum} vs {checksum}"
+    h2d = int(pts_h.nbytes)
+    d2h = int(N * F * 8 + 8)
+    del nodes_p, fields_p, pts_p, vals_p
+
+    # ---- north star: BASELINE configs[4] at this run's N (strong scaling) ---------------------------
+    north_star = None
+    if w["name"] == "S2" and not args.no_north_star:
+        torch.cuda.empty_cache()
+        w5 = dict(WORKLOADS["S5"], name="S5")
+        ns_args = argparse.Namespace(**vars(args))
+        ns_args.steps = max(1, min(args.steps, 5))
+        north_star = run_device_gen(ns_args, w5, lib, ops, world, rank, dev, with_clocks=False)[0]
+        torch.cuda.empty_cache()
 
     if rank != 0:
         if world > 1:
@@ -426,75 +779,69 @@ def run_ours(args, w):
         return
 
     # ---- roofline of the dominant kernel (SURVEY 8d algorithmic bytes per target point) ----------
-    peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
-    if os.path.exists(peaks_path):
-        peak = float(json.load(open(peaks_path))["hbm_gbs"])
-        peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)"
-    else:
-        peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
-    d = 3
-    k1 = min(k, 4 if w.get("form") == "centroid" else 8)  # candidates the first pass materialises
-    n_rerun = int(st[9]) if len(st) > 9 else 0
-    bytes_pt = {
-        "K1_knn": 8 * d + 4 * k1,                                  # first pass materialises k1 candidates
-        "K2_locate": 8 * d + 1.0 * (8 * d * P + 16 * d) + (4 + 8 * d),  # c = 1 candidate tested per point
-        "K3_interp": (8 * d + 4) + 8 * F * P + 8 * F,
-    }
     traffic_db = {}
     tpath = os.path.join(ROOT, "profiles", "traffic.json")
     if os.path.exists(tpath):
         traffic_db = json.load(open(tpath)).get(w["name"], {})
-    kernels = {}
-    for name, ms in (("K1_knn", stages[1]), ("K2_locate", stages[2]), ("K3_interp", stages[4])):
-        gbs = bytes_pt[name] * N / (ms * 1e-3) / 1e9
-        kernels[name] = {"ms": round(float(ms), 4), "alg_bytes_per_point": bytes_pt[name],
-                         "achieved_gbs": round(gbs, 1), "frac": round(gbs / peak, 4),
-                         "traffic": traffic_db.get(name)}
-    other = {"query_sort_ms": round(float(stages[0]), 4), "rerun_unresolved_ms": round(float(stages[3]), 4),
-             "unpermute_ms": round(float(stages[5]), 4)}
+    bytes_pt, kernels, other = kernel_report(N, order, F, k, form, stages, peak, traffic_db)
     dom = max(kernels, key=lambda n: kernels[n]["ms"])
     step_bytes = sum(bytes_pt.values()) * N
-    step_gbs = step_bytes / (ms_per_step * 1e-3) / 1e9 if world == 1 or not device_gen else None
+    step_gbs = step_bytes / (ms_per_step * 1e-3) / 1e9
+    # K3 against the bytes that MUST move (fields once + sorted inputs + outputs), not only the no-reuse model
+    k3_compulsory = fields_h.nbytes + N * ((8 * 3 + 4 + 1 + 4) + 8 * F + (4 + 8 * 3 + 1))
+    k3 = kernels["K3_interp"]
+    k3["compulsory_bytes"] = int(k3_compulsory)
+    k3["compulsory_frac"] = round(k3_compulsory / (k3["ms"] * 1e-3) / 1e9 / peak, 4)
     roofline = {"bound": "hbm", "kernel": dom, "achieved": kernels[dom]["achieved_gbs"], "peak": peak,
                 "unit": "GB/s", "frac": kernels[dom]["frac"], "traffic": kernels[dom]["traffic"],
-                "peak_source": peak_src, "graded_kernel_K3": kernels["K3_interp"],
-                "whole_step": None if step_gbs is None else {
-                    "alg_bytes_per_point": sum(bytes_pt.values()), "achieved_gbs": round(step_gbs, 1),
-                    "frac": round(step_gbs / peak, 4)},
+                "peak_source": peak_src, "graded_kernel_K3": k3,
+                "whole_step": {"alg_bytes_per_point": sum(bytes_pt.values()), "achieved_gbs": round(step_gbs, 1),
+                               "frac": round(step_gbs / peak, 4)},
                 "note": "achieved = SURVEY 8d no-reuse algorithmic bytes x points of one launch / CUDA-event "
-                        "duration of that kernel inside the timed step. K1 (k-NN) moves only 8d + 4k' algorithmic "
-                        "B/point and is instruction-issue / latency bound (64 % issue-active, ncu), so its HBM fraction is small "
-                        "by construction; K2/K3 serve most bytes from L2/shared memory (points are processed in spatial "
-                        "order, one copy per distinct element per warp) and are latency / fp64-pipe bound (fp64 pipe "
-                        "26-37 % active), so their algorithmic rate may exceed the HBM peak -- `traffic` is the DRAM bytes "
-                        "ncu saw; whole_step = all three kernels' algorithmic bytes / the step time (sort included)"}
+                        "duration of that kernel inside the timed step; `traffic` = DRAM bytes per launch from the "
+                        "committed ncu capture (profiles/traffic.json). K1 moves only 8d + 4k' algorithmic B/point and is "
+                        "instruction-issue bound, so its HBM fraction is small by construction; K2/K3 serve most "
+                        "algorithmic bytes from L2 / shared memory (points are processed in spatial order, one copy per "
+                        "distinct element per warp), so their no-reuse fraction can exceed 1 -- compulsory_frac is K3 "
+                        "against the bytes that must move at least once (fields + inputs + outputs)"}
 
-    # ---- CPU baseline, rank 0, N = 1 only -------------------------------------------------------
-    cpu = None
-    if world == 1 and not args.no_cpu and not device_gen:
-        crop_src, crop_tgt = (40, 36) if w["src"] >= 40 else (w["src"], w["tgt"] - 2)
-        r = cpu_port_run(w, crop_src, crop_tgt, steps=1, warmup=0)
-        cpu = {"value": r["value"], "unit": UNIT, "cores": r["cores"], "kind": "port", "sample": r["sample"]}
+    # ---- CPU baselines, rank 0, N = 1 only --------------------------------------------------------
+    cpu = cpu_ref_c = None
+    if world == 1 and not args.no_cpu:
+        os.sched_setaffinity(0, ALL_CPUS)
+        port = CpuPort(w, nodes_h, fields_h)
+        r = port.run(pts_h, min(N, 3_000_000), steps=1, warmup=0)
+        cpu = {"value": r["value"], "unit": UNIT, "cores": r["cores"], "kind": "port", "sample": r["sample"],
+               "nfailed": r["nfailed"]}
+        del port
+        try:
+            cpu_ref_c = cpu_ref_c_baseline()
+        except Exception as exc:  # oracle/_ref not built on this box
+            cpu_ref_c = {"unavailable": repr(exc)}
 
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
         "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True,
-        "scaling": "strong" if device_gen else "weak",
-        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": {"workload": workload_name(w), "points_per_gpu": N, "source_elements": E, "fields": F,
-                   "l2": f"inputs larger than L2: source {(nodes.numel() + fields.numel()) * 8 / 1e9:.2f} GB + targets "
-                         f"{pts.numel() * 8 / 1e9:.2f} GB read per step, no flush"},
+                   "l2": f"inputs larger than L2: source {(nodes_h.nbytes + fields_h.nbytes) / 1e9:.2f} GB + targets "
+                         f"{pts_h.nbytes / 1e9:.2f} GB read per step, no flush"},
         "roofline": roofline, "kernels": kernels, "other_stages": other,
-        "cpu_baseline": cpu,
-        "e2e": None if e2e_value is None else {
-                "value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+        "parity_check": parity,
+        "cpu_baseline": cpu, "cpu_baseline_ref_c": cpu_ref_c,
+        "e2e": {"value": world * N / e2e_s, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                 "ms_per_step": e2e_s * 1e3, "steps": e2e_steps,
-                "call": "mm_interpolate_host (C-ABI, pinned host buffers; H2D source mesh + targets, index "
-                        "build, K1-K3, D2H values every step)"},
-        # per step: histogram, 3 scan kernels, query scatter, first-pass k-NN, locate, gather (+ full k-NN and
-        # locate again when the first pass left points unresolved)
-        "gpu_launches": (8 + (2 if n_rerun else 0)) * args.steps, "clocks": clocks, "index_build_ms": build_ms, "nfailed": nfailed,
-        "status_histogram": st, "checksum": checksum, "e2e_checksum": e2e_checksum,
+                "call": "mm_source_interpolate_host (C-ABI, pinned host buffers): source mesh + index resident in HBM "
+                        "(mm_source_create_host, untimed like the reference arm's KD-tree build); every step copies the "
+                        "target points H2D, runs K1-K3 and copies the values D2H, chunked over three streams",
+                "cold_one_shot": {"value": world * N / cold_s, "ms_per_step": cold_s * 1e3, "steps": cold_steps,
+                                  "h2d_bytes_per_step": int(nodes_h.nbytes + fields_h.nbytes + pts_h.nbytes),
+                                  "d2h_bytes_per_step": d2h,
+                                  "call": "mm_interpolate_host: additionally uploads the source mesh and builds "
+                                          "geometry + index + site table inside every step"}},
+        "north_star": north_star,
+        "gpu_launches": launches_per_step(N, True) * args.steps, "clocks": clocks, "index_build_ms": build_ms,
+        "nfailed": nfailed, "status_histogram": st, "checksum": checksum, "e2e_checksum": e2e_checksum,
     }
     print(json.dumps(line), flush=True)
     if world > 1:
@@ -508,7 +855,9 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="S2", choices=sorted(WORKLOADS))
-    ap.add_argument("--no-cpu", action="store_true", help="skip the CPU baseline leg")
+    ap.add_argument("--no-cpu", action="store_true", help="skip the CPU baseline legs")
+    ap.add_argument("--no-north-star", action="store_true", help="skip the S5 strong-scaling leg of the S2 run")
+    ap.add_argument("--no-parity", action="store_true", help="skip the oracle check of the timed result")
     args = ap.parse_args()
     w = dict(WORKLOADS[args.workload], name=args.workload)
     if args.impl == "reference":

@@ -81,6 +81,41 @@ constexpr int MM_QREC = 4;  // doubles per sorted-query record
 int mm_index_sort_queries(const mm_index_t *ix, int64_t N, const double *pts, double *sorted_rec,
                           int32_t *rank_tmp, void *scratch, void *stream);
 
+// Opt-in to large dynamic shared memory once per (kernel, device) and cache the occupancy query: both are
+// host-side driver calls that need not be repeated for every launch (and keeps launches free of anything but
+// the launch itself, e.g. under CUDA-graph capture).  One instance per kernel (function-local static).
+struct mm_kernel_cfg {
+    size_t smem_set[16] = {};
+    size_t occ_smem[16] = {};
+    int occ_threads[16] = {};
+    int occ[16] = {};
+    template <class K>
+    cudaError_t prepare(K kern, int threads, size_t smem, int *per_sm)
+    {
+        int dev = 0;
+        cudaError_t rc = cudaGetDevice(&dev);
+        if (rc != cudaSuccess) return rc;
+        const int d = dev & 15;
+        if (smem > smem_set[d]) {
+            rc = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            if (rc != cudaSuccess) return rc;
+            smem_set[d] = smem;
+        }
+        if (per_sm) {
+            if (occ[d] == 0 || occ_smem[d] != smem || occ_threads[d] != threads) {
+                int v = 1;
+                rc = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&v, kern, threads, smem);
+                if (rc != cudaSuccess) return rc;
+                occ[d] = v < 1 ? 1 : v;
+                occ_smem[d] = smem;
+                occ_threads[d] = threads;
+            }
+            *per_sm = occ[d];
+        }
+        return cudaSuccess;
+    }
+};
+
 static inline bool mm_valid_order(int order) { return order == 1 || order == 2 || order == 4; }
 static inline int mm_pow(int m, int dim) { return dim == 2 ? m * m : m * m * m; }
 

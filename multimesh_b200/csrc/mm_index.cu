@@ -1047,8 +1047,8 @@ int mm_knn_strided(const mm_index_t *ix, int64_t N, const double *pts, int pts_s
             g, N, pts, pts_stride, k, fast_div(divisor), ix->recs, ix->cell_start, idx, d2, n_dev, n_off);
     } else {
         size_t smem = (size_t)k * KNN_BLOCK * (sizeof(double) + sizeof(int32_t));
-        MM_CUDA(cudaFuncSetAttribute(knn_kernel<smem_list>,
-                                     cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        static mm_kernel_cfg kcfg;
+        MM_CUDA(kcfg.prepare(knn_kernel<smem_list>, KNN_BLOCK, smem, nullptr));
         int per_sm = (int)std::max<size_t>(1, std::min<size_t>(8, (200 * 1024) / smem));
         knn_kernel<smem_list><<<launch_blocks(N, KNN_BLOCK, per_sm), KNN_BLOCK, smem, st>>>(
             g, N, pts, pts_stride, k, fast_div(divisor), ix->recs, ix->cell_start, idx, d2, n_dev, n_off);

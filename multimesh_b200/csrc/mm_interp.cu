@@ -214,10 +214,9 @@ int launch_interp(int64_t E, int F, const double *fields, int64_t N, const int32
     while (cfg.warps > 1 && smem_of(cfg.warps) > 200 * 1024) --cfg.warps;
     size_t smem = smem_of(cfg.warps);
     MM_REQUIRE(smem <= 227 * 1024, MM_ERR_UNSUPPORTED, "mm_interp: staging needs %zu B of shared memory", smem);
-    MM_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    static mm_kernel_cfg kcfg;
     int per_sm = 1;
-    MM_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, cfg.warps * 32, smem));
-    if (per_sm < 1) per_sm = 1;
+    MM_CUDA(kcfg.prepare(kern, cfg.warps * 32, smem, &per_sm));
     const int sms = mm_num_sms() > 0 ? mm_num_sms() : 148;
     int64_t nbatch = (N + 31) / 32;
     int64_t grid = (int64_t)sms * per_sm;  // persistent CTAs, multiple of the SM count
@@ -432,10 +431,9 @@ int launch_interp_coherent(int64_t E, int F, const double *fields, int64_t N, co
     while (cfg.warps > 1 && smem_of(cfg.warps) > 110 * 1024) --cfg.warps;  // two CTAs per SM
     size_t smem = smem_of(cfg.warps);
     MM_REQUIRE(smem <= 227 * 1024, MM_ERR_UNSUPPORTED, "mm_interp: staging needs %zu B of shared memory", smem);
-    MM_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    static mm_kernel_cfg kcfg;
     int per_sm = 1;
-    MM_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, cfg.warps * 32, smem));
-    if (per_sm < 1) per_sm = 1;
+    MM_CUDA(kcfg.prepare(kern, cfg.warps * 32, smem, &per_sm));
     const int sms = mm_num_sms() > 0 ? mm_num_sms() : 148;
     int64_t nbatch = (N + 31) / 32;
     int64_t grid = (int64_t)sms * per_sm;

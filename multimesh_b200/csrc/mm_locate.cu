@@ -321,10 +321,9 @@ int launch_locate(const mm_locate_params &prm, int64_t E, const double *nodes,
     mm_make_table(ORDER, &T);
     auto kern = locate_kernel<ORDER, DIM, WARPS, SLOTS, MINB>;
     const size_t smem = (size_t)WARPS * SLOTS * tr::SLOT_BYTES + WARPS * sizeof(uint64_t);
-    MM_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    static mm_kernel_cfg kcfg;
     int per_sm = 1;
-    MM_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, WARPS * 32, smem));
-    if (per_sm < 1) per_sm = 1;
+    MM_CUDA(kcfg.prepare(kern, WARPS * 32, smem, &per_sm));
     const int sms = mm_num_sms() > 0 ? mm_num_sms() : 148;
     int64_t batches = (N + 32 * WARPS - 1) / (32 * WARPS);
     int64_t grid = (int64_t)sms * per_sm;  // persistent: resident CTAs loop over point batches

@@ -29,14 +29,14 @@ static thread_local mm_profile *g_profile = nullptr;
 namespace {
 
 // points per re-run chunk: the number of unresolved points is only known on the device, so the host
-// enqueues ceil(N / chunk) <= 8 rounds and the kernels of a round that has nothing to do exit at once
+// enqueues ceil(N / chunk) <= 4 rounds and the kernels of a round that has nothing to do exit at once
 inline int64_t rerun_chunk(int64_t N)
 {
     if (const char *e = getenv("MM_RERUN_CHUNK")) {  // tests: force several rounds on small inputs
         const long long v = atoll(e);
         if (v > 0) return v;
     }
-    return std::max<int64_t>((int64_t)1 << 20, (N + 7) / 8);
+    return std::max<int64_t>((int64_t)1 << 20, (N + 3) / 4);
 }
 
 inline size_t align_up(size_t x) { return (x + 255) & ~(size_t)255; }
