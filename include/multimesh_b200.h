@@ -147,6 +147,11 @@ int mm_locate(int order, int dim, int64_t E, const double *nodes, const double *
               const mm_locate_params *params, int32_t *elem, double *xi, uint8_t *status,
               int64_t *num_failed, void *stream);
 
+/* Statistics for the benchmarks: while a device array of two int64 is set, the calling thread's mm_locate /
+ * mm_interpolate launches add {candidates that reached Newton, map evaluations (Newton iterations)} to it
+ * (a separate kernel instantiation; the regular kernels carry no counters).  NULL switches it off. */
+int mm_locate_set_stats(int64_t *device_counters);
+
 /* ------------------------------------------------------------------------------------------
  * K3  fused Lagrange weights + multi-field gather.
  *   out[n][f] = sum_a w_a(xi_n) * fields[elem_n][f][a];  rows with elem < 0 are zero.
@@ -175,6 +180,26 @@ int mm_coeffs(int order, int dim, int64_t N, const int32_t *elem, const double *
  *   out[n][f] = sum_a fields[elem_n][f][a] * coeffs[n][a]   (sequential in a). */
 int mm_gather_coeffs(int P, int64_t E, int F, const double *fields, int64_t N,
                      const int32_t *elem, const double *coeffs, double *out, void *stream);
+
+/* ------------------------------------------------------------------------------------------
+ * K4  target-side de-duplication and write-back (device pointers).
+ * mm_unique_points replaces utils.get_unique_points = np.unique(points, axis=0, return_inverse=True)
+ *   (utils.py:465-515): unique [n_unique][dim] (caller provides room for N rows) in numpy's lexicographic order,
+ *   inverse [N] int32 with points[i] == unique[inverse[i]]; *n_unique is written on the HOST (the call
+ *   synchronises).  -0.0 is folded onto +0.0; non-finite coordinates are rejected.
+ * mm_scatter_back replaces values[recon].reshape(E, P, F).swapaxes(1, 2) (components/interpolator.py:822-826,
+ *   412-427): out[e][f][p] = values[inverse[e * P + p]][f]; inverse == NULL means the identity (every GLL node was
+ *   interpolated itself).
+ * mm_fluid_fixup replaces the fluid / solid repair of gll_2_gll (components/interpolator.py:829-841), in place:
+ *   elements with fluid[e] != 0 keep old_values; a solid element with any values[e][vs_index][p] == 0.0 is
+ *   restored from old_values as a whole (vs_index < 0 skips that test).
+ * ---------------------------------------------------------------------------------------- */
+int mm_unique_points(int dim, int64_t N, const double *pts, int64_t *n_unique, double *unique, int32_t *inverse,
+                     void *stream);
+int mm_scatter_back(int64_t E, int P, int F, const double *values, const int32_t *inverse, double *out,
+                    void *stream);
+int mm_fluid_fixup(int64_t E, int P, int F, double *values, const double *old_values, const uint8_t *fluid,
+                   int vs_index, void *stream);
 
 /* ------------------------------------------------------------------------------------------
  * Order-1 nodal (Exodus HEX8) path, device pointers.  Arithmetic is bit-identical to

@@ -65,6 +65,10 @@ _SIGNATURES = {
     "mm_gather_nodal": (_int, [_int, _i64, _vp, _i64, _vp, _vp, _vp, _vp]),
     "mm_interpolate_host": (_int, [_int, _int, _i64, _vp, _int, _vp, _i64, _vp, _int, _int,
                                    C.POINTER(LocateParams), _vp, _vp, _vp, C.POINTER(_i64)]),
+    "mm_locate_set_stats": (_int, [_vp]),
+    "mm_unique_points": (_int, [_int, _i64, _vp, C.POINTER(_i64), _vp, _vp, _vp]),
+    "mm_scatter_back": (_int, [_i64, _int, _int, _vp, _vp, _vp, _vp]),
+    "mm_fluid_fixup": (_int, [_i64, _int, _int, _vp, _vp, _vp, _int, _vp]),
     "mm_host_release": (_int, []),
     "mm_pool_trim": (_int, []),
     "mm_index_prepare_sites": (_int, [_vp, _vp]),

@@ -19,7 +19,7 @@ LIB_DIR = os.path.join(HERE, "lib")
 OBJ_DIR = os.path.join(HERE, "lib", "obj")
 LIB_PATH = os.path.join(LIB_DIR, "multi_mesh_b200.so")
 SOURCES = ["mm_core.cu", "mm_geometry.cu", "mm_index.cu", "mm_locate.cu", "mm_interp.cu",
-           "mm_trilinear.cu", "mm_pipeline.cu", "mm_source.cu", "mm_host.cu"]
+           "mm_trilinear.cu", "mm_pipeline.cu", "mm_source.cu", "mm_dedup.cu", "mm_host.cu"]
 NVCC_FLAGS = [
     "-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
     "-fmad=false", "-Xcompiler", "-fPIC,-ffp-contract=off,-fno-fast-math", "-Xptxas", "-v",

@@ -16,7 +16,7 @@ from typing import Dict, List, Tuple, Union
 import numpy as np
 import torch
 
-from .. import ops, utils
+from .. import ops, parallel, utils
 from ..gll import order_from_npoints
 from ..io.exodus import Exodus
 from ..io.store import open_store
@@ -67,14 +67,30 @@ class _Source:
     def locate(self, pts, cands, spec):
         return ops.locate(self.nodes, self.centroid, self.aabb, pts, cands, spec, presolve=self.presolve)
 
-    def find(self, pts, k, spec, form="centroid", fields=None):
+    def find(self, pts, k, spec, form="centroid", fields=None, shard=True):
         """Fused k-NN -> locate (-> gather when `fields` [E,F,P] is given): the mm_interpolate
         pipeline (spatially sorted points, progressive search).  Same results as
-        candidates() + locate() (+ ops.interp).  -> (values or None, elem, xi, status, nfail)"""
+        candidates() + locate() (+ ops.interp).  -> (values or None, elem, xi, status, nfail)
+
+        Multi-GPU: when the process runs under torchrun (torch.distributed initialised, one rank
+        per GPU, every rank calling the same driver with the same arguments) the target points are split into
+        contiguous shards, each rank interpolates its own shard against its replica of the source mesh, and
+        the shards are exchanged so that every rank returns the complete result -- bit-identical to the
+        single-GPU result, because no arithmetic depends on the partition."""
         index, div = (self.gll_index(), self.P) if form == "gll" else (self.centroid_index(), 1)
         f = None if fields is None else _dev_f64(fields, self.device)
-        out, elem, xi, status, nfail = ops.interpolate(index, div, self.nodes, self.centroid, self.aabb, f,
-                                                        pts, k, spec, presolve=self.presolve)
+        world, rank = parallel._world()
+        n = pts.shape[0]
+        if shard and world > 1 and n >= world:
+            sl = parallel.local_slice(n, rank, world)
+            out, elem, xi, status, nfail = ops.interpolate(index, div, self.nodes, self.centroid, self.aabb, f,
+                                                            pts[sl].contiguous(), k, spec, presolve=self.presolve)
+            out = parallel.allgather_rows(out, n) if fields is not None else out
+            elem, xi, status = (parallel.allgather_rows(t, n) for t in (elem, xi, status))
+            torch.distributed.all_reduce(nfail)
+        else:
+            out, elem, xi, status, nfail = ops.interpolate(index, div, self.nodes, self.centroid, self.aabb, f,
+                                                            pts, k, spec, presolve=self.presolve)
         return (out if fields is not None else None), elem, xi, status, nfail
 
 
@@ -290,14 +306,14 @@ def _all_points(points, layers=None, mesh=None):
     which on the GPU is cheaper than the lexicographic np.unique of 1e7-1e8 rows."""
     if mesh is None:
         allp = points.reshape(points.shape[0] * points.shape[1], points.shape[2])
-        return allp, np.arange(allp.shape[0])
+        return allp, None  # inverse = identity
     layers, _ = utils._assess_layers(mesh=mesh, layers=layers)
     mask, _ = utils._create_mask(mesh=mesh, layers=layers)
     out = {}
     for layer in layers:
         nodes = mesh.get_element_nodes()[mask[str(layer)]]
         allp = nodes.reshape(nodes.shape[0] * nodes.shape[1], nodes.shape[2])
-        out[str(layer)] = (allp, np.arange(allp.shape[0]))
+        out[str(layer)] = (allp, None)  # inverse = identity
     return out, mask, layers
 
 
@@ -313,7 +329,9 @@ def _layer_setup(from_gll, to_gll, layers, parameters, make_spherical, dedup=Tru
     if make_spherical:
         map_to_sphere(new_mesh)
     if dedup:
-        unique_new_points, mask, layers = utils.get_unique_points(points=new_mesh, mesh=True, layers=layers)
+        # K4 on the device; (unique, inverse) stay there
+        unique_new_points, mask, layers = utils.get_unique_points(points=new_mesh, mesh=True, layers=layers,
+                                                                  as_numpy=False)
     else:
         unique_new_points, mask, layers = _all_points(None, layers=layers, mesh=new_mesh)
     parameters = utils.pick_parameters(parameters)
@@ -354,6 +372,35 @@ def _save_interp_info(stored_array, coeffs, elements):
             st.write(f"elements/{k}", np.asarray(v))
 
 
+COMPACT_CACHE = "interp_compact.npz"
+
+
+def _save_compact_cache(stored_array, located, order):
+    """Native cache next to the reference's formats: per key (layer name, or "all") the owning element (int32) and
+    the reference coordinates xi (f64 [N, d]) -- 4 + 8 d bytes per point instead of the 8 P bytes of a stored
+    weight row (1 000 B at order 4).  A re-run is then pure K3 (fused weights + gather) straight from the cache."""
+    os.makedirs(stored_array, exist_ok=True)
+    arrays = {"order": np.int64(order)}
+    for k, (elem, xi) in located.items():
+        arrays[f"elem/{k}"] = elem.cpu().numpy().astype(np.int32)
+        arrays[f"xi/{k}"] = xi.cpu().numpy()
+    np.savez(os.path.join(stored_array, COMPACT_CACHE), **arrays)
+
+
+def _load_compact_cache(stored_array, keys, device):
+    """{key: (elem, xi)} on the device, or None when the directory holds no compact cache for these keys."""
+    if stored_array is None:
+        return None
+    p = os.path.join(stored_array, COMPACT_CACHE)
+    if not os.path.exists(p):
+        return None
+    with np.load(p) as z:
+        if any(f"elem/{k}" not in z.files for k in keys):
+            return None
+        return {k: (torch.from_numpy(z[f"elem/{k}"]).to(device), torch.from_numpy(z[f"xi/{k}"]).to(device))
+                for k in keys}
+
+
 def _layered_write_back(original_mesh, original_mask, new_mesh, unique_new_points, mask, parameters, located,
                         keep_outside=False):
     """values[inverse] -> reshape -> new_field[mask] per parameter, then attach (:415-427).
@@ -374,10 +421,11 @@ def _layered_write_back(original_mesh, original_mask, new_mesh, unique_new_point
         else:
             vals = _gather_cached(dev, fields, loc["elements"], loc["coeffs"])
             num_failed += int((np.asarray(loc["elements"]) < 0).sum())
-        vals = vals.cpu().numpy()[unique_new_points[layer][1]]  # scatter back to all GLL nodes
+        # K4: scatter back to all GLL nodes and re-lay out as [E_layer, F, P] on the device; one D2H copy per layer
         shape = new_mesh.element_nodal_fields[parameters[0]][mask[layer]].shape
+        block = ops.scatter_back(vals, unique_new_points[layer][1], shape[0], shape[1]).cpu().numpy()
         for f, p in enumerate(parameters):
-            new_fields[p][mask[layer]] = vals[:, f].reshape(shape)
+            new_fields[p][mask[layer]] = block[:, f, :]
     for p in parameters:
         new_mesh.attach_field(name=p, data=new_fields[p])
     return num_failed
@@ -390,9 +438,14 @@ def _gll_2_gll_layered_impl(from_gll, to_gll, layers, nelem_to_search, parameter
                                 dedup=stored_array is not None)
     order = original_mesh.shape_order
     keys = list(unique_new_points.keys())
-    cached = _load_interp_info(stored_array, keys)
+    compact = _load_compact_cache(stored_array, keys, _device())
+    cached = None if compact is not None else _load_interp_info(stored_array, keys)
     located = {}
-    if cached is not None:
+    if compact is not None:
+        print("No need for looping, we have the (element, xi) cache")
+        for k in keys:
+            located[k] = {"elem": compact[k][0], "xi": compact[k][1]}
+    elif cached is not None:
         for k in keys:
             located[k] = {"coeffs": cached[0][k], "elements": cached[1][k]}
     else:
@@ -403,11 +456,12 @@ def _gll_2_gll_layered_impl(from_gll, to_gll, layers, nelem_to_search, parameter
             pts = _dev_f64(unique_new_points[k][0], src.device)
             _, elem, xi, _, _ = src.find(pts, nelem_to_search, spec)
             located[k] = {"elem": elem, "xi": xi}
-        if stored_array is not None:
+        if stored_array is not None and parallel._world()[1] == 0:
             _save_interp_info(
                 stored_array,
                 {k: ops.coeffs(v["elem"], v["xi"], order).cpu().numpy() for k, v in located.items()},
                 {k: v["elem"].cpu().numpy().astype(int) for k, v in located.items()})
+            _save_compact_cache(stored_array, {k: (v["elem"], v["xi"]) for k, v in located.items()}, order)
     num_failed = _layered_write_back(original_mesh, original_mask, new_mesh, unique_new_points, mask,
                                      parameters, located, keep_outside=keep_outside)
     if num_failed > 0:
@@ -461,7 +515,8 @@ def gll_2_gll(from_gll, to_gll, nelem_to_search=20, parameters="ISO", from_model
     parameters = original_params  # the reference interpolates every source parameter (:668)
     src = _Source(original_points)
 
-    with open_store(to_gll, "r+") as new:
+    writer = parallel._world()[1] == 0  # under torchrun every rank computes, rank 0 writes files
+    with open_store(to_gll, "r+" if writer else "r") as new:
         new_points = np.array(new.read(to_coordinates_path), dtype=np.float64)
         elem_params = new.labels("MODEL/element_data")
         fluid_elements = new.read("MODEL/element_data")[:, elem_params.index("fluid")].astype(bool)
@@ -470,18 +525,23 @@ def gll_2_gll(from_gll, to_gll, nelem_to_search=20, parameters="ISO", from_model
         gll_points = new_points.shape[1]
 
         element = coeffs = None
-        if stored_array and os.path.exists(os.path.join(stored_array, "coeffs.npy")) and os.path.exists(
+        compact = _load_compact_cache(stored_array, ["all"], src.device) if stored_array else None
+        if compact is not None:
+            print("Matrix was already stored (compact element / xi cache). Will use that one")
+        elif stored_array and os.path.exists(os.path.join(stored_array, "coeffs.npy")) and os.path.exists(
                 os.path.join(stored_array, "elements.npy")):
             coeffs = np.load(os.path.join(stored_array, "coeffs.npy"), allow_pickle=True)
             element = np.load(os.path.join(stored_array, "elements.npy"), allow_pickle=True)
             assert not np.isnan(coeffs).any(), "Stored coeffs matrix has NaNs"
             print("Matrix was already stored. Will use that one")
 
-        if stored_array:  # the stored matrices are defined on the unique points (:744, :797-810)
-            unique_new_points, recon = utils.get_unique_points(points=new_points)
+        if stored_array:  # the stored matrices are defined on the unique points (:744, :797-810); K4 on the device
+            unique_new_points, recon = utils.get_unique_points(points=new_points, device=src.device, as_numpy=False)
         else:
             unique_new_points, recon = _all_points(new_points)
-        if element is None:
+        if compact is not None:
+            vals = ops.interp(_dev_f64(original_data, src.device), compact["all"][0], compact["all"][1])
+        elif element is None:
             print("Now we start interpolating")
             pts = _dev_f64(unique_new_points, src.device)
             # V1, ignore_hard_elements=True (:781)
@@ -491,7 +551,7 @@ def gll_2_gll(from_gll, to_gll, nelem_to_search=20, parameters="ISO", from_model
             num_failed = int(nfail.item())
             if num_failed > 0:
                 print(f"{num_failed} points could not find an enclosing element.")
-            if stored_array:
+            if stored_array and writer:
                 os.makedirs(stored_array, exist_ok=True)
                 print("Will save matrices for later usage")
                 w = ops.coeffs(elem, xi, from_gll_order).cpu().numpy()  # [N, P]
@@ -500,23 +560,24 @@ def gll_2_gll(from_gll, to_gll, nelem_to_search=20, parameters="ISO", from_model
                         allow_pickle=True)
                 np.save(os.path.join(stored_array, "coeffs.npy"),
                         np.broadcast_to(w.T[None], (len(parameters),) + w.T.shape).copy(), allow_pickle=True)
+                _save_compact_cache(stored_array, {"all": (elem, xi)}, from_gll_order)
         else:
             vals = _gather_cached(src.device, original_data, element, np.ascontiguousarray(coeffs[0].T))
-        # [N_unique, F] -> all GLL nodes -> [E_t, F, P_t]  (:822-826)
-        values = vals.cpu().numpy()[recon, :].reshape((new_points.shape[0], gll_points, len(parameters)))
-        values = np.ascontiguousarray(values.swapaxes(1, 2))
-        assert not np.isnan(values).any(), "Interpolation failed somehow"
+        # K4 on the device: [N_unique, F] -> all GLL nodes -> [E_t, F, P_t]  (:822-826), then the fluid / solid
+        # repair (:829-841); only the final array crosses PCIe
+        values_d = ops.scatter_back(vals, recon, new_points.shape[0], gll_points)
+        assert not bool(torch.isnan(values_d).any().item()), "Interpolation failed somehow"
         if not gradient:
             # keep fluid elements untouched and repair solids that picked up fluid (VS = 0) values
-            values[~solid_elements] = new_values[~solid_elements]
             vs_index = parameters.index("VS") if "VS" in parameters else parameters.index("VSV")
-            zero_vs = np.where(values[:, vs_index, :] == 0.0)
             print("If any fluid values accidentally went to the solid part we fix it")
-            for elem_id in np.unique(zero_vs[0]):
-                if solid_elements[elem_id]:
-                    values[elem_id, :, :] = new_values[elem_id, :, :]
-        utils.remove_and_create_empty_dataset(new, parameters, to_model_path, to_coordinates_path)
-        new.write(to_model_path, values)
+            ops.fluid_fixup_(values_d, _dev_f64(new_values, src.device).contiguous(),
+                             torch.from_numpy(fluid_elements.astype(np.uint8)).to(src.device), vs_index)
+        values = values_d.cpu().numpy()
+        if writer:
+            utils.remove_and_create_empty_dataset(new, parameters, to_model_path, to_coordinates_path)
+            new.write(to_model_path, values)
+    parallel.barrier()
 
 
 def exodus_2_gll(mesh, gll_model, gll_order=4, dimensions=3, nelem_to_search=20, parameters="TTI",

@@ -67,8 +67,18 @@ size_t mm_index_sort_scratch_bytes(const mm_index_t *ix);
 // site table (distinct coordinates; built by the public mm_index_prepare_sites) and the site-level first
 // pass of the progressive search
 bool mm_index_has_sites(const mm_index_t *ix);
+struct mm_index_sites_view {
+    int64_t nsites, M;
+    const double4 *site_recs;    // [nsites + 1] {x, y, z, first record}
+    const int32_t *site_first;   // [nsites + 1]
+    const int32_t *rec_id;       // [M] point id of record t (records of one site are contiguous, ids ascending)
+};
+bool mm_index_sites_view_get(const mm_index_t *ix, mm_index_sites_view *out);
 int mm_knn_sites(const mm_index_t *ix, int64_t N, const double *pts, int pts_stride, int kout,
                  int32_t divisor, int32_t *idx, void *stream);
+// first pass of the pipeline over SORTED queries (warp-cooperative block kernel when k = 4, else mm_knn)
+int mm_knn_first_pass(const mm_index_t *ix, int64_t N, const double *pts, int pts_stride, int k,
+                      int32_t divisor, int32_t *idx, void *stream);
 // mm_knn with a stride (in doubles) between consecutive query points
 // n_dev (optional, device): the kernel processes points [0, min(N, *n_dev - n_off)) -- for work lists whose
 // length is only known on the device (no host synchronisation)

@@ -15,6 +15,7 @@
 #include <vector>
 
 #include "mm_common.cuh"
+#include "mm_scan.cuh"
 
 struct mm_index {
     int dim = 0;
@@ -24,6 +25,7 @@ struct mm_index {
     int n[3] = {1, 1, 1};
     int64_t ncells = 1;
     int64_t nonempty = 0;
+    double distinct_est = 0.0;  // estimated number of distinct coordinates (probe grid)
     double4 *recs = nullptr;
     int32_t *cell_start = nullptr;
     size_t bytes = 0;
@@ -33,6 +35,15 @@ struct mm_index {
     int64_t nsites = 0;
     double4 *site_recs = nullptr;        // [nsites + 1] {x, y, z, first record of the site}
     int32_t *site_cell_start = nullptr;  // [ncells + 1] first site of each cell
+    // compact tables of the warp-cooperative first pass (knn_block_kernel):
+    //   recf     [M] (plain form) or [nsites] (site form): float4 {x, y, z relative to the corner of the
+    //            record's own cell, record / site position}
+    //   rec_id   [M] int32: point id of record t (recs[t].w), 4 bytes instead of a 32-byte record per look-up
+    //   site_first [nsites + 1] int32: first record of each site
+    float4 *recf = nullptr;
+    bool recf_sites = false;
+    int32_t *rec_id = nullptr;
+    int32_t *site_first = nullptr;
     cudaStream_t stream = nullptr;       // stream the buffers were allocated on (stream-ordered pool)
 };
 
@@ -138,83 +149,6 @@ count_nonempty_kernel(int64_t ncells, const int32_t *__restrict__ counts,
         local += counts[i] > 0;
     for (int o = 16; o > 0; o >>= 1) local += __shfl_xor_sync(0xffffffffu, local, o);
     if ((threadIdx.x & 31) == 0 && local) atomicAdd(nonempty, local);
-}
-
-// ---- exclusive scan of int32 counts (n entries -> n + 1 starts), three small kernels -----------
-constexpr int SCAN_BLOCK = 256;
-constexpr int SCAN_ITEMS = 16;
-constexpr int SCAN_TILE = SCAN_BLOCK * SCAN_ITEMS;
-
-__global__ void __launch_bounds__(SCAN_BLOCK)
-scan_tile_sums(int64_t n, const int32_t *__restrict__ in, int32_t *__restrict__ tile_sums)
-{
-    int64_t base = (int64_t)blockIdx.x * SCAN_TILE;
-    int32_t s = 0;
-    for (int i = threadIdx.x; i < SCAN_TILE; i += SCAN_BLOCK)
-        if (base + i < n) s += in[base + i];
-    __shared__ int32_t sh[SCAN_BLOCK];
-    sh[threadIdx.x] = s;
-    __syncthreads();
-    for (int w = SCAN_BLOCK / 2; w > 0; w >>= 1) {
-        if (threadIdx.x < w) sh[threadIdx.x] += sh[threadIdx.x + w];
-        __syncthreads();
-    }
-    if (threadIdx.x == 0) tile_sums[blockIdx.x] = sh[0];
-}
-
-__global__ void __launch_bounds__(1024)
-scan_tile_offsets(int64_t ntiles, int32_t *__restrict__ tile_sums)  // in-place exclusive, 1 block
-{
-    __shared__ int32_t sh[1024];
-    __shared__ int32_t carry;
-    if (threadIdx.x == 0) carry = 0;
-    __syncthreads();
-    for (int64_t base = 0; base < ntiles; base += 1024) {
-        int64_t i = base + threadIdx.x;
-        int32_t v = i < ntiles ? tile_sums[i] : 0;
-        sh[threadIdx.x] = v;
-        __syncthreads();
-        for (int o = 1; o < 1024; o <<= 1) {
-            int32_t t = threadIdx.x >= o ? sh[threadIdx.x - o] : 0;
-            __syncthreads();
-            sh[threadIdx.x] += t;
-            __syncthreads();
-        }
-        if (i < ntiles) tile_sums[i] = carry + sh[threadIdx.x] - v;
-        __syncthreads();
-        if (threadIdx.x == 0) carry += sh[1023];
-        __syncthreads();
-    }
-}
-
-__global__ void __launch_bounds__(SCAN_BLOCK)
-scan_apply(int64_t n, const int32_t *__restrict__ in, const int32_t *__restrict__ tile_offsets,
-           int32_t *__restrict__ out /* n + 1 */)
-{
-    int64_t base = (int64_t)blockIdx.x * SCAN_TILE + (int64_t)threadIdx.x * SCAN_ITEMS;
-    int32_t v[SCAN_ITEMS];
-    int32_t s = 0;
-#pragma unroll
-    for (int i = 0; i < SCAN_ITEMS; ++i) {
-        v[i] = base + i < n ? in[base + i] : 0;
-        s += v[i];
-    }
-    __shared__ int32_t sh[SCAN_BLOCK];
-    sh[threadIdx.x] = s;
-    __syncthreads();
-    for (int o = 1; o < SCAN_BLOCK; o <<= 1) {
-        int32_t t = threadIdx.x >= o ? sh[threadIdx.x - o] : 0;
-        __syncthreads();
-        sh[threadIdx.x] += t;
-        __syncthreads();
-    }
-    int32_t run = tile_offsets[blockIdx.x] + sh[threadIdx.x] - s;
-#pragma unroll
-    for (int i = 0; i < SCAN_ITEMS; ++i) {
-        if (base + i < n) out[base + i] = run;
-        run += v[i];
-        if (base + i == n - 1) out[n] = run;
-    }
 }
 
 __global__ void __launch_bounds__(256)
@@ -426,6 +360,224 @@ __device__ __forceinline__ void scan_range(List &L, const double4 *__restrict__ 
 // increasing; that prefix is written (up to k entries, idx / divisor, -1 padded).  At the first
 // exact tie between site distances the prefix stops (copies of tied sites interleave by id) and
 // the caller's full search handles the point.
+struct knn_query {
+    double px, py, pz;
+    int ci[3];
+    double out2;  // squared distance from the query to the grid's bounding box (0 inside)
+};
+
+// cell coordinates + out-of-box distance of one query; false for a non-finite / overflowing query
+__device__ __forceinline__ bool knn_setup_query(const grid_t &g, double px, double py, double pz, double margin,
+                                                knn_query &q)
+{
+    const bool three_d = g.dim == 3;
+    q.px = px;
+    q.py = py;
+    q.pz = pz;
+    // a NaN / infinite query (or one so far away that its squared distances overflow) has no nearest
+    // neighbours: every comparison is false; without this guard it would walk the whole grid before
+    // reporting the same thing
+    if (!(fabs(px) <= 1e150 && fabs(py) <= 1e150 && fabs(pz) <= 1e150)) return false;
+    q.ci[0] = cell_coord(g, px, 0);
+    q.ci[1] = cell_coord(g, py, 1);
+    q.ci[2] = three_d ? cell_coord(g, pz, 2) : 0;
+    // squared distance from the query to the grid's bounding box (0 for queries inside it): every
+    // indexed point is at least that far away, which tightens the termination bound for targets
+    // that lie outside the source mesh
+    const double p[3] = {px, py, pz};
+    double out2 = 0.0;
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+        if (c >= g.dim) break;
+        const double o = box_gap(g, p[c], c, margin);
+        out2 += o * o;
+    }
+    q.out2 = out2;
+    return true;
+}
+
+// rings 0 and 1 merged: the 3 x 3 block of cell rows around the query's cell, each row ONE
+// contiguous record range [cx-1, cx+1], own row first, then face, edge neighbours; rows the
+// current k-th distance cannot reach are skipped.  (With cells of about one distinct coordinate
+// this is where almost every first-pass query ends.)
+template <class List, bool SITES>
+__device__ __forceinline__ void knn_block_pass(const grid_t &g, const knn_query &q, List &L,
+                                               const double4 *__restrict__ recs,
+                                               const int32_t *__restrict__ cell_start)
+{
+    const bool three_d = g.dim == 3;
+    const double h = g.cell, margin = h * 1e-6;
+    const double px = q.px, py = q.py, pz = q.pz;
+    const int xa = max(q.ci[0] - 1, 0), xb = min(q.ci[0] + 1, g.n[0] - 1);
+    const int nrow = three_d ? 9 : 3;
+    // record range of row `it` (empty when the row lies outside the grid); the bounds of the
+    // NEXT row are loaded before the current row is scanned, so their latency is hidden
+    auto row_bounds = [&](int it, int32_t &lo, int32_t &hi) {
+        const int dy = (int)((0x22161u >> (2 * it)) & 3u) - 1;   // 0,-1,+1, 0, 0,-1,+1,-1,+1
+        const int dz = (int)((0x28215u >> (2 * it)) & 3u) - 1;   // 0, 0, 0,-1,+1,-1,-1,+1,+1
+        const int yy = q.ci[1] + dy, zz = q.ci[2] + dz;
+        lo = hi = 0;
+        if (it < nrow && yy >= 0 && yy < g.n[1] && zz >= 0 && zz < g.n[2]) {
+            const int base = g.n[0] * (yy + g.n[1] * zz);  // ncells <= MAX_CELLS = 2^26
+            lo = cell_start[base + xa];
+            hi = cell_start[base + xb + 1];
+        }
+    };
+    int32_t nlo, nhi;
+    row_bounds(0, nlo, nhi);
+    for (int it = 0; it < nrow; ++it) {
+        const int32_t lo = nlo, hi = nhi;
+        row_bounds(it + 1, nlo, nhi);
+        if (lo >= hi) continue;
+        if (L.full()) {
+            const int dy = (int)((0x22161u >> (2 * it)) & 3u) - 1;
+            const int dz = (int)((0x28215u >> (2 * it)) & 3u) - 1;
+            const int yy = q.ci[1] + dy, zz = q.ci[2] + dz;
+            double yl = g.origin[1] + yy * h, yh = yl + h;
+            double gy = fmax(fmax(yl - py, py - yh) - margin, 0.0);
+            double gz = 0.0;
+            if (three_d) {
+                double zl = g.origin[2] + zz * h, zh = zl + h;
+                gz = fmax(fmax(zl - pz, pz - zh) - margin, 0.0);
+            }
+            if (L.worst() - (gy * gy + gz * gz) < 0.0) continue;
+        }
+        scan_range<SITES, true>(L, recs, lo, hi, px, py, pz, three_d);
+    }
+}
+
+// rings r = r0, r0 + 1, ... around the query's cell until the k-th distance bounds every unvisited cell
+// (r0 = 1 after knn_block_pass: ring 1 itself is done, only its termination test remains)
+template <class List, bool SITES>
+__device__ __forceinline__ void knn_ring_search(const grid_t &g, const knn_query &q, List &L,
+                                                const double4 *__restrict__ recs,
+                                                const int32_t *__restrict__ cell_start, int r0)
+{
+    const bool three_d = g.dim == 3;
+    const double h = g.cell, margin = h * 1e-6;
+    const double px = q.px, py = q.py, pz = q.pz;
+    const double p[3] = {px, py, pz};
+    const int *ci = q.ci;
+    const double out2 = q.out2;
+    for (int r = r0;; ++r) {
+        const int zlo = max(ci[2] - r, 0), zhi = min(ci[2] + r, g.n[2] - 1);
+        const int ylo = max(ci[1] - r, 0), yhi = min(ci[1] + r, g.n[1] - 1);
+        const int xlo = max(ci[0] - r, 0), xhi = min(ci[0] + r, g.n[0] - 1);
+        // rows of the shell are visited nearest-first (offsets 0, -1, +1, -2, +2, ...), so the
+        // list tightens early and the farther rows are pruned
+        const int nz = (MM_KNN_MERGED && r == 1) ? 0 : (three_d ? 2 * r + 1 : 1);  // r = 1: done by the block pass
+        for (int iz = 0; iz < nz; ++iz) {
+            const int zz = ci[2] + ((iz & 1) ? -((iz + 1) >> 1) : ((iz + 1) >> 1));
+            if (zz < zlo || zz > zhi) continue;
+            double gz = 0.0;
+            if (three_d) {
+                double zl = g.origin[2] + zz * h, zh = zl + h;
+                gz = fmax(fmax(zl - pz, pz - zh) - margin, 0.0);
+            }
+            const bool zedge = three_d && (abs(zz - ci[2]) == r);
+            for (int iy = 0; iy < 2 * r + 1; ++iy) {
+                const int yy = ci[1] + ((iy & 1) ? -((iy + 1) >> 1) : ((iy + 1) >> 1));
+                if (yy < ylo || yy > yhi) continue;
+                double yl = g.origin[1] + yy * h, yh = yl + h;
+                double gy = fmax(fmax(yl - py, py - yh) - margin, 0.0);
+                const double g2 = gy * gy + gz * gz;
+                int xa = xlo, xb = xhi;
+                if (L.full()) {
+                    // rows farther than the current k-th neighbour cannot contribute, and
+                    // inside a row only the cells that the k-th-neighbour ball reaches can
+                    const double w2 = L.worst() - g2;
+                    if (w2 < 0.0) continue;
+                    if (!SITES || r > 1) {  // site rows are short: the x restriction costs more
+                        const double wx = sqrt(w2) + margin;
+                        xa = max(xa, cell_coord(g, px - wx, 0));
+                        xb = min(xb, cell_coord(g, px + wx, 0));
+                        if (xa > xb) continue;
+                    }
+                }
+                const int base = g.n[0] * (yy + g.n[1] * zz);  // ncells <= MAX_CELLS = 2^26
+                if (zedge || abs(yy - ci[1]) == r) {
+                    scan_range<SITES, false>(L, recs, cell_start[base + xa], cell_start[base + xb + 1], px,
+                                      py, pz, three_d);
+                } else {  // interior row of the shell: only its two end cells are new
+                    const int x0 = ci[0] - r, x1 = ci[0] + r;
+                    if (x0 >= xa && x0 <= xb)
+                        scan_range<SITES, false>(L, recs, cell_start[base + x0], cell_start[base + x0 + 1],
+                                          px, py, pz, three_d);
+                    if (r > 0 && x1 >= xa && x1 <= xb)
+                        scan_range<SITES, false>(L, recs, cell_start[base + x1], cell_start[base + x1 + 1],
+                                          px, py, pz, three_d);
+                }
+            }
+        }
+        // every point not yet visited lies outside the block of cells [ci-r, ci+r]; its
+        // distance to p is at least the gap to the nearest block face that has cells beyond it
+        double bound = INFINITY;
+        bool remaining = false;
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+            if (c >= g.dim) break;
+            if (ci[c] - r > 0) {
+                remaining = true;
+                bound = fmin(bound, p[c] - (g.origin[c] + (ci[c] - r) * h));
+            }
+            if (ci[c] + r < g.n[c] - 1) {
+                remaining = true;
+                bound = fmin(bound, (g.origin[c] + (ci[c] + r + 1) * h) - p[c]);
+            }
+        }
+        if (!remaining) break;
+        if (!L.full()) continue;
+        bound = fmax(bound - margin, 0.0);
+        if (L.worst() < bound * bound) break;
+        if (out2 > 0.0) {
+            // query outside the grid's box: a point beyond the face of axis c is also at least
+            // the out-of-box distance away along the other axes
+            double bound2 = INFINITY;
+#pragma unroll
+            for (int c = 0; c < 3; ++c) {
+                if (c >= g.dim) break;
+                const double o = box_gap(g, p[c], c, margin);
+                const double other = out2 - o * o;
+                if (ci[c] - r > 0) {
+                    const double gap = fmax(p[c] - (g.origin[c] + (ci[c] - r) * h) - margin, 0.0);
+                    bound2 = fmin(bound2, gap * gap + other);
+                }
+                if (ci[c] + r < g.n[c] - 1) {
+                    const double gap = fmax((g.origin[c] + (ci[c] + r + 1) * h) - p[c] - margin, 0.0);
+                    bound2 = fmin(bound2, gap * gap + other);
+                }
+            }
+            if (L.worst() < bound2) break;
+        }
+    }
+}
+
+// writes the result row of one query: the site prefix expanded to point copies (SITES) or the list itself
+template <class List, bool SITES>
+__device__ __forceinline__ void knn_emit(List &L, int k, const fast_div &divisor,
+                                         const double4 *__restrict__ recs,
+                                         const double4 *__restrict__ point_recs, int32_t *__restrict__ o,
+                                         double *__restrict__ od)
+{
+    if constexpr (SITES) {
+        // expand: copies of site j continue the prefix only while d2[j] < d2[j+1] strictly
+        int c = 0;
+#pragma unroll
+        for (int j = 0; j < 3; ++j) {
+            const bool have = L.d2[j] < INFINITY;
+            const bool strict = L.d2[j] < L.d2[j + 1];  // slot j+1 is +inf without such a site
+            if (!(have && strict)) break;
+            const int32_t r0 = (int32_t)__double_as_longlong(recs[L.id[j]].w);
+            const int32_t r1 = (int32_t)__double_as_longlong(recs[L.id[j] + 1].w);
+            for (int32_t t = r0; t < r1 && c < k; ++t)
+                o[c++] = divisor((int32_t)__double_as_longlong(point_recs[t].w));
+        }
+        for (; c < k; ++c) o[c] = -1;
+    } else {
+        L.write(o, od, divisor);
+    }
+}
+
 template <class List, bool SITES>
 __device__ __forceinline__ void
 knn_body(const grid_t &g, int64_t N, const double *__restrict__ pts, int pstride, int k,
@@ -441,195 +593,310 @@ knn_body(const grid_t &g, int64_t N, const double *__restrict__ pts, int pstride
     }
     List L;
     L.init(smem, SITES ? 4 : k);
-
     const bool three_d = g.dim == 3;
-    const double h = g.cell;
-    const double margin = h * 1e-6;
+    const double margin = g.cell * 1e-6;
 
     for (int64_t n = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; n < N;
          n += (int64_t)gridDim.x * blockDim.x) {
-        const double px = pts[n * pstride + 0], py = pts[n * pstride + 1];
-        const double pz = three_d ? pts[n * pstride + 2] : 0.0;
-        const double p[3] = {px, py, pz};
-        if (!(fabs(px) <= 1e150 && fabs(py) <= 1e150 && fabs(pz) <= 1e150)) {
-            // a NaN / infinite query (or one so far away that its squared distances overflow) has no
-            // nearest neighbours: every comparison is false; without this guard it would walk the whole
-            // grid before reporting the same thing
+        knn_query q;
+        if (!knn_setup_query(g, pts[n * pstride + 0], pts[n * pstride + 1], three_d ? pts[n * pstride + 2] : 0.0,
+                             margin, q)) {
             for (int t = 0; t < k; ++t) {
                 out_idx[n * k + t] = -1;
                 if (out_d2) out_d2[n * k + t] = INFINITY;
             }
             continue;
         }
-        int ci[3];
-        ci[0] = cell_coord(g, px, 0);
-        ci[1] = cell_coord(g, py, 1);
-        ci[2] = three_d ? cell_coord(g, pz, 2) : 0;
         L.reset();
-        // squared distance from the query to the grid's bounding box (0 for queries inside it): every
-        // indexed point is at least that far away, which tightens the termination bound for targets
-        // that lie outside the source mesh
-        double out2 = 0.0;
+        if (MM_KNN_MERGED) knn_block_pass<List, SITES>(g, q, L, recs, cell_start);
+        knn_ring_search<List, SITES>(g, q, L, recs, cell_start, MM_KNN_MERGED ? 1 : 0);
+        knn_emit<List, SITES>(L, k, divisor, recs, point_recs, out_idx + n * k, out_d2 ? out_d2 + n * k : nullptr);
+    }
+}
+
+// ================================================================================================
+// First pass of the pipeline, k' <= 4 (site table of the GLL-point form, or centroid records):
+// WARP-COOPERATIVE block scan with an fp32 pre-filter.
+//
+// The queries arrive sorted by index cell (mm_index_sort_queries), so the 32 queries of a warp sit in
+// a short run of cells of one cell row and their 3 x 3 x 3 neighbourhoods overlap almost completely.
+// Per run ("segment" = lanes of one cell row whose cells span at most XSPAN cells):
+//   1. the warp stages the union of the neighbourhoods ONCE, from the index's compact fp32 table (16-byte
+//      records {x, y, z relative to the record's own cell, position}; half the bytes of the binary64 records
+//      and no conversions): the 9 (3 in 2-D) cell rows x the cells [x_first - 1, x_last + 1].  The staging
+//      buffer is COLUMN-major -- all records of the 9 cells that share an x index are contiguous -- so the
+//      3 x 3 x 3 neighbourhood of a query is ONE contiguous range of the buffer;
+//   2. every lane scans its range in fp32 and keeps the 5 smallest keys (d2 bits truncated to 24 bits |
+//      8-bit slot number: one 32-bit min/max network, no fp64, no global loads, no branches, one flat loop);
+//   3. if the 5th key exceeds the 4th by more than the fp32 error bound, the SET of the 4 nearest records
+//      is certain; those 4 are evaluated exactly in binary64 and ordered by the canonical (d2, id) order.
+//      With ties or near-ties around the 4th distance a second fp32 sweep ranks exactly, in binary64, every
+//      record whose fp32 distance does not exceed the 4th's by more than the error bound (a handful).
+//      Segments with more than CAP records and lone lanes take the exact per-thread block pass.  Either way the
+//      list then equals the exact top-4 of the 3^3 block, and the common termination test / outer rings follow.
+//      Results are bit-identical to knn_kernel.
+//
+// fp32 error bound (h = cell size, h32 = fl32(h)).  A staged coordinate is X = fma(c, h32, rel) with c the
+// cell offset inside the segment (|c| <= XSPAN + 1 = 13 in x, <= 1 in y / z) and rel the cell-relative coordinate
+// (|rel| <= h, fp32 rounding 2^-24 h): |X - exact| <= 2^-24 (14 h) + 13 * 2^-24 h + 2^-24 h = 1.7e-6 h in x and
+// <= 2.4e-7 h in y, z; the query's coordinates are formed the same way.  dx (|dx| <= 3 h): error <= 3.6e-6 h,
+// dy, dz (|.| <= 2 h): <= 6e-7 h.  |dx32^2 - dx^2| <= 2 * 3 h * 3.6e-6 h = 2.2e-5 h^2, dy, dz: 2.4e-6 h^2 each,
+// the three roundings of the sum <= 3 * 2^-24 * 17 h^2 = 3e-6 h^2: total <= 3e-5 h^2; KNN_EPS = 1e-4 h^2 is used.
+// Truncating the key to 24 bits under-states d2 by at most 2^-15 relative.  The binary64 reference distances
+// carry ~1e-16 relative error, far below the margin.
+// ================================================================================================
+constexpr int KB_WARPS = 4;          // warps per CTA
+constexpr int KB_CAP = 256;          // staged records per segment (8-bit slot number in the key)
+constexpr int KB_XSPAN = 12;         // cells of one row a segment may span
+constexpr int KB_ROWLEN = 16;        // staged cell_start entries per row: (XSPAN + 2) cells + 1, rounded up
+constexpr int KB_MIN_MEMBERS = 3;    // smaller segments are cheaper on the per-thread path
+
+struct kb_smem {
+    float4 rec[KB_CAP];
+    int32_t cs[9][KB_ROWLEN];        // cell_start of the staged cells, per row
+    int32_t dst[9][KB_ROWLEN];       // slot of the first record of cell (row, column)
+    int32_t colstart[KB_ROWLEN];     // first slot of each column (+ total)
+};
+
+template <bool SITES>
+__global__ void __launch_bounds__(KB_WARPS * 32, 8)
+knn_block_kernel(grid_t g, int64_t N, const double *__restrict__ pts, int pstride, int k,
+                 const fast_div divisor, const double4 *__restrict__ recs,
+                 const int32_t *__restrict__ cell_start, const float4 *__restrict__ recf,
+                 const int32_t *__restrict__ rec_id, const int32_t *__restrict__ site_first,
+                 int32_t *__restrict__ out_idx)
+{
+    __shared__ kb_smem sm_all[KB_WARPS];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    kb_smem &sm = sm_all[warp];
+    const bool three_d = g.dim == 3;
+    const int nrow = three_d ? 9 : 3;
+    const double h = g.cell, margin = h * 1e-6;
+    const float h32 = (float)h;
+    const float eps = (float)(1e-4 * h * h);
+    using List = reg_list<4>;
+    List L;
+    L.init(nullptr, 4);
+
+    const int64_t warps_total = (int64_t)gridDim.x * KB_WARPS;
+    for (int64_t batch = (int64_t)blockIdx.x * KB_WARPS + warp; batch * 32 < N; batch += warps_total) {
+        const int64_t n = batch * 32 + lane;
+        const bool valid = n < N;
+        knn_query q;
+        bool pending = false;
+        if (valid) {
+            pending = knn_setup_query(g, pts[n * pstride + 0], pts[n * pstride + 1],
+                                      three_d ? pts[n * pstride + 2] : 0.0, margin, q);
+            if (!pending)
+                for (int t = 0; t < k; ++t) out_idx[n * k + t] = -1;
+        }
+        if (!pending) q.ci[0] = q.ci[1] = q.ci[2] = -1;
+        // the fp32 pass needs small relative coordinates: queries inside the grid's box only
+        bool eligible = pending && q.out2 == 0.0;
+        bool fast_done = false;
+        L.reset();
+
+        while (true) {
+            const unsigned cand = __ballot_sync(0xffffffffu, eligible);
+            if (!cand) break;
+            const int leader = __ffs(cand) - 1;
+            const int lcx = __shfl_sync(0xffffffffu, q.ci[0], leader);
+            const int lcy = __shfl_sync(0xffffffffu, q.ci[1], leader);
+            const int lcz = __shfl_sync(0xffffffffu, q.ci[2], leader);
+            // sorted queries: the leader has the smallest cell of its row among the lanes still eligible
+            const bool member = eligible && q.ci[1] == lcy && q.ci[2] == lcz && q.ci[0] >= lcx &&
+                                q.ci[0] < lcx + KB_XSPAN;
+            const unsigned mmask = __ballot_sync(0xffffffffu, member);
+            eligible = eligible && !member;  // every lane joins at most one segment
+            if (__popc(mmask) < KB_MIN_MEMBERS) continue;
+            const int xhi = __reduce_max_sync(0xffffffffu, member ? q.ci[0] : lcx);
+            const int xa = max(lcx - 1, 0), xb = min(xhi + 1, g.n[0] - 1);
+            const int ncol = xb - xa + 1;  // staged cells per row, <= XSPAN + 2
+            // 1a. cell_start rows: entries [xa, xb + 1] of each row inside the grid, zeros otherwise
 #pragma unroll
-        for (int c = 0; c < 3; ++c) {
-            if (c >= g.dim) break;
-            const double o = box_gap(g, p[c], c, margin);
-            out2 += o * o;
-        }
-
-        // rings 0 and 1 merged: the 3 x 3 block of cell rows around the query's cell, each row ONE
-        // contiguous record range [cx-1, cx+1], own row first, then face, edge neighbours; rows the
-        // current k-th distance cannot reach are skipped.  (With cells of about one distinct coordinate
-        // this is where almost every first-pass query ends.)
-        if (MM_KNN_MERGED) {
-            const int xa = max(ci[0] - 1, 0), xb = min(ci[0] + 1, g.n[0] - 1);
-            const int nrow = three_d ? 9 : 3;
-            // record range of row `it` (empty when the row lies outside the grid); the bounds of the
-            // NEXT row are loaded before the current row is scanned, so their latency is hidden
-            auto row_bounds = [&](int it, int32_t &lo, int32_t &hi) {
-                const int dy = (int)((0x22161u >> (2 * it)) & 3u) - 1;   // 0,-1,+1, 0, 0,-1,+1,-1,+1
-                const int dz = (int)((0x28215u >> (2 * it)) & 3u) - 1;   // 0, 0, 0,-1,+1,-1,-1,+1,+1
-                const int yy = ci[1] + dy, zz = ci[2] + dz;
-                lo = hi = 0;
-                if (it < nrow && yy >= 0 && yy < g.n[1] && zz >= 0 && zz < g.n[2]) {
-                    const int base = g.n[0] * (yy + g.n[1] * zz);  // ncells <= MAX_CELLS = 2^26
-                    lo = cell_start[base + xa];
-                    hi = cell_start[base + xb + 1];
+            for (int i = 0; i < (9 * KB_ROWLEN + 31) / 32; ++i) {
+                const int t = lane + 32 * i;
+                const int r = t / KB_ROWLEN, c = t % KB_ROWLEN;
+                if (r < nrow) {
+                    const int dy = (int)((0x22161u >> (2 * r)) & 3u) - 1;
+                    const int dz = (int)((0x28215u >> (2 * r)) & 3u) - 1;
+                    const int yy = lcy + dy, zz = lcz + dz;
+                    int32_t v = 0;
+                    if (yy >= 0 && yy < g.n[1] && zz >= 0 && zz < g.n[2])
+                        v = __ldg(&cell_start[g.n[0] * (yy + g.n[1] * zz) + xa + min(c, ncol)]);
+                    sm.cs[r][c] = v;
                 }
-            };
-            int32_t nlo, nhi;
-            row_bounds(0, nlo, nhi);
-            for (int it = 0; it < nrow; ++it) {
-                const int32_t lo = nlo, hi = nhi;
-                row_bounds(it + 1, nlo, nhi);
-                if (lo >= hi) continue;
-                if (L.full()) {
-                    const int dy = (int)((0x22161u >> (2 * it)) & 3u) - 1;
-                    const int dz = (int)((0x28215u >> (2 * it)) & 3u) - 1;
-                    const int yy = ci[1] + dy, zz = ci[2] + dz;
-                    double yl = g.origin[1] + yy * h, yh = yl + h;
-                    double gy = fmax(fmax(yl - py, py - yh) - margin, 0.0);
-                    double gz = 0.0;
-                    if (three_d) {
-                        double zl = g.origin[2] + zz * h, zh = zl + h;
-                        gz = fmax(fmax(zl - pz, pz - zh) - margin, 0.0);
-                    }
-                    if (L.worst() - (gy * gy + gz * gz) < 0.0) continue;
-                }
-                scan_range<SITES, true>(L, recs, lo, hi, px, py, pz, three_d);
             }
-        }
-
-        for (int r = MM_KNN_MERGED ? 1 : 0;; ++r) {
-            const int zlo = max(ci[2] - r, 0), zhi = min(ci[2] + r, g.n[2] - 1);
-            const int ylo = max(ci[1] - r, 0), yhi = min(ci[1] + r, g.n[1] - 1);
-            const int xlo = max(ci[0] - r, 0), xhi = min(ci[0] + r, g.n[0] - 1);
-            // rows of the shell are visited nearest-first (offsets 0, -1, +1, -2, +2, ...), so the
-            // list tightens early and the farther rows are pruned
-            const int nz = (MM_KNN_MERGED && r == 1) ? 0 : (three_d ? 2 * r + 1 : 1);  // r = 1: done above
-            for (int iz = 0; iz < nz; ++iz) {
-                const int zz = ci[2] + ((iz & 1) ? -((iz + 1) >> 1) : ((iz + 1) >> 1));
-                if (zz < zlo || zz > zhi) continue;
-                double gz = 0.0;
-                if (three_d) {
-                    double zl = g.origin[2] + zz * h, zh = zl + h;
-                    gz = fmax(fmax(zl - pz, pz - zh) - margin, 0.0);
+            __syncwarp();
+            // 1b. column-major slots: lane c owns column c
+            {
+                int size = 0;
+                if (lane < ncol)
+                    for (int r = 0; r < nrow; ++r) size += sm.cs[r][lane + 1] - sm.cs[r][lane];
+                int off = size;
+#pragma unroll
+                for (int o = 1; o < 16; o <<= 1) {
+                    const int t = __shfl_up_sync(0xffffffffu, off, o);
+                    if (lane >= o) off += t;
                 }
-                const bool zedge = three_d && (abs(zz - ci[2]) == r);
-                for (int iy = 0; iy < 2 * r + 1; ++iy) {
-                    const int yy = ci[1] + ((iy & 1) ? -((iy + 1) >> 1) : ((iy + 1) >> 1));
-                    if (yy < ylo || yy > yhi) continue;
-                    double yl = g.origin[1] + yy * h, yh = yl + h;
-                    double gy = fmax(fmax(yl - py, py - yh) - margin, 0.0);
-                    const double g2 = gy * gy + gz * gz;
-                    int xa = xlo, xb = xhi;
-                    if (L.full()) {
-                        // rows farther than the current k-th neighbour cannot contribute, and
-                        // inside a row only the cells that the k-th-neighbour ball reaches can
-                        const double w2 = L.worst() - g2;
-                        if (w2 < 0.0) continue;
-                        if (!SITES || r > 1) {  // site rows are short: the x restriction costs more
-                            const double wx = sqrt(w2) + margin;
-                            xa = max(xa, cell_coord(g, px - wx, 0));
-                            xb = min(xb, cell_coord(g, px + wx, 0));
-                            if (xa > xb) continue;
+                if (lane < KB_ROWLEN) sm.colstart[lane] = off - size;  // exclusive; colstart[ncol] = total
+                if (lane < ncol) {
+                    int at = off - size;
+                    for (int r = 0; r < nrow; ++r) {
+                        sm.dst[r][lane] = at;
+                        at += sm.cs[r][lane + 1] - sm.cs[r][lane];
+                    }
+                }
+            }
+            __syncwarp();
+            const int total = sm.colstart[ncol];
+            if (total > KB_CAP) continue;  // crowded cells: per-thread path
+            // 1c. records: one (row, column) cell per task; coordinates move from the cell's frame to the segment's
+            //     (corner of cell (xa, lcy, lcz)) with one fma each
+#pragma unroll
+            for (int i = 0; i < (9 * KB_ROWLEN + 31) / 32; ++i) {
+                const int t = lane + 32 * i;
+                const int r = t / KB_ROWLEN, c = t % KB_ROWLEN;
+                if (r < nrow && c < ncol) {
+                    const int32_t lo = sm.cs[r][c], cnt = sm.cs[r][c + 1] - lo, at = sm.dst[r][c];
+                    const float fx = (float)c;
+                    const float fy = (float)((int)((0x22161u >> (2 * r)) & 3u) - 1);
+                    const float fz = (float)((int)((0x28215u >> (2 * r)) & 3u) - 1);
+                    for (int j = 0; j < cnt; ++j) {
+                        float4 f = __ldg(&recf[lo + j]);
+                        f.x = fmaf(fx, h32, f.x);
+                        f.y = fmaf(fy, h32, f.y);
+                        f.z = fmaf(fz, h32, f.z);
+                        sm.rec[at + j] = f;
+                    }
+                }
+            }
+            __syncwarp();
+            // 2. fp32 scan of this lane's 3 columns (one contiguous range): five smallest keys
+            if (member) {
+                const double ox = g.origin[0] + q.ci[0] * h, oy = g.origin[1] + lcy * h, oz = g.origin[2] + lcz * h;
+                const float qx = fmaf((float)(q.ci[0] - xa), h32, (float)(q.px - ox));
+                const float qy = (float)(q.py - oy);
+                const float qz = three_d ? (float)(q.pz - oz) : 0.0f;
+                unsigned a0 = 0xffffffffu, a1 = a0, a2 = a0, a3 = a0, a4 = a0;
+                const int lo = sm.colstart[max(q.ci[0] - 1, 0) - xa];
+                const int hi = sm.colstart[min(q.ci[0] + 1, g.n[0] - 1) + 1 - xa];
+                for (int j = lo; j < hi; ++j) {
+                    const float4 s = sm.rec[j];
+                    const float dx = qx - s.x, dy = qy - s.y, dz = qz - s.z;
+                    const float d = fmaf(dz, dz, fmaf(dy, dy, dx * dx));
+                    const unsigned key = (__float_as_uint(d) & 0xffffff00u) | (unsigned)j;
+                    // sorted insertion, all five updates independent of one another
+                    const unsigned n4 = max(a3, min(a4, key)), n3 = max(a2, min(a3, key));
+                    const unsigned n2 = max(a1, min(a2, key)), n1 = max(a0, min(a1, key));
+                    a0 = min(a0, key);
+                    a1 = n1;
+                    a2 = n2;
+                    a3 = n3;
+                    a4 = n4;
+                }
+                // 3. is the set of the 4 nearest certain?  (fewer than 5 records in the block: it is all of them)
+                bool certain = true;
+                if (a4 != 0xffffffffu) {
+                    const float d4 = __uint_as_float(a3 & 0xffffff00u), d5 = __uint_as_float(a4 & 0xffffff00u);
+                    certain = d5 - eps > d4 * (1.0f + 6.2e-5f) + eps;  // 2^-15 truncation + fp32 error both ways
+                }
+                if (certain) {
+                    const unsigned keys[4] = {a0, a1, a2, a3};
+#pragma unroll
+                    for (int t = 0; t < 4; ++t) {
+                        if (keys[t] == 0xffffffffu) break;
+                        const int32_t pos = __float_as_int(sm.rec[keys[t] & 0xffu].w);
+                        const double2 *src = reinterpret_cast<const double2 *>(&recs[pos]);
+                        rank_record<SITES>(L, __ldg(src), __ldg(src + 1), pos, q.px, q.py, q.pz, three_d);
+                    }
+                } else {
+                    // ties / near-ties around the 4th distance (structured meshes produce exact ones): every record
+                    // that can still belong to the 4 nearest has an fp32 distance <= cut; rank exactly those
+                    // (typically 5-8 of ~34) in binary64 -- the canonical (d2, id) order settles the ties
+                    const float cut = __uint_as_float(a3 & 0xffffff00u) * (1.0f + 6.2e-5f) + 2.0f * eps;
+                    for (int j = lo; j < hi; ++j) {
+                        const float4 s = sm.rec[j];
+                        const float dx = qx - s.x, dy = qy - s.y, dz = qz - s.z;
+                        const float d = fmaf(dz, dz, fmaf(dy, dy, dx * dx));
+                        if (d <= cut) {
+                            const int32_t pos = __float_as_int(s.w);
+                            const double2 *src = reinterpret_cast<const double2 *>(&recs[pos]);
+                            rank_record<SITES>(L, __ldg(src), __ldg(src + 1), pos, q.px, q.py, q.pz, three_d);
                         }
                     }
-                    const int base = g.n[0] * (yy + g.n[1] * zz);  // ncells <= MAX_CELLS = 2^26
-                    if (zedge || abs(yy - ci[1]) == r) {
-                        scan_range<SITES, false>(L, recs, cell_start[base + xa], cell_start[base + xb + 1], px,
-                                          py, pz, three_d);
-                    } else {  // interior row of the shell: only its two end cells are new
-                        const int x0 = ci[0] - r, x1 = ci[0] + r;
-                        if (x0 >= xa && x0 <= xb)
-                            scan_range<SITES, false>(L, recs, cell_start[base + x0], cell_start[base + x0 + 1],
-                                              px, py, pz, three_d);
-                        if (r > 0 && x1 >= xa && x1 <= xb)
-                            scan_range<SITES, false>(L, recs, cell_start[base + x1], cell_start[base + x1 + 1],
-                                              px, py, pz, three_d);
-                    }
                 }
+                fast_done = true;
             }
-            // every point not yet visited lies outside the block of cells [ci-r, ci+r]; its
-            // distance to p is at least the gap to the nearest block face that has cells beyond it
-            double bound = INFINITY;
-            bool remaining = false;
-#pragma unroll
-            for (int c = 0; c < 3; ++c) {
-                if (c >= g.dim) break;
-                if (ci[c] - r > 0) {
-                    remaining = true;
-                    bound = fmin(bound, p[c] - (g.origin[c] + (ci[c] - r) * h));
-                }
-                if (ci[c] + r < g.n[c] - 1) {
-                    remaining = true;
-                    bound = fmin(bound, (g.origin[c] + (ci[c] + r + 1) * h) - p[c]);
-                }
-            }
-            if (!remaining) break;
-            if (!L.full()) continue;
-            bound = fmax(bound - margin, 0.0);
-            if (L.worst() < bound * bound) break;
-            if (out2 > 0.0) {
-                // query outside the grid's box: a point beyond the face of axis c is also at least
-                // the out-of-box distance away along the other axes
-                double bound2 = INFINITY;
-#pragma unroll
-                for (int c = 0; c < 3; ++c) {
-                    if (c >= g.dim) break;
-                    const double o = box_gap(g, p[c], c, margin);
-                    const double other = out2 - o * o;
-                    if (ci[c] - r > 0) {
-                        const double gap = fmax(p[c] - (g.origin[c] + (ci[c] - r) * h) - margin, 0.0);
-                        bound2 = fmin(bound2, gap * gap + other);
-                    }
-                    if (ci[c] + r < g.n[c] - 1) {
-                        const double gap = fmax((g.origin[c] + (ci[c] + r + 1) * h) - p[c] - margin, 0.0);
-                        bound2 = fmin(bound2, gap * gap + other);
-                    }
-                }
-                if (L.worst() < bound2) break;
-            }
+            __syncwarp();  // the staging buffer is re-used by the next segment
         }
-        if constexpr (SITES) {
-            // expand: copies of site j continue the prefix only while d2[j] < d2[j+1] strictly
+        if (pending) {
+            if (!fast_done) knn_block_pass<List, SITES>(g, q, L, recs, cell_start);
+            knn_ring_search<List, SITES>(g, q, L, recs, cell_start, 1);
             int32_t *o = out_idx + n * k;
-            int c = 0;
+            if constexpr (SITES) {
+                // expand: copies of site j continue the prefix only while d2[j] < d2[j+1] strictly
+                int c = 0;
 #pragma unroll
-            for (int j = 0; j < 3; ++j) {
-                const bool have = L.d2[j] < INFINITY;
-                const bool strict = L.d2[j] < L.d2[j + 1];  // slot j+1 is +inf without such a site
-                if (!(have && strict)) break;
-                const int32_t r0 = (int32_t)__double_as_longlong(recs[L.id[j]].w);
-                const int32_t r1 = (int32_t)__double_as_longlong(recs[L.id[j] + 1].w);
-                for (int32_t t = r0; t < r1 && c < k; ++t)
-                    o[c++] = divisor((int32_t)__double_as_longlong(point_recs[t].w));
+                for (int j = 0; j < 3; ++j) {
+                    const bool have = L.d2[j] < INFINITY;
+                    const bool strict = L.d2[j] < L.d2[j + 1];  // slot j+1 is +inf without such a site
+                    if (!(have && strict)) break;
+                    const int32_t r0 = __ldg(&site_first[L.id[j]]), r1 = __ldg(&site_first[L.id[j] + 1]);
+                    for (int32_t t = r0; t < r1 && c < k; ++t) o[c++] = divisor(__ldg(&rec_id[t]));
+                }
+                for (; c < k; ++c) o[c] = -1;
+            } else {
+                L.write(o, nullptr, divisor);
             }
-            for (; c < k; ++c) o[c] = -1;
-        } else {
-            L.write(out_idx + n * k, out_d2 ? out_d2 + n * k : nullptr, divisor);
         }
     }
+}
+
+// ---- compact tables of the block kernel ----------------------------------------------------------
+// plain form: recf[t] = {cell-relative coordinates of record t, t}, rec_id[t] = point id
+__global__ void __launch_bounds__(256)
+recf_plain_kernel(grid_t g, int64_t M, const double4 *__restrict__ recs, float4 *__restrict__ recf,
+                  int32_t *__restrict__ rec_id)
+{
+    for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < M; t += (int64_t)gridDim.x * blockDim.x) {
+        const double4 r = recs[t];
+        const double p[3] = {r.x, r.y, r.z};
+        float4 f;
+        f.x = (float)(r.x - (g.origin[0] + cell_coord(g, p[0], 0) * g.cell));
+        f.y = (float)(r.y - (g.origin[1] + cell_coord(g, p[1], 1) * g.cell));
+        f.z = g.dim == 3 ? (float)(r.z - (g.origin[2] + cell_coord(g, p[2], 2) * g.cell)) : 0.0f;
+        f.w = __int_as_float((int32_t)t);
+        recf[t] = f;
+        rec_id[t] = (int32_t)__double_as_longlong(r.w);
+    }
+}
+
+// site form: recf[s] = {cell-relative coordinates of site s, s}, site_first[s] = first record of site s
+__global__ void __launch_bounds__(256)
+recf_sites_kernel(grid_t g, int64_t nsites, const double4 *__restrict__ site_recs, float4 *__restrict__ recf,
+                  int32_t *__restrict__ site_first)
+{
+    for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t <= nsites;
+         t += (int64_t)gridDim.x * blockDim.x) {
+        const double4 r = site_recs[t];
+        site_first[t] = (int32_t)__double_as_longlong(r.w);
+        if (t == nsites) break;  // sentinel: only its first-record entry is meaningful
+        const double p[3] = {r.x, r.y, r.z};
+        float4 f;
+        f.x = (float)(r.x - (g.origin[0] + cell_coord(g, p[0], 0) * g.cell));
+        f.y = (float)(r.y - (g.origin[1] + cell_coord(g, p[1], 1) * g.cell));
+        f.z = g.dim == 3 ? (float)(r.z - (g.origin[2] + cell_coord(g, p[2], 2) * g.cell)) : 0.0f;
+        f.w = __int_as_float((int32_t)t);
+        recf[t] = f;
+    }
+}
+
+__global__ void __launch_bounds__(256)
+rec_id_kernel(int64_t M, const double4 *__restrict__ recs, int32_t *__restrict__ rec_id)
+{
+    for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < M; t += (int64_t)gridDim.x * blockDim.x)
+        rec_id[t] = (int32_t)__double_as_longlong(recs[t].w);
 }
 
 template <class List>
@@ -806,6 +1073,9 @@ extern "C" int mm_index_destroy(mm_index_t *ix)
     if (ix->cell_start) cudaFreeAsync(ix->cell_start, ix->stream);
     if (ix->site_recs) cudaFreeAsync(ix->site_recs, ix->stream);
     if (ix->site_cell_start) cudaFreeAsync(ix->site_cell_start, ix->stream);
+    if (ix->recf) cudaFreeAsync(ix->recf, ix->stream);
+    if (ix->rec_id) cudaFreeAsync(ix->rec_id, ix->stream);
+    if (ix->site_first) cudaFreeAsync(ix->site_first, ix->stream);
     delete ix;
     return MM_OK;
 }
@@ -982,6 +1252,7 @@ extern "C" int mm_index_create(mm_index_t **out, int dim, int64_t M, const doubl
             }
         }
         ix->nonempty = nonempty;
+        ix->distinct_est = distinct;
     }
     for (int c = 0; c < 3; ++c) {
         ix->origin[c] = g.origin[c];
@@ -1012,6 +1283,15 @@ extern "C" int mm_index_create(mm_index_t **out, int dim, int64_t M, const doubl
         scatter_kernel<<<launch_blocks(M, 256, 8), 256, 0, stream>>>(g, M, points, ix->cell_start,
                                                                      counts, ix->recs);
         MM_CUDA(cudaGetLastError());
+        // compact fp32 table of the warp-cooperative first pass -- unless the data is full of duplicates (the
+        // GLL-point form), where the site table of mm_index_prepare_sites takes its place
+        if (ix->distinct_est >= 0.7 * (double)M) {
+            MM_CUDA(pool_alloc((void **)&ix->recf, sizeof(float4) * (size_t)M, stream));
+            MM_CUDA(pool_alloc((void **)&ix->rec_id, sizeof(int32_t) * (size_t)M, stream));
+            ix->bytes += (sizeof(float4) + sizeof(int32_t)) * (size_t)M;
+            recf_plain_kernel<<<launch_blocks(M, 256, 8), 256, 0, stream>>>(g, M, ix->recs, ix->recf, ix->rec_id);
+            MM_CUDA(cudaGetLastError());
+        }
     }
     MM_CUDA(cudaStreamSynchronize(stream));
     guard.p = nullptr;
@@ -1123,17 +1403,76 @@ extern "C" int mm_index_prepare_sites(mm_index_t *ix, void *stream_)
     cudaFreeAsync(per_cell, stream);
     cudaFreeAsync(tile_sums, stream);
     ix->bytes += sizeof(int32_t) * (size_t)(ix->ncells + 1) + sizeof(double4) * (size_t)(ns + 1);
+    // compact tables of the block kernel; the in-cell sort above moved the records, so a plain-form table is stale
+    if (ix->recf) {
+        cudaFreeAsync(ix->recf, stream);
+        ix->recf = nullptr;
+        ix->bytes -= sizeof(float4) * (size_t)ix->M;
+    }
+    if (!ix->rec_id) {
+        MM_CUDA(pool_alloc((void **)&ix->rec_id, sizeof(int32_t) * (size_t)ix->M, stream));
+        ix->bytes += sizeof(int32_t) * (size_t)ix->M;
+    }
+    MM_CUDA(pool_alloc((void **)&ix->recf, sizeof(float4) * (size_t)std::max<int64_t>(ns, 1), stream));
+    MM_CUDA(pool_alloc((void **)&ix->site_first, sizeof(int32_t) * (size_t)(ns + 1), stream));
+    ix->bytes += sizeof(float4) * (size_t)ns + sizeof(int32_t) * (size_t)(ns + 1);
+    ix->recf_sites = true;
+    rec_id_kernel<<<launch_blocks(ix->M, 256, 8), 256, 0, stream>>>(ix->M, ix->recs, ix->rec_id);
+    recf_sites_kernel<<<launch_blocks(ns + 1, 256, 8), 256, 0, stream>>>(grid_of(ix), ns, ix->site_recs, ix->recf,
+                                                                         ix->site_first);
+    MM_CUDA(cudaGetLastError());
     MM_CUDA(cudaStreamSynchronize(stream));  // the table is complete when this returns: any stream may use it
     return MM_OK;
 }
 
 bool mm_index_has_sites(const mm_index_t *ix) { return ix && ix->site_recs != nullptr; }
 
+bool mm_index_sites_view_get(const mm_index_t *ix, mm_index_sites_view *out)
+{
+    if (!ix || !ix->site_recs || !ix->site_first || !ix->rec_id) return false;
+    out->nsites = ix->nsites;
+    out->M = ix->M;
+    out->site_recs = ix->site_recs;
+    out->site_first = ix->site_first;
+    out->rec_id = ix->rec_id;
+    return true;
+}
+
+// first pass over SORTED queries with the warp-cooperative block kernel, when it applies
+static bool block_kernel_applies(const mm_index_t *ix)
+{
+    if (const char *e = getenv("MM_KNN_BLOCK"))
+        if (e[0] == '0') return false;
+    return ix->cell > 1e-15 && ix->cell < 1e15;  // relative coordinates and the error margin must be normal floats
+}
+
+int mm_knn_first_pass(const mm_index_t *ix, int64_t N, const double *pts, int pts_stride, int k,
+                      int32_t divisor, int32_t *idx, void *stream)
+{
+    MM_REQUIRE(ix, MM_ERR_INVALID, "mm_knn_first_pass: null index");
+    if (N == 0) return MM_OK;
+    if (k == 4 && ix->recf && !ix->recf_sites && block_kernel_applies(ix)) {
+        knn_block_kernel<false><<<launch_blocks(N, KB_WARPS * 32, 8), KB_WARPS * 32, 0, (cudaStream_t)stream>>>(
+            grid_of(ix), N, pts, pts_stride, k, fast_div(divisor), ix->recs, ix->cell_start, ix->recf, ix->rec_id,
+            nullptr, idx);
+        MM_CUDA(cudaGetLastError());
+        return MM_OK;
+    }
+    return mm_knn_strided(ix, N, pts, pts_stride, k, divisor, idx, nullptr, stream);
+}
+
 int mm_knn_sites(const mm_index_t *ix, int64_t N, const double *pts, int pts_stride, int kout,
                  int32_t divisor, int32_t *idx, void *stream)
 {
     MM_REQUIRE(ix && ix->site_recs, MM_ERR_INVALID, "mm_knn_sites: site table not built");
     if (N == 0) return MM_OK;
+    if (ix->recf_sites && block_kernel_applies(ix)) {
+        knn_block_kernel<true><<<launch_blocks(N, KB_WARPS * 32, 8), KB_WARPS * 32, 0, (cudaStream_t)stream>>>(
+            grid_of(ix), N, pts, pts_stride, kout, fast_div(divisor), ix->site_recs, ix->site_cell_start, ix->recf,
+            ix->rec_id, ix->site_first, idx);
+        MM_CUDA(cudaGetLastError());
+        return MM_OK;
+    }
     knn_sites_kernel<<<launch_blocks(N, KNN_BLOCK, 8), KNN_BLOCK, 0, (cudaStream_t)stream>>>(
         grid_of(ix), N, pts, pts_stride, kout, fast_div(divisor), ix->site_recs, ix->site_cell_start, idx,
         ix->recs);

@@ -46,7 +46,10 @@ __device__ __forceinline__ bool accept_xi(const mm_locate_params &prm, const dou
     return ok;
 }
 
-template <int ORDER, int DIM, int WARPS, int SLOTS, int MINB>
+// STATS: also counts, over all points, the candidates that reached Newton and the map evaluations (Newton
+// iterations) -- stats[0] += candidates, stats[1] += evaluations; a separate instantiation, used by the
+// benchmarks only (mm_locate_set_stats)
+template <int ORDER, int DIM, int WARPS, int SLOTS, int MINB, bool STATS>
 __global__ void __launch_bounds__(WARPS * 32, MINB)
 locate_kernel(const mm_gll_table T, const mm_locate_params prm, int64_t E,
               const double *__restrict__ nodes, const double *__restrict__ centroid,
@@ -56,9 +59,10 @@ locate_kernel(const mm_gll_table T, const mm_locate_params prm, int64_t E,
               double *__restrict__ xi_out, uint8_t *__restrict__ status_out,
               unsigned long long *__restrict__ num_failed, int32_t *__restrict__ unresolved_list,
               unsigned long long *__restrict__ unresolved_count, const long long *__restrict__ n_dev,
-              int64_t n_off)
+              int64_t n_off, unsigned long long *__restrict__ stats)
 {
     using tr = elem_traits<ORDER, DIM>;
+    int st_cand = 0, st_eval = 0;
     if (n_dev) {  // point count known only on the device: [n_off, *n_dev)
         const long long have = *n_dev - n_off;
         N = have < 0 ? 0 : (have < N ? have : N);
@@ -240,7 +244,8 @@ locate_kernel(const mm_gll_table T, const mm_locate_params prm, int64_t E,
             }
             __syncwarp();  // plain-load tail path: make the leader's stores visible to its group
             if (served) {
-                const bool ok = newton_iterate<ORDER, DIM>(T, X, p, x);
+                if (STATS) ++st_cand;
+                const bool ok = newton_iterate<ORDER, DIM>(T, X, p, x, STATS ? &st_eval : nullptr);
                 if (fb_newton) {  // V1: nearest-centre element, interpolator.py:1460-1473
                     bool big = false;
 #pragma unroll
@@ -306,7 +311,19 @@ locate_kernel(const mm_gll_table T, const mm_locate_params prm, int64_t E,
         for (int o = 16; o > 0; o >>= 1) failed_local += __shfl_xor_sync(0xffffffffu, failed_local, o);
         if (lane == 0 && failed_local) atomicAdd(num_failed, failed_local);
     }
+    if (STATS && stats) {
+        for (int o = 16; o > 0; o >>= 1) {
+            st_cand += __shfl_xor_sync(0xffffffffu, st_cand, o);
+            st_eval += __shfl_xor_sync(0xffffffffu, st_eval, o);
+        }
+        if (lane == 0) {
+            atomicAdd(stats, (unsigned long long)st_cand);
+            atomicAdd(stats + 1, (unsigned long long)st_eval);
+        }
+    }
 }
+
+static thread_local unsigned long long *g_locate_stats = nullptr;
 
 template <int ORDER, int DIM, int WARPS, int SLOTS, int MINB>
 int launch_locate(const mm_locate_params &prm, int64_t E, const double *nodes,
@@ -319,11 +336,13 @@ int launch_locate(const mm_locate_params &prm, int64_t E, const double *nodes,
     using tr = elem_traits<ORDER, DIM>;
     mm_gll_table T;
     mm_make_table(ORDER, &T);
-    auto kern = locate_kernel<ORDER, DIM, WARPS, SLOTS, MINB>;
+    unsigned long long *stats = g_locate_stats;
+    auto kern = stats ? locate_kernel<ORDER, DIM, WARPS, SLOTS, MINB, true>
+                      : locate_kernel<ORDER, DIM, WARPS, SLOTS, MINB, false>;
     const size_t smem = (size_t)WARPS * SLOTS * tr::SLOT_BYTES + WARPS * sizeof(uint64_t);
-    static mm_kernel_cfg kcfg;
+    static mm_kernel_cfg kcfg[2];
     int per_sm = 1;
-    MM_CUDA(kcfg.prepare(kern, WARPS * 32, smem, &per_sm));
+    MM_CUDA(kcfg[stats ? 1 : 0].prepare(kern, WARPS * 32, smem, &per_sm));
     const int sms = mm_num_sms() > 0 ? mm_num_sms() : 148;
     int64_t batches = (N + 32 * WARPS - 1) / (32 * WARPS);
     int64_t grid = (int64_t)sms * per_sm;  // persistent: resident CTAs loop over point batches
@@ -334,7 +353,7 @@ int launch_locate(const mm_locate_params &prm, int64_t E, const double *nodes,
                                                   reinterpret_cast<unsigned long long *>(num_failed),
                                                   unresolved_list,
                                                   reinterpret_cast<unsigned long long *>(unresolved_count),
-                                                  reinterpret_cast<const long long *>(n_dev), n_off);
+                                                  reinterpret_cast<const long long *>(n_dev), n_off, stats);
     MM_CUDA(cudaGetLastError());
     return MM_OK;
 }
@@ -386,6 +405,14 @@ int mm_locate_impl(int order, int dim, int64_t E, const double *nodes, const dou
 #undef MM_LOC
     mm_set_error("mm_locate: unsupported order/dim");
     return MM_ERR_UNSUPPORTED;
+}
+
+// benchmarks: make the calling thread's mm_locate / mm_interpolate launches accumulate {candidates that reached
+// Newton, map evaluations} into a device array of two uint64 (NULL switches it off again)
+extern "C" int mm_locate_set_stats(int64_t *device_counters)
+{
+    g_locate_stats = reinterpret_cast<unsigned long long *>(device_counters);
+    return MM_OK;
 }
 
 extern "C" int mm_locate(int order, int dim, int64_t E, const double *nodes,

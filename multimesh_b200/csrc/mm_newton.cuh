@@ -133,10 +133,12 @@ __device__ __forceinline__ void newton_start(const double (&p)[DIM], const doubl
 template <int ORDER, int DIM>
 __device__ __forceinline__ bool newton_iterate(const mm_gll_table &T,
                                                const double *__restrict__ X,
-                                               const double (&p)[DIM], double (&xi)[DIM])
+                                               const double (&p)[DIM], double (&xi)[DIM],
+                                               int *evaluations = nullptr)
 {
 #pragma unroll 1
     for (int it = 0; it < MM_NEWTON_MAXIT; ++it) {
+        if (evaluations) ++*evaluations;  // statistics build only (compile-time null otherwise)
         double x[DIM], J[DIM][DIM], delta[DIM];
         eval_map<ORDER, DIM>(T, X, p, xi, x, J);
         if constexpr (DIM == 2) {

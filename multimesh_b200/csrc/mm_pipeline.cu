@@ -203,7 +203,7 @@ int mm_interpolate_impl(const mm_index_t *index, int32_t divisor, int order, int
     if (site_pass) {
         MM_TRY(mm_knn_sites(index, N, sorted, MM_QREC, k1, divisor, cands1, stream));
     } else {
-        MM_TRY(mm_knn_strided(index, N, sorted, MM_QREC, k1, divisor, cands1, nullptr, stream));
+        MM_TRY(mm_knn_first_pass(index, N, sorted, MM_QREC, k1, divisor, cands1, stream));
     }
     mark(2);
     mm_locate_params p1 = *params;

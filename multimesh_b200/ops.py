@@ -24,7 +24,7 @@ from .gll import SUPPORTED_ORDERS
 __all__ = [
     "LocateSpec", "V1", "V2", "V3", "V4", "V5", "GridIndex", "element_geometry", "locate", "interp",
     "coeffs", "gather_coeffs", "trilinear", "centroid_conn", "gather_nodal", "map_to_sphere_",
-    "interpolate", "element_presolve", "ResidentSource",
+    "interpolate", "element_presolve", "ResidentSource", "unique_points", "scatter_back", "fluid_fixup_",
 ]
 
 
@@ -471,6 +471,53 @@ def interpolate(index: "GridIndex", divisor: int, nodes, centroid, aabb, fields,
     if out is not None and fields.numel():
         return (out,) + tuple(res[1:])
     return res
+
+
+# ----------------------------------------------------------------------------------------------
+# K4: target-side de-duplication and write-back
+# ----------------------------------------------------------------------------------------------
+def unique_points(pts: torch.Tensor):
+    """Device twin of np.unique(pts, axis=0, return_inverse=True) (utils.get_unique_points, utils.py:465-515):
+    pts [N,d] -> (unique [N_u,d] in lexicographic order, inverse [N] int32)."""
+    pts = _need_cuda(pts, "pts", torch.float64)
+    N, d = pts.shape
+    with torch.cuda.device(pts.device):
+        uniq = torch.empty((N, d), dtype=torch.float64, device=pts.device)
+        inv = torch.empty((N,), dtype=torch.int32, device=pts.device)
+        n = C.c_int64(0)
+        check(load_lib().mm_unique_points(d, N, _ptr(pts), C.byref(n), _ptr(uniq), _ptr(inv), _stream()),
+              "mm_unique_points")
+    return uniq[: n.value], inv
+
+
+def scatter_back(values: torch.Tensor, inverse, E: int, P: int) -> torch.Tensor:
+    """values [N_u,F] (+ inverse [E*P] int32, or None for the identity) -> [E,F,P]: the
+    values[recon].reshape(E, P, F).swapaxes(1, 2) of the reference's drivers (interpolator.py:822-826)."""
+    values = _need_cuda(values, "values", torch.float64)
+    F = values.shape[1]
+    if inverse is not None:
+        inverse = _need_cuda(inverse, "inverse", torch.int32)
+        assert inverse.numel() == E * P
+    else:
+        assert values.shape[0] == E * P
+    with torch.cuda.device(values.device):
+        out = torch.empty((E, F, P), dtype=torch.float64, device=values.device)
+        check(load_lib().mm_scatter_back(E, P, F, _ptr(values), _ptr(inverse), _ptr(out), _stream()), "mm_scatter_back")
+    return out
+
+
+def fluid_fixup_(values: torch.Tensor, old_values: torch.Tensor, fluid: torch.Tensor, vs_index: int) -> torch.Tensor:
+    """In place on values [E,F,P]: fluid elements keep old_values, solid elements that picked up VS == 0 are
+    restored (interpolator.py:829-841).  fluid: uint8 / bool [E]."""
+    values = _need_cuda(values, "values", torch.float64)
+    old_values = _need_cuda(old_values, "old_values", torch.float64)
+    fluid = _need_cuda(fluid.to(torch.uint8), "fluid", torch.uint8)
+    E, F, P = values.shape
+    assert old_values.shape == values.shape and fluid.numel() == E
+    with torch.cuda.device(values.device):
+        check(load_lib().mm_fluid_fixup(E, P, F, _ptr(values), _ptr(old_values), _ptr(fluid), int(vs_index), _stream()),
+              "mm_fluid_fixup")
+    return values
 
 
 class ResidentSource:

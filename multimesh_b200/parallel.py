@@ -49,6 +49,11 @@ def _world(group=None) -> Tuple[int, int]:
     return 1, 0
 
 
+def barrier(group=None) -> None:
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
+        dist.barrier(group)
+
+
 def _global_rank(r: int, group=None) -> int:
     return r if group is None else dist.get_global_rank(group, r)
 
@@ -90,6 +95,32 @@ def gather_rows(local: torch.Tensor, n_total: int, dst: int = 0, group=None,
         for req in dist.batch_isend_irecv(ops):
             req.wait()
     return full if rank == dst else None
+
+
+def allgather_rows(local: torch.Tensor, n_total: int, group=None) -> torch.Tensor:
+    """Every rank ends up with the full [n_total, ...] result (for in-memory target meshes each rank owns a copy
+    of): every rank's shard goes straight into its rows of every other rank's result with grouped point-to-point
+    transfers; ragged shards need no padding."""
+    world, rank = _world(group)
+    if world == 1:
+        return local
+    b = shard_bounds(n_total, world)
+    assert local.shape[0] == int(b[rank + 1] - b[rank]), "shard size does not match shard_bounds"
+    full = torch.empty((int(n_total),) + tuple(local.shape[1:]), dtype=local.dtype, device=local.device)
+    full[int(b[rank]): int(b[rank + 1])].copy_(local)
+    ops = []
+    src = local.contiguous()
+    for r in range(world):
+        if r == rank:
+            continue
+        if src.shape[0] > 0:
+            ops.append(dist.P2POp(dist.isend, src, _global_rank(r, group), group))
+        if b[r + 1] > b[r]:
+            ops.append(dist.P2POp(dist.irecv, full[int(b[r]): int(b[r + 1])], _global_rank(r, group), group))
+    if ops:
+        for req in dist.batch_isend_irecv(ops):
+            req.wait()
+    return full
 
 
 def slab_partition(points: np.ndarray, world: int, axis: Optional[int] = None) -> List[np.ndarray]:

@@ -92,21 +92,36 @@ def create_layer_mask(mesh, layers):
     return _create_mask(mesh=mesh, layers=layers)
 
 
-def get_unique_points(points, mesh=False, layers=None):
+def _unique_rows(allp, device=None, as_numpy=True):
+    """K4 on the device (ops.unique_points = mm_unique_points): the rows of np.unique(allp, axis=0) in the same
+    lexicographic order, and the inverse map.  There is no host fallback."""
+    import torch
+
+    from . import ops
+    from .kdtree import _device
+
+    dev = _device(device)
+    t = allp if isinstance(allp, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(allp, dtype=np.float64))
+    u, inv = ops.unique_points(t.to(dev, dtype=torch.float64).contiguous())
+    if as_numpy:
+        return u.cpu().numpy(), inv.cpu().numpy().astype(np.int64)
+    return u, inv
+
+
+def get_unique_points(points, mesh=False, layers=None, device=None, as_numpy=True):
     """Lexicographic unique rows + inverse (np.unique(axis=0, return_inverse=True)), for a
-    coordinate array [E,P,d] or, per layer, for a mesh object (:465-515)."""
-    if isinstance(points, np.ndarray):
+    coordinate array [E,P,d] or, per layer, for a mesh object (:465-515).  Computed on the GPU (K4);
+    `as_numpy=False` leaves (unique, inverse int32) on the device for the drivers."""
+    if not hasattr(points, "get_element_nodes"):
         allp = points.reshape(points.shape[0] * points.shape[1], points.shape[2])
-        u, inv = np.unique(allp, return_inverse=True, axis=0)
-        return u, inv.reshape(-1)
+        return _unique_rows(allp, device, as_numpy)
     layers, _ = _assess_layers(mesh=points, layers=layers)
     mask, _ = _create_mask(mesh=points, layers=layers)
     unique_points = {}
     for layer in layers:
         nodes = points.get_element_nodes()[mask[str(layer)]]
-        u, inv = np.unique(nodes.reshape(nodes.shape[0] * nodes.shape[1], nodes.shape[2]),
-                           return_inverse=True, axis=0)
-        unique_points[str(layer)] = (u, inv.reshape(-1))
+        unique_points[str(layer)] = _unique_rows(nodes.reshape(nodes.shape[0] * nodes.shape[1], nodes.shape[2]),
+                                                 device, as_numpy)
     return unique_points, mask, layers
 
 

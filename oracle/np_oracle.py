@@ -176,3 +176,10 @@ def knn(data, pts, k):
 def gather(fields, elements, coeffs):
     """values[n, f] = sum_a fields[elem_n, f, a] * coeffs[n, a]  (interpolator.py:814-826)."""
     return np.sum(fields[elements] * coeffs[:, None, :], axis=2)
+
+
+def unique_points(points):
+    """utils.get_unique_points of the reference (utils.py:484-492): np.unique over the flattened GLL nodes."""
+    allp = points.reshape(points.shape[0] * points.shape[1], points.shape[2])
+    u, inv = np.unique(allp, return_inverse=True, axis=0)
+    return u, inv.reshape(-1)

@@ -14,6 +14,8 @@ import os
 import numpy as np
 import pytest
 
+from oracle import np_oracle
+
 from multimesh_b200 import meshgen, utils
 
 GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
@@ -245,7 +247,7 @@ def test_oracle_gll_2_gll_driver(oracle):
     g, src, tgt = gll2gll_inputs()
     E, P, d = src.shape
     fields = g["source_fields"]
-    uniq, recon = utils.get_unique_points(tgt)
+    uniq, recon = np_oracle.unique_points(tgt)
     cands = oracle.knn_bruteforce(src.reshape(-1, d), uniq, 20) // P
     elem, xi, _, _ = oracle.locate(2, d, src, uniq, cands.astype(np.int32), oracle.V1())
     vals = oracle.interp(2, d, fields, elem, xi)
@@ -495,7 +497,7 @@ def test_oracle_gll_2_gll_driver_2d(oracle):
                            warp=float(g["tgt_warp"]))
     fields = meshgen.analytic_fields(src, names)
     E, P, d = src.shape
-    uniq, recon = utils.get_unique_points(tgt)
+    uniq, recon = np_oracle.unique_points(tgt)
     cands = oracle.knn_bruteforce(src.reshape(-1, d), uniq, 20) // P
     elem, xi, _, _ = oracle.locate(4, d, src, uniq, cands.astype(np.int32), oracle.V1())
     vals = oracle.interp(4, d, fields, elem, xi)

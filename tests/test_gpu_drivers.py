@@ -9,6 +9,8 @@ import os
 import numpy as np
 import pytest
 
+from oracle import np_oracle
+
 from multimesh_b200 import meshgen, utils
 from multimesh_b200.components.salvus_mesh_reader import SalvusMesh
 from multimesh_b200.io.exodus import Exodus
@@ -30,7 +32,7 @@ def _oracle_gll_2_gll(oracle, src_nodes, src_data, tgt_nodes, k):
     order = round(src_nodes.shape[1] ** (1.0 / src_nodes.shape[2])) - 1
     dim = src_nodes.shape[2]
     P = src_nodes.shape[1]
-    uniq, recon = utils.get_unique_points(tgt_nodes)
+    uniq, recon = np_oracle.unique_points(tgt_nodes)
     cands = oracle.knn_bruteforce(src_nodes.reshape(-1, dim), uniq, k) // P
     elem, xi, _, _ = oracle.locate(order, dim, src_nodes, uniq, cands.astype(np.int32), oracle.V1())
     vals = oracle.interp(order, dim, src_data, elem, xi)

@@ -151,3 +151,148 @@ def test_ops_reject_hidden_copies(cuda):
     flat = torch.zeros((4 * 81 + 1,), dtype=torch.float64, device=cuda)
     with pytest.raises(ValueError, match="16-byte aligned"):
         ops.element_geometry(flat[1:].view(4, 27, 3))
+
+
+@pytest.mark.parametrize("case", ["lattice_ties", "random_centroids", "clustered", "quads_2d", "outside", "big_coords"])
+def test_block_first_pass_matches_per_thread_kernel_and_oracle(cuda, oracle, case, monkeypatch):
+    """The warp-cooperative fp32-prefiltered first pass (knn_block_kernel) must give the same final result as the
+    per-thread exact kernel and as the oracle: identical target mesh (every 4th/5th distance tied), sparse and
+    crowded cells, 2-D, targets outside the source box, coordinates of O(6.4e6) with small elements."""
+    import torch
+    from multimesh_b200 import ops
+
+    rng = np.random.default_rng(abs(hash(case)) % 1000)
+    dim, order, form = 3, 2, "gll"
+    if case == "lattice_ties":
+        nodes = meshgen.box_mesh((7, 6, 5), 2)
+        pts = nodes.reshape(-1, 3).copy()  # every target coincides with a source GLL point: maximal ties
+    elif case == "random_centroids":
+        nodes = meshgen.box_mesh((9, 9, 9), 2, warp=0.04)
+        pts = rng.uniform(0.0, 1.0, (20000, 3))
+        form = "centroid"
+    elif case == "clustered":
+        # strongly graded element sizes: crowded and empty cells in one index
+        nodes = meshgen.box_mesh((10, 10, 10), 2)
+        nodes = nodes ** 3
+        pts = rng.uniform(0.0, 1.0, (15000, 3)) ** 3
+        form = "centroid"
+    elif case == "quads_2d":
+        dim = 2
+        nodes = meshgen.box_mesh((30, 25), 2, warp=0.02)
+        pts = np.concatenate([rng.uniform(-0.05, 1.05, (8000, 2)), nodes.reshape(-1, 2)[::3]])
+    elif case == "outside":
+        nodes = meshgen.box_mesh((6, 6, 6), 2, warp=0.02)
+        pts = rng.uniform(-0.6, 1.6, (12000, 3))
+    else:
+        nodes = meshgen.box_mesh((8, 8, 8), 2, lo=[6.2e6, -4e4, -4e4], hi=[6.28e6, 4e4, 4e4], warp=0.01)
+        pts = rng.uniform([6.2e6, -4e4, -4e4], [6.28e6, 4e4, 4e4], (15000, 3))
+    E, P, _ = nodes.shape
+    fields = rng.normal(size=(E, 3, P))
+    if form == "gll":
+        cands = (oracle.knn_bruteforce(nodes.reshape(-1, dim), pts, 20) // P).astype(np.int32)
+    else:
+        cands = oracle.knn_bruteforce(oracle.centroids(nodes), pts, 20)
+    o_elem, o_xi, o_st, o_nf = oracle.locate(order, dim, nodes, pts, cands, oracle.V1())
+    want = oracle.interp(order, dim, fields, o_elem, o_xi)
+    tn, tf, tp = (torch.from_numpy(np.ascontiguousarray(a)).to(cuda) for a in (nodes, fields, pts))
+    cent, box = ops.element_geometry(tn)
+    pre = ops.element_presolve(tn)
+    index = ops.GridIndex(tn.view(E * P, dim) if form == "gll" else cent)
+    div = P if form == "gll" else 1
+    for flag in ("1", "0"):
+        monkeypatch.setenv("MM_KNN_BLOCK", flag)
+        out, elem, xi, st, nf = ops.interpolate(index, div, tn, cent, box, tf, tp, 20, ops.V1(), presolve=pre)
+        assert np.array_equal(elem.cpu().numpy(), o_elem), (case, flag)
+        assert np.array_equal(st.cpu().numpy(), o_st), (case, flag)
+        assert np.array_equal(xi.cpu().numpy(), o_xi) and int(nf.item()) == o_nf
+        assert np.array_equal(out.cpu().numpy(), want)
+
+
+@pytest.mark.parametrize("case", ["gll3d", "gll2d", "random_dups", "signed", "single"])
+def test_unique_points_equals_numpy(cuda, case):
+    """K4 (mm_unique_points): rows and inverse identical to np.unique(axis=0, return_inverse=True)."""
+    import torch
+    from multimesh_b200 import ops
+
+    rng = np.random.default_rng(3)
+    if case == "gll3d":
+        pts = meshgen.box_mesh((9, 7, 8), 2, warp=0.03).reshape(-1, 3)
+    elif case == "gll2d":
+        pts = meshgen.box_mesh((21, 17), 4, warp=0.02).reshape(-1, 2)
+    elif case == "random_dups":
+        base = rng.uniform(-3.0, 5.0, (4000, 3))
+        base[:, 0] = np.round(base[:, 0], 1)  # many equal x: the order is decided by y, then z
+        base[::3, 1] = np.round(base[::3, 1], 0)
+        pts = base[rng.integers(0, len(base), 30000)]
+    elif case == "signed":
+        pts = np.concatenate([rng.normal(size=(5000, 3)) * 1e6, np.zeros((5, 3)), -np.zeros((5, 3)),
+                              np.array([[0.0, -0.0, 1.0], [-0.0, 0.0, 1.0], [1e-300, -1e-300, 0.0]])])
+        pts = np.concatenate([pts, pts[:100]])
+    else:
+        pts = np.full((37, 3), 1.25)
+    pts = np.ascontiguousarray(pts)
+    u, inv = ops.unique_points(torch.from_numpy(pts).to(cuda))
+    nu, ninv = np.unique(pts, return_inverse=True, axis=0)
+    assert u.shape == nu.shape
+    assert np.array_equal(u.cpu().numpy(), nu)  # (-0.0 == 0.0 compares equal, as in numpy's own grouping)
+    assert np.array_equal(inv.cpu().numpy(), ninv.reshape(-1))
+    assert np.array_equal(u.cpu().numpy()[inv.cpu().numpy()], pts)
+
+
+def test_scatter_back_and_fluid_fixup_equal_numpy(cuda):
+    import torch
+    from multimesh_b200 import ops
+
+    rng = np.random.default_rng(9)
+    E, P, F, Nu = 50, 27, 5, 700
+    vals = rng.normal(size=(Nu, F))
+    inv = rng.integers(0, Nu, E * P).astype(np.int32)
+    want = vals[inv].reshape(E, P, F).swapaxes(1, 2)
+    got = ops.scatter_back(torch.from_numpy(vals).to(cuda), torch.from_numpy(inv).to(cuda), E, P)
+    assert np.array_equal(got.cpu().numpy(), want)
+    full = rng.normal(size=(E * P, F))
+    got = ops.scatter_back(torch.from_numpy(full).to(cuda), None, E, P)
+    assert np.array_equal(got.cpu().numpy(), full.reshape(E, P, F).swapaxes(1, 2))
+    # fluid / solid repair (interpolator.py:829-841)
+    new = want.copy()
+    new[7, 4, 3] = 0.0   # a solid element that picked up a fluid value
+    new[20, 4, :] = 0.0  # a fluid element (kept anyway)
+    old = rng.normal(size=new.shape)
+    fluid = np.zeros(E, dtype=bool)
+    fluid[[3, 20]] = True
+    ref = new.copy()
+    ref[fluid] = old[fluid]
+    for e in np.unique(np.where(ref[:, 4, :] == 0.0)[0]):
+        if not fluid[e]:
+            ref[e] = old[e]
+    t = torch.from_numpy(new.copy()).to(cuda)
+    ops.fluid_fixup_(t, torch.from_numpy(old).to(cuda), torch.from_numpy(fluid).to(cuda), 4)
+    assert np.array_equal(t.cpu().numpy(), ref)
+
+
+def test_gll_2_gll_cache_formats_round_trip(cuda, oracle, tmp_path):
+    """stored_array: the first run writes the reference's elements.npy / coeffs.npy AND the compact (elem, xi)
+    cache; re-runs from the compact cache (pure K3) and from the reference format (explicit-matrix gather) give the
+    same file, bit for bit the first and within 1e-10 the second (different summation order)."""
+    import multi_mesh.api as api
+    from multimesh_b200.components import interpolator as itp
+    from multimesh_b200.io.store import open_store, write_gll_model
+
+    src = meshgen.box_mesh((6, 6, 6), 2, warp=0.02)
+    tgt = meshgen.box_mesh((5, 5, 5), 2, lo=[0.02] * 3, hi=[0.98] * 3)
+    a, store = str(tmp_path / "from.npz"), str(tmp_path / "stored")
+    write_gll_model(a, src, meshgen.analytic_fields(src, NAMES), NAMES, np.zeros((216, 2)), ["fluid", "layer"])
+    results = []
+    for run in range(3):
+        b = str(tmp_path / f"to{run}.npz")
+        write_gll_model(b, tgt, np.zeros((125, 5, 27)), NAMES, np.zeros((125, 2)), ["fluid", "layer"])
+        if run == 2:
+            os.remove(os.path.join(store, itp.COMPACT_CACHE))  # force the reference format
+        api.gll_2_gll(a, b, stored_array=store, gradient=True)
+        with open_store(b, "r") as st:
+            results.append(st.read("MODEL/data"))
+        assert os.path.exists(os.path.join(store, "elements.npy")) and os.path.exists(os.path.join(store, "coeffs.npy"))
+        if run < 2:
+            assert os.path.exists(os.path.join(store, itp.COMPACT_CACHE))
+    assert np.array_equal(results[0], results[1])
+    assert np.max(np.abs(results[2] - results[0]) / np.abs(results[0])) <= 1e-10

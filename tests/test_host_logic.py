@@ -44,9 +44,17 @@ def test_assess_layers_and_masks():
     assert not (masks["1"] & masks["3"]).any()
 
 
+@pytest.mark.gpu
 def test_get_unique_points_array_and_mesh():
+    """utils.get_unique_points runs on the GPU (K4); the array form must equal np.unique bit for bit."""
+    import torch
+
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
     nodes = meshgen.box_mesh((3, 3, 3), 2)
     u, inv = utils.get_unique_points(nodes)
+    nu, ninv = np.unique(nodes.reshape(-1, 3), return_inverse=True, axis=0)
+    assert np.array_equal(u, nu) and np.array_equal(inv, ninv.reshape(-1))
     assert u.shape == (7 ** 3, 3)
     assert np.array_equal(u[inv].reshape(nodes.shape), nodes)
     assert (np.diff(u.view([("x", "f8"), ("y", "f8"), ("z", "f8")]).ravel().argsort(order=("x", "y", "z"))) == 1).all()

@@ -70,10 +70,24 @@ def _gather_worker(rank, world, port, tmpdir):
     sys.path.insert(0, ROOT)
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
     dist.init_process_group("gloo", rank=rank, world_size=world)
-    from multimesh_b200.parallel import gather_rows, local_slice
+    from multimesh_b200.parallel import (allgather_rows, broadcast_source, gather_buffer, gather_rows, local_slice,
+                                         shard_bounds)
 
     full = torch.arange(11 * 4, dtype=torch.float64).reshape(11, 4)
     out = gather_rows(full[local_slice(11, rank, world)], 11, dst=1)
+    # every rank gets everything; ragged shards, no padding
+    assert torch.equal(allgather_rows(full[local_slice(11, rank, world)].clone(), 11), full)
+    # the destination computes its shard in place inside the gather buffer
+    buf, mine = gather_buffer(11, (4,), torch.float64, "cpu", rank, 1, shard_bounds(11, world))
+    if rank == 1:
+        mine.copy_(full[local_slice(11, rank, world)])
+        assert torch.equal(gather_rows(mine, 11, dst=1, full=buf), full) and buf.data_ptr() == mine.data_ptr() - mine.storage_offset() * 8
+    else:
+        assert buf is None and gather_rows(full[local_slice(11, rank, world)], 11, dst=1) is None
+    # source mesh: one rank holds it, everybody ends up with it
+    a = np.arange(24, dtype=np.float64).reshape(2, 4, 3)
+    got = broadcast_source([a, 2 * a] if rank == 0 else [None, None], "cpu", src=0)
+    assert np.array_equal(got[0].numpy(), a) and np.array_equal(got[1].numpy(), 2 * a)
     if rank == 1:
         assert torch.equal(out, full)
         open(os.path.join(tmpdir, "ok"), "w").write("ok")
