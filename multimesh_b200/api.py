@@ -15,7 +15,44 @@ from typing import List, Union
 import numpy as np
 
 
+def _pick_device(kwargs):
+    """`device=` (int / str / torch.device) or `devices=[...]` -- the one additive kwarg of every entry point (SURVEY
+    section 5).  One process drives ONE GPU; several GPUs = one process per GPU under torchrun, where every rank calls
+    the same entry point and the drivers shard the target points between the ranks (components/interpolator._Source.find)."""
+    device = kwargs.pop("device", None)
+    devices = kwargs.pop("devices", None)
+    if devices is not None:
+        devices = list(devices) if isinstance(devices, (list, tuple)) else [devices]
+        if len(devices) != 1:
+            raise ValueError(
+                f"devices={devices}: one process drives one GPU; for {len(devices)} GPUs launch one process per GPU "
+                "(`python -m torch.distributed.run --nproc-per-node N script.py`), every rank calling this function "
+                "with the same arguments -- the target points are then sharded over the ranks")
+        device = devices[0]
+    return device
+
+
+def _on_device(fn):
+    """Runs the entry point with `device=` / `devices=[d]` as the current CUDA device."""
+    @functools.wraps(fn)
+    def wrapper(*args, **kwargs):
+        import contextlib
+
+        device = _pick_device(kwargs)
+        ctx = contextlib.nullcontext()
+        if device is not None:
+            import torch
+
+            ctx = torch.cuda.device(torch.device(device) if not isinstance(device, int) else device)
+        with ctx:
+            return fn(*args, **kwargs)
+
+    return wrapper
+
+
 def _timed(fn):
+    fn = _on_device(fn)
+
     @functools.wraps(fn)
     def wrapper(*args, **kwargs):
         start = time.time()
@@ -96,6 +133,7 @@ def gll_2_exodus(gll_model, exodus_model, gll_order=4, dimensions=3, nelem_to_se
           coordinates_path, gradient)
 
 
+@_on_device
 def interpolate_to_points(mesh, points, params_to_interp, make_spherical=False, geocentric=False):
     """Mesh -> point cloud (xyz, or lat/lon/depth when `geocentric`); returns [N, F]
     (api.py:320-350)."""
@@ -108,6 +146,7 @@ def interpolate_to_points(mesh, points, params_to_interp, make_spherical=False, 
     return _impl(mesh=mesh, points=points, params_to_interp=params_to_interp, make_spherical=make_spherical)
 
 
+@_on_device
 def interpolate_to_mesh(old_mesh, new_mesh, params_to_interp=["VSV", "VSH", "VPV", "VPH"]):
     """Map both meshes to the sphere, interpolate old -> new at the new mesh's nodes, restore the
     coordinates; points that are not found get zero (api.py:353-393).  Meshes are SalvusMesh

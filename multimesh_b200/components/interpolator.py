@@ -262,11 +262,11 @@ def _gather_cached(device, fields_np, elements, coeffs):
 def query_model(coordinates, model, nelem_to_search, model_path, coordinates_path):
     """Model parameters at (lat, lon, depth_in_m) coordinates (:60-139)."""
     print("Initialization stage")
-    original_points, original_data, original_params = utils.load_hdf5_params_to_memory(
-        model, model_path, coordinates_path)
+    staged, original_params = utils.load_hdf5_params_to_device(model, model_path, coordinates_path)
     assert coordinates.shape[1] == 3, "Make sure coordinates array has shape N,3"
     xyz = utils.latlondepth_to_xyz(latlondepth=coordinates)
-    src = _Source(original_points)
+    src = _Source(staged[coordinates_path])
+    original_data = staged[model_path]
     pts = _dev_f64(xyz, src.device)
     vals, elem, xi, status, _ = src.find(pts, nelem_to_search, ops.V1(), form="gll", fields=original_data)
     _raise_if_hard(status, False)  # ignore_hard_elements=False (:128)
@@ -508,12 +508,15 @@ def gll_2_gll(from_gll, to_gll, nelem_to_search=20, parameters="ISO", from_model
     F identical copies, as the reference stores them)."""
     print("Initialization stage")
     print(f"Stored array: {stored_array}")
-    original_points, original_data, original_params = utils.load_hdf5_params_to_memory(
-        from_gll, from_model_path, from_coordinates_path)
+    # file -> pinned memory -> HBM, asynchronously; the index is built from the coordinates while the fields
+    # are still being read / copied (io/staging.py)
+    staged, original_params = utils.load_hdf5_params_to_device(from_gll, from_model_path, from_coordinates_path)
+    original_points = staged[from_coordinates_path]
     dimensions = original_points.shape[2]
-    from_gll_order = order_from_npoints(original_data.shape[2], dimensions)
     parameters = original_params  # the reference interpolates every source parameter (:668)
     src = _Source(original_points)
+    original_data = staged[from_model_path]
+    from_gll_order = order_from_npoints(original_data.shape[2], dimensions)
 
     writer = parallel._world()[1] == 0  # under torchrun every rank computes, rank 0 writes files
     with open_store(to_gll, "r+" if writer else "r") as new:

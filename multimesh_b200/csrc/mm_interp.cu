@@ -446,6 +446,240 @@ int launch_interp_coherent(int64_t E, int F, const double *fields, int64_t N, co
     return MM_OK;
 }
 
+// ================================================================================================
+// K3, CTA-tile variant (the fused pipeline's gather): a CTA owns a tile of 256 consecutive points of the
+// spatially sorted order.  Their owning elements are de-duplicated for the WHOLE tile with a shared-memory
+// hash table (a tile of 256 sorted points touches 10-40 source elements; a warp of 32 points alone would fetch
+// 2-4 of them again in every warp), each distinct element block is fetched ONCE per tile with one bulk-async
+// copy (UBLKCP) into a slot of the current stage, and every thread contracts out of the slot of its element
+// (threads of one element read the same addresses: broadcast).  Two stages: while the threads contract item i
+// (a round of up to `slots` elements x one chunk of FC fields), the copies of item i + 1 are in flight.  Every
+// thread arrives once per item on the stage's mbarrier (element owners with their byte count), so the barrier
+// needs no per-item re-initialisation.  Slot stride: a multiple of 16 B whose 8-byte count is = 2 (mod 4), so that
+// consecutive slots start in different bank pairs (the warp-variant's stride of 136 x 8 B put every second slot on
+// the same banks).  Same arithmetic as the other K3 kernels: bit-identical results.
+// ================================================================================================
+constexpr int TILE_THREADS = 256;
+constexpr int TILE_HASH = 512;  // >= 2 x tile size: short probe sequences, never full
+
+struct tile_cfg {
+    int F, FC, chunks, slots, slot_bytes, odd_p, perm_stride;
+};
+
+__host__ __device__ inline int tile_slot_bytes(int bytes)
+{
+    int q = (bytes + 15) / 16 * 2;  // 8-byte words, even
+    while ((q & 3) != 2) q += 2;
+    return q * 8;
+}
+
+template <int ORDER, int DIM>
+__global__ void __launch_bounds__(TILE_THREADS, 3)
+interp_tile_kernel(const mm_gll_table T, const tile_cfg cfg, int64_t E, const double *__restrict__ fields, int64_t N,
+                   const int32_t *__restrict__ elem, const double *__restrict__ xi,
+                   const int32_t *__restrict__ perm, double *__restrict__ out,
+                   const uint8_t *__restrict__ status, int32_t *__restrict__ elem_u, double *__restrict__ xi_u,
+                   uint8_t *__restrict__ status_u)
+{
+    constexpr int M = ORDER + 1;
+    constexpr int P = DIM == 2 ? M * M : M * M * M;
+    extern __shared__ __align__(128) unsigned char smem[];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const size_t stage_bytes = (size_t)cfg.slots * cfg.slot_bytes;
+    unsigned char *stage0 = smem;
+    int32_t *keys = reinterpret_cast<int32_t *>(smem + 2 * stage_bytes);  // [TILE_HASH] element id or -1
+    int32_t *dense = keys + TILE_HASH;                                   // [TILE_HASH] dense id of the entry
+    int32_t *wsum = dense + TILE_HASH;                                   // [TILE_HASH / 32] + total
+    uint64_t *bars = reinterpret_cast<uint64_t *>(wsum + TILE_HASH / 32 + 2);
+    if (tid < 2) mbar_init(&bars[tid], TILE_THREADS);
+    fence_mbar_init();
+    __syncthreads();
+
+    const int64_t total_bytes = E * (int64_t)cfg.F * P * 8;
+    const int64_t ntiles = (N + TILE_THREADS - 1) / TILE_THREADS;
+    uint32_t uses[2] = {0, 0};  // completed phases of each stage barrier
+
+    for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        const int64_t n = tile * TILE_THREADS + tid;
+        const bool valid = n < N;
+        const int32_t e = valid ? valid_elem(elem[n], E) : -1;
+        // ---- de-duplicate the tile's elements ---------------------------------------------------------
+        __syncthreads();  // everybody is done with the previous tile's table and slots
+        for (int i = tid; i < TILE_HASH; i += TILE_THREADS) keys[i] = -1;
+        __syncthreads();
+        int hpos = -1;
+        if (e >= 0) {
+            unsigned h = ((unsigned)e * 2654435761u) >> 23;  // top 9 bits
+            while (true) {
+                h &= TILE_HASH - 1;
+                const int32_t old = atomicCAS(&keys[h], -1, e);
+                if (old == -1 || old == e) break;
+                ++h;
+            }
+            hpos = (int)h;
+        }
+        __syncthreads();
+        // dense ids of the occupied entries (entry i is handled by thread i and thread i + 256)
+        int occ[TILE_HASH / TILE_THREADS];
+#pragma unroll
+        for (int j = 0; j < TILE_HASH / TILE_THREADS; ++j) {
+            const int i = tid + j * TILE_THREADS;
+            const bool o = keys[i] >= 0;
+            const unsigned b = __ballot_sync(0xffffffffu, o);
+            occ[j] = o ? __popc(b & ((1u << lane) - 1)) : -1;
+            if (lane == 0) wsum[warp + j * (TILE_THREADS / 32)] = __popc(b);
+        }
+        __syncthreads();
+        if (tid == 0) {
+            int run = 0;
+            for (int w = 0; w < TILE_HASH / 32; ++w) {
+                const int t = wsum[w];
+                wsum[w] = run;
+                run += t;
+            }
+            wsum[TILE_HASH / 32] = run;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int j = 0; j < TILE_HASH / TILE_THREADS; ++j)
+            if (occ[j] >= 0) dense[tid + j * TILE_THREADS] = wsum[warp + j * (TILE_THREADS / 32)] + occ[j];
+        __syncthreads();
+        const int D = wsum[TILE_HASH / 32];
+        const int my_id = hpos >= 0 ? dense[hpos] : -1;
+        // this thread owns (fetches) the elements of table entries tid and tid + 256
+        int32_t own_e[TILE_HASH / TILE_THREADS];
+        int own_id[TILE_HASH / TILE_THREADS];
+#pragma unroll
+        for (int j = 0; j < TILE_HASH / TILE_THREADS; ++j) {
+            own_e[j] = keys[tid + j * TILE_THREADS];
+            own_id[j] = own_e[j] >= 0 ? dense[tid + j * TILE_THREADS] : -1;
+        }
+        // ---- per-point preparation: Lagrange values, un-permuted location outputs ----------------------
+        double L[DIM][M];
+        int64_t orow = 0;
+        if (valid) {
+            double x[DIM];
+#pragma unroll
+            for (int ax = 0; ax < DIM; ++ax) x[ax] = xi[n * DIM + ax];
+            orow = perm ? (int64_t)perm[n * cfg.perm_stride] : n;
+            if (elem_u) {
+                elem_u[orow] = e;
+                if (status_u) status_u[orow] = status[n];
+                if (xi_u) {
+#pragma unroll
+                    for (int ax = 0; ax < DIM; ++ax) xi_u[orow * DIM + ax] = x[ax];
+                }
+            }
+            if (e >= 0) {
+#pragma unroll
+                for (int ax = 0; ax < DIM; ++ax) lagrange_values<ORDER>(T, x[ax], L[ax]);
+            } else {
+                for (int f = 0; f < cfg.F; ++f) out[orow * cfg.F + f] = 0.0;  // failed point: zero row
+            }
+        }
+        // ---- items: (round of `slots` elements) x (chunk of FC fields) -------------------------------
+        const int rounds = (D + cfg.slots - 1) / cfg.slots;
+        const int items = rounds * cfg.chunks;
+        auto issue = [&](int item, int s) {
+            const int r = item / cfg.chunks, ch = item % cfg.chunks;
+            const int f0 = ch * cfg.FC, nf = min(cfg.FC, cfg.F - f0);
+            const int bytes = chunk_copy_bytes(nf, P, cfg.odd_p);
+            uint32_t tx = 0;
+#pragma unroll
+            for (int j = 0; j < TILE_HASH / TILE_THREADS; ++j) {
+                const int slot = own_id[j] - r * cfg.slots;
+                if (own_id[j] < 0 || slot < 0 || slot >= cfg.slots) continue;
+                const int64_t off = (((int64_t)own_e[j] * cfg.F + f0) * P) * 8;
+                const int shift = cfg.odd_p ? (int)(off & 8) : 0;
+                unsigned char *dst = stage0 + s * stage_bytes + (size_t)slot * cfg.slot_bytes;
+                if ((off - shift + bytes) <= total_bytes) {
+                    tx += (uint32_t)bytes;
+                } else {  // last bytes of the array: plain loads (visible to the others through the barrier's release)
+                    const double *src = reinterpret_cast<const double *>(
+                        reinterpret_cast<const unsigned char *>(fields) + off);
+                    double *d2 = reinterpret_cast<double *>(dst + shift);
+                    for (int q = 0; q < nf * P; ++q) d2[q] = src[q];
+                }
+            }
+            if (tx) mbar_arrive_expect_tx(&bars[s], tx);
+            else asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&bars[s])) : "memory");
+#pragma unroll
+            for (int j = 0; j < TILE_HASH / TILE_THREADS; ++j) {
+                const int slot = own_id[j] - r * cfg.slots;
+                if (own_id[j] < 0 || slot < 0 || slot >= cfg.slots) continue;
+                const int64_t off = (((int64_t)own_e[j] * cfg.F + f0) * P) * 8;
+                const int shift = cfg.odd_p ? (int)(off & 8) : 0;
+                if ((off - shift + bytes) <= total_bytes)
+                    bulk_copy_g2s(stage0 + s * stage_bytes + (size_t)slot * cfg.slot_bytes,
+                                  reinterpret_cast<const unsigned char *>(fields) + off - shift, (uint32_t)bytes,
+                                  &bars[s]);
+            }
+        };
+        // generic-proxy reads of the previous tile's slots happened before the __syncthreads above
+        fence_proxy_async_smem();
+        if (items > 0) issue(0, 0);
+        for (int item = 0; item < items; ++item) {
+            const int s = item & 1;
+            if (item + 1 < items) {
+                // stage (item + 1) & 1 was read at item - 1: every thread must be past that before it is refilled
+                fence_proxy_async_smem();
+                __syncthreads();
+                issue(item + 1, (item + 1) & 1);
+            }
+            mbar_wait(&bars[s], uses[s] & 1);
+            ++uses[s];
+            const int r = item / cfg.chunks, ch = item % cfg.chunks;
+            const int slot = my_id - r * cfg.slots;
+            if (my_id >= 0 && slot >= 0 && slot < cfg.slots) {
+                const int f0 = ch * cfg.FC, nf = min(cfg.FC, cfg.F - f0);
+                const int64_t off = (((int64_t)e * cfg.F + f0) * P) * 8;
+                const int shift = cfg.odd_p ? (int)(off & 8) : 0;
+                const double *v = reinterpret_cast<const double *>(stage0 + s * stage_bytes +
+                                                                   (size_t)slot * cfg.slot_bytes + shift);
+                double *o = out + orow * cfg.F + f0;
+                for (int f = 0; f < nf; ++f) o[f] = contract_field<ORDER, DIM>(v + f * P, L);
+            }
+        }
+    }
+}
+
+template <int ORDER, int DIM>
+int launch_interp_tile(int64_t E, int F, const double *fields, int64_t N, const int32_t *elem, const double *xi,
+                       const int32_t *perm, double *out, cudaStream_t stream, const uint8_t *status, int32_t *elem_u,
+                       double *xi_u, uint8_t *status_u, int perm_stride)
+{
+    constexpr int M = ORDER + 1;
+    constexpr int P = DIM == 2 ? M * M : M * M * M;
+    mm_gll_table T;
+    mm_make_table(ORDER, &T);
+    tile_cfg cfg;
+    cfg.F = F;
+    cfg.perm_stride = perm_stride;
+    cfg.odd_p = P % 2;
+    int fc = std::max(1, std::min(F, 1100 / (P * 8)));  // ~1 KB slots: whole block at order <= 2, one field at order 4
+    if (const char *e = getenv("MM_TILE_FC")) fc = std::max(1, std::min(F, atoi(e)));
+    cfg.FC = fc;
+    cfg.chunks = (F + fc - 1) / fc;
+    cfg.slot_bytes = tile_slot_bytes(chunk_copy_bytes(fc, P, cfg.odd_p));
+    cfg.slots = std::max(4, std::min(48, (32 * 1024) / cfg.slot_bytes));  // ~32 KB per stage
+    if (const char *e = getenv("MM_TILE_SLOTS")) cfg.slots = std::max(1, std::min(256, atoi(e)));
+    auto kern = interp_tile_kernel<ORDER, DIM>;
+    size_t smem = 2 * (size_t)cfg.slots * cfg.slot_bytes + sizeof(int32_t) * (2 * TILE_HASH + TILE_HASH / 32 + 2) +
+                  2 * sizeof(uint64_t);
+    MM_REQUIRE(smem <= 227 * 1024, MM_ERR_UNSUPPORTED, "mm_interp: staging needs %zu B of shared memory", smem);
+    static mm_kernel_cfg kcfg;
+    int per_sm = 1;
+    MM_CUDA(kcfg.prepare(kern, TILE_THREADS, smem, &per_sm));
+    const int sms = mm_num_sms() > 0 ? mm_num_sms() : 148;
+    const int64_t ntiles = (N + TILE_THREADS - 1) / TILE_THREADS;
+    int64_t grid = std::min<int64_t>((int64_t)sms * per_sm, ntiles);
+    if (grid < 1) grid = 1;
+    kern<<<(int)grid, TILE_THREADS, smem, stream>>>(T, cfg, E, fields, N, elem, xi, perm, out, status, elem_u, xi_u,
+                                                    status_u);
+    MM_CUDA(cudaGetLastError());
+    return MM_OK;
+}
+
 // ---- coefficient write-out: coeffs[n][a] = (Lx[i] * Ly[j]) * Lz[k] -----------------------------
 template <int ORDER, int DIM>
 __global__ void __launch_bounds__(256)
@@ -599,10 +833,14 @@ int mm_interp_fused(int order, int dim, int64_t E, int F, const double *fields, 
 {
     cudaStream_t stream = (cudaStream_t)stream_;
     MM_REQUIRE(((uintptr_t)fields & 15) == 0, MM_ERR_INVALID, "mm_interpolate: fields must be 16-byte aligned");
+    const char *mode = getenv("MM_INTERP_MODE");  // "w": the warp-level variant (A/B comparisons)
+    const bool tile = !(mode && mode[0] == 'w');
 #define MM_INTF(O, D)                                                                             \
     if (order == O && dim == D)                                                                   \
-        return launch_interp_coherent<O, D>(E, F, fields, N, elem_s, xi_s, perm, out, stream,     \
-                                            status_s, elem_u, xi_u, status_u, perm_stride);
+        return tile ? launch_interp_tile<O, D>(E, F, fields, N, elem_s, xi_s, perm, out, stream,  \
+                                               status_s, elem_u, xi_u, status_u, perm_stride)     \
+                    : launch_interp_coherent<O, D>(E, F, fields, N, elem_s, xi_s, perm, out, stream, \
+                                                   status_s, elem_u, xi_u, status_u, perm_stride);
     MM_INTF(1, 2) MM_INTF(2, 2) MM_INTF(4, 2) MM_INTF(1, 3) MM_INTF(2, 3) MM_INTF(4, 3)
 #undef MM_INTF
     mm_set_error("mm_interpolate: unsupported order/dim");

@@ -391,11 +391,6 @@ int mm_locate_impl(int order, int dim, int64_t E, const double *nodes, const dou
                                             cands,                                                \
                                             elem, xi, status, num_failed, unresolved_list,       \
                                             unresolved_count, stream, n_dev, n_off);
-    if (const char *v = getenv("MM_LOC_VARIANT")) {  // profiling only
-        if (atoi(v) == 1) { MM_LOC(4, 3, 2, 16, 1) MM_LOC(2, 3, 4, 16, 4) }
-        if (atoi(v) == 2) { MM_LOC(4, 3, 2, 12, 1) MM_LOC(2, 3, 4, 12, 4) }
-        if (atoi(v) == 3) { MM_LOC(4, 3, 3, 12, 1) }
-    }
     MM_LOC(1, 2, 4, 8, 1)
     MM_LOC(2, 2, 4, 8, 1)
     MM_LOC(4, 2, 4, 8, 1)

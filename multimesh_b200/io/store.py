@@ -25,14 +25,48 @@ def _format_labels(names):
     return "[ " + " | ".join(names) + " ]"  # utils.py:165
 
 
+def _pinned_empty(shape, dtype):
+    """A pinned (page-locked) host tensor and its numpy view: the staging buffer of an asynchronous H2D copy."""
+    import torch
+
+    t = torch.empty(tuple(int(v) for v in shape), dtype=getattr(torch, np.dtype(dtype).name), pin_memory=True)
+    return t, t.numpy()
+
+
+class _LazyArrays(dict):
+    """name -> array of an .npz file, each member read on first access (np.load's NpzFile is lazy per key)."""
+
+    def __init__(self, path):
+        super().__init__()
+        self._z = np.load(path, allow_pickle=False)
+        self._names = set(self._z.files)
+
+    def __contains__(self, k):
+        return dict.__contains__(self, k) or k in self._names
+
+    def __missing__(self, k):
+        if k not in self._names:
+            raise KeyError(k)
+        v = self._z[k]
+        self[k] = v
+        return v
+
+    def load_all(self):
+        for k in sorted(self._names):
+            self[k]
+        return dict(self)
+
+    def close(self):
+        self._z.close()
+
+
 class NpzStore:
     def __init__(self, path, mode="r"):
         self.path, self.mode = str(path), mode
         self._dirty = False
         self._arrays = {}
         if os.path.exists(self.path):
-            with np.load(self.path, allow_pickle=False) as z:
-                self._arrays = {k: z[k] for k in z.files}
+            self._arrays = _LazyArrays(self.path)
         elif mode == "r":
             raise FileNotFoundError(self.path)
 
@@ -42,8 +76,44 @@ class NpzStore:
     def read(self, name):
         return self._arrays[name]
 
+    def _member_header(self, name):
+        """(zip member, shape, dtype, fortran_order) of an array without reading its data."""
+        import zipfile
+
+        zf = zipfile.ZipFile(self.path)
+        fh = zf.open(name + ".npy")
+        major, minor = np.lib.format.read_magic(fh)
+        shape, fortran, dtype = (np.lib.format.read_array_header_1_0(fh) if major == 1
+                                 else np.lib.format.read_array_header_2_0(fh))
+        return zf, fh, shape, dtype, fortran
+
     def shape(self, name):
+        if isinstance(self._arrays, _LazyArrays) and not dict.__contains__(self._arrays, name):
+            zf, fh, shape, _, _ = self._member_header(name)
+            fh.close()
+            zf.close()
+            return tuple(shape)
         return self._arrays[name].shape
+
+    def read_pinned(self, name):
+        """The array as a PINNED host tensor, read from the file straight into the page-locked buffer (no
+        intermediate pageable copy), ready for an asynchronous H2D copy (io/staging.py)."""
+        zf, fh, shape, dtype, fortran = self._member_header(name)
+        try:
+            if fortran or dtype.hasobject:
+                raise ValueError(f"{name}: only C-ordered plain arrays can be staged")
+            t, view = _pinned_empty(shape, dtype)
+            buf = memoryview(view.reshape(-1).view(np.uint8))
+            got = 0
+            while got < len(buf):
+                n = fh.readinto(buf[got:got + (64 << 20)])
+                if not n:
+                    raise IOError(f"{self.path}:{name}: short read")
+                got += n
+            return t
+        finally:
+            fh.close()
+            zf.close()
 
     def write(self, name, array):
         assert self.mode != "r", "store opened read-only"
@@ -66,9 +136,17 @@ class NpzStore:
         self.write(group + "@attrs", np.array(json.dumps(a)))
 
     def close(self):
+        lazy = isinstance(self._arrays, _LazyArrays)
         if self._dirty and self.mode != "r":
-            np.savez(self.path if self.path.endswith(".npz") else self.path + ".npz", **self._arrays)
+            arrays = self._arrays.load_all() if lazy else dict(self._arrays)
+            if lazy:
+                self._arrays.close()
+                self._arrays = arrays
+            np.savez(self.path if self.path.endswith(".npz") else self.path + ".npz", **arrays)
             self._dirty = False
+        elif lazy:
+            self._arrays.close()
+            self._arrays = dict(self._arrays)
 
     def __enter__(self):
         return self
@@ -91,6 +169,13 @@ class H5Store:
 
     def shape(self, name):
         return self.f[name].shape
+
+    def read_pinned(self, name):
+        """The dataset as a PINNED host tensor: HDF5 reads straight into the page-locked buffer (read_direct)."""
+        ds = self.f[name]
+        t, view = _pinned_empty(ds.shape, ds.dtype)
+        ds.read_direct(view)
+        return t
 
     def write(self, name, array):
         if name in self.f:

@@ -33,6 +33,20 @@ def load_hdf5_params_to_memory(gll: str, model: str, coordinates: str):
     return points, data, params
 
 
+def load_hdf5_params_to_device(gll: str, model: str, coordinates: str, device=None):
+    """Device twin of load_hdf5_params_to_memory: (points [E,P,d], data [E,F,P]) as CUDA tensors + params.  Each
+    array is read from the file straight into pinned memory and copied asynchronously (io/staging.py), the
+    coordinates first, so that geometry and index can be built while the field array is still in flight.
+    Returns (staged, params): `staged[coordinates]` / `staged[model]` wait (stream-ordered) for their copy."""
+    from .io.staging import stage_arrays
+    from .kdtree import _device
+
+    with open_store(gll, "r") as st:
+        params = [p.replace("grad", "") for p in st.labels(model)]
+        staged = stage_arrays(st, [coordinates, model], _device(device))
+    return staged, params
+
+
 def remove_and_create_empty_dataset(gll_model, parameters: list, model: str, coordinates: str):
     """Replace `model` by an empty [E, len(parameters), P] float64 dataset with fresh dimension
     labels (:137-168).  `gll_model` is an open store."""
@@ -147,3 +161,53 @@ def load_exodus(file, find_centroids=True):
     if not find_centroids:
         return exodus
     return exodus, KDTree(exodus.get_element_centroid())
+
+
+# ----------------------------------------------------------------------------------------------
+# geodesy helpers used by the point-cloud generators of the plotter (utils.py:95-134, 545-604)
+# ----------------------------------------------------------------------------------------------
+def sph2cart(col, lon, rad):
+    """(colatitude [rad], longitude [rad], radius) -> x, y, z (utils.py:577-594)."""
+    col, lon, rad = np.asarray(col), np.asarray(lon), np.asarray(rad)
+    if (0 > col).any() or (col > np.pi).any():
+        raise ValueError("Colatitude must be in range [0, pi].")
+    return rad * np.sin(col) * np.cos(lon), rad * np.sin(col) * np.sin(lon), rad * np.cos(col)
+
+
+def cart2sph(x, y, z):
+    """x, y, z -> (colatitude, longitude, radius); the centre maps to colatitude pi/2 (utils.py:597-617)."""
+    x, y, z = np.asarray(x), np.asarray(y), np.asarray(z)
+    r = np.sqrt(x ** 2 + y ** 2 + z ** 2)
+    with np.errstate(invalid="ignore", divide="ignore"):
+        c = np.nan_to_num(np.divide(z, r))
+    return np.arccos(c), np.arctan2(y, x), r
+
+
+def elliptic_to_geocentric_latitude(lat, axis_a=6378137.0, axis_b=6356752.314245):
+    """WGS84 geographic -> geocentric latitude in degrees: atan((1 - e^2) tan(lat)).  The reference imports this
+    from LASIF (components/plotter.py:8), which is not installed here; this is LASIF's published formula."""
+    f = (axis_a - axis_b) / axis_a
+    e2 = 2.0 * f - f ** 2
+    if abs(lat) < 1e-6 or abs(lat - 90.0) < 1e-6 or abs(lat + 90.0) < 1e-6:
+        return lat
+    return float(np.rad2deg(np.arctan((1.0 - e2) * np.tan(np.deg2rad(lat)))))
+
+
+def greatcircle_points(point_1_lat, point_1_lng, point_2_lat, point_2_lng, npts=101):
+    """npts points [lat, lon] from point 1 towards point 2, the i-th at i / npts of the way (the last point stops
+    one step short of point 2, as in the reference, utils.py:545-574).  The reference walks the WGS84 geodesic with
+    geographiclib, which is not installed here; this walks the great circle of the sphere (differences are below
+    0.2 degrees and only move the plotted section slightly)."""
+    if npts < 3:
+        raise Exception("You should supply at least 3 points")
+    a = np.deg2rad([point_1_lat, point_1_lng])
+    b = np.deg2rad([point_2_lat, point_2_lng])
+    va = np.array([np.cos(a[0]) * np.cos(a[1]), np.cos(a[0]) * np.sin(a[1]), np.sin(a[0])])
+    vb = np.array([np.cos(b[0]) * np.cos(b[1]), np.cos(b[0]) * np.sin(b[1]), np.sin(b[0])])
+    omega = np.arccos(np.clip(va @ vb, -1.0, 1.0))
+    out = []
+    for i in range(npts):
+        t = i / float(npts)
+        v = va if omega < 1e-15 else (np.sin((1 - t) * omega) * va + np.sin(t * omega) * vb) / np.sin(omega)
+        out.append([np.rad2deg(np.arcsin(np.clip(v[2], -1.0, 1.0))), np.rad2deg(np.arctan2(v[1], v[0]))])
+    return np.array(out)

@@ -265,3 +265,49 @@ def test_map_to_sphere(cuda):
     r = np.sqrt(x ** 2 + y ** 2 + z ** 2)
     want = np.stack([x * 6371000 * z1d / r, y * 6371000 * z1d / r, z * 6371000 * z1d / r], axis=-1)
     assert np.array_equal(m.points, want)
+
+
+def test_interpolate_to_mesh_and_plotter_values(cuda, oracle):
+    """api.interpolate_to_mesh (api.py:353-393): both meshes mapped to the sphere, old -> new at the new mesh's
+    nodes (V2, k = 25), coordinates restored; and the arrays the plotter draws (depth slice, cross section)."""
+    import multi_mesh.api as api
+    from multi_mesh.components import plotter
+
+    names = ["VSV", "VSH", "VPV", "VPH", "z_node_1D"]
+
+    def shell(n_lat, squash):
+        coords, el, z1d = meshgen.shell_mesh(n_lat, meshgen.default_shell_layers(), 2)
+        ell = coords * np.array([1.0, 1.0, squash])  # an "elliptic" mesh; z_node_1D keeps the spherical radius
+        data = meshgen.analytic_fields(coords / 6371000.0, names[:4])
+        data = np.concatenate([data, z1d[:, None, :]], axis=1)
+        return coords, ell, SalvusMesh.from_arrays(ell.copy(), data.copy(), names), data
+
+    sph_old, ell_old, old, data_old = shell(4, 0.995)
+    sph_new, ell_new, new, _ = shell(3, 0.995)
+    out = api.interpolate_to_mesh(old, new, params_to_interp=["VSV", "VPH"])
+    assert out is new
+    assert np.array_equal(old.points, ell_old) and np.array_equal(new.points, ell_new)  # coordinates restored
+    # oracle on the sphere-mapped meshes (map_to_sphere is bit-equal to the numpy formula, test_map_to_sphere)
+    def to_sphere(ell, z1d):  # the operation order of interpolator.py:1138-1143, as in test_map_to_sphere
+        x, y, z = ell[..., 0], ell[..., 1], ell[..., 2]
+        r = np.sqrt(x ** 2 + y ** 2 + z ** 2)
+        return np.stack([x * 6371000 * z1d / r, y * 6371000 * z1d / r, z * 6371000 * z1d / r], axis=-1)
+
+    s_old = to_sphere(ell_old, data_old[:, 4, :])
+    s_new = to_sphere(ell_new, new.element_nodal_fields["z_node_1D"])
+    pts = s_new.reshape(-1, 3)
+    cands = oracle.knn_bruteforce(oracle.centroids(s_old), pts, 25)
+    elem, xi, _, _ = oracle.locate(2, 3, s_old, pts, cands, oracle.V2())
+    want = oracle.interp(2, 3, np.ascontiguousarray(data_old[:, [0, 3], :]), elem, xi)
+    assert np.array_equal(new.element_nodal_fields["VSV"], want[:, 0].reshape(new.nelem, 27))
+    assert np.array_equal(new.element_nodal_fields["VPH"], want[:, 1].reshape(new.nelem, 27))
+    # depth slice through a spherical mesh: the generator's cloud -> latlondepth_to_xyz -> interpolate_to_points
+    sphere_mesh = SalvusMesh.from_arrays(sph_old.copy(), data_old.copy(), names)
+    vals = plotter.depth_slice_values(sphere_mesh, 300.0, 12, "VSV", lat_extent=(-40.0, 40.0), lon_extent=(-60.0, 60.0))
+    cloud = utils.latlondepth_to_xyz(plotter._create_depthslice(300e3, 12, (-40.0, 40.0), (-60.0, 60.0)))
+    c2 = oracle.knn_bruteforce(oracle.centroids(sph_old), cloud, 25)
+    e2, x2, _, _ = oracle.locate(2, 3, sph_old, cloud, c2, oracle.V2())
+    assert np.array_equal(vals, oracle.interp(2, 3, np.ascontiguousarray(data_old[:, :1, :]), e2, x2).reshape(12, 12))
+    sec = plotter.cross_section_values(sphere_mesh, 10.0, 20.0, -30.0, 80.0, "VSV", npoints=9, nrads=5,
+                                       min_depth_in_km=50.0, max_depth_in_km=2000.0, relative=False)
+    assert sec.shape == (5, 9) and np.isfinite(sec).all() and (sec != 0).any()

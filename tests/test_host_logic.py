@@ -154,3 +154,34 @@ def test_meshgen_shapes_and_shell_radii():
     assert set(np.unique(el["layer"])) == {1.0, 2.0, 3.0}
     pts, conn = meshgen.hex8_mesh((2, 3, 4))
     assert pts.shape == (3 * 4 * 5, 3) and conn.shape == (24, 8) and conn.max() == len(pts) - 1
+
+
+def test_plotter_point_generators_and_geodesy():
+    """Point-cloud generators of the plotter (components/plotter.py:159-187, 361-380) and their geodesy helpers."""
+    from multi_mesh.components import plotter
+
+    pts = plotter._create_depthslice(150e3, 5, lat_extent=(-10.0, 10.0), lon_extent=(20.0, 40.0))
+    lat, lon = np.linspace(-10, 10, 5), np.linspace(20, 40, 5)
+    xx, yy = np.meshgrid(lat, lon)
+    assert pts.shape == (25, 3) and np.array_equal(pts[:, 0], xx.ravel()) and np.array_equal(pts[:, 1], yy.ravel())
+    assert (pts[:, 2] == 150e3).all()
+    gc = utils.greatcircle_points(10.0, 20.0, -30.0, 80.0, npts=50)
+    assert gc.shape == (50, 2) and np.allclose(gc[0], [10.0, 20.0])
+    v = np.stack([np.cos(np.deg2rad(gc[:, 0])) * np.cos(np.deg2rad(gc[:, 1])),
+                  np.cos(np.deg2rad(gc[:, 0])) * np.sin(np.deg2rad(gc[:, 1])), np.sin(np.deg2rad(gc[:, 0]))], axis=1)
+    step = np.arccos(np.clip((v[1:] * v[:-1]).sum(axis=1), -1, 1))
+    assert np.allclose(step, step[0], rtol=1e-9)          # equally spaced ...
+    normal = np.cross(v[0], v[-1])
+    assert np.allclose(v @ normal, 0.0, atol=1e-12)       # ... on one great circle
+    with pytest.raises(Exception):
+        utils.greatcircle_points(0, 0, 1, 1, npts=2)
+    assert utils.elliptic_to_geocentric_latitude(0.0) == 0.0 and utils.elliptic_to_geocentric_latitude(90.0) == 90.0
+    assert abs(utils.elliptic_to_geocentric_latitude(45.0) - 44.80757678) < 1e-6   # known WGS84 value
+    x, y, z = utils.sph2cart(np.array([0.3]), np.array([1.1]), np.array([6.0e6]))
+    c, l, r = utils.cart2sph(x, y, z)
+    assert np.allclose([c[0], l[0], r[0]], [0.3, 1.1, 6.0e6])
+    with pytest.raises(ValueError):
+        utils.sph2cart(np.array([-0.1]), np.array([0.0]), np.array([1.0]))
+    xyz, rads = plotter.cross_section_points(10.0, 20.0, -30.0, 80.0, npoints=7, nrads=4, min_depth_in_km=0.0,
+                                             max_depth_in_km=600.0)
+    assert xyz.shape == (28, 3) and np.allclose(np.linalg.norm(xyz, axis=1).reshape(4, 7), rads[:, None])
