@@ -56,7 +56,9 @@ WORKLOADS = {
     "S5": dict(src=216, tgt=0, order=4, k=20, npoints=100_000_000, form="centroid", device_gen=True),
     "S5small": dict(src=48, tgt=0, order=4, k=20, npoints=4_000_000, form="centroid", device_gen=True),
     # BASELINE configs[2]: cubed-sphere shell, order 4, layered (see bench_extra.py)
-    "S3": dict(kind="shell", n_lat=128, rad=(94, 6, 4), tgt_lat=112, tgt_rad=(80, 5, 3), order=4, k=20),
+    # (source 10.2 M elements = 82 GB of nodes + fields; target 1.1 M elements = 138 M GLL points, so that source, targets,
+    # results of both variants and the workspace of the largest layer fit the 180 GB of one GPU)
+    "S3": dict(kind="shell", n_lat=128, rad=(94, 6, 4), tgt_lat=64, tgt_rad=(40, 3, 2), order=4, k=20),
     "S3small": dict(kind="shell", n_lat=24, rad=(18, 2, 2), tgt_lat=20, tgt_rad=(15, 2, 1), order=4, k=20),
     # BASELINE configs[3]: exodus (HEX8 nodal) <-> order-4 GLL round trip with gradient fields
     "S4": dict(kind="exodus", hex=128, gll=40, order=4, k=20),

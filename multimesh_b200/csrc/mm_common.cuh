@@ -79,6 +79,10 @@ int mm_knn_sites(const mm_index_t *ix, int64_t N, const double *pts, int pts_str
 // first pass of the pipeline over SORTED queries (warp-cooperative block kernel when k = 4, else mm_knn)
 int mm_knn_first_pass(const mm_index_t *ix, int64_t N, const double *pts, int pts_stride, int k,
                       int32_t divisor, int32_t *idx, void *stream);
+// CTA-tile first pass over SORTED queries, prefix semantics (mm_index.cu: knn_tile_kernel); *applied = false when it
+// does not apply and the caller has to take one of the two above
+int mm_knn_tile_first_pass(const mm_index_t *ix, int64_t N, const double *sorted, const void *sort_scratch, int kout,
+                           int32_t divisor, bool sites, int32_t *idx, void *stream, bool *applied);
 // mm_knn with a stride (in doubles) between consecutive query points
 // n_dev (optional, device): the kernel processes points [0, min(N, *n_dev - n_off)) -- for work lists whose
 // length is only known on the device (no host synchronisation)

@@ -35,13 +35,9 @@ struct mm_index {
     int64_t nsites = 0;
     double4 *site_recs = nullptr;        // [nsites + 1] {x, y, z, first record of the site}
     int32_t *site_cell_start = nullptr;  // [ncells + 1] first site of each cell
-    // compact tables of the warp-cooperative first pass (knn_block_kernel):
-    //   recf     [M] (plain form) or [nsites] (site form): float4 {x, y, z relative to the corner of the
-    //            record's own cell, record / site position}
-    //   rec_id   [M] int32: point id of record t (recs[t].w), 4 bytes instead of a 32-byte record per look-up
+    // compact id tables (site form; K1's CTA-tile pass and K4 read 4-byte ids instead of 32-byte records):
+    //   rec_id   [M] int32: point id of record t (recs[t].w)
     //   site_first [nsites + 1] int32: first record of each site
-    float4 *recf = nullptr;
-    bool recf_sites = false;
     int32_t *rec_id = nullptr;
     int32_t *site_first = nullptr;
     cudaStream_t stream = nullptr;       // stream the buffers were allocated on (stream-ordered pool)
@@ -615,281 +611,359 @@ knn_body(const grid_t &g, int64_t N, const double *__restrict__ pts, int pstride
 }
 
 // ================================================================================================
-// First pass of the pipeline, k' <= 4 (site table of the GLL-point form, or centroid records):
-// WARP-COOPERATIVE block scan with an fp32 pre-filter.
-//
-// The queries arrive sorted by index cell (mm_index_sort_queries), so the 32 queries of a warp sit in
-// a short run of cells of one cell row and their 3 x 3 x 3 neighbourhoods overlap almost completely.
-// Per run ("segment" = lanes of one cell row whose cells span at most XSPAN cells):
-//   1. the warp stages the union of the neighbourhoods ONCE, from the index's compact fp32 table (16-byte
-//      records {x, y, z relative to the record's own cell, position}; half the bytes of the binary64 records
-//      and no conversions): the 9 (3 in 2-D) cell rows x the cells [x_first - 1, x_last + 1].  The staging
-//      buffer is COLUMN-major -- all records of the 9 cells that share an x index are contiguous -- so the
-//      3 x 3 x 3 neighbourhood of a query is ONE contiguous range of the buffer;
-//   2. every lane scans its range in fp32 and keeps the 5 smallest keys (d2 bits truncated to 24 bits |
-//      8-bit slot number: one 32-bit min/max network, no fp64, no global loads, no branches, one flat loop);
-//   3. if the 5th key exceeds the 4th by more than the fp32 error bound, the SET of the 4 nearest records
-//      is certain; those 4 are evaluated exactly in binary64 and ordered by the canonical (d2, id) order.
-//      With ties or near-ties around the 4th distance a second fp32 sweep ranks exactly, in binary64, every
-//      record whose fp32 distance does not exceed the 4th's by more than the error bound (a handful).
-//      Segments with more than CAP records and lone lanes take the exact per-thread block pass.  Either way the
-//      list then equals the exact top-4 of the 3^3 block, and the common termination test / outer rings follow.
-//      Results are bit-identical to knn_kernel.
-//
-// fp32 error bound (h = cell size, h32 = fl32(h)).  A staged coordinate is X = fma(c, h32, rel) with c the
-// cell offset inside the segment (|c| <= XSPAN + 1 = 13 in x, <= 1 in y / z) and rel the cell-relative coordinate
-// (|rel| <= h, fp32 rounding 2^-24 h): |X - exact| <= 2^-24 (14 h) + 13 * 2^-24 h + 2^-24 h = 1.7e-6 h in x and
-// <= 2.4e-7 h in y, z; the query's coordinates are formed the same way.  dx (|dx| <= 3 h): error <= 3.6e-6 h,
-// dy, dz (|.| <= 2 h): <= 6e-7 h.  |dx32^2 - dx^2| <= 2 * 3 h * 3.6e-6 h = 2.2e-5 h^2, dy, dz: 2.4e-6 h^2 each,
-// the three roundings of the sum <= 3 * 2^-24 * 17 h^2 = 3e-6 h^2: total <= 3e-5 h^2; KNN_EPS = 1e-4 h^2 is used.
-// Truncating the key to 24 bits under-states d2 by at most 2^-15 relative.  The binary64 reference distances
-// carry ~1e-16 relative error, far below the margin.
+// First pass of the pipeline in PREFIX mode (mm_pipeline.cu), CTA-TILE form: one CTA per tile of TX x TY x TZ index
+// cells.  The queries are sorted by cell (mm_index_sort_queries), so the queries of one cell row of the tile are
+// one contiguous range of the sorted records (the sort's own `starts` table gives the ranges): the tile's queries
+// are a handful of ranges, and all of them look at the same halo of (TX+2) x (TY+2) x (TZ+2) cells.
+//   1. the CTA stages the halo ONCE: every halo row is one contiguous run of site (or point) records, copied
+//      coalesced into shared memory twice -- the binary64 record {x, y, z, first copy / id} and a binary32 record
+//      {x, y, z relative to the tile centre, |.|^2} -- plus a table cs[row][column] of the first slot of every cell;
+//   2. thread per query: the 3 x 3 x 3 neighbourhood is 9 (3 in 2-D) short slot ranges.  Every candidate costs one
+//      LDS.128, four fp32 operations (d' = |s|^2 + (|q|^2 + bias) - 2 q.s), one LOP3 (key = d' bits with the
+//      slot number in the low 10 bits) and a branch-free min/max network that keeps the NK smallest keys;
+//   3. the NK candidates are evaluated exactly, in binary64 with the canonical operation order, from the staged
+//      records and sorted by exact distance e_0 <= ... <= e_{NK-1}.  Site j is emitted -- all its copies, ids
+//      ascending -- while   e_j < e_{j+1}  (strictly: equidistant sites interleave by id)
+//                           e_j < L        (L = lower bound of the exact distance of every candidate that is NOT among
+//                                           the NK: the truncated fp32 key of the NK-th, less bias and error bound)
+//                           e_j < B^2      (B = distance to the nearest face of the 3^3 block that has cells beyond it:
+//                                           every record outside the block is at least that far away)
+//      so what is written is a PREFIX of the canonical (d2, id) list (possibly shorter than the old kernels' when
+//      distances nearly tie, never different), padded with -1.  Points the prefix does not resolve are re-run with
+//      the complete search by the pipeline, as are queries outside the grid and tiles whose halo does not fit.
+// fp32 error bound: coordinates relative to the tile centre, |x| <= 9.5 h, |y|, |z| <= 9.5 h (2-D tiles) => terms up
+// to ~200 h^2, ten roundings of 2^-24 each: 1.2e-4 h^2; coordinate roundings 2 * 1.5 h * 2 * 2^-24 * 9.5 h per axis:
+// 1e-5 h^2.  KT_EPS = 3e-4 h^2 is used, and the same amount is added to every d' as a bias so that keys are positive.
 // ================================================================================================
-constexpr int KB_WARPS = 4;          // warps per CTA
-constexpr int KB_CAP = 256;          // staged records per segment (8-bit slot number in the key)
-constexpr int KB_XSPAN = 12;         // cells of one row a segment may span
-constexpr int KB_ROWLEN = 16;        // staged cell_start entries per row: (XSPAN + 2) cells + 1, rounded up
-constexpr int KB_MIN_MEMBERS = 3;    // smaller segments are cheaper on the per-thread path
+constexpr int KT_THREADS = 256;
+constexpr int KT_CAP = 1024;      // staged records per tile (10-bit slot number in the key)
+constexpr int KT_MAXROWS = 36;    // halo rows (TY + 2) * (TZ + 2)
+constexpr int KT_MAXCOLS = 20;    // halo columns + 1
+constexpr int KT_MAXQROWS = 16;   // tile rows TY * TZ
+constexpr double KT_EPS = 3e-4;
 
-struct kb_smem {
-    float4 rec[KB_CAP];
-    int32_t cs[9][KB_ROWLEN];        // cell_start of the staged cells, per row
-    int32_t dst[9][KB_ROWLEN];       // slot of the first record of cell (row, column)
-    int32_t colstart[KB_ROWLEN];     // first slot of each column (+ total)
+struct kt_dims {
+    int tx, ty, tz;     // tile size in cells
+    int ntx, nty, ntz;  // tiles per axis
+    int cap;            // staged records a (sub-)tile may use, <= KT_CAP (smaller in tests: forces the split paths)
 };
 
-template <bool SITES>
-__global__ void __launch_bounds__(KB_WARPS * 32, 8)
-knn_block_kernel(grid_t g, int64_t N, const double *__restrict__ pts, int pstride, int k,
-                 const fast_div divisor, const double4 *__restrict__ recs,
-                 const int32_t *__restrict__ cell_start, const float4 *__restrict__ recf,
-                 const int32_t *__restrict__ rec_id, const int32_t *__restrict__ site_first,
-                 int32_t *__restrict__ out_idx)
+struct kt_smem {
+    double4 sd[KT_CAP];
+    float4 sf[KT_CAP];
+    int32_t cs[KT_MAXROWS][KT_MAXCOLS];
+    int32_t rowslot[KT_MAXROWS + 1];  // first slot of each halo row (+ total)
+    int32_t rowg[KT_MAXROWS];         // global index of the row's first staged record
+    int32_t rowbase[KT_MAXROWS];      // linear id of the row's cell 0, or -1 outside the grid
+    int32_t qpre[KT_MAXQROWS + 1];    // queries before each tile row (+ total)
+    int32_t qlo[KT_MAXQROWS];         // first sorted query of each tile row
+};
+
+// one (sub-)tile of sx x sy x sz cells at cell (tx0, ty0, tz0); false: its halo does not fit the staging buffers
+// (nothing written).  Called by all threads of the CTA.
+template <bool SITES, int NK, int OUTK>
+__device__ __forceinline__ bool
+kt_run(kt_smem &sm, const grid_t &g, const int tx0, const int ty0, const int tz0, const int sx, const int sy,
+       const int sz, const double4 *__restrict__ qrecs, const int32_t *__restrict__ qstart,
+       const double4 *__restrict__ srecs, const int32_t *__restrict__ scs, const int32_t *__restrict__ rec_id,
+       const fast_div &divisor, int32_t *__restrict__ out_idx, const bool give_up, const int cap)
 {
-    __shared__ kb_smem sm_all[KB_WARPS];
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    kb_smem &sm = sm_all[warp];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const bool three_d = g.dim == 3;
-    const int nrow = three_d ? 9 : 3;
-    const double h = g.cell, margin = h * 1e-6;
+    const int nx = g.n[0], ny = g.n[1], nz = g.n[2];
+    const int qrows = sy * sz;
+    const int hy = sy + 2, hz = three_d ? sz + 2 : 1, hrows = hy * hz;
+    const int xa = max(tx0 - 1, 0), xb = min(tx0 + sx, nx - 1), ncol = xb - xa + 1;
+    struct tile_dims { int tx, ty, tz; } td{sx, sy, sz};
+    __syncthreads();  // the previous (sub-)tile is done with the staging buffers
+
+    // ---- 1. query ranges of the tile rows, record ranges of the halo rows -------------------------------------
+    if (tid < qrows) {
+        const int y = ty0 + tid % td.ty, z = tz0 + tid / td.ty;
+        int lo = 0, hi = 0;
+        if (y < ny && z < nz) {
+            const int base = nx * (y + ny * z);
+            lo = qstart[base + tx0];
+            hi = qstart[base + min(tx0 + td.tx, nx)];
+        }
+        sm.qlo[tid] = lo;
+        sm.qpre[tid] = hi - lo;
+    } else if (tid >= 32 && tid < 32 + hrows) {
+        const int r = tid - 32;
+        const int y = ty0 - 1 + r % hy, z = three_d ? tz0 - 1 + r / hy : 0;
+        int base = -1, glo = 0, len = 0;
+        if (y >= 0 && y < ny && z >= 0 && z < nz) {
+            base = nx * (y + ny * z);
+            glo = scs[base + xa];
+            len = scs[base + xb + 1] - glo + (SITES ? 1 : 0);  // + the next site: its `first` ends the last one
+        }
+        sm.rowbase[r] = base;
+        sm.rowg[r] = glo;
+        sm.rowslot[r] = len;
+    }
+    __syncthreads();
+    if (tid == 0) {
+        int run = 0;
+        for (int r = 0; r < qrows; ++r) {
+            const int c = sm.qpre[r];
+            sm.qpre[r] = run;
+            run += c;
+        }
+        sm.qpre[qrows] = run;
+    } else if (tid == 32) {
+        int run = 0;
+        for (int r = 0; r < hrows; ++r) {
+            const int c = sm.rowslot[r];
+            sm.rowslot[r] = run;
+            run += c;
+        }
+        sm.rowslot[hrows] = run;
+    }
+    __syncthreads();
+    const int T = sm.qpre[qrows];
+    if (T == 0) return true;
+    // sorted position of the tile's i-th query
+    auto query_of = [&](int i, int &row) -> int {
+        int r = 0;
+#pragma unroll
+        for (int step = KT_MAXQROWS / 2; step > 0; step >>= 1)
+            if (r + step < qrows && sm.qpre[r + step] <= i) r += step;
+        row = r;
+        return sm.qlo[r] + (i - sm.qpre[r]);
+    };
+    if (sm.rowslot[hrows] > cap) {  // crowded halo
+        if (!give_up) return false;    // the caller splits the tile
+        for (int i = tid; i < T; i += KT_THREADS) {  // the complete search takes these points (re-run)
+            int row;
+            int32_t *o = out_idx + (int64_t)query_of(i, row) * OUTK;
+#pragma unroll
+            for (int c = 0; c < OUTK; ++c) o[c] = -1;
+        }
+        return true;
+    }
+    // ---- 2. stage the halo ---------------------------------------------------------------------------------
+    const double h = g.cell;
+    const double cxo = g.origin[0] + (tx0 + 0.5 * td.tx) * h, cyo = g.origin[1] + (ty0 + 0.5 * td.ty) * h;
+    const double czo = three_d ? g.origin[2] + (tz0 + 0.5 * td.tz) * h : 0.0;
+    for (int i = tid; i < hrows * (ncol + 1); i += KT_THREADS) {
+        const int r = i / (ncol + 1), c = i - r * (ncol + 1);
+        int v = sm.rowslot[r];
+        const int base = sm.rowbase[r];
+        if (base >= 0) v += scs[base + xa + c] - sm.rowg[r];
+        sm.cs[r][c] = v;
+    }
+    for (int r = warp; r < hrows; r += KT_THREADS / 32) {
+        const int slot0 = sm.rowslot[r], len = sm.rowslot[r + 1] - slot0;
+        const double4 *src = srecs + sm.rowg[r];
+        for (int j = lane; j < len; j += 32) {
+            const double2 *q = reinterpret_cast<const double2 *>(src + j);
+            const double2 xy = __ldg(q), zw = __ldg(q + 1);
+            double4 d;
+            d.x = xy.x;
+            d.y = xy.y;
+            d.z = zw.x;
+            d.w = zw.y;
+            sm.sd[slot0 + j] = d;
+            float4 f;
+            f.x = (float)(xy.x - cxo);
+            f.y = (float)(xy.y - cyo);
+            f.z = three_d ? (float)(zw.x - czo) : 0.0f;
+            f.w = fmaf(f.z, f.z, fmaf(f.y, f.y, f.x * f.x));
+            sm.sf[slot0 + j] = f;
+        }
+    }
+    __syncthreads();
+
+    // ---- 3. the tile's queries -----------------------------------------------------------------------------
     const float h32 = (float)h;
-    const float eps = (float)(1e-4 * h * h);
-    using List = reg_list<4>;
-    List L;
-    L.init(nullptr, 4);
-
-    const int64_t warps_total = (int64_t)gridDim.x * KB_WARPS;
-    for (int64_t batch = (int64_t)blockIdx.x * KB_WARPS + warp; batch * 32 < N; batch += warps_total) {
-        const int64_t n = batch * 32 + lane;
-        const bool valid = n < N;
-        knn_query q;
-        bool pending = false;
-        if (valid) {
-            pending = knn_setup_query(g, pts[n * pstride + 0], pts[n * pstride + 1],
-                                      three_d ? pts[n * pstride + 2] : 0.0, margin, q);
-            if (!pending)
-                for (int t = 0; t < k; ++t) out_idx[n * k + t] = -1;
-        }
-        if (!pending) q.ci[0] = q.ci[1] = q.ci[2] = -1;
-        // the fp32 pass needs small relative coordinates: queries inside the grid's box only
-        bool eligible = pending && q.out2 == 0.0;
-        bool fast_done = false;
-        L.reset();
-
-        while (true) {
-            const unsigned cand = __ballot_sync(0xffffffffu, eligible);
-            if (!cand) break;
-            const int leader = __ffs(cand) - 1;
-            const int lcx = __shfl_sync(0xffffffffu, q.ci[0], leader);
-            const int lcy = __shfl_sync(0xffffffffu, q.ci[1], leader);
-            const int lcz = __shfl_sync(0xffffffffu, q.ci[2], leader);
-            // sorted queries: the leader has the smallest cell of its row among the lanes still eligible
-            const bool member = eligible && q.ci[1] == lcy && q.ci[2] == lcz && q.ci[0] >= lcx &&
-                                q.ci[0] < lcx + KB_XSPAN;
-            const unsigned mmask = __ballot_sync(0xffffffffu, member);
-            eligible = eligible && !member;  // every lane joins at most one segment
-            if (__popc(mmask) < KB_MIN_MEMBERS) continue;
-            const int xhi = __reduce_max_sync(0xffffffffu, member ? q.ci[0] : lcx);
-            const int xa = max(lcx - 1, 0), xb = min(xhi + 1, g.n[0] - 1);
-            const int ncol = xb - xa + 1;  // staged cells per row, <= XSPAN + 2
-            // 1a. cell_start rows: entries [xa, xb + 1] of each row inside the grid, zeros otherwise
+    const float eps = (float)(KT_EPS * h * h);
+    // low corner of the tile relative to the centre: the faces of a query's 3^3 block in the fp32 frame
+    const float fx0 = (float)(-0.5 * td.tx * h), fy0 = (float)(-0.5 * td.ty * h), fz0 = (float)(-0.5 * td.tz * h);
+    const float fmargin = 1e-4f * h32;
+    for (int i = tid; i < T; i += KT_THREADS) {
+        int row;
+        const int64_t n = query_of(i, row);
+        const double2 *qp = reinterpret_cast<const double2 *>(qrecs + n);
+        const double2 pxy = __ldg(qp);
+        const double px = pxy.x, py = pxy.y, pz = three_d ? __ldg(qp + 1).x : 0.0;
+        const int ry = row % td.ty, rz = row / td.ty;
+        const int cy = ty0 + ry, cz = tz0 + rz;
+        // the query's cell along x (y and z are those of the tile row: the sort used the same cell_coord)
+        const int cx = cell_coord(g, px, 0);
+        // relative position inside the own cell, in cells: a query that the sort CLAMPED into the grid is not
+        // within its cell -- its fp32 coordinates would not obey the error bound
+        const double ux = (px - g.origin[0]) * g.inv_cell - cx, uy = (py - g.origin[1]) * g.inv_cell - cy;
+        const double uz = three_d ? (pz - g.origin[2]) * g.inv_cell - cz : 0.5;
+        int32_t res[OUTK];
 #pragma unroll
-            for (int i = 0; i < (9 * KB_ROWLEN + 31) / 32; ++i) {
-                const int t = lane + 32 * i;
-                const int r = t / KB_ROWLEN, c = t % KB_ROWLEN;
-                if (r < nrow) {
-                    const int dy = (int)((0x22161u >> (2 * r)) & 3u) - 1;
-                    const int dz = (int)((0x28215u >> (2 * r)) & 3u) - 1;
-                    const int yy = lcy + dy, zz = lcz + dz;
-                    int32_t v = 0;
-                    if (yy >= 0 && yy < g.n[1] && zz >= 0 && zz < g.n[2])
-                        v = __ldg(&cell_start[g.n[0] * (yy + g.n[1] * zz) + xa + min(c, ncol)]);
-                    sm.cs[r][c] = v;
-                }
-            }
-            __syncwarp();
-            // 1b. column-major slots: lane c owns column c
-            {
-                int size = 0;
-                if (lane < ncol)
-                    for (int r = 0; r < nrow; ++r) size += sm.cs[r][lane + 1] - sm.cs[r][lane];
-                int off = size;
+        for (int c = 0; c < OUTK; ++c) res[c] = -1;
+        const bool inside = ux >= -0.01 && ux <= 1.01 && uy >= -0.01 && uy <= 1.01 && uz >= -0.01 && uz <= 1.01;
+        if (inside) {
+            const float qx = (float)(px - cxo), qy = (float)(py - cyo), qz = three_d ? (float)(pz - czo) : 0.0f;
+            const float q2 = fmaf(qz, qz, fmaf(qy, qy, qx * qx)) + eps;
+            const float mx = -2.0f * qx, my = -2.0f * qy, mz = -2.0f * qz;
+            unsigned a[NK];
 #pragma unroll
-                for (int o = 1; o < 16; o <<= 1) {
-                    const int t = __shfl_up_sync(0xffffffffu, off, o);
-                    if (lane >= o) off += t;
-                }
-                if (lane < KB_ROWLEN) sm.colstart[lane] = off - size;  // exclusive; colstart[ncol] = total
-                if (lane < ncol) {
-                    int at = off - size;
-                    for (int r = 0; r < nrow; ++r) {
-                        sm.dst[r][lane] = at;
-                        at += sm.cs[r][lane + 1] - sm.cs[r][lane];
-                    }
-                }
-            }
-            __syncwarp();
-            const int total = sm.colstart[ncol];
-            if (total > KB_CAP) continue;  // crowded cells: per-thread path
-            // 1c. records: one (row, column) cell per task; coordinates move from the cell's frame to the segment's
-            //     (corner of cell (xa, lcy, lcz)) with one fma each
+            for (int u = 0; u < NK; ++u) a[u] = 0xffffffffu;
+            const int ca = max(cx - 1, 0) - xa, cb = min(cx + 1, nx - 1) + 1 - xa;
+            const int ly = ry + 1, lz = three_d ? rz + 1 : 0;
+            for (int dz = three_d ? -1 : 0; dz <= (three_d ? 1 : 0); ++dz) {
 #pragma unroll
-            for (int i = 0; i < (9 * KB_ROWLEN + 31) / 32; ++i) {
-                const int t = lane + 32 * i;
-                const int r = t / KB_ROWLEN, c = t % KB_ROWLEN;
-                if (r < nrow && c < ncol) {
-                    const int32_t lo = sm.cs[r][c], cnt = sm.cs[r][c + 1] - lo, at = sm.dst[r][c];
-                    const float fx = (float)c;
-                    const float fy = (float)((int)((0x22161u >> (2 * r)) & 3u) - 1);
-                    const float fz = (float)((int)((0x28215u >> (2 * r)) & 3u) - 1);
-                    for (int j = 0; j < cnt; ++j) {
-                        float4 f = __ldg(&recf[lo + j]);
-                        f.x = fmaf(fx, h32, f.x);
-                        f.y = fmaf(fy, h32, f.y);
-                        f.z = fmaf(fz, h32, f.z);
-                        sm.rec[at + j] = f;
-                    }
-                }
-            }
-            __syncwarp();
-            // 2. fp32 scan of this lane's 3 columns (one contiguous range): five smallest keys
-            if (member) {
-                const double ox = g.origin[0] + q.ci[0] * h, oy = g.origin[1] + lcy * h, oz = g.origin[2] + lcz * h;
-                const float qx = fmaf((float)(q.ci[0] - xa), h32, (float)(q.px - ox));
-                const float qy = (float)(q.py - oy);
-                const float qz = three_d ? (float)(q.pz - oz) : 0.0f;
-                unsigned a0 = 0xffffffffu, a1 = a0, a2 = a0, a3 = a0, a4 = a0;
-                const int lo = sm.colstart[max(q.ci[0] - 1, 0) - xa];
-                const int hi = sm.colstart[min(q.ci[0] + 1, g.n[0] - 1) + 1 - xa];
-                for (int j = lo; j < hi; ++j) {
-                    const float4 s = sm.rec[j];
-                    const float dx = qx - s.x, dy = qy - s.y, dz = qz - s.z;
-                    const float d = fmaf(dz, dz, fmaf(dy, dy, dx * dx));
-                    const unsigned key = (__float_as_uint(d) & 0xffffff00u) | (unsigned)j;
-                    // sorted insertion, all five updates independent of one another
-                    const unsigned n4 = max(a3, min(a4, key)), n3 = max(a2, min(a3, key));
-                    const unsigned n2 = max(a1, min(a2, key)), n1 = max(a0, min(a1, key));
-                    a0 = min(a0, key);
-                    a1 = n1;
-                    a2 = n2;
-                    a3 = n3;
-                    a4 = n4;
-                }
-                // 3. is the set of the 4 nearest certain?  (fewer than 5 records in the block: it is all of them)
-                bool certain = true;
-                if (a4 != 0xffffffffu) {
-                    const float d4 = __uint_as_float(a3 & 0xffffff00u), d5 = __uint_as_float(a4 & 0xffffff00u);
-                    certain = d5 - eps > d4 * (1.0f + 6.2e-5f) + eps;  // 2^-15 truncation + fp32 error both ways
-                }
-                if (certain) {
-                    const unsigned keys[4] = {a0, a1, a2, a3};
-#pragma unroll
-                    for (int t = 0; t < 4; ++t) {
-                        if (keys[t] == 0xffffffffu) break;
-                        const int32_t pos = __float_as_int(sm.rec[keys[t] & 0xffu].w);
-                        const double2 *src = reinterpret_cast<const double2 *>(&recs[pos]);
-                        rank_record<SITES>(L, __ldg(src), __ldg(src + 1), pos, q.px, q.py, q.pz, three_d);
-                    }
-                } else {
-                    // ties / near-ties around the 4th distance (structured meshes produce exact ones): every record
-                    // that can still belong to the 4 nearest has an fp32 distance <= cut; rank exactly those
-                    // (typically 5-8 of ~34) in binary64 -- the canonical (d2, id) order settles the ties
-                    const float cut = __uint_as_float(a3 & 0xffffff00u) * (1.0f + 6.2e-5f) + 2.0f * eps;
+                for (int dy = -1; dy <= 1; ++dy) {
+                    const int hr = (ly + dy) + hy * (lz + dz);
+                    const int lo = sm.cs[hr][ca], hi = sm.cs[hr][cb];
                     for (int j = lo; j < hi; ++j) {
-                        const float4 s = sm.rec[j];
-                        const float dx = qx - s.x, dy = qy - s.y, dz = qz - s.z;
-                        const float d = fmaf(dz, dz, fmaf(dy, dy, dx * dx));
-                        if (d <= cut) {
-                            const int32_t pos = __float_as_int(s.w);
-                            const double2 *src = reinterpret_cast<const double2 *>(&recs[pos]);
-                            rank_record<SITES>(L, __ldg(src), __ldg(src + 1), pos, q.px, q.py, q.pz, three_d);
-                        }
+                        const float4 s = sm.sf[j];
+                        const float d = fmaf(mx, s.x, fmaf(my, s.y, fmaf(mz, s.z, s.w + q2)));
+                        const unsigned key = (__float_as_uint(d) & 0xfffffc00u) | (unsigned)j;
+#pragma unroll
+                        for (int u = NK - 1; u > 0; --u) a[u] = max(a[u - 1], min(a[u], key));
+                        a[0] = min(a[0], key);
                     }
                 }
-                fast_done = true;
             }
-            __syncwarp();  // the staging buffer is re-used by the next segment
-        }
-        if (pending) {
-            if (!fast_done) knn_block_pass<List, SITES>(g, q, L, recs, cell_start);
-            knn_ring_search<List, SITES>(g, q, L, recs, cell_start, 1);
-            int32_t *o = out_idx + n * k;
-            if constexpr (SITES) {
-                // expand: copies of site j continue the prefix only while d2[j] < d2[j+1] strictly
-                int c = 0;
+            // exact distances of the NK candidates, canonical operation order
+            double e[NK + 1];
+            int sl[NK];
 #pragma unroll
-                for (int j = 0; j < 3; ++j) {
-                    const bool have = L.d2[j] < INFINITY;
-                    const bool strict = L.d2[j] < L.d2[j + 1];  // slot j+1 is +inf without such a site
-                    if (!(have && strict)) break;
-                    const int32_t r0 = __ldg(&site_first[L.id[j]]), r1 = __ldg(&site_first[L.id[j] + 1]);
-                    for (int32_t t = r0; t < r1 && c < k; ++t) o[c++] = divisor(__ldg(&rec_id[t]));
+            for (int u = 0; u < NK; ++u) {
+                sl[u] = (int)(a[u] & 0x3ffu);
+                e[u] = INFINITY;
+                if (a[u] != 0xffffffffu) {
+                    const double4 r = sm.sd[sl[u]];
+                    const double dx = px - r.x, dy = py - r.y;
+                    double s2 = dx * dx + dy * dy;
+                    if (three_d) {
+                        const double dz = pz - r.z;
+                        s2 = s2 + dz * dz;
+                    }
+                    e[u] = s2;
                 }
-                for (; c < k; ++c) o[c] = -1;
+            }
+            e[NK] = INFINITY;
+            // every record outside the NK has an exact distance of at least L
+            double L = INFINITY;
+            if (a[NK - 1] != 0xffffffffu)
+                L = (double)(__uint_as_float(a[NK - 1] & 0xfffffc00u) - 2.01f * eps);
+            // distance to the faces of the 3^3 block that have cells beyond them (fp32 frame, conservative margin)
+            float B = INFINITY;
+            {
+                const float xl = fx0 + (float)(cx - 1 - tx0) * h32, yl = fy0 + (float)(ry - 1) * h32;
+                if (cx - 1 > 0) B = fminf(B, qx - xl);
+                if (cx + 1 < nx - 1) B = fminf(B, xl + 3.0f * h32 - qx);
+                if (cy - 1 > 0) B = fminf(B, qy - yl);
+                if (cy + 1 < ny - 1) B = fminf(B, yl + 3.0f * h32 - qy);
+                if (three_d) {
+                    const float zl = fz0 + (float)(rz - 1) * h32;
+                    if (cz - 1 > 0) B = fminf(B, qz - zl);
+                    if (cz + 1 < nz - 1) B = fminf(B, zl + 3.0f * h32 - qz);
+                }
+                B = fmaxf(B - fmargin, 0.0f);
+            }
+            const double lim = fmin(L, (double)B * (double)B);
+            // sort the NK by exact distance (ties: the emission stops there anyway)
+#define MM_KT_CE(I, J)                                   \
+    {                                                    \
+        const bool sw = e[J] < e[I];                     \
+        const double e_lo = sw ? e[J] : e[I];            \
+        const double e_hi = sw ? e[I] : e[J];            \
+        const int s_lo = sw ? sl[J] : sl[I];             \
+        const int s_hi = sw ? sl[I] : sl[J];             \
+        e[I] = e_lo;                                     \
+        e[J] = e_hi;                                     \
+        sl[I] = s_lo;                                    \
+        sl[J] = s_hi;                                    \
+    }
+            if constexpr (NK == 4) {
+                MM_KT_CE(0, 1) MM_KT_CE(2, 3) MM_KT_CE(0, 2) MM_KT_CE(1, 3) MM_KT_CE(1, 2)
             } else {
-                L.write(o, nullptr, divisor);
+                static_assert(NK == 5, "network sizes 4 and 5");
+                MM_KT_CE(0, 1) MM_KT_CE(3, 4) MM_KT_CE(2, 4) MM_KT_CE(2, 3) MM_KT_CE(1, 4)
+                MM_KT_CE(0, 3) MM_KT_CE(0, 2) MM_KT_CE(1, 3) MM_KT_CE(1, 2)
+            }
+#undef MM_KT_CE
+            bool go = true;
+            if constexpr (SITES) {
+                int first[NK - 1], upto[NK - 1];  // first record of site j, entries emitted up to and including site j
+                int run = 0;
+#pragma unroll
+                for (int u = 0; u < NK - 1; ++u) {
+                    go = go && e[u] < e[u + 1] && e[u] < lim;
+                    first[u] = 0;
+                    if (go) {
+                        const int32_t *w0 = reinterpret_cast<const int32_t *>(&sm.sd[sl[u]].w);
+                        const int32_t *w1 = reinterpret_cast<const int32_t *>(&sm.sd[sl[u] + 1].w);
+                        first[u] = *w0;
+                        run += *w1 - *w0;
+                    }
+                    upto[u] = run;
+                }
+#pragma unroll
+                for (int c = 0; c < OUTK; ++c) {
+                    int tpos = -1;
+#pragma unroll
+                    for (int u = NK - 2; u >= 0; --u)
+                        if (c < upto[u]) tpos = first[u] + c - (u > 0 ? upto[u - 1] : 0);
+                    // (descending u: the smallest u with c < upto[u] wins)
+                    if (tpos >= 0) res[c] = divisor(__ldg(&rec_id[tpos]));
+                }
+            } else {
+#pragma unroll
+                for (int u = 0; u < NK - 1 && u < OUTK; ++u) {
+                    go = go && e[u] < e[u + 1] && e[u] < lim;
+                    if (go) res[u] = divisor((int32_t)__double_as_longlong(sm.sd[sl[u]].w));
+                }
             }
         }
+        int4 *o = reinterpret_cast<int4 *>(out_idx + n * OUTK);
+#pragma unroll
+        for (int c = 0; c < OUTK / 4; ++c) o[c] = make_int4(res[4 * c], res[4 * c + 1], res[4 * c + 2], res[4 * c + 3]);
+    }
+    return true;
+}
+
+template <bool SITES, int NK, int OUTK>
+__global__ void __launch_bounds__(KT_THREADS, 4)
+knn_tile_kernel(const grid_t g, const kt_dims td, const double4 *__restrict__ qrecs,
+                const int32_t *__restrict__ qstart, const double4 *__restrict__ srecs,
+                const int32_t *__restrict__ scs, const int32_t *__restrict__ rec_id, const fast_div divisor,
+                int32_t *__restrict__ out_idx)
+{
+    extern __shared__ __align__(32) unsigned char kt_raw[];
+    kt_smem &sm = *reinterpret_cast<kt_smem *>(kt_raw);
+    int t = blockIdx.x;
+    const int tix = t % td.ntx;
+    t /= td.ntx;
+    const int tiy = t % td.nty, tiz = t / td.nty;
+    const int tx0 = tix * td.tx, ty0 = tiy * td.ty, tz0 = tiz * td.tz;
+    // pass 0: the whole tile.  A crowded tile (locally dense source) is split into eight (four in 2-D) sub-tiles,
+    // each with its own, smaller halo (passes 1 .. nsub); one call site, so the body is instantiated once
+    const int sx = max(td.tx / 2, 1), sy = max(td.ty / 2, 1), sz = max(td.tz / 2, 1);
+    const int px = (td.tx + sx - 1) / sx, py = (td.ty + sy - 1) / sy, pz = (td.tz + sz - 1) / sz;
+    for (int pass = 0; pass <= px * py * pz; ++pass) {
+        int x0 = tx0, y0 = ty0, z0 = tz0, ex = td.tx, ey = td.ty, ez = td.tz;
+        if (pass > 0) {
+            const int q = pass - 1;
+            x0 = tx0 + (q % px) * sx;
+            y0 = ty0 + ((q / px) % py) * sy;
+            z0 = tz0 + (q / (px * py)) * sz;
+            ex = min(sx, tx0 + td.tx - x0);
+            ey = min(sy, ty0 + td.ty - y0);
+            ez = min(sz, tz0 + td.tz - z0);
+            if (x0 >= g.n[0] || y0 >= g.n[1] || z0 >= g.n[2]) continue;
+        }
+        const bool ok = kt_run<SITES, NK, OUTK>(sm, g, x0, y0, z0, ex, ey, ez, qrecs, qstart, srecs, scs, rec_id,
+                                                divisor, out_idx, pass > 0, td.cap);
+        if (pass == 0 && ok) return;
     }
 }
 
-// ---- compact tables of the block kernel ----------------------------------------------------------
-// plain form: recf[t] = {cell-relative coordinates of record t, t}, rec_id[t] = point id
+// ---- compact id tables: rec_id[t] = point id of record t; site_first[s] = first record of site s ------------
 __global__ void __launch_bounds__(256)
-recf_plain_kernel(grid_t g, int64_t M, const double4 *__restrict__ recs, float4 *__restrict__ recf,
-                  int32_t *__restrict__ rec_id)
+site_first_kernel(int64_t nsites, const double4 *__restrict__ site_recs, int32_t *__restrict__ site_first)
 {
-    for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < M; t += (int64_t)gridDim.x * blockDim.x) {
-        const double4 r = recs[t];
-        const double p[3] = {r.x, r.y, r.z};
-        float4 f;
-        f.x = (float)(r.x - (g.origin[0] + cell_coord(g, p[0], 0) * g.cell));
-        f.y = (float)(r.y - (g.origin[1] + cell_coord(g, p[1], 1) * g.cell));
-        f.z = g.dim == 3 ? (float)(r.z - (g.origin[2] + cell_coord(g, p[2], 2) * g.cell)) : 0.0f;
-        f.w = __int_as_float((int32_t)t);
-        recf[t] = f;
-        rec_id[t] = (int32_t)__double_as_longlong(r.w);
-    }
-}
-
-// site form: recf[s] = {cell-relative coordinates of site s, s}, site_first[s] = first record of site s
-__global__ void __launch_bounds__(256)
-recf_sites_kernel(grid_t g, int64_t nsites, const double4 *__restrict__ site_recs, float4 *__restrict__ recf,
-                  int32_t *__restrict__ site_first)
-{
-    for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t <= nsites;
-         t += (int64_t)gridDim.x * blockDim.x) {
-        const double4 r = site_recs[t];
-        site_first[t] = (int32_t)__double_as_longlong(r.w);
-        if (t == nsites) break;  // sentinel: only its first-record entry is meaningful
-        const double p[3] = {r.x, r.y, r.z};
-        float4 f;
-        f.x = (float)(r.x - (g.origin[0] + cell_coord(g, p[0], 0) * g.cell));
-        f.y = (float)(r.y - (g.origin[1] + cell_coord(g, p[1], 1) * g.cell));
-        f.z = g.dim == 3 ? (float)(r.z - (g.origin[2] + cell_coord(g, p[2], 2) * g.cell)) : 0.0f;
-        f.w = __int_as_float((int32_t)t);
-        recf[t] = f;
-    }
+    for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t <= nsites; t += (int64_t)gridDim.x * blockDim.x)
+        site_first[t] = (int32_t)__double_as_longlong(site_recs[t].w);
 }
 
 __global__ void __launch_bounds__(256)
@@ -1073,7 +1147,6 @@ extern "C" int mm_index_destroy(mm_index_t *ix)
     if (ix->cell_start) cudaFreeAsync(ix->cell_start, ix->stream);
     if (ix->site_recs) cudaFreeAsync(ix->site_recs, ix->stream);
     if (ix->site_cell_start) cudaFreeAsync(ix->site_cell_start, ix->stream);
-    if (ix->recf) cudaFreeAsync(ix->recf, ix->stream);
     if (ix->rec_id) cudaFreeAsync(ix->rec_id, ix->stream);
     if (ix->site_first) cudaFreeAsync(ix->site_first, ix->stream);
     delete ix;
@@ -1167,19 +1240,18 @@ extern "C" int mm_index_create(mm_index_t **out, int dim, int64_t M, const doubl
                 vol *= ext[c];
             }
         }
-        // 2. cell size.  Target: ~1.25 DISTINCT coordinates per cell by volume (measured optimum of the
-        //    ring search on lattice-like and random data, tools/exp_cell.py) -- the GLL-point form
-        //    stores shared nodes 2-8 times and duplicates never separate, so the number of distinct
-        //    coordinates is first estimated as the number of non-empty cells of a probe grid twice as
-        //    fine as "2 points per cell".  Then refine while cells stay crowded and halving the cell
-        //    still separates points (clustered data).
+        // 2. cell size.  Target: ~1.25 DISTINCT coordinates per cell of the OCCUPIED volume (measured optimum of the
+        //    searches on lattice-like and random data, tools/exp_cell.py).  Neither quantity is known up front:
+        //    * the occupied volume V is far below the bounding box for the meshes this path sees (a spherical shell
+        //      fills half of its box, a 25 km crust layer a fraction of a per cent): V = (non-empty cells of a grid
+        //      twice as coarse as the candidate) x (their volume), iterated to a fixed point of h = (1.25 V / D)^(1/d);
+        //    * the number of distinct coordinates D is M unless the points repeat (the GLL-point form stores shared
+        //      nodes 2-8 times, and duplicates never separate): when a grid twice as fine as the fixed point finds
+        //      hardly any new non-empty cells although most cells hold several points, every non-empty cell of it IS
+        //      one distinct coordinate, D = that count, and the fixed point is taken again.
+        //    Multi-scale (clustered) data is then refined while cells stay crowded and halving still separates points.
         double h = 1.0;
         double emax = std::max(ext[0], std::max(ext[1], ext[2]));
-        if (nd > 0) {
-            h = std::pow(vol * 2.0 / (double)M, 1.0 / nd);
-            if (!(h > 0.0) || !std::isfinite(h)) h = emax;
-            h = std::max(h, emax / 4096.0);
-        }
         MM_CUDA(pool_alloc((void **)&d_nonempty, sizeof(unsigned long long), stream));
         auto evaluate = [&](double hh, int64_t *nonempty) -> int {
             choose_dims(ext, dim, hh, g.n);
@@ -1205,36 +1277,60 @@ extern "C" int mm_index_create(mm_index_t **out, int dim, int64_t M, const doubl
             choose_dims(ext, dim, hh, nn);
             return (int64_t)nn[0] * nn[1] * nn[2];
         };
-        while (cells_at(h) > MAX_CELLS) h *= 1.25;
+        auto feasible = [&](double hh) {  // inside the per-axis and total cell caps
+            if (!(hh > 0.0) || !std::isfinite(hh)) hh = emax;
+            hh = std::min(std::max(hh, emax / 4096.0), emax);
+            while (cells_at(hh) > MAX_CELLS) hh *= 1.1;
+            return hh;
+        };
         int64_t nonempty = 0;
         int rc = MM_OK;
         double distinct = (double)M;  // estimate of the number of distinct coordinates
+        const double target = 1.25;
         if (nd > 0) {
-            double hp = std::max(0.5 * h, emax / 4096.0);
-            while (cells_at(hp) > MAX_CELLS) hp *= 1.1;
-            int64_t ne = 0;
-            rc = evaluate(hp, &ne);
+            h = feasible(std::pow(vol * target / distinct, 1.0 / nd));
+            auto fixed_point = [&]() -> int {
+                for (int it = 0; it < 6; ++it) {
+                    const double hc = feasible(2.0 * h);
+                    int64_t ne = 0;
+                    int r = evaluate(hc, &ne);
+                    if (r != MM_OK) return r;
+                    const double v_occ = (double)std::max<int64_t>(ne, 1) * std::pow(hc, nd);
+                    const double hn = feasible(std::pow(target * v_occ / distinct, 1.0 / nd));
+                    const bool converged = std::fabs(hn / h - 1.0) < 0.08;
+                    h = hn;
+                    if (converged) break;
+                }
+                return MM_OK;
+            };
+            rc = fixed_point();
             if (rc != MM_OK) return rc;
-            distinct = (double)std::max<int64_t>(ne, 1);
-            double ht = std::pow(vol * 1.25 / distinct, 1.0 / nd);
-            if (ht > 0.0 && std::isfinite(ht)) h = std::min(std::max(ht, emax / 4096.0), emax);
-            while (cells_at(h) > MAX_CELLS) h *= 1.25;
+            rc = evaluate(h, &nonempty);
+            if (rc != MM_OK) return rc;
+            const double h2 = feasible(0.5 * h);  // as fine as the cell caps allow
+            if (h2 <= 0.8 * h && cells_at(h2) > cells_at(h)) {
+                int64_t ne2 = 0;
+                rc = evaluate(h2, &ne2);
+                if (rc != MM_OK) return rc;
+                if ((double)ne2 < 0.6 * distinct && (double)ne2 <= 1.15 * (double)nonempty) {
+                    distinct = (double)std::max<int64_t>(ne2, 1);
+                    rc = fixed_point();
+                    if (rc != MM_OK) return rc;
+                }
+            }
         }
         rc = evaluate(h, &nonempty);
         if (rc != MM_OK) return rc;
         for (int it = 0; it < 8 && nd > 0; ++it) {
-            if ((double)M / (double)std::max<int64_t>(nonempty, 1) <= 4.0) break;
+            if (distinct / (double)std::max<int64_t>(nonempty, 1) <= 4.0) break;
             double h2 = 0.5 * h;
             if (h2 < emax / 4096.0) break;  // keep every axis below the per-axis cell cap
             if (cells_at(h2) > MAX_CELLS || cells_at(h2) == cells_at(h)) break;
             int64_t ne2 = 0;
             rc = evaluate(h2, &ne2);
             if (rc != MM_OK) return rc;
-            // accept only if the finer grid finds coordinates the probe did not know about (clusters);
-            // merely separating lattice neighbours that the target density keeps together is a loss
-            const bool finds_more = (double)ne2 > 1.25 * distinct;
-            distinct = std::max(distinct, (double)ne2);
-            if (finds_more && (double)ne2 >= 1.5 * (double)nonempty) {
+            // accept only if the finer grid separates points (clusters); duplicates never separate
+            if ((double)ne2 >= 1.5 * (double)nonempty) {
                 h = h2;
                 nonempty = ne2;
             } else {
@@ -1283,15 +1379,6 @@ extern "C" int mm_index_create(mm_index_t **out, int dim, int64_t M, const doubl
         scatter_kernel<<<launch_blocks(M, 256, 8), 256, 0, stream>>>(g, M, points, ix->cell_start,
                                                                      counts, ix->recs);
         MM_CUDA(cudaGetLastError());
-        // compact fp32 table of the warp-cooperative first pass -- unless the data is full of duplicates (the
-        // GLL-point form), where the site table of mm_index_prepare_sites takes its place
-        if (ix->distinct_est >= 0.7 * (double)M) {
-            MM_CUDA(pool_alloc((void **)&ix->recf, sizeof(float4) * (size_t)M, stream));
-            MM_CUDA(pool_alloc((void **)&ix->rec_id, sizeof(int32_t) * (size_t)M, stream));
-            ix->bytes += (sizeof(float4) + sizeof(int32_t)) * (size_t)M;
-            recf_plain_kernel<<<launch_blocks(M, 256, 8), 256, 0, stream>>>(g, M, ix->recs, ix->recf, ix->rec_id);
-            MM_CUDA(cudaGetLastError());
-        }
     }
     MM_CUDA(cudaStreamSynchronize(stream));
     guard.p = nullptr;
@@ -1403,23 +1490,15 @@ extern "C" int mm_index_prepare_sites(mm_index_t *ix, void *stream_)
     cudaFreeAsync(per_cell, stream);
     cudaFreeAsync(tile_sums, stream);
     ix->bytes += sizeof(int32_t) * (size_t)(ix->ncells + 1) + sizeof(double4) * (size_t)(ns + 1);
-    // compact tables of the block kernel; the in-cell sort above moved the records, so a plain-form table is stale
-    if (ix->recf) {
-        cudaFreeAsync(ix->recf, stream);
-        ix->recf = nullptr;
-        ix->bytes -= sizeof(float4) * (size_t)ix->M;
-    }
+    // compact id tables (K1's CTA-tile pass, K4)
     if (!ix->rec_id) {
         MM_CUDA(pool_alloc((void **)&ix->rec_id, sizeof(int32_t) * (size_t)ix->M, stream));
         ix->bytes += sizeof(int32_t) * (size_t)ix->M;
     }
-    MM_CUDA(pool_alloc((void **)&ix->recf, sizeof(float4) * (size_t)std::max<int64_t>(ns, 1), stream));
     MM_CUDA(pool_alloc((void **)&ix->site_first, sizeof(int32_t) * (size_t)(ns + 1), stream));
-    ix->bytes += sizeof(float4) * (size_t)ns + sizeof(int32_t) * (size_t)(ns + 1);
-    ix->recf_sites = true;
+    ix->bytes += sizeof(int32_t) * (size_t)(ns + 1);
     rec_id_kernel<<<launch_blocks(ix->M, 256, 8), 256, 0, stream>>>(ix->M, ix->recs, ix->rec_id);
-    recf_sites_kernel<<<launch_blocks(ns + 1, 256, 8), 256, 0, stream>>>(grid_of(ix), ns, ix->site_recs, ix->recf,
-                                                                         ix->site_first);
+    site_first_kernel<<<launch_blocks(ns + 1, 256, 8), 256, 0, stream>>>(ns, ix->site_recs, ix->site_first);
     MM_CUDA(cudaGetLastError());
     MM_CUDA(cudaStreamSynchronize(stream));  // the table is complete when this returns: any stream may use it
     return MM_OK;
@@ -1438,26 +1517,12 @@ bool mm_index_sites_view_get(const mm_index_t *ix, mm_index_sites_view *out)
     return true;
 }
 
-// first pass over SORTED queries with the warp-cooperative block kernel, when it applies
-static bool block_kernel_applies(const mm_index_t *ix)
-{
-    if (const char *e = getenv("MM_KNN_BLOCK"))
-        if (e[0] == '0') return false;
-    return ix->cell > 1e-15 && ix->cell < 1e15;  // relative coordinates and the error margin must be normal floats
-}
-
+// first pass when the CTA-tile kernel does not apply (complete semantics, sparse query sets): thread per query
 int mm_knn_first_pass(const mm_index_t *ix, int64_t N, const double *pts, int pts_stride, int k,
                       int32_t divisor, int32_t *idx, void *stream)
 {
     MM_REQUIRE(ix, MM_ERR_INVALID, "mm_knn_first_pass: null index");
     if (N == 0) return MM_OK;
-    if (k == 4 && ix->recf && !ix->recf_sites && block_kernel_applies(ix)) {
-        knn_block_kernel<false><<<launch_blocks(N, KB_WARPS * 32, 8), KB_WARPS * 32, 0, (cudaStream_t)stream>>>(
-            grid_of(ix), N, pts, pts_stride, k, fast_div(divisor), ix->recs, ix->cell_start, ix->recf, ix->rec_id,
-            nullptr, idx);
-        MM_CUDA(cudaGetLastError());
-        return MM_OK;
-    }
     return mm_knn_strided(ix, N, pts, pts_stride, k, divisor, idx, nullptr, stream);
 }
 
@@ -1466,16 +1531,72 @@ int mm_knn_sites(const mm_index_t *ix, int64_t N, const double *pts, int pts_str
 {
     MM_REQUIRE(ix && ix->site_recs, MM_ERR_INVALID, "mm_knn_sites: site table not built");
     if (N == 0) return MM_OK;
-    if (ix->recf_sites && block_kernel_applies(ix)) {
-        knn_block_kernel<true><<<launch_blocks(N, KB_WARPS * 32, 8), KB_WARPS * 32, 0, (cudaStream_t)stream>>>(
-            grid_of(ix), N, pts, pts_stride, kout, fast_div(divisor), ix->site_recs, ix->site_cell_start, ix->recf,
-            ix->rec_id, ix->site_first, idx);
-        MM_CUDA(cudaGetLastError());
-        return MM_OK;
-    }
     knn_sites_kernel<<<launch_blocks(N, KNN_BLOCK, 8), KNN_BLOCK, 0, (cudaStream_t)stream>>>(
         grid_of(ix), N, pts, pts_stride, kout, fast_div(divisor), ix->site_recs, ix->site_cell_start, idx,
         ix->recs);
     MM_CUDA(cudaGetLastError());
+    return MM_OK;
+}
+
+// CTA-tile first pass of the pipeline (knn_tile_kernel): PREFIX semantics only -- the caller re-runs the points
+// whose row comes back (partly) empty.  `sorted`: the 32-byte query records and `sort_scratch`: the scratch of the
+// mm_index_sort_queries call that produced them (its `starts` table locates the queries of every cell).
+// *applied = false when the kernel does not apply (the caller then takes mm_knn_sites / mm_knn_first_pass).
+int mm_knn_tile_first_pass(const mm_index_t *ix, int64_t N, const double *sorted, const void *sort_scratch, int kout,
+                           int32_t divisor, bool sites, int32_t *idx, void *stream, bool *applied)
+{
+    MM_REQUIRE(ix && applied, MM_ERR_INVALID, "mm_knn_tile_first_pass: null");
+    *applied = false;
+    if (N == 0 || ix->M == 0) return MM_OK;
+    if (const char *e = getenv("MM_KNN_TILE"))
+        if (e[0] == '0') return MM_OK;
+    if (!(ix->cell > 1e-15 && ix->cell < 1e15)) return MM_OK;  // fp32 frame and error bound need normal floats
+    if (kout != 4 && kout != 8) return MM_OK;
+    if (sites && !(ix->site_recs && ix->rec_id && kout == 8)) return MM_OK;
+    // sparse query sets: staging a halo for a handful of queries costs more than the per-query search
+    if ((double)N < 0.25 * (double)ix->ncells) return MM_OK;
+    // tile: 16 x 4 x 4 cells (halo 18 x 6 x 6) when a halo of that many typically occupied cells fits the staging
+    // buffers with 10 % to spare, else 8 x 4 x 4; crowded tiles split themselves once more inside the kernel
+    kt_dims td{};
+    const double per_cell = (double)(sites ? ix->nsites : ix->M) / (double)std::max<int64_t>(ix->nonempty, 1);
+    td.tx = ix->dim == 3 ? (648.0 * per_cell * 1.1 + 36.0 <= (double)KT_CAP ? 16 : 8) : 16;
+    td.ty = ix->dim == 3 ? 4 : 16;
+    td.tz = ix->dim == 3 ? 4 : 1;
+    if (const char *e = getenv("MM_KT_TILE")) {  // tuning experiments: "tx,ty,tz"
+        int a = 0, b = 0, c = 0;
+        if (sscanf(e, "%d,%d,%d", &a, &b, &c) == 3 && a >= 1 && b >= 1 && c >= 1) {
+            td.tx = a;
+            td.ty = b;
+            td.tz = ix->dim == 3 ? c : 1;
+        }
+    }
+    td.cap = KT_CAP;
+    if (const char *e = getenv("MM_KT_CAP")) td.cap = std::max(1, std::min(KT_CAP, atoi(e)));  // tests
+    MM_REQUIRE(td.tx + 3 <= KT_MAXCOLS && td.ty * td.tz <= KT_MAXQROWS &&
+                   (td.ty + 2) * (ix->dim == 3 ? td.tz + 2 : 1) <= KT_MAXROWS,
+               MM_ERR_INVALID, "mm_knn_tile_first_pass: tile %d x %d x %d too large", td.tx, td.ty, td.tz);
+    td.ntx = (ix->n[0] + td.tx - 1) / td.tx;
+    td.nty = (ix->n[1] + td.ty - 1) / td.ty;
+    td.ntz = (ix->n[2] + td.tz - 1) / td.tz;
+    const int64_t ntiles = (int64_t)td.ntx * td.nty * td.ntz;
+    const int32_t *qstart = static_cast<const int32_t *>(sort_scratch) + (ix->ncells + 1);
+    const double4 *qrecs = reinterpret_cast<const double4 *>(sorted);
+    const size_t smem = sizeof(kt_smem);
+    cudaStream_t st = (cudaStream_t)stream;
+    const grid_t g = grid_of(ix);
+    const fast_div dv(divisor);
+#define MM_KT_LAUNCH(S, NK, OK, RECS, CS)                                                                     \
+    {                                                                                                         \
+        static mm_kernel_cfg kcfg;                                                                            \
+        MM_CUDA(kcfg.prepare(knn_tile_kernel<S, NK, OK>, KT_THREADS, smem, nullptr));                         \
+        knn_tile_kernel<S, NK, OK><<<(unsigned)ntiles, KT_THREADS, smem, st>>>(g, td, qrecs, qstart, RECS, CS, \
+                                                                               ix->rec_id, dv, idx);          \
+    }
+    if (sites) MM_KT_LAUNCH(true, 4, 8, ix->site_recs, ix->site_cell_start)
+    else if (kout == 4) MM_KT_LAUNCH(false, 5, 4, ix->recs, ix->cell_start)
+    else MM_KT_LAUNCH(false, 5, 8, ix->recs, ix->cell_start)
+#undef MM_KT_LAUNCH
+    MM_CUDA(cudaGetLastError());
+    *applied = true;
     return MM_OK;
 }

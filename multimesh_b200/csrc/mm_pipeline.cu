@@ -200,7 +200,12 @@ int mm_interpolate_impl(const mm_index_t *index, int32_t divisor, int order, int
     // GLL-point form: shared nodes are stored up to 8 times; search over distinct coordinates when the
     // index has a site table (mm_index_prepare_sites)
     const bool site_pass = divisor > 1 && k1 < k && mm_index_has_sites(index) && !getenv("MM_NO_SITES");
-    if (site_pass) {
+    bool tiled = false;
+    if (k1 < k)  // prefix mode: the CTA-tile kernel may write shorter prefixes, the re-run below completes them
+        MM_TRY(mm_knn_tile_first_pass(index, N, sorted, ws + L.sort_scratch, k1, divisor, site_pass, cands1, stream,
+                                      &tiled));
+    if (tiled) {
+    } else if (site_pass) {
         MM_TRY(mm_knn_sites(index, N, sorted, MM_QREC, k1, divisor, cands1, stream));
     } else {
         MM_TRY(mm_knn_first_pass(index, N, sorted, MM_QREC, k1, divisor, cands1, stream));

@@ -154,10 +154,12 @@ def test_ops_reject_hidden_copies(cuda):
 
 
 @pytest.mark.parametrize("case", ["lattice_ties", "random_centroids", "clustered", "quads_2d", "outside", "big_coords"])
-def test_block_first_pass_matches_per_thread_kernel_and_oracle(cuda, oracle, case, monkeypatch):
-    """The warp-cooperative fp32-prefiltered first pass (knn_block_kernel) must give the same final result as the
-    per-thread exact kernel and as the oracle: identical target mesh (every 4th/5th distance tied), sparse and
-    crowded cells, 2-D, targets outside the source box, coordinates of O(6.4e6) with small elements."""
+def test_tile_first_pass_matches_per_thread_kernel_and_oracle(cuda, oracle, case, monkeypatch):
+    """The CTA-tile fp32-prefiltered first pass (knn_tile_kernel; writes certified PREFIXES of the canonical list,
+    the pipeline re-runs what they do not resolve) must give the same final result as the per-thread exact kernels
+    and as the oracle: identical target mesh (distances tied everywhere), sparse and crowded cells, 2-D, targets
+    outside the source box, coordinates of O(6.4e6) with small elements; also with a tiny staging capacity, which
+    forces the sub-tile split and the give-up (everything re-run) paths."""
     import torch
     from multimesh_b200 import ops
 
@@ -199,8 +201,12 @@ def test_block_first_pass_matches_per_thread_kernel_and_oracle(cuda, oracle, cas
     pre = ops.element_presolve(tn)
     index = ops.GridIndex(tn.view(E * P, dim) if form == "gll" else cent)
     div = P if form == "gll" else 1
-    for flag in ("1", "0"):
-        monkeypatch.setenv("MM_KNN_BLOCK", flag)
+    for flag, cap in (("1", None), ("1", "200"), ("1", "40"), ("0", None)):
+        monkeypatch.setenv("MM_KNN_TILE", flag)
+        if cap:
+            monkeypatch.setenv("MM_KT_CAP", cap)
+        else:
+            monkeypatch.delenv("MM_KT_CAP", raising=False)
         out, elem, xi, st, nf = ops.interpolate(index, div, tn, cent, box, tf, tp, 20, ops.V1(), presolve=pre)
         assert np.array_equal(elem.cpu().numpy(), o_elem), (case, flag)
         assert np.array_equal(st.cpu().numpy(), o_st), (case, flag)
