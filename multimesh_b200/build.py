@@ -18,7 +18,7 @@ CSRC = os.path.join(HERE, "csrc")
 LIB_DIR = os.path.join(HERE, "lib")
 OBJ_DIR = os.path.join(HERE, "lib", "obj")
 LIB_PATH = os.path.join(LIB_DIR, "multi_mesh_b200.so")
-SOURCES = ["mm_core.cu", "mm_geometry.cu", "mm_index.cu", "mm_locate.cu", "mm_interp.cu",
+SOURCES = ["mm_core.cu", "mm_geometry.cu", "mm_index.cu", "mm_locate.cu", "mm_interp.cu", "mm_interp_elem.cu",
            "mm_trilinear.cu", "mm_pipeline.cu", "mm_source.cu", "mm_dedup.cu", "mm_host.cu"]
 NVCC_FLAGS = [
     "-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",

@@ -63,6 +63,14 @@ int mm_interp_fused(int order, int dim, int64_t E, int F, const double *fields, 
                     const int32_t *elem_s, const double *xi_s, const uint8_t *status_s,
                     const int32_t *perm, int perm_stride, double *out, int32_t *elem_u, double *xi_u,
                     uint8_t *status_u, void *stream);
+// K3 of the fused pipeline, element-centric (mm_interp_elem.cu): points grouped by element with a counting sort,
+// then one pass over the elements in memory order; scratch: mm_interp_elem_scratch_bytes(E or an upper bound, N)
+size_t mm_interp_elem_scratch_bytes(int64_t E, int64_t N);
+int mm_interp_by_element(int order, int dim, int64_t E, int F, const double *fields, int64_t N,
+                         const int32_t *elem_s, const double *xi_s, const uint8_t *status_s, const int32_t *perm,
+                         int perm_stride, double *out, int32_t *elem_u, double *xi_u, uint8_t *status_u,
+                         void *scratch, void *stream);
+int64_t mm_index_size(const mm_index_t *ix);  // number of indexed points
 size_t mm_index_sort_scratch_bytes(const mm_index_t *ix);
 // site table (distinct coordinates; built by the public mm_index_prepare_sites) and the site-level first
 // pass of the progressive search

@@ -1506,6 +1506,8 @@ extern "C" int mm_index_prepare_sites(mm_index_t *ix, void *stream_)
 
 bool mm_index_has_sites(const mm_index_t *ix) { return ix && ix->site_recs != nullptr; }
 
+int64_t mm_index_size(const mm_index_t *ix) { return ix ? ix->M : 0; }
+
 bool mm_index_sites_view_get(const mm_index_t *ix, mm_index_sites_view *out)
 {
     if (!ix || !ix->site_recs || !ix->site_first || !ix->rec_id) return false;

@@ -42,7 +42,7 @@ inline int64_t rerun_chunk(int64_t N)
 inline size_t align_up(size_t x) { return (x + 255) & ~(size_t)255; }
 
 struct ws_layout {
-    size_t sorted, perm, cands1, elem, xi, status, list, counters, sort_scratch;
+    size_t sorted, perm, cands1, elem, xi, status, list, counters, sort_scratch, k3_scratch;
     size_t b_pts, b_cands, b_elem, b_xi, b_status, total;
 };
 
@@ -65,6 +65,9 @@ ws_layout make_layout(const mm_index_t *ix, int dim, int64_t N, int k)
     L.list = take(sizeof(int32_t) * N);
     L.counters = take(64);
     L.sort_scratch = take(mm_index_sort_scratch_bytes(ix));
+    // element tables of K3: the number of source elements is not an argument of the workspace query; the number of
+    // indexed points (>= elements in both k-NN forms) bounds it
+    L.k3_scratch = take(mm_interp_elem_scratch_bytes(mm_index_size(ix), N));
     const int64_t cb = std::min<int64_t>(N, rerun_chunk(N));
     L.b_pts = take(sizeof(double) * cb * dim);
     L.b_cands = take(sizeof(int32_t) * cb * k);
@@ -252,8 +255,14 @@ int mm_interpolate_impl(const mm_index_t *index, int32_t divisor, int order, int
     if (fields) {
         MM_REQUIRE(out, MM_ERR_INVALID, "mm_interpolate: null out");
         if (fields_ready) MM_CUDA(cudaStreamWaitEvent(stream, (cudaEvent_t)fields_ready, 0));
-        MM_TRY(mm_interp_fused(order, dim, E, F, fields, N, elem_s, xi_s, status_s, perm, PERM_STRIDE, out, elem, xi,
-                               status, stream));
+        const char *mode = getenv("MM_INTERP_MODE");  // "t" / "w": the point-order variants (A/B comparisons)
+        if (!mode && E <= mm_index_size(index)) {
+            MM_TRY(mm_interp_by_element(order, dim, E, F, fields, N, elem_s, xi_s, status_s, perm, PERM_STRIDE, out,
+                                        elem, xi, status, ws + L.k3_scratch, stream));
+        } else {
+            MM_TRY(mm_interp_fused(order, dim, E, F, fields, N, elem_s, xi_s, status_s, perm, PERM_STRIDE, out, elem,
+                                   xi, status, stream));
+        }
         unpermuted = elem != nullptr;
     }
     mark(5);

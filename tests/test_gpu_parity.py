@@ -599,3 +599,53 @@ def test_interp_coherent_variant_bit_exact(cuda, oracle, order, dim, F):
         assert np.array_equal(got, want)
         got = ops.interp_perm(_t(fields, cuda), _t(elem, cuda), _t(xi, cuda), _t(perm, cuda)).cpu().numpy()
         assert np.array_equal(got[perm], want)
+
+
+@pytest.mark.parametrize("order,dim,F,nelem,npts", [
+    (4, 3, 5, 3, 4000),    # one group of 25 lanes; hundreds of points per element: many chunks
+    (4, 3, 8, 3, 3000),    # TTI: two field passes (6 + 2) AND several chunks -> Lagrange values recomputed per pass
+    (2, 3, 5, 4, 5000),    # two groups of 15 lanes
+    (2, 3, 13, 3, 2000),   # F > 10: two passes at order 2
+    (1, 3, 5, 5, 3000),    # three groups of 10 lanes
+    (1, 3, 40, 3, 500),    # three passes
+    (2, 2, 3, 9, 4000),    # quads: one group of 9 lanes x 3 groups
+    (4, 2, 7, 6, 3000),    # quads, two passes (6 + 1)
+])
+def test_pipeline_element_centric_gather(cuda, oracle, order, dim, F, nelem, npts, monkeypatch):
+    """K3 of mm_interpolate in its element-centric form (mm_interp_elem.cu: points grouped by element, field slabs in
+    registers, canonical operation order redistributed over lanes): bit-identical to the oracle's gather and to the
+    point-order tile kernel; elements with zero, one and hundreds of points, points outside the mesh (zero rows)."""
+    from multimesh_b200 import ops
+
+    rng = np.random.default_rng(100 * order + 10 * dim + F)
+    nodes = _mesh(order, dim, nelem, 0.02)
+    E, P, _ = nodes.shape
+    fields = rng.normal(size=(E, F, P)) * 1000.0
+    # clustered targets: most in a corner (some elements get hundreds of points, others none), some outside the mesh
+    pts = np.concatenate([rng.uniform(0.0, 0.45, (npts, dim)), rng.uniform(-0.3, 1.3, (npts // 10, dim)),
+                          nodes.reshape(-1, dim)[::5]])
+    tn, tf, tp = _t(nodes, cuda), _t(fields, cuda), _t(pts, cuda)
+    cent, box = ops.element_geometry(tn)
+    pre = ops.element_presolve(tn)
+    index = ops.GridIndex(cent)
+    cands = oracle.knn_bruteforce(oracle.centroids(nodes), pts, 20)
+    seen_failed = seen_crowded = False
+    for spec, prm in ((ops.V3(), oracle.V3()), (ops.V1(), oracle.V1())):
+        o_elem, o_xi, o_st, o_nf = oracle.locate(order, dim, nodes, pts, cands, prm)
+        seen_failed |= bool((o_elem < 0).any())
+        seen_crowded |= bool(np.bincount(o_elem[o_elem >= 0], minlength=E).max() > 64)
+        want = oracle.interp(order, dim, fields, o_elem, o_xi)
+        res = {}
+        for mode in (None, "t"):
+            if mode:
+                monkeypatch.setenv("MM_INTERP_MODE", mode)
+            else:
+                monkeypatch.delenv("MM_INTERP_MODE", raising=False)
+            out, elem, xi, st, nf = ops.interpolate(index, 1, tn, cent, box, tf, tp, 20, spec, presolve=pre)
+            assert np.array_equal(elem.cpu().numpy(), o_elem) and np.array_equal(st.cpu().numpy(), o_st)
+            assert np.array_equal(xi.cpu().numpy(), o_xi) and int(nf.item()) == o_nf
+            assert np.array_equal(out.cpu().numpy(), want), mode
+            res[mode] = out
+        out2, e2, _, _, _ = ops.interpolate(index, 1, tn, cent, box, tf, tp, 20, spec, presolve=pre, want_location=False)
+        assert e2.numel() == 0 and np.array_equal(out2.cpu().numpy(), want)
+    assert seen_failed and seen_crowded  # the cases this test is about did occur
