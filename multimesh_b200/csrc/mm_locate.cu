@@ -107,38 +107,6 @@ locate_kernel(const mm_gll_table T, const mm_locate_params prm, int64_t E,
 #pragma unroll
         for (int c = 0; c < DIM; ++c) best_xi[c] = 0.0;
 
-        // First pass of the progressive search (prefix mode, k <= 8): the whole candidate row lives in registers and
-        // ALL bounding-box tests are issued up front (independent loads, one memory round trip instead of a chain of
-        // dependent ones: candidate id -> its box -> next candidate ...); `pending` = candidates still to be tried
-        const bool row_in_regs = (prm.reserved & 1) && k <= 8;
-        int32_t crow[8];
-        unsigned pending = 0;
-        if (row_in_regs) {
-            if (k == 8) {  // rows of 8 ids are 32-byte aligned in the pipeline's workspace
-                const int4 a = done ? make_int4(-1, -1, -1, -1) : __ldg(reinterpret_cast<const int4 *>(cl));
-                const int4 b = done ? make_int4(-1, -1, -1, -1) : __ldg(reinterpret_cast<const int4 *>(cl) + 1);
-                crow[0] = a.x, crow[1] = a.y, crow[2] = a.z, crow[3] = a.w;
-                crow[4] = b.x, crow[5] = b.y, crow[6] = b.z, crow[7] = b.w;
-            } else {
-#pragma unroll
-                for (int u = 0; u < 8; ++u) crow[u] = (!done && u < k) ? cl[u] : -1;
-            }
-#pragma unroll
-            for (int u = 0; u < 8; ++u) {
-                const int32_t c = crow[u];
-                bool ok = c >= 0 && c < E;
-#pragma unroll
-                for (int w = 0; w < u; ++w) ok = ok && crow[w] != c;  // a repeated id is tested once
-                if (ok && prm.aabb_prefilter) {
-                    const double *lo = aabb + ((int64_t)c * 2 + 0) * DIM;
-                    const double *hi = lo + DIM;
-#pragma unroll
-                    for (int q = 0; q < DIM; ++q)
-                        if (!(p[q] >= lo[q] && p[q] <= hi[q])) ok = false;
-                }
-                if (ok) pending |= 1u << u;
-            }
-        }
         int32_t deferred_e = -1;  // candidate selected but not staged yet (more groups than SLOTS)
         bool deferred_fb = false;
         while (true) {
@@ -148,17 +116,6 @@ locate_kernel(const mm_gll_table T, const mm_locate_params prm, int64_t E,
                 e = deferred_e;
                 fb_newton = deferred_fb;
                 deferred_e = -1;
-            } else if (!done && row_in_regs) {
-                if (pending) {
-                    const int u = __ffs(pending) - 1;
-                    pending &= pending - 1;
-#pragma unroll
-                    for (int w = 0; w < 8; ++w)
-                        if (w == u) e = crow[w];
-                } else {  // prefix exhausted without acceptance: re-run with all k candidates
-                    done = true;
-                    r_status = MM_ST_UNRESOLVED;
-                }
             } else if (!done) {
                 while (t < k) {
                     int32_t c = cl[t];

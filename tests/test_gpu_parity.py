@@ -610,6 +610,10 @@ def test_interp_coherent_variant_bit_exact(cuda, oracle, order, dim, F):
     (1, 3, 40, 3, 500),    # three passes
     (2, 2, 3, 9, 4000),    # quads: one group of 9 lanes x 3 groups
     (4, 2, 7, 6, 3000),    # quads, two passes (6 + 1)
+    (2, 3, 2, 4, 3000),    # few fields: five groups of 6 lanes (five elements per warp)
+    (1, 3, 1, 5, 3000),    # sixteen groups of 2 lanes
+    (4, 3, 1, 3, 2000),    # six groups of 5 lanes
+    (1, 2, 1, 8, 2000),    # quads, sixteen groups
 ])
 def test_pipeline_element_centric_gather(cuda, oracle, order, dim, F, nelem, npts, monkeypatch):
     """K3 of mm_interpolate in its element-centric form (mm_interp_elem.cu: points grouped by element, field slabs in
