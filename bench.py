@@ -55,6 +55,9 @@ WORKLOADS = {
     # scaling over the GPUs (source generated on the device; random target points; centroid k-NN form)
     "S5": dict(src=216, tgt=0, order=4, k=20, npoints=100_000_000, form="centroid", device_gen=True),
     "S5small": dict(src=48, tgt=0, order=4, k=20, npoints=4_000_000, form="centroid", device_gen=True),
+    # BASELINE configs[0]: 2-D quads (the reference's own CPU-runnable case), every point checked against the oracle
+    "S1": dict(kind="quads", src=256, tgt=200, order=2, k=20),
+    "S1o4": dict(kind="quads", src=128, tgt=100, order=4, k=20),
     # BASELINE configs[2]: cubed-sphere shell, order 4, layered (see bench_extra.py)
     # (source 10.2 M elements = 82 GB of nodes + fields; target 1.1 M elements = 138 M GLL points, so that source, targets,
     # results of both variants and the workspace of the largest layer fit the 180 GB of one GPU)
@@ -71,6 +74,10 @@ def workload_name(w):
         return (f"{w['name']}: layered gll_2_gll on a cubed-sphere shell, order {w['order']}, source n_lat={w['n_lat']} "
                 f"radial {w['rad']} (mantle, lower crust, thin upper crust), target n_lat={w['tgt_lat']} radial "
                 f"{w['tgt_rad']}, per-layer centroid index, k={w['k']}")
+    if w.get("kind") == "quads":
+        return (f"{w['name']}: 2-D gll_2_gll on quads, source {w['src']}^2 order-{w['order']} F=3 (VP, VS, RHO), targets = "
+                f"GLL points of a non-nested {w['tgt']}^2 order-{w['order']} mesh, k={w['k']}, V1 location, GLL-point "
+                f"k-NN form")
     if w.get("kind") == "exodus":
         return (f"{w['name']}: exodus_2_gll (HEX8 {w['hex']}^3 nodal -> order-{w['order']} GLL {w['gll']}^3, V6 trilinear) "
                 f"and gll_2_exodus (V1) back, 5 fields + 5 gradient fields")

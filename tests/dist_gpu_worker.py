@@ -85,12 +85,15 @@ def main():
     dist.barrier()
     api.gll_2_gll(a, t_multi, parameters="ISO", gradient=True)
     if rank == 0:
-        from multimesh_b200.components.interpolator import _Source
-
-        orig = _Source.find
-        _Source.find = lambda self, *a_, **k_: orig(self, *a_, **{**k_, "shard": False})
-        api.gll_2_gll(a, t_single, parameters="ISO", gradient=True)
-        _Source.find = orig
+        # the single-GPU reference: this rank alone, with the driver blind to the process group (no sharding, and
+        # above all no collective -- the other rank is not inside the driver)
+        orig_world, orig_barrier = parallel._world, parallel.barrier
+        parallel._world = lambda group=None: (1, 0)
+        parallel.barrier = lambda group=None: None
+        try:
+            api.gll_2_gll(a, t_single, parameters="ISO", gradient=True)
+        finally:
+            parallel._world, parallel.barrier = orig_world, orig_barrier
         with open_store(t_multi, "r") as s1, open_store(t_single, "r") as s2:
             assert np.array_equal(s1.read("MODEL/data"), s2.read("MODEL/data")), "api.gll_2_gll differs under torchrun"
         open(os.path.join(out_dir, "ok"), "w").write(f"world {world}: bit-identical\n")
