@@ -710,6 +710,44 @@ def run_ours(args, w):
     o2 = ops.interp(fields, e2, x2)
     assert torch.equal(o2, out[:nchk]) and torch.equal(e2, elem[:nchk]) and torch.equal(x2, xi[:nchk])
     assert torch.equal(s2, status[:nchk])
+    # ---- the complete gll_2_gll driver flow on the device: K4 de-duplicates the target GLL points
+    #      (utils.get_unique_points), the pipeline runs on the unique points only, the values are scattered back into
+    #      the [E_t, F, P_t] layout of MODEL/data and the fluid / solid repair is applied -- what api.gll_2_gll does
+    #      between reading and writing the files.  Timed with CUDA events; the result must equal the direct run.
+    flow = None
+    if "tgt" in w and w["tgt"] and not args.no_parity:
+        Pt = (order + 1) ** 3
+        Et = N // Pt
+        old_vals = torch.zeros((Et, F, Pt), dtype=torch.float64, device=dev)
+        fluid = torch.zeros((Et,), dtype=torch.uint8, device=dev)
+        ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
+
+        def gll_flow():
+            ev[0].record()
+            uniq, inv = ops.unique_points(pts)
+            ev[1].record()
+            v = ops.interpolate(index, divisor, nodes, cent, box, fields, uniq, k, spec, want_location=False,
+                                presolve=presolve)[0]
+            ev[2].record()
+            vals3 = ops.scatter_back(v, inv, Et, Pt)
+            ops.fluid_fixup_(vals3, old_vals, fluid, NAMES.index("VS"))
+            ev[3].record()
+            return uniq.shape[0], vals3
+
+        gll_flow()
+        n_unique, vals3 = gll_flow()
+        torch.cuda.synchronize()
+        direct = out.view(Et, Pt, F).transpose(1, 2)
+        flow = {"target_points": int(N), "unique_points": int(n_unique),
+                "ms": {"K4_unique_points": round(ev[0].elapsed_time(ev[1]), 3),
+                       "pipeline_on_unique_points": round(ev[1].elapsed_time(ev[2]), 3),
+                       "scatter_back_and_fluid_fixup": round(ev[2].elapsed_time(ev[3]), 3),
+                       "total": round(ev[0].elapsed_time(ev[3]), 3)},
+                "equals_direct_run": bool(torch.equal(vals3, direct)),
+                "what": "api.gll_2_gll between file read and file write, all on the device: np.unique(axis=0) twin "
+                        "(K4), K1-K3 on the unique points, values[recon] -> [E_t, F, P_t], fluid / solid repair"}
+        assert flow["equals_direct_run"], "gll_2_gll flow (dedup + scatter-back) differs from the direct run"
+        del old_vals, fluid, vals3, direct
     del res, cands, e2, x2, s2, o2, elem, xi, status, out
     del index, cent, box, presolve, nodes, fields, pts
     torch.cuda.empty_cache()
@@ -807,12 +845,14 @@ def run_ours(args, w):
                 "whole_step": {"alg_bytes_per_point": sum(bytes_pt.values()), "achieved_gbs": round(step_gbs, 1),
                                "frac": round(step_gbs / peak, 4)},
                 "note": "achieved = SURVEY 8d no-reuse algorithmic bytes x points of one launch / CUDA-event "
-                        "duration of that kernel inside the timed step; `traffic` = DRAM bytes per launch from the "
-                        "committed ncu capture (profiles/traffic.json). K1 moves only 8d + 4k' algorithmic B/point and is "
-                        "instruction-issue bound, so its HBM fraction is small by construction; K2/K3 serve most "
-                        "algorithmic bytes from L2 / shared memory (points are processed in spatial order, one copy per "
-                        "distinct element per warp), so their no-reuse fraction can exceed 1 -- compulsory_frac is K3 "
-                        "against the bytes that must move at least once (fields + inputs + outputs)"}
+                        "duration of that kernel (stage) inside the timed step; `traffic` = DRAM bytes per launch from the "
+                        "committed ncu captures (profiles/traffic.json, static). None of the kernels is HBM-bound: K1 (CTA-tile "
+                        "first pass) moves 8d + 4k' algorithmic B/point and is instruction-issue bound (fp32 scan of the 3^3 "
+                        "cell block out of shared memory); K2 serves element blocks from L2 / shared memory (one copy per "
+                        "distinct element per warp) and is latency / fp64-pipe bound; K3 (element-centric: every field block "
+                        "read once, slabs in registers) moves about its compulsory bytes -- compulsory_frac is K3 against "
+                        "the bytes that must move at least once (fields + inputs + outputs), the no-reuse fraction can "
+                        "exceed 1 because all points of an element share one read of its block"}
 
     # ---- CPU baselines, rank 0, N = 1 only --------------------------------------------------------
     cpu = cpu_ref_c = None
@@ -848,6 +888,7 @@ def run_ours(args, w):
                                   "d2h_bytes_per_step": d2h,
                                   "call": "mm_interpolate_host: additionally uploads the source mesh and builds "
                                           "geometry + index + site table inside every step"}},
+        "gll_2_gll_flow": flow,
         "north_star": north_star,
         "gpu_launches": launches_per_step(N, True) * args.steps, "clocks": clocks, "index_build_ms": build_ms,
         "nfailed": nfailed, "status_histogram": st, "checksum": checksum, "e2e_checksum": e2e_checksum,
