@@ -10,8 +10,7 @@
 //      for the next round.  With spatially sorted points (mm_interpolate) a warp needs 1-4 copies;
 //   3. each lane runs Newton on the order-n map with the sum-factorised canonical evaluation
 //      order, reading its element's nodes from the shared slot (lanes of one group read the same
-//      addresses: broadcast); the block is shifted once per copy by the element's first control node (Y = X - ref,
-//      the group's lanes share that pass) and the residual is (sum_a w_a Y_a) - (p - ref);
+//      addresses: broadcast) and shifting them by its own point on the fly (Y = X - p);
 //   4. accept test / best tracking; lanes that run out of candidates take the variant's fallback.
 // Rounds repeat until every lane is resolved (~1-2 rounds typically).
 //
@@ -244,33 +243,9 @@ locate_kernel(const mm_gll_table T, const mm_locate_params prm, int64_t E,
                 phase ^= 1;
             }
             __syncwarp();  // plain-load tail path: make the leader's stores visible to its group
-            // Shift the staged block by the element's first control node, Y_a = X_a - ref, ONCE per copy: the lanes
-            // of the group share the work, and all their Newton evaluations read Y as it is (the residual subtracts
-            // p - ref from the three sums instead of p from every node coordinate in every evaluation).
-            double pp[DIM];
-#pragma unroll
-            for (int c = 0; c < DIM; ++c) pp[c] = 0.0;
-            double ref[DIM];
-            if (served) {
-#pragma unroll
-                for (int c = 0; c < DIM; ++c) {
-                    ref[c] = X[c];
-                    pp[c] = p[c] - ref[c];
-                }
-            }
-            __syncwarp();  // every lane has read ref before the first node is overwritten
-            if (served) {
-                double *Y = reinterpret_cast<double *>(slot + shift);
-                const int gsize = __popc(same), gidx = __popc(same & ((1u << lane) - 1));
-                for (int a = gidx; a < tr::P; a += gsize) {
-#pragma unroll
-                    for (int c = 0; c < DIM; ++c) Y[a * DIM + c] = Y[a * DIM + c] - ref[c];
-                }
-            }
-            __syncwarp();
             if (served) {
                 if (STATS) ++st_cand;
-                const bool ok = newton_iterate<ORDER, DIM>(T, X, pp, x, STATS ? &st_eval : nullptr);
+                const bool ok = newton_iterate<ORDER, DIM>(T, X, p, x, STATS ? &st_eval : nullptr);
                 if (fb_newton) {  // V1: nearest-centre element, interpolator.py:1460-1473
                     bool big = false;
 #pragma unroll

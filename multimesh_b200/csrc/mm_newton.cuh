@@ -8,10 +8,7 @@
 // Every accumulation of the contraction is ONE fused multiply-add, acc <- fma(w, v, acc) (explicit
 // __fma_rn; the build keeps -fmad=false, so nothing else is contracted) -- the oracle uses C fma()
 // at the same places, which is what keeps CPU and GPU bit-identical.
-// SHIFTED = true: Xn already holds the shifted block Y (K2: the staged copy is shifted once by the element's
-// first control node); false: Y_a = Xn_a - p is formed on the fly (K0's pre-solve, p = the first control node --
-// the same subtraction, so both ways see bit-identical Y).
-template <int ORDER, int DIM, bool SHIFTED = false>
+template <int ORDER, int DIM>
 __device__ __forceinline__ void eval_map(const mm_gll_table &T, const double *__restrict__ Xn,
                                          const double (&p)[DIM], const double (&xi)[DIM],
                                          double (&x)[DIM], double (&J)[DIM][DIM])
@@ -30,8 +27,7 @@ __device__ __forceinline__ void eval_map(const mm_gll_table &T, const double *__
             for (int i = 0; i < M; ++i) {
 #pragma unroll
                 for (int c = 0; c < 2; ++c) {
-                    const double v0 = Xn[(i + M * j) * 2 + c];
-                    const double y = SHIFTED ? v0 : v0 - p[c];
+                    double y = Xn[(i + M * j) * 2 + c] - p[c];
                     a[c] = __fma_rn(L[0][i], y, a[c]);
                     b[c] = __fma_rn(dL[0][i], y, b[c]);
                 }
@@ -70,8 +66,7 @@ __device__ __forceinline__ void eval_map(const mm_gll_table &T, const double *__
                 for (int i = 0; i < M; ++i) {
 #pragma unroll
                     for (int c = 0; c < 3; ++c) {
-                        const double v0 = Xk[(i + M * j) * 3 + c];
-                        const double y = SHIFTED ? v0 : v0 - p[c];
+                        double y = Xk[(i + M * j) * 3 + c] - p[c];
                         a[c] = __fma_rn(L[0][i], y, a[c]);
                         b[c] = __fma_rn(dL[0][i], y, b[c]);
                     }
@@ -102,8 +97,7 @@ __device__ __forceinline__ void eval_map(const mm_gll_table &T, const double *__
     }
 }
 
-// Newton on the element's reference-shifted nodes Y_a = X_a - ref (ref = first control node; `Y` is that block) with
-// the residual  x(xi) - p = (sum_a w_a Y_a) - (p - ref)  (`pp` = p - ref); true when max|delta| <= 1e-13.
+// Newton on the point-shifted nodes Y = X - p; true when max|delta| <= 1e-13.
 // Start: xi0 = Jinv0 ((p - ref) - x0) from the element's affine pre-solve
 // `pre` = {ref[DIM], x0[DIM], Jinv[DIM][DIM]} (K0, mm_element_presolve; ref = first control node,
 // x0 and Jinv evaluated on ref-shifted nodes) -- an exactly affine element then needs one
@@ -138,17 +132,15 @@ __device__ __forceinline__ void newton_start(const double (&p)[DIM], const doubl
 // and the point, so K2 computes it while the element block is still in flight).
 template <int ORDER, int DIM>
 __device__ __forceinline__ bool newton_iterate(const mm_gll_table &T,
-                                               const double *__restrict__ Y,
-                                               const double (&pp)[DIM], double (&xi)[DIM],
+                                               const double *__restrict__ X,
+                                               const double (&p)[DIM], double (&xi)[DIM],
                                                int *evaluations = nullptr)
 {
 #pragma unroll 1
     for (int it = 0; it < MM_NEWTON_MAXIT; ++it) {
         if (evaluations) ++*evaluations;  // statistics build only (compile-time null otherwise)
         double x[DIM], J[DIM][DIM], delta[DIM];
-        eval_map<ORDER, DIM, true>(T, Y, pp, xi, x, J);
-#pragma unroll
-        for (int c = 0; c < DIM; ++c) x[c] = x[c] - pp[c];
+        eval_map<ORDER, DIM>(T, X, p, xi, x, J);
         if constexpr (DIM == 2) {
             double r0 = -x[0], r1 = -x[1];
             double det = J[0][0] * J[1][1] - J[0][1] * J[1][0];
@@ -185,3 +177,13 @@ __device__ __forceinline__ bool newton_iterate(const mm_gll_table &T,
     return false;
 }
 
+
+template <int ORDER, int DIM>
+__device__ __forceinline__ bool newton_inverse(const mm_gll_table &T,
+                                               const double *__restrict__ X,
+                                               const double (&p)[DIM],
+                                               const double *__restrict__ pre, double (&xi)[DIM])
+{
+    newton_start<DIM>(p, pre, xi);
+    return newton_iterate<ORDER, DIM>(T, X, p, xi);
+}

@@ -182,7 +182,7 @@ int mmo_coeffs(int order, int dim, long long N, const int32_t *elem, const doubl
 
 /* ------------------------------------------------------------------------------------------
  * Isoparametric map evaluated on point-shifted control nodes Y_a = X_a - p.
- *   x[c]      = sum_a w_a Y_a[c]            ( = x(xi) - ref for Y = X - ref )
+ *   x[c]      = sum_a w_a Y_a[c]            ( = x(xi) - p )
  *   J[c][s]   = sum_a (dw_a/dxi_s) Y_a[c]
  * in the canonical nested (sum-factorised) order:  i innermost, then j, then k.
  * Generalises dNdR/dNdS/dNdT + dot_product_matrix_matrix (trilinearinterpolator.c:214-257)
@@ -325,11 +325,8 @@ void mmo_presolve(int order, int dim, long long E, const double *nodes, double *
  * (trilinearinterpolator.c:329-341), non-convergence => reject (the Python drivers'
  * "NaN" branch, interpolator.py:1200,1286,1436).  Differences, all deliberate:
  *   - the map is the order-n Lagrange map over all P control nodes;
- *   - nodes are shifted by the element's first control node first (Y_a = X_a - ref, a
- *     point-independent block, the same one the pre-solve is evaluated on) and the residual is
- *     x(xi) - p = (sum_a w_a Y_a) - (p - ref), so roundoff scales with the element, not with
- *     |x| ~ 6.4e6 m on global meshes, and the shift is made once per element instead of once
- *     per point and evaluation;
+ *   - nodes are shifted by p first (Y = X - p) so roundoff scales with the element,
+ *     not with |x| ~ 6.4e6 m on global meshes;
  *   - convergence test is on the update, max|delta| <= 1e-13 (the C twin's
  *     1e-8*scale residual test cannot deliver 1e-12 on xi and checks component 0
  *     twice, trilinearinterpolator.c:290-291 -- not replicated here).
@@ -341,10 +338,8 @@ static int newton_inverse(const basis_t *b, int dim, const double *nodes, const 
     double Y[MMO_MAXM * MMO_MAXM * MMO_MAXM * 3];
     int m = b->m;
     int P = dim == 2 ? m * m : m * m * m;
-    double pp[3] = {0, 0, 0};
     for (int a = 0; a < P; ++a)
-        for (int c = 0; c < dim; ++c) Y[a * dim + c] = nodes[a * dim + c] - nodes[c];
-    for (int c = 0; c < dim; ++c) pp[c] = p[c] - nodes[c];
+        for (int c = 0; c < dim; ++c) Y[a * dim + c] = nodes[a * dim + c] - p[c];
     for (int c = 0; c < dim; ++c) xi[c] = 0.0;
     if (pre) {
         /* affine pre-solve (mmo_presolve): xi0 = Jinv0 (p - x0), the first Newton step from the
@@ -366,7 +361,6 @@ static int newton_inverse(const basis_t *b, int dim, const double *nodes, const 
     for (int it = 0; it < MMO_NEWTON_MAXIT; ++it) {
         double x[3], J[3][3], delta[3];
         eval_map(b, dim, Y, xi, x, J);
-        for (int c = 0; c < dim; ++c) x[c] = x[c] - pp[c];
         if (dim == 2) {
             double r0 = -x[0], r1 = -x[1];
             double det = J[0][0] * J[1][1] - J[0][1] * J[1][0];
