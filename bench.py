@@ -23,7 +23,11 @@ The same JSON line carries
                 N GPUs of this run, with and without the NCCL gather of the values onto rank 0
   cpu_baseline  the CPU port (scipy cKDTree on the FULL source + the C oracle, all host threads) on a bounded
                 sample of the targets;  cpu_baseline_ref_c: the reference's own compiled C (oracle/_ref)
-Other workloads: S3 (cubed-sphere shell, order 4, layered), S4 (exodus <-> GLL round trip), S5 alone.
+  gll_2_gll_flow  the complete driver flow on the device: K4 de-duplication, pipeline on the unique points,
+                scatter-back + fluid fix-up (must equal the direct run)
+  other_configs N = 1 only: short runs of BASELINE configs[0], [3], [2] = S1 (2-D quads, EVERY point checked against
+                the oracle), S4 (exodus <-> GLL), S3 (layered, curved 10 M-element shell), see bench_extra.py
+Other workloads on their own: --workload S1 | S3 | S4 | S5 (full records incl. per-layer statistics).
 `--impl reference` times the CPU port of the same path on the box's host cores.
 """
 import argparse
@@ -496,6 +500,8 @@ def kernel_report(N, order, F, k, form, stages, peak, traffic_db):
         kernels[name] = {"ms": round(float(ms), 4), "alg_bytes_per_point": bytes_pt[name],
                          "achieved_gbs": round(gbs, 1), "frac": round(gbs / peak, 4),
                          "traffic": traffic_db.get(name)}
+        if traffic_db.get(name):  # DRAM bytes that actually moved (ncu) / this run's time / peak
+            kernels[name]["traffic_frac"] = round(traffic_db[name] / (ms * 1e-3) / 1e9 / peak, 4)
     other = {"query_sort_ms": round(float(stages[0]), 4), "rerun_unresolved_ms": round(float(stages[3]), 4),
              "unpermute_ms": round(float(stages[5]), 4)}
     return bytes_pt, kernels, other
@@ -820,6 +826,38 @@ def run_ours(args, w):
         north_star = run_device_gen(ns_args, w5, lib, ops, world, rank, dev, with_clocks=False)[0]
         torch.cuda.empty_cache()
 
+    # ---- the other BASELINE configurations, N = 1 only (kept out of the scaling runs): short runs of S1 (2-D quads,
+    #      every point checked against the oracle), S4 (exodus <-> GLL round trip) and S3 (layered, curved shell, 10 M
+    #      elements); full records: `bench.py --workload S1|S3|S4` (profiles/r2_bench_S*.json)
+    other_configs = None
+    if w["name"] == "S2" and world == 1 and not args.no_configs:
+        import bench_extra
+
+        other_configs = {}
+        for name in ("S1", "S4", "S3"):
+            torch.cuda.empty_cache()
+            wx = dict(WORKLOADS[name], name=name)
+            xa = argparse.Namespace(**vars(args))
+            xa.steps, xa.no_cpu = max(1, min(args.steps, 3)), True
+            try:
+                full = bench_extra.run(xa, wx, lib, ops, world, rank, dev, ALL_CPUS)
+            except Exception as exc:  # a config that does not fit this box must not cost the headline line
+                other_configs[name] = {"error": repr(exc)[:300]}
+                continue
+            keep = {k: full.get(k) for k in ("value", "unit", "ms_per_step", "parity_check", "kernels", "nfailed",
+                                              "exodus_2_gll", "gll_2_exodus", "round_trip_max_rel_error")
+                    if full.get(k) is not None}
+            keep["workload"] = full["config"]["workload"]
+            if "variants" in full:
+                keep["variants"] = {vn: {"ms_per_step": v["ms_per_step"], "value": v["value"],
+                                         "per_layer": [{"layer": L["layer"], "points": L["points"], "ms": L["ms"],
+                                                        "map_evaluations_per_point": L["map_evaluations_per_point"],
+                                                        "candidates_tested_per_point": L["candidates_tested_per_point"],
+                                                        "nfailed": L["nfailed"]} for L in v["per_layer"]]}
+                                    for vn, v in full["variants"].items()}
+            other_configs[name] = keep
+        torch.cuda.empty_cache()
+
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -841,6 +879,7 @@ def run_ours(args, w):
     k3["compulsory_frac"] = round(k3_compulsory / (k3["ms"] * 1e-3) / 1e9 / peak, 4)
     roofline = {"bound": "hbm", "kernel": dom, "achieved": kernels[dom]["achieved_gbs"], "peak": peak,
                 "unit": "GB/s", "frac": kernels[dom]["frac"], "traffic": kernels[dom]["traffic"],
+                "traffic_frac": kernels[dom].get("traffic_frac"),
                 "peak_source": peak_src, "graded_kernel_K3": k3,
                 "whole_step": {"alg_bytes_per_point": sum(bytes_pt.values()), "achieved_gbs": round(step_gbs, 1),
                                "frac": round(step_gbs / peak, 4)},
@@ -889,7 +928,7 @@ def run_ours(args, w):
                                   "call": "mm_interpolate_host: additionally uploads the source mesh and builds "
                                           "geometry + index + site table inside every step"}},
         "gll_2_gll_flow": flow,
-        "north_star": north_star,
+        "north_star": north_star, "other_configs": other_configs,
         "gpu_launches": launches_per_step(N, True) * args.steps, "clocks": clocks, "index_build_ms": build_ms,
         "nfailed": nfailed, "status_histogram": st, "checksum": checksum, "e2e_checksum": e2e_checksum,
     }
@@ -908,6 +947,7 @@ def main():
     ap.add_argument("--no-cpu", action="store_true", help="skip the CPU baseline legs")
     ap.add_argument("--no-north-star", action="store_true", help="skip the S5 strong-scaling leg of the S2 run")
     ap.add_argument("--no-parity", action="store_true", help="skip the oracle check of the timed result")
+    ap.add_argument("--no-configs", action="store_true", help="skip the short S1 / S4 / S3 legs of the S2 run")
     args = ap.parse_args()
     w = dict(WORKLOADS[args.workload], name=args.workload)
     if args.impl == "reference":

@@ -151,8 +151,6 @@ interp_elem_kernel(const mm_gll_table T, const ie_cfg cfg, int64_t E, const doub
     const int npass = (F + Fc - 1) / Fc;
     const int64_t total_bytes = E * (int64_t)F * P * 8;
     if (group0 >= E) return;
-    const int64_t nbatch = (E - group0 + groups_total - 1) / groups_total;
-    const int64_t nunits = nbatch * npass;
     uint32_t phase = 0;
 
     // stage the field chunks of unit u (lane g < ng copies the chunk of group g, if its element has any points)
@@ -184,13 +182,26 @@ interp_elem_kernel(const mm_gll_table T, const ie_cfg cfg, int64_t E, const doub
         }
     };
 
-    issue(group0, 0);
-    int64_t ebase = group0;
-    int pass = -1;
-    for (int64_t u = 0; u < nunits; ++u) {
-        if (++pass == npass) {
+    // first batch at or after `from` in which at least one of the warp's groups has points (E when there is none):
+    // batches without points cost two loads and a vote, not a trip through the pipeline (under strong scaling a
+    // rank owns points in a fraction of the elements only)
+    auto next_batch = [&](int64_t from) -> int64_t {
+        for (int64_t b = from; b < E; b += groups_total) {
+            const int64_t e = b + lane;
+            const bool any = lane < ng && e < E && starts[e + 1] > starts[e];
+            if (__ballot_sync(0xffffffffu, any)) return b;
+        }
+        return E;
+    };
+    int64_t ebase = next_batch(group0);
+    if (ebase >= E) return;
+    issue(ebase, 0);
+    int64_t enext = -1;  // the batch after `ebase`, looked up when the last pass of `ebase` starts
+    for (int pass = 0; ebase < E; ++pass) {
+        if (pass == npass) {
             pass = 0;
-            ebase += groups_total;
+            ebase = enext;
+            if (ebase >= E) break;
         }
         const int f0 = pass * Fc;
         const int nf = min(Fc, F - f0);
@@ -222,9 +233,11 @@ interp_elem_kernel(const mm_gll_table T, const ie_cfg cfg, int64_t E, const doub
         // the buffer is free: order the generic-proxy reads before the async-proxy writes of the next unit's copies
         fence_proxy_async_smem();
         __syncwarp();
-        if (u + 1 < nunits) {
-            if (pass + 1 < npass) issue(ebase, f0 + Fc);
-            else issue(ebase + groups_total, 0);
+        if (pass + 1 < npass) {
+            issue(ebase, f0 + Fc);
+        } else {
+            enext = next_batch(ebase + groups_total);
+            if (enext < E) issue(enext, 0);
         }
         if (cmax == 0) continue;
         const int nchunk = (cmax + PCg - 1) / PCg;
