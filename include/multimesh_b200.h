@@ -226,9 +226,11 @@ int mm_gather_nodal(int F, int64_t npoints_mesh, const double *param, int64_t N,
  * Same results as mm_knn -> mm_locate -> mm_interp, but
  *   - the points are first counting-sorted by index cell (coherent warps, L2 locality) and the
  *     results are written back through the permutation;
- *   - the search is progressive: a first pass with the min(k, 8) nearest candidates resolves
- *     most points (any prefix of the canonical k-NN list is the k'-NN list); only points whose
- *     prefix is exhausted are re-run with all k candidates and the variant's fallback;
+ *   - the search is progressive: a first pass over a certified prefix of the canonical k-NN list (up to
+ *     min(k, 8) entries) resolves most points (any prefix of the canonical list is the list of the nearest);
+ *     only points whose prefix is exhausted are re-run with all k candidates and the variant's fallback;
+ *   - the gather walks the source elements in memory order (points grouped by element): every field block is
+ *     read once per call;
  *   - the call is STREAM-ORDERED: it never synchronises with the host (the number of points to re-run
  *     stays on the device), so it can be captured in a CUDA graph.  0 <= N < 2^31 per call.
  *   index    : over element centroids (divisor = 1) or over all GLL points (divisor = P)

@@ -1,5 +1,6 @@
-// mm_interp.cu -- K3: fused Lagrange weights + multi-field gather (the roofline-graded kernel),
-//                 plus coefficient write-out and the explicit-matrix gather for cached weights.
+// mm_interp.cu -- K3, point-order kernels: fused Lagrange weights + multi-field gather for caller-supplied (elem, xi)
+//                 (mm_interp / mm_interp_perm; the fused pipeline uses the element-centric mm_interp_elem.cu), plus
+//                 coefficient write-out and the explicit-matrix gather for cached weights.
 //
 // out[n][f] = sum_a w_a(xi_n) * fields[elem_n][f][a]
 //
@@ -13,7 +14,7 @@
 //
 // Arithmetic: nested tensor contraction, i innermost --
 //   t[j,k] = sum_i Lx[i] v[i,j,k];  u[k] = sum_j Ly[j] t[j,k];  out = sum_k Lz[k] u[k]
-// one rounding per operation, no FMA; bit-identical to oracle/mm_oracle.c:mmo_interp.
+// every accumulation one explicit fma; bit-identical to oracle/mm_oracle.c:mmo_interp.
 #include <algorithm>
 #include <cstdlib>
 

@@ -1,16 +1,17 @@
 // mm_pipeline.cu -- fused device pipeline K1 -> K2 -> K3 over one batch of target points.
 //
-//   1. counting-sort the points by index cell (coherent warps, L2 locality); everything below
-//      runs in sorted order and results are written back through the permutation;
-//   2. progressive search: K1 with k1 = min(k, 8) candidates (register top-k list), K2 in
-//      "prefix" mode -- a point is final if one of its first k1 candidates accepts it, which is
-//      exactly what the full list would have decided, because any prefix of the canonical k-NN
-//      list IS the k1-NN list; points that exhaust the prefix are appended to a work list;
+//   1. counting-sort the points by index cell (coherent warps, L2 locality); K1 and K2 run in sorted order and
+//      results are written back through the permutation;
+//   2. progressive search: K1 writes a certified PREFIX of the canonical k-NN list (up to k1 = 8 / 4 entries; CTA-tile
+//      kernel over the cells, mm_index.cu), K2 runs in "prefix" mode -- a point is final if one of the prefix's
+//      candidates accepts it, which is exactly what the full list would have decided, because any prefix of the
+//      canonical k-NN list IS the list of the nearest; points that exhaust the prefix are appended to a work list;
 //   3. the work list (typically a few per cent) is re-run in chunks with all k candidates and
 //      the variant's complete fallback logic, and scattered back; its length stays on the device
 //      (the re-run kernels read it there), so the whole call is stream-ordered: no host
 //      synchronisation, capturable in a CUDA graph;
-//   4. K3 gathers in sorted order and writes out[perm[n]].
+//   4. K3 groups the located points by source element and gathers element by element (mm_interp_elem.cu),
+//      writing out[perm[n]] and the un-permuted location outputs.
 // Results are identical to mm_knn -> mm_locate -> mm_interp (tests/test_gpu_parity.py).
 #include <algorithm>
 #include <cstdlib>
