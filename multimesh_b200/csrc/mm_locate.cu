@@ -49,7 +49,10 @@ __device__ __forceinline__ bool accept_xi(const mm_locate_params &prm, const dou
 // STATS: also counts, over all points, the candidates that reached Newton and the map evaluations (Newton
 // iterations) -- stats[0] += candidates, stats[1] += evaluations; a separate instantiation, used by the
 // benchmarks only (mm_locate_set_stats)
-template <int ORDER, int DIM, int WARPS, int SLOTS, int MINB, bool STATS>
+// PREFIX: the first pass of the progressive search (mm_pipeline.cu) -- accept only, no fallback; a compile-time
+// switch, so that none of the fallback bookkeeping (first AABB hit, nearest centre, best snap candidate) occupies
+// registers in the pass that handles (almost) all points: the order-2 kernel sits at its 128-register cap.
+template <int ORDER, int DIM, int WARPS, int SLOTS, int MINB, bool STATS, bool PREFIX>
 __global__ void __launch_bounds__(WARPS * 32, MINB)
 locate_kernel(const mm_gll_table T, const mm_locate_params prm, int64_t E,
               const double *__restrict__ nodes, const double *__restrict__ centroid,
@@ -134,7 +137,7 @@ locate_kernel(const mm_gll_table T, const mm_locate_params prm, int64_t E,
                         if (!inside) {
                             // prefix mode takes no fallback (unresolved points are re-run with the
                             // full list), so the nearest-centre bookkeeping is not needed there
-                            if (prm.reserved & 1) continue;
+                            if (PREFIX) continue;
                             const double *cc = centroid + (int64_t)c * DIM;
                             double dx = p[0] - cc[0], dy = p[1] - cc[1];
                             double s = dx * dx + dy * dy;
@@ -149,14 +152,14 @@ locate_kernel(const mm_gll_table T, const mm_locate_params prm, int64_t E,
                             }
                             continue;
                         }
-                        if (first_inside < 0) first_inside = c;
+                        if (!PREFIX && first_inside < 0) first_inside = c;
                     }
                     e = c;
                     break;
                 }
                 if (e < 0) {  // candidates exhausted without acceptance: fallback
                     done = true;
-                    if (prm.reserved & 1) {
+                    if (PREFIX) {
                         // first pass of the progressive search: the list is only a PREFIX of the
                         // k-NN list, so no fallback may be taken; the point is re-run with all k
                         r_status = MM_ST_UNRESOLVED;
@@ -246,7 +249,7 @@ locate_kernel(const mm_gll_table T, const mm_locate_params prm, int64_t E,
             if (served) {
                 if (STATS) ++st_cand;
                 const bool ok = newton_iterate<ORDER, DIM>(T, X, p, x, STATS ? &st_eval : nullptr);
-                if (fb_newton) {  // V1: nearest-centre element, interpolator.py:1460-1473
+                if (!PREFIX && fb_newton) {  // V1: nearest-centre element, interpolator.py:1460-1473
                     bool big = false;
 #pragma unroll
                     for (int c = 0; c < DIM; ++c)
@@ -258,9 +261,9 @@ locate_kernel(const mm_gll_table T, const mm_locate_params prm, int64_t E,
                         r_xi[c] = (r_status == MM_ST_FB_NEAR_OK) ? x[c] : prm.magic_xi[c];
                     done = true;
                 } else if (!ok) {
-                    if (e == first_inside) first_inside_nan = true;
+                    if (!PREFIX && e == first_inside) first_inside_nan = true;
                 } else {
-                    if (prm.fallback == MM_FB_SNAP || prm.fallback == MM_FB_MINL1) {
+                    if (!PREFIX && (prm.fallback == MM_FB_SNAP || prm.fallback == MM_FB_MINL1)) {
                         double key = 0.0;
 #pragma unroll
                         for (int c = 0; c < DIM; ++c) {
@@ -337,12 +340,15 @@ int launch_locate(const mm_locate_params &prm, int64_t E, const double *nodes,
     mm_gll_table T;
     mm_make_table(ORDER, &T);
     unsigned long long *stats = g_locate_stats;
-    auto kern = stats ? locate_kernel<ORDER, DIM, WARPS, SLOTS, MINB, true>
-                      : locate_kernel<ORDER, DIM, WARPS, SLOTS, MINB, false>;
+    const bool prefix = (prm.reserved & 1) != 0;
+    auto kern = stats ? (prefix ? locate_kernel<ORDER, DIM, WARPS, SLOTS, MINB, true, true>
+                                : locate_kernel<ORDER, DIM, WARPS, SLOTS, MINB, true, false>)
+                      : (prefix ? locate_kernel<ORDER, DIM, WARPS, SLOTS, MINB, false, true>
+                                : locate_kernel<ORDER, DIM, WARPS, SLOTS, MINB, false, false>);
     const size_t smem = (size_t)WARPS * SLOTS * tr::SLOT_BYTES + WARPS * sizeof(uint64_t);
-    static mm_kernel_cfg kcfg[2];
+    static mm_kernel_cfg kcfg[4];
     int per_sm = 1;
-    MM_CUDA(kcfg[stats ? 1 : 0].prepare(kern, WARPS * 32, smem, &per_sm));
+    MM_CUDA(kcfg[(stats ? 1 : 0) + (prefix ? 2 : 0)].prepare(kern, WARPS * 32, smem, &per_sm));
     const int sms = mm_num_sms() > 0 ? mm_num_sms() : 148;
     int64_t batches = (N + 32 * WARPS - 1) / (32 * WARPS);
     int64_t grid = (int64_t)sms * per_sm;  // persistent: resident CTAs loop over point batches
