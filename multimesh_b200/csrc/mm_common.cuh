@@ -52,7 +52,12 @@ int mm_locate_impl(int order, int dim, int64_t E, const double *nodes, const dou
                    const int32_t *cands,
                    const mm_locate_params *params, int32_t *elem, double *xi, uint8_t *status,
                    int64_t *num_failed, bool zero_num_failed, int32_t *unresolved_list,
-                   int64_t *unresolved_count, void *stream, const int64_t *n_dev = nullptr, int64_t n_off = 0);
+                   int64_t *unresolved_count, void *stream, const int64_t *n_dev = nullptr, int64_t n_off = 0,
+                   const int32_t *point_order = nullptr);  // [N] (prefix mode only): lane m works on point point_order[m]
+// order[] that groups the points 0..N-1 by key[n * key_stride] (keys outside [0, E) go last), stable inside a group
+// up to atomics; scratch: mm_interp_elem_scratch_bytes(E, N) bytes (K3's tables, free until K3 runs)
+int mm_group_by_key(int64_t E, int64_t N, const int32_t *key, int key_stride, void *scratch, int32_t **order,
+                    void *stream);
 int mm_interpolate_impl(const mm_index_t *index, int32_t divisor, int order, int dim, int64_t E,
                         const double *nodes, const double *centroid, const double *aabb,
                         const double *presolve, int F, const double *fields, int64_t N,

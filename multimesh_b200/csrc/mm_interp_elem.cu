@@ -67,6 +67,27 @@ elem_place_kernel(int64_t N, const int32_t *__restrict__ elem_s, const int32_t *
     }
 }
 
+// grouping of arbitrary points by an integer key (the pipeline groups K2's points by their first candidate element)
+__global__ void __launch_bounds__(256)
+key_rank_kernel(int64_t N, int64_t E, const int32_t *__restrict__ key, int key_stride, int32_t *__restrict__ counts,
+                int32_t *__restrict__ rank)
+{
+    for (int64_t n = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; n < N; n += (int64_t)gridDim.x * blockDim.x) {
+        const int32_t e = valid_elem_e(key[n * key_stride], E);
+        rank[n] = atomicAdd(&counts[e >= 0 ? e : E], 1);
+    }
+}
+
+__global__ void __launch_bounds__(256)
+key_place_kernel(int64_t N, int64_t E, const int32_t *__restrict__ key, int key_stride,
+                 const int32_t *__restrict__ starts, const int32_t *__restrict__ rank, int32_t *__restrict__ order)
+{
+    for (int64_t n = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; n < N; n += (int64_t)gridDim.x * blockDim.x) {
+        const int32_t e = valid_elem_e(key[n * key_stride], E);
+        order[starts[e >= 0 ? e : E] + rank[n]] = (int32_t)n;
+    }
+}
+
 constexpr int IE_WARPS = 4;  // 4 CTAs / SM at order 4 (registers), 5 at lower orders (shared memory)
 
 // per-warp shared-memory layout, computed identically on the host (size) and on the device
@@ -423,4 +444,33 @@ int mm_interp_by_element(int order, int dim, int64_t E, int F, const double *fie
 #undef MM_IE
     mm_set_error("mm_interpolate: unsupported order/dim");
     return MM_ERR_UNSUPPORTED;
+}
+
+int mm_group_by_key(int64_t E, int64_t N, const int32_t *key, int key_stride, void *scratch, int32_t **order,
+                    void *stream_)
+{
+    cudaStream_t stream = (cudaStream_t)stream_;
+    MM_REQUIRE(E >= 0 && N >= 0 && key && scratch && order, MM_ERR_INVALID, "mm_group_by_key: arguments");
+    const ie_layout L = ie_make_layout(E, N);  // counts [E + 1] | starts [E + 1] | tiles | erank [N] | erec [8 N bytes]
+    unsigned char *ws = static_cast<unsigned char *>(scratch);
+    int32_t *counts = reinterpret_cast<int32_t *>(ws + L.counts);
+    int32_t *starts = reinterpret_cast<int32_t *>(ws + L.starts);
+    int32_t *tiles = reinterpret_cast<int32_t *>(ws + L.tiles);
+    int32_t *rank = reinterpret_cast<int32_t *>(ws + L.erank);
+    *order = reinterpret_cast<int32_t *>(ws + L.erec);
+    if (N == 0) return MM_OK;
+    // E + 1 buckets (the last one: no usable key); the scan tables hold E + 1 counts and E + 1 starts -- the total
+    // (starts[E + 1]) is not needed
+    MM_CUDA(cudaMemsetAsync(counts, 0, sizeof(int32_t) * (size_t)(E + 1), stream));
+    key_rank_kernel<<<ie_blocks(N), 256, 0, stream>>>(N, E, key, key_stride, counts, rank);
+    // exclusive scan of E + 1 counts writes E + 2 values: the starts table has E + 1 entries, so scan E counts (their
+    // total lands in starts[E], which is exactly the start of the last bucket)
+    if (E > 0) {
+        mm_exclusive_scan_i32(E, counts, starts, tiles, stream);
+    } else {
+        MM_CUDA(cudaMemsetAsync(starts, 0, sizeof(int32_t), stream));
+    }
+    key_place_kernel<<<ie_blocks(N), 256, 0, stream>>>(N, E, key, key_stride, starts, rank, *order);
+    MM_CUDA(cudaGetLastError());
+    return MM_OK;
 }

@@ -52,7 +52,9 @@ __device__ __forceinline__ bool accept_xi(const mm_locate_params &prm, const dou
 // PREFIX: the first pass of the progressive search (mm_pipeline.cu) -- accept only, no fallback; a compile-time
 // switch, so that none of the fallback bookkeeping (first AABB hit, nearest centre, best snap candidate) occupies
 // registers in the pass that handles (almost) all points: the order-2 kernel sits at its 128-register cap.
-template <int ORDER, int DIM, int WARPS, int SLOTS, int MINB, bool STATS, bool PREFIX>
+// ORDERED: lane m works on point order[m] instead of point m (the pipeline groups the points by their first
+// candidate element: the lanes of a warp then share a few elements whatever the point order is).
+template <int ORDER, int DIM, int WARPS, int SLOTS, int MINB, bool STATS, bool PREFIX, bool ORDERED>
 __global__ void __launch_bounds__(WARPS * 32, MINB)
 locate_kernel(const mm_gll_table T, const mm_locate_params prm, int64_t E,
               const double *__restrict__ nodes, const double *__restrict__ centroid,
@@ -62,7 +64,7 @@ locate_kernel(const mm_gll_table T, const mm_locate_params prm, int64_t E,
               double *__restrict__ xi_out, uint8_t *__restrict__ status_out,
               unsigned long long *__restrict__ num_failed, int32_t *__restrict__ unresolved_list,
               unsigned long long *__restrict__ unresolved_count, const long long *__restrict__ n_dev,
-              int64_t n_off, unsigned long long *__restrict__ stats)
+              int64_t n_off, unsigned long long *__restrict__ stats, const int32_t *__restrict__ order)
 {
     using tr = elem_traits<ORDER, DIM>;
     int st_cand = 0, st_eval = 0;
@@ -83,9 +85,11 @@ locate_kernel(const mm_gll_table T, const mm_locate_params prm, int64_t E,
 
     const int64_t warps_total = (int64_t)gridDim.x * WARPS;
     for (int64_t batch = (int64_t)blockIdx.x * WARPS + warp; batch * 32 < N; batch += warps_total) {
-        const int64_t n = batch * 32 + lane;
-        bool done = n >= N;
-        {  // the warp's next batch: pull its points and candidate rows towards L2 now
+        const int64_t m = batch * 32 + lane;
+        const bool valid = m < N;
+        bool done = !valid;
+        const int64_t n = ORDERED ? (valid ? (int64_t)order[m] : 0) : m;
+        if (!ORDERED) {  // the warp's next batch: pull its points and candidate rows towards L2 now
             const int64_t nn = n + warps_total * 32;
             if (nn < N) {
                 prefetch_l2(pts + nn * pstride);
@@ -292,7 +296,7 @@ locate_kernel(const mm_gll_table T, const mm_locate_params prm, int64_t E,
             fence_proxy_async_smem();
             __syncwarp();
         }
-        if (n < N) {
+        if (valid) {
             elem_out[n] = r_elem;
 #pragma unroll
             for (int c = 0; c < DIM; ++c) xi_out[n * DIM + c] = r_elem < 0 ? 0.0 : r_xi[c];
@@ -300,7 +304,7 @@ locate_kernel(const mm_gll_table T, const mm_locate_params prm, int64_t E,
             if (r_elem < 0 && r_status != MM_ST_UNRESOLVED) failed_local += 1;
         }
         if (unresolved_list) {  // warp-aggregated append of the points that need the full search
-            const unsigned um = __ballot_sync(0xffffffffu, n < N && r_status == MM_ST_UNRESOLVED);
+            const unsigned um = __ballot_sync(0xffffffffu, valid && r_status == MM_ST_UNRESOLVED);
             if (um) {
                 unsigned long long base = 0;
                 if (lane == 0) base = atomicAdd(unresolved_count, (unsigned long long)__popc(um));
@@ -334,21 +338,24 @@ int launch_locate(const mm_locate_params &prm, int64_t E, const double *nodes,
                   const double *pts, int pstride, int k,
                   const int32_t *cands, int32_t *elem, double *xi, uint8_t *status,
                   int64_t *num_failed, int32_t *unresolved_list, int64_t *unresolved_count,
-                  cudaStream_t stream, const int64_t *n_dev, int64_t n_off)
+                  cudaStream_t stream, const int64_t *n_dev, int64_t n_off, const int32_t *order)
 {
     using tr = elem_traits<ORDER, DIM>;
     mm_gll_table T;
     mm_make_table(ORDER, &T);
     unsigned long long *stats = g_locate_stats;
     const bool prefix = (prm.reserved & 1) != 0;
-    auto kern = stats ? (prefix ? locate_kernel<ORDER, DIM, WARPS, SLOTS, MINB, true, true>
-                                : locate_kernel<ORDER, DIM, WARPS, SLOTS, MINB, true, false>)
-                      : (prefix ? locate_kernel<ORDER, DIM, WARPS, SLOTS, MINB, false, true>
-                                : locate_kernel<ORDER, DIM, WARPS, SLOTS, MINB, false, false>);
+    MM_REQUIRE(!order || prefix, MM_ERR_INVALID, "mm_locate: an order array is a first-pass (prefix mode) option");
+    auto kern = stats ? (prefix ? (order ? locate_kernel<ORDER, DIM, WARPS, SLOTS, MINB, true, true, true>
+                                         : locate_kernel<ORDER, DIM, WARPS, SLOTS, MINB, true, true, false>)
+                                : locate_kernel<ORDER, DIM, WARPS, SLOTS, MINB, true, false, false>)
+                      : (prefix ? (order ? locate_kernel<ORDER, DIM, WARPS, SLOTS, MINB, false, true, true>
+                                         : locate_kernel<ORDER, DIM, WARPS, SLOTS, MINB, false, true, false>)
+                                : locate_kernel<ORDER, DIM, WARPS, SLOTS, MINB, false, false, false>);
     const size_t smem = (size_t)WARPS * SLOTS * tr::SLOT_BYTES + WARPS * sizeof(uint64_t);
-    static mm_kernel_cfg kcfg[4];
+    static mm_kernel_cfg kcfg[8];
     int per_sm = 1;
-    MM_CUDA(kcfg[(stats ? 1 : 0) + (prefix ? 2 : 0)].prepare(kern, WARPS * 32, smem, &per_sm));
+    MM_CUDA(kcfg[(stats ? 1 : 0) + (prefix ? 2 : 0) + (order ? 4 : 0)].prepare(kern, WARPS * 32, smem, &per_sm));
     const int sms = mm_num_sms() > 0 ? mm_num_sms() : 148;
     int64_t batches = (N + 32 * WARPS - 1) / (32 * WARPS);
     int64_t grid = (int64_t)sms * per_sm;  // persistent: resident CTAs loop over point batches
@@ -359,7 +366,7 @@ int launch_locate(const mm_locate_params &prm, int64_t E, const double *nodes,
                                                   reinterpret_cast<unsigned long long *>(num_failed),
                                                   unresolved_list,
                                                   reinterpret_cast<unsigned long long *>(unresolved_count),
-                                                  reinterpret_cast<const long long *>(n_dev), n_off, stats);
+                                                  reinterpret_cast<const long long *>(n_dev), n_off, stats, order);
     MM_CUDA(cudaGetLastError());
     return MM_OK;
 }
@@ -372,7 +379,8 @@ int mm_locate_impl(int order, int dim, int64_t E, const double *nodes, const dou
                    const int32_t *cands,
                    const mm_locate_params *params, int32_t *elem, double *xi, uint8_t *status,
                    int64_t *num_failed, bool zero_num_failed, int32_t *unresolved_list,
-                   int64_t *unresolved_count, void *stream_, const int64_t *n_dev, int64_t n_off)
+                   int64_t *unresolved_count, void *stream_, const int64_t *n_dev, int64_t n_off,
+                   const int32_t *point_order)
 {
     cudaStream_t stream = (cudaStream_t)stream_;
     MM_REQUIRE(mm_valid_order(order), MM_ERR_INVALID, "mm_locate: order %d (supported 1, 2, 4)", order);
@@ -396,7 +404,7 @@ int mm_locate_impl(int order, int dim, int64_t E, const double *nodes, const dou
                                             pts_stride, k,                                        \
                                             cands,                                                \
                                             elem, xi, status, num_failed, unresolved_list,       \
-                                            unresolved_count, stream, n_dev, n_off);
+                                            unresolved_count, stream, n_dev, n_off, point_order);
     MM_LOC(1, 2, 4, 8, 1)
     MM_LOC(2, 2, 4, 8, 1)
     MM_LOC(4, 2, 4, 8, 1)

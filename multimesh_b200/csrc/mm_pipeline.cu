@@ -217,9 +217,18 @@ int mm_interpolate_impl(const mm_index_t *index, int32_t divisor, int order, int
     mark(2);
     mm_locate_params p1 = *params;
     p1.reserved = (k1 < k) ? 1 : 0;
+    // Centroid form: the first candidate is (almost always) the owner, and the points of a cell belong to up to 8
+    // elements -- a warp of 32 cell-sorted points stages ~10 element blocks for ~3 lanes each (S5: 101 GB of DRAM reads
+    // for a 30 GB node array, 15 of 32 lanes active).  Grouped by first candidate, a warp shares 3-4 blocks.
+    const int32_t *k2_order = nullptr;
+    if (k1 < k && divisor == 1 && E > 0 && E <= mm_index_size(index) && !getenv("MM_K2_NO_GROUPING")) {
+        int32_t *ord = nullptr;
+        MM_TRY(mm_group_by_key(E, N, cands1, k1, ws + L.k3_scratch, &ord, stream));
+        k2_order = ord;
+    }
     MM_TRY(mm_locate_impl(order, dim, E, nodes, centroid, aabb, presolve, N, sorted, MM_QREC, k1, cands1, &p1, elem_s,
                           xi_s, status_s, counters + 1, false, (k1 < k) ? list : nullptr,
-                          (k1 < k) ? counters : nullptr, stream));
+                          (k1 < k) ? counters : nullptr, stream, nullptr, 0, k2_order));
 
     mark(3);
     // 3. re-run the unresolved points with the full candidate list.  Their number lives in counters[0] on the
