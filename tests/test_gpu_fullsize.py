@@ -88,3 +88,45 @@ def test_polynomial_reproduction_linearity_permutation(cuda, big):
     _, e4, x4, _, _ = ops.interpolate(big["cen"], 1, *args, None, sub, 20, ops.V1(), presolve=big["pre"])
     inner = (x3.abs().max(dim=1).values < 0.95)
     assert torch.equal(e4[inner], e3[inner]) and torch.equal(x4[inner], x3[inner])
+
+
+def test_layered_shell_54k_elements_order4_vs_oracle(cuda, oracle):
+    """BASELINE config 3 at a size the oracle still finishes in seconds: cubed-sphere shell of 54 000 curved order-4
+    elements (coordinates of O(6.4e6) m, mantle + lower crust + a 25 km upper crust), one index PER LAYER over the
+    layer's centroids with layer-local element ids (components/interpolator.py:363-373), targets = all GLL points of
+    a differently resolved shell with the same layer radii (257 k points); V1 (gll_2_gll_layered) and V2 with
+    snap_to_nearest (gll_2_gll_layered_multi_two) -- elements, xi, status, failed counts and values bit-equal to the
+    CPU oracle.  Exercises the occupied-volume cell size on thin shells, the CTA-tile K1, the grouped K2 with three
+    Newton evaluations per point, and the element-centric K3 at order 4."""
+    import torch
+    from multimesh_b200 import ops
+
+    radii = ((3480e3, 6291e3, 3), (6291e3, 6346e3, 2), (6346e3, 6371e3, 1))
+    src_layers = [(r0, r1, nr, lid, 0) for (r0, r1, lid), nr in zip(radii, (8, 1, 1))]
+    tgt_layers = [(r0, r1, nr, lid, 0) for (r0, r1, lid), nr in zip(radii, (5, 1, 1))]
+    src, sel, _ = meshgen.shell_mesh(30, src_layers, 4)   # 6 * 30^2 * 10 = 54 000 elements
+    tgt, tel, _ = meshgen.shell_mesh(7, tgt_layers, 4)    # 6 * 7^2 * 7 = 2 058 elements = 257 250 GLL points
+    assert src.shape == (54000, 125, 3)
+    names = ["QKAPPA", "QMU", "RHO", "VP", "VS"]
+    fields = meshgen.analytic_fields(src / 6371000.0, names)
+    total = 0
+    for lid in (3, 2, 1):
+        sm, tm = sel["layer"] == lid, tel["layer"] == lid
+        nodes = np.ascontiguousarray(src[sm])
+        f = np.ascontiguousarray(fields[sm])
+        pts = np.ascontiguousarray(tgt[tm].reshape(-1, 3))
+        tn, tf, tp = (torch.from_numpy(a).to(cuda) for a in (nodes, f, pts))
+        cent, box = ops.element_geometry(tn)
+        pre = ops.element_presolve(tn)
+        index = ops.GridIndex(cent)
+        o_cent = oracle.centroids(nodes)
+        for spec, prm, k in ((ops.V1(), oracle.V1(), 20), (ops.V2(1.05, True), oracle.V2(1.05, True), 30)):
+            out, elem, xi, st, nf = ops.interpolate(index, 1, tn, cent, box, tf, tp, k, spec, presolve=pre)
+            cands = oracle.knn_ckdtree_canonical(o_cent, pts, k, pad=16)
+            o_elem, o_xi, o_st, o_nf = oracle.locate(4, 3, nodes, pts, cands, prm)
+            assert np.array_equal(elem.cpu().numpy(), o_elem), (lid, k)
+            assert np.array_equal(st.cpu().numpy(), o_st) and int(nf.item()) == o_nf, (lid, k)
+            assert np.array_equal(xi.cpu().numpy(), o_xi), (lid, k)
+            assert np.array_equal(out.cpu().numpy(), oracle.interp(4, 3, f, o_elem, o_xi)), (lid, k)
+        total += len(pts)
+    assert total == 2058 * 125
