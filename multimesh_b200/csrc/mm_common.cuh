@@ -17,6 +17,8 @@
 #define MM_MAXM 5
 #define MM_NEWTON_MAXIT 50
 #define MM_NEWTON_TOL 1e-13
+#define MM_NEWTON_TOL_FAST 1e-7     // accepted when the iteration is visibly quadratic (see newton_iterate)
+#define MM_NEWTON_FAST_RATIO 1e-3
 #define MM_NEWTON_DIVERGE 1e10
 
 // ------------------------------------------------------------------------------------------------

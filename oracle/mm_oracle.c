@@ -45,6 +45,8 @@
 #define MMO_MAXM 5            /* order <= 4 */
 #define MMO_NEWTON_MAXIT 50   /* iteration cap, as trilinearinterpolator.c:264 */
 #define MMO_NEWTON_TOL 1e-13  /* on max|delta xi|; see DESIGN.md 3.3 */
+#define MMO_NEWTON_TOL_FAST 1e-7    /* accepted when the iteration is visibly quadratic (newton_inverse) */
+#define MMO_NEWTON_FAST_RATIO 1e-3
 #define MMO_NEWTON_DIVERGE 1e10
 
 /* ------------------------------------------------------------------------------------------
@@ -358,6 +360,7 @@ static int newton_inverse(const basis_t *b, int dim, const double *nodes, const 
         if (ok)
             for (int c = 0; c < dim; ++c) xi[c] = g[c];
     }
+    double dprev = INFINITY; /* max|delta| of the previous iteration */
     for (int it = 0; it < MMO_NEWTON_MAXIT; ++it) {
         double x[3], J[3][3], delta[3];
         eval_map(b, dim, Y, xi, x, J);
@@ -392,7 +395,10 @@ static int newton_inverse(const basis_t *b, int dim, const double *nodes, const 
         }
         if (iters) *iters = it + 1;
         if (bad) return 0;
-        if (dmax <= MMO_NEWTON_TOL) return 1;
+        /* converged: update below 1e-13, or below 1e-7 and a thousand times smaller than the previous one (quadratic
+           regime: the update just applied leaves an error of O(dmax^2) <= 1e-14; the confirming evaluation is saved) */
+        if (dmax <= MMO_NEWTON_TOL || (dmax <= MMO_NEWTON_TOL_FAST && dmax <= MMO_NEWTON_FAST_RATIO * dprev)) return 1;
+        dprev = dmax;
     }
     return 0;
 }
