@@ -589,6 +589,13 @@ def run_device_gen(args, w, lib, ops, world, rank, dev, with_clocks=True, gather
         with full_affinity():
             parity = parity_check(w["src"], order, form, k, nodes, fields, pts, elem, out_local,
                                   (a, min(w["src"], a + 20)))
+    # the same step returning the values only, as the reference's point-cloud entry point does (interpolate_to_points
+    # returns [N, F]): no un-permuted element / xi / status arrays -- three scattered partial-sector writes per point
+    def step_values():
+        return ops.interpolate(index, divisor, nodes, cent, box, fields, pts, k, spec, want_location=False,
+                               presolve=presolve, out=out_local)
+
+    ms_values, stages_v, _ = measure_pipeline(lib, ops, step_values, args.steps, args.warmup, world, dev, None)
     ms_gather = None
     if gather and world > 1:
         ms_gather, _, _ = measure_pipeline(lib, ops, step_gather, args.steps, args.warmup, world, dev, None)
@@ -600,6 +607,9 @@ def run_device_gen(args, w, lib, ops, world, rank, dev, with_clocks=True, gather
         "source_elements": int(E), "source_gb_per_gpu": round((nodes.numel() + fields.numel()) * 8 / 1e9, 1),
         "partition": "x-slabs" if slab else "index ranges", "ms_per_step": ms,
         "value": w["npoints"] / (ms * 1e-3), "unit": UNIT,
+        "values_only": {"ms_per_step": ms_values, "value": w["npoints"] / (ms_values * 1e-3), "K3_interp_ms": round(float(stages_v[4]), 4),
+                        "what": "same step without the un-permuted location outputs (elem, xi, status): what the reference's "
+                                "interpolate_to_points returns"},
         "ms_per_step_with_gather_to_rank0": ms_gather,
         "value_with_gather": None if ms_gather is None else w["npoints"] / (ms_gather * 1e-3),
         "gather": None if world == 1 else "grouped ncclSend/ncclRecv (batch_isend_irecv) into the rows of the full "
