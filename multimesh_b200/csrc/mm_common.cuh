@@ -96,8 +96,9 @@ int mm_knn_first_pass(const mm_index_t *ix, int64_t N, const double *pts, int pt
                       int32_t divisor, int32_t *idx, void *stream);
 // CTA-tile first pass over SORTED queries, prefix semantics (mm_index.cu: knn_tile_kernel); *applied = false when it
 // does not apply and the caller has to take one of the two above
+// perm_out (optional, [N]): the original index of every sorted query, as a compact array
 int mm_knn_tile_first_pass(const mm_index_t *ix, int64_t N, const double *sorted, const void *sort_scratch, int kout,
-                           int32_t divisor, bool sites, int32_t *idx, void *stream, bool *applied);
+                           int32_t divisor, bool sites, int32_t *idx, int32_t *perm_out, void *stream, bool *applied);
 // mm_knn with a stride (in doubles) between consecutive query points
 // n_dev (optional, device): the kernel processes points [0, min(N, *n_dev - n_off)) -- for work lists whose
 // length is only known on the device (no host synchronisation)

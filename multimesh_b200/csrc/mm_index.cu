@@ -666,7 +666,8 @@ __device__ __forceinline__ bool
 kt_run(kt_smem &sm, const grid_t &g, const int tx0, const int ty0, const int tz0, const int sx, const int sy,
        const int sz, const double4 *__restrict__ qrecs, const int32_t *__restrict__ qstart,
        const double4 *__restrict__ srecs, const int32_t *__restrict__ scs, const int32_t *__restrict__ rec_id,
-       const fast_div &divisor, int32_t *__restrict__ out_idx, const bool give_up, const int cap)
+       const fast_div &divisor, int32_t *__restrict__ out_idx, int32_t *__restrict__ perm_out, const bool give_up,
+       const int cap)
 {
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const bool three_d = g.dim == 3;
@@ -735,9 +736,11 @@ kt_run(kt_smem &sm, const grid_t &g, const int tx0, const int ty0, const int tz0
         if (!give_up) return false;    // the caller splits the tile
         for (int i = tid; i < T; i += KT_THREADS) {  // the complete search takes these points (re-run)
             int row;
-            int32_t *o = out_idx + (int64_t)query_of(i, row) * OUTK;
+            const int64_t n = query_of(i, row);
+            int32_t *o = out_idx + n * OUTK;
 #pragma unroll
             for (int c = 0; c < OUTK; ++c) o[c] = -1;
+            if (perm_out) perm_out[n] = (int32_t)__double_as_longlong(__ldg(reinterpret_cast<const double *>(qrecs + n) + 3));
         }
         return true;
     }
@@ -784,8 +787,11 @@ kt_run(kt_smem &sm, const grid_t &g, const int tx0, const int ty0, const int tz0
         int row;
         const int64_t n = query_of(i, row);
         const double2 *qp = reinterpret_cast<const double2 *>(qrecs + n);
-        const double2 pxy = __ldg(qp);
-        const double px = pxy.x, py = pxy.y, pz = three_d ? __ldg(qp + 1).x : 0.0;
+        const double2 pxy = __ldg(qp), pzw = __ldg(qp + 1);
+        const double px = pxy.x, py = pxy.y, pz = three_d ? pzw.x : 0.0;
+        // the original index of the query, once more as a compact array: later passes (K3's grouping) read 4 bytes
+        // per point instead of a 32-byte record
+        if (perm_out) perm_out[n] = (int32_t)__double_as_longlong(pzw.y);
         const int ry = row % td.ty, rz = row / td.ty;
         const int cy = ty0 + ry, cz = tz0 + rz;
         // the query's cell along x (y and z are those of the tile row: the sort used the same cell_coord)
@@ -927,7 +933,7 @@ __global__ void __launch_bounds__(KT_THREADS, 4)
 knn_tile_kernel(const grid_t g, const kt_dims td, const double4 *__restrict__ qrecs,
                 const int32_t *__restrict__ qstart, const double4 *__restrict__ srecs,
                 const int32_t *__restrict__ scs, const int32_t *__restrict__ rec_id, const fast_div divisor,
-                int32_t *__restrict__ out_idx)
+                int32_t *__restrict__ out_idx, int32_t *__restrict__ perm_out)
 {
     extern __shared__ __align__(32) unsigned char kt_raw[];
     kt_smem &sm = *reinterpret_cast<kt_smem *>(kt_raw);
@@ -953,7 +959,7 @@ knn_tile_kernel(const grid_t g, const kt_dims td, const double4 *__restrict__ qr
             if (x0 >= g.n[0] || y0 >= g.n[1] || z0 >= g.n[2]) continue;
         }
         const bool ok = kt_run<SITES, NK, OUTK>(sm, g, x0, y0, z0, ex, ey, ez, qrecs, qstart, srecs, scs, rec_id,
-                                                divisor, out_idx, pass > 0, td.cap);
+                                                divisor, out_idx, perm_out, pass > 0, td.cap);
         if (pass == 0 && ok) return;
     }
 }
@@ -1545,7 +1551,7 @@ int mm_knn_sites(const mm_index_t *ix, int64_t N, const double *pts, int pts_str
 // mm_index_sort_queries call that produced them (its `starts` table locates the queries of every cell).
 // *applied = false when the kernel does not apply (the caller then takes mm_knn_sites / mm_knn_first_pass).
 int mm_knn_tile_first_pass(const mm_index_t *ix, int64_t N, const double *sorted, const void *sort_scratch, int kout,
-                           int32_t divisor, bool sites, int32_t *idx, void *stream, bool *applied)
+                           int32_t divisor, bool sites, int32_t *idx, int32_t *perm_out, void *stream, bool *applied)
 {
     MM_REQUIRE(ix && applied, MM_ERR_INVALID, "mm_knn_tile_first_pass: null");
     *applied = false;
@@ -1592,7 +1598,7 @@ int mm_knn_tile_first_pass(const mm_index_t *ix, int64_t N, const double *sorted
         static mm_kernel_cfg kcfg;                                                                            \
         MM_CUDA(kcfg.prepare(knn_tile_kernel<S, NK, OK>, KT_THREADS, smem, nullptr));                         \
         knn_tile_kernel<S, NK, OK><<<(unsigned)ntiles, KT_THREADS, smem, st>>>(g, td, qrecs, qstart, RECS, CS, \
-                                                                               ix->rec_id, dv, idx);          \
+                                                                               ix->rec_id, dv, idx, perm_out); \
     }
     if (sites) MM_KT_LAUNCH(true, 4, 8, ix->site_recs, ix->site_cell_start)
     else if (kout == 4) MM_KT_LAUNCH(false, 5, 4, ix->recs, ix->cell_start)

@@ -43,7 +43,7 @@ inline int64_t rerun_chunk(int64_t N)
 inline size_t align_up(size_t x) { return (x + 255) & ~(size_t)255; }
 
 struct ws_layout {
-    size_t sorted, perm, cands1, elem, xi, status, list, counters, sort_scratch, k3_scratch;
+    size_t sorted, perm, perm_c, cands1, elem, xi, status, list, counters, sort_scratch, k3_scratch;
     size_t b_pts, b_cands, b_elem, b_xi, b_status, total;
 };
 
@@ -59,6 +59,7 @@ ws_layout make_layout(const mm_index_t *ix, int dim, int64_t N, int k)
     const int k1 = std::min(k, 8);  // sized for the larger first pass
     L.sorted = take(sizeof(double) * N * MM_QREC);  // 32-byte records {x, y, z, original index}
     L.perm = 0;
+    L.perm_c = take(sizeof(int32_t) * N);  // the permutation once more, compact (written by K1's tile kernel)
     L.cands1 = take(sizeof(int32_t) * N * k1);
     L.elem = take(sizeof(int32_t) * N);
     L.xi = take(sizeof(double) * N * dim);
@@ -206,8 +207,8 @@ int mm_interpolate_impl(const mm_index_t *index, int32_t divisor, int order, int
     const bool site_pass = divisor > 1 && k1 < k && mm_index_has_sites(index) && !getenv("MM_NO_SITES");
     bool tiled = false;
     if (k1 < k)  // prefix mode: the CTA-tile kernel may write shorter prefixes, the re-run below completes them
-        MM_TRY(mm_knn_tile_first_pass(index, N, sorted, ws + L.sort_scratch, k1, divisor, site_pass, cands1, stream,
-                                      &tiled));
+        MM_TRY(mm_knn_tile_first_pass(index, N, sorted, ws + L.sort_scratch, k1, divisor, site_pass, cands1,
+                                      reinterpret_cast<int32_t *>(ws + L.perm_c), stream, &tiled));
     if (tiled) {
     } else if (site_pass) {
         MM_TRY(mm_knn_sites(index, N, sorted, MM_QREC, k1, divisor, cands1, stream));
@@ -267,8 +268,10 @@ int mm_interpolate_impl(const mm_index_t *index, int32_t divisor, int order, int
         if (fields_ready) MM_CUDA(cudaStreamWaitEvent(stream, (cudaEvent_t)fields_ready, 0));
         const char *mode = getenv("MM_INTERP_MODE");  // "t" / "w": the point-order variants (A/B comparisons)
         if (!mode && E <= mm_index_size(index)) {
-            MM_TRY(mm_interp_by_element(order, dim, E, F, fields, N, elem_s, xi_s, status_s, perm, PERM_STRIDE, out,
-                                        elem, xi, status, ws + L.k3_scratch, stream));
+            // (K1's tile kernel left a compact copy of the permutation: 4 bytes per point instead of a record)
+            const int32_t *perm3 = tiled ? reinterpret_cast<const int32_t *>(ws + L.perm_c) : perm;
+            MM_TRY(mm_interp_by_element(order, dim, E, F, fields, N, elem_s, xi_s, status_s, perm3,
+                                        tiled ? 1 : PERM_STRIDE, out, elem, xi, status, ws + L.k3_scratch, stream));
         } else {
             MM_TRY(mm_interp_fused(order, dim, E, F, fields, N, elem_s, xi_s, status_s, perm, PERM_STRIDE, out, elem,
                                    xi, status, stream));
