@@ -91,7 +91,7 @@ struct mm_index_sites_view {
 bool mm_index_sites_view_get(const mm_index_t *ix, mm_index_sites_view *out);
 int mm_knn_sites(const mm_index_t *ix, int64_t N, const double *pts, int pts_stride, int kout,
                  int32_t divisor, int32_t *idx, void *stream);
-// first pass of the pipeline over SORTED queries (warp-cooperative block kernel when k = 4, else mm_knn)
+// first pass of the pipeline when the CTA-tile kernel does not apply (complete k' = k semantics, sparse query sets)
 int mm_knn_first_pass(const mm_index_t *ix, int64_t N, const double *pts, int pts_stride, int k,
                       int32_t divisor, int32_t *idx, void *stream);
 // CTA-tile first pass over SORTED queries, prefix semantics (mm_index.cu: knn_tile_kernel); *applied = false when it
