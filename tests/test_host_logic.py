@@ -185,3 +185,28 @@ def test_plotter_point_generators_and_geodesy():
     xyz, rads = plotter.cross_section_points(10.0, 20.0, -30.0, 80.0, npoints=7, nrads=4, min_depth_in_km=0.0,
                                              max_depth_in_km=600.0)
     assert xyz.shape == (28, 3) and np.allclose(np.linalg.norm(xyz, axis=1).reshape(4, 7), rads[:, None])
+
+
+def test_bench_reference_arm_contract():
+    """`bench.py --impl reference` (the CPU port of the path on the host cores; the one place outside tests/ that may
+    execute oracle/) prints ONE JSON line with the contract's keys, the same `config` object our arm prints, and a
+    cpu_baseline / e2e description of the run -- checked on the small workload, no GPU involved."""
+    import json
+    import os
+    import subprocess
+    import sys
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--workload", "small",
+                        "--steps", "1", "--warmup", "0"], capture_output=True, text=True, timeout=300, cwd=root)
+    assert r.returncode == 0, r.stderr[-2000:]
+    lines = [l for l in r.stdout.splitlines() if l.startswith("{")]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    for key in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling",
+                "vs_baseline", "dtype", "data", "config", "cpu_baseline", "e2e", "impl"):
+        assert key in d, key
+    assert d["impl"] == "reference" and d["value"] > 0 and d["unit"] == "points/s" and d["nfailed"] == 0
+    assert set(d["config"]) == {"workload", "points_per_gpu", "source_elements", "fields", "l2"}
+    assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1
+    assert d["e2e"]["value"] == d["value"] and d["e2e"]["h2d_bytes_per_step"] == 0
