@@ -218,6 +218,21 @@ int mm_gather_nodal(int F, int64_t npoints_mesh, const double *param, int64_t N,
                     const int64_t *enclosing, const double *weights, double *values,
                     void *stream);
 
+/* The two calls every exodus driver makes back to back -- centroid_tree.query(points, k=nelem_to_search) and
+ * lib.triLinearInterpolator (components/interpolator.py:193-224; scripts/cli.py:74-99) -- as ONE stream-ordered call
+ * with the progressive search of mm_interpolate: points sorted by index cell, certified 4-prefix of the k-NN list,
+ * trilinear candidate loop on the prefix, re-run of the points it did not accept with all k candidates.  enclosing /
+ * weights / num_failed are those of mm_knn(k) + mm_trilinear, bit for bit (a point accepted by a candidate of the
+ * prefix is accepted by the same candidate of the full list: the loop of trilinearinterpolator.c:63-111 stops there).
+ *   index: over the nelem element centroids (mm_centroid_conn + mm_index_create);
+ *   connectivity [nelem, 8] in the C routine's vertex order; enclosing [N, 8] / weights [N, 8]: rows of points that
+ *   fail keep what the caller put there (the drivers pass zeros); num_failed: device int64 (out);
+ *   workspace: mm_trilinear_indexed_workspace_bytes(index, N, k) bytes, 256-byte aligned. */
+size_t mm_trilinear_indexed_workspace_bytes(const mm_index_t *index, int64_t N, int k);
+int mm_trilinear_indexed(const mm_index_t *index, int64_t nelem, const int64_t *connectivity, const double *nodes,
+                         int64_t N, const double *pts, int k, int64_t *enclosing, double *weights,
+                         int64_t *num_failed, void *workspace, size_t workspace_bytes, void *stream);
+
 /* ------------------------------------------------------------------------------------------
  * Fused device pipeline K1 -> K2 -> K3 over one batch of target points (the bench's "step").
  * Replaces the body of the reference's drivers between "arrays loaded" and "values computed":

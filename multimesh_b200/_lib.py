@@ -62,6 +62,8 @@ _SIGNATURES = {
     "mm_gather_coeffs": (_int, [_int, _i64, _int, _vp, _i64, _vp, _vp, _vp, _vp]),
     "mm_trilinear": (_int, [_i64, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "mm_centroid_conn": (_int, [_i64, _i64, _i64, _vp, _vp, _vp, _vp]),
+    "mm_trilinear_indexed_workspace_bytes": (C.c_size_t, [_vp, _i64, _int]),
+    "mm_trilinear_indexed": (_int, [_vp, _i64, _vp, _vp, _i64, _vp, _int, _vp, _vp, _vp, _vp, C.c_size_t, _vp]),
     "mm_gather_nodal": (_int, [_int, _i64, _vp, _i64, _vp, _vp, _vp, _vp]),
     "mm_interpolate_host": (_int, [_int, _int, _i64, _vp, _int, _vp, _i64, _vp, _int, _int,
                                    C.POINTER(LocateParams), _vp, _vp, _vp, C.POINTER(_i64)]),

@@ -602,8 +602,9 @@ def exodus_2_gll(mesh, gll_model, gll_order=4, dimensions=3, nelem_to_search=20,
         utils.remove_and_create_empty_dataset(gll, parameters, model_path, coordinates_path)
         # all GLL points in one batch (the reference loops over the P node slots, :205-224)
         pts = _dev_f64(gll_coords.reshape(-1, 3), dev)
-        _, nearest = centroid_tree.query(pts, k=nelem_to_search, return_distance=False)
-        nfail, enclosing, weights = ops.trilinear(nearest.to(torch.int64), connectivity, exopoints, pts)
+        # centroid_tree.query(k=nelem_to_search) + lib.triLinearInterpolator (:205-218) as one progressive call
+        nfail, enclosing, weights = ops.trilinear_indexed(centroid_tree.index, connectivity, exopoints, pts,
+                                                          nelem_to_search)
         nfailed = int(nfail.item())
         assert nfailed == 0, f"{nfailed} points could not be interpolated."
         values = ops.gather_nodal(param_exodus, enclosing, weights)  # [F, N]

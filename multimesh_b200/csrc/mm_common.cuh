@@ -77,6 +77,12 @@ int mm_interp_by_element(int order, int dim, int64_t E, int F, const double *fie
                          const int32_t *elem_s, const double *xi_s, const uint8_t *status_s, const int32_t *perm,
                          int perm_stride, double *out, int32_t *elem_u, double *xi_u, uint8_t *status_u,
                          void *scratch, void *stream);
+// trilinear candidate search over sorted query records (mm_trilinear.cu), first pass (prefix) and re-run of
+// mm_trilinear_indexed
+int mm_trilinear_records(bool prefix, int k, int64_t npoints, const int64_t *n_dev, int64_t n_off, const int32_t *list,
+                         const double *recs, const int32_t *cands, const int64_t *connectivity, const double *nodes,
+                         int64_t *enclosing, double *weights, int64_t *num_failed, int32_t *unresolved_list,
+                         int64_t *unresolved_count, void *stream);
 int64_t mm_index_size(const mm_index_t *ix);  // number of indexed points
 size_t mm_index_sort_scratch_bytes(const mm_index_t *ix);
 // site table (distinct coordinates; built by the public mm_index_prepare_sites) and the site-level first

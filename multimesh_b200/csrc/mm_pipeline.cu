@@ -301,6 +301,101 @@ extern "C" int mm_interpolate(const mm_index_t *index, int32_t divisor, int orde
                                workspace_bytes, stream, nullptr);
 }
 
+// ------------------------------------------------------------------------------------------------
+// Order-1 nodal (Exodus HEX8) path, progressive: the same three steps as above with the trilinear
+// candidate loop (mm_trilinear.cu) in the place of K2 -- sort, certified 4-prefix of the k-NN list,
+// search in prefix mode, re-run of the points without acceptance with all k candidates and the
+// C routine's complete logic.  Results are those of mm_knn(k) + mm_trilinear, bit for bit.
+// ------------------------------------------------------------------------------------------------
+namespace {
+struct tri_layout {
+    size_t sorted, cands1, rank, list, counters, sort_scratch, b_pts, b_cands, total;
+};
+
+constexpr int TRI_K1 = 4;
+
+tri_layout make_tri_layout(const mm_index_t *ix, int64_t N, int k)
+{
+    tri_layout L{};
+    size_t o = 0;
+    auto take = [&](size_t bytes) { size_t at = o; o += align_up(bytes); return at; };
+    L.sorted = take(sizeof(double) * N * MM_QREC);
+    L.cands1 = take(sizeof(int32_t) * N * TRI_K1);
+    L.rank = take(sizeof(int32_t) * N);
+    L.list = take(sizeof(int32_t) * N);
+    L.counters = take(64);
+    L.sort_scratch = take(mm_index_sort_scratch_bytes(ix));
+    const int64_t cb = std::min<int64_t>(N, rerun_chunk(N));
+    L.b_pts = take(sizeof(double) * cb * 3);
+    L.b_cands = take(sizeof(int32_t) * cb * k);
+    L.total = o;
+    return L;
+}
+}  // namespace
+
+extern "C" size_t mm_trilinear_indexed_workspace_bytes(const mm_index_t *index, int64_t N, int k)
+{
+    if (!index || N < 0 || k < 1) return 0;
+    return make_tri_layout(index, N, k).total;
+}
+
+extern "C" int mm_trilinear_indexed(const mm_index_t *index, int64_t nelem, const int64_t *connectivity,
+                                    const double *nodes, int64_t N, const double *pts, int k, int64_t *enclosing,
+                                    double *weights, int64_t *num_failed, void *workspace, size_t workspace_bytes,
+                                    void *stream_)
+{
+    cudaStream_t stream = (cudaStream_t)stream_;
+    MM_REQUIRE(index && num_failed, MM_ERR_INVALID, "mm_trilinear_indexed: null index/num_failed");
+    MM_REQUIRE(k >= 1 && k <= 64, MM_ERR_INVALID, "mm_trilinear_indexed: k=%d outside [1, 64]", k);
+    MM_REQUIRE(N >= 0 && N <= (int64_t)INT32_MAX, MM_ERR_INVALID, "mm_trilinear_indexed: N=%lld outside [0, 2^31)",
+               (long long)N);
+    int64_t info[8];
+    MM_TRY(mm_index_info(index, info, nullptr));
+    MM_REQUIRE(info[1] == 3, MM_ERR_INVALID, "mm_trilinear_indexed: the index must be 3-D (HEX8 centroids)");
+    MM_REQUIRE(nelem == mm_index_size(index), MM_ERR_INVALID,
+               "mm_trilinear_indexed: the index holds %lld points for %lld elements (it must be built over the "
+               "element centroids)", (long long)mm_index_size(index), (long long)nelem);
+    MM_CUDA(cudaMemsetAsync(num_failed, 0, sizeof(int64_t), stream));
+    if (N == 0) return MM_OK;
+    MM_REQUIRE(connectivity && nodes && pts && enclosing && weights, MM_ERR_INVALID, "mm_trilinear_indexed: null buffer");
+    const tri_layout L = make_tri_layout(index, N, k);
+    MM_REQUIRE(workspace && workspace_bytes >= L.total, MM_ERR_INVALID,
+               "mm_trilinear_indexed: workspace of %zu bytes needed, %zu given", L.total, workspace_bytes);
+    MM_REQUIRE(((uintptr_t)workspace & 255) == 0, MM_ERR_INVALID, "mm_trilinear_indexed: workspace must be 256-byte aligned");
+    unsigned char *ws = static_cast<unsigned char *>(workspace);
+    double *sorted = reinterpret_cast<double *>(ws + L.sorted);
+    int32_t *cands1 = reinterpret_cast<int32_t *>(ws + L.cands1);
+    int32_t *list = reinterpret_cast<int32_t *>(ws + L.list);
+    int64_t *counters = reinterpret_cast<int64_t *>(ws + L.counters);  // [0] points without acceptance in the prefix
+    const int k1 = std::min(k, TRI_K1);
+
+    MM_TRY(mm_index_sort_queries(index, N, pts, sorted, reinterpret_cast<int32_t *>(ws + L.rank), ws + L.sort_scratch,
+                                 stream));
+    MM_CUDA(cudaMemsetAsync(counters, 0, 64, stream));
+    bool tiled = false;
+    if (k1 < k)
+        MM_TRY(mm_knn_tile_first_pass(index, N, sorted, ws + L.sort_scratch, k1, 1, false, cands1, nullptr, stream,
+                                      &tiled));
+    if (!tiled) MM_TRY(mm_knn_first_pass(index, N, sorted, MM_QREC, k1, 1, cands1, stream));
+    MM_TRY(mm_trilinear_records(k1 < k, k1, N, nullptr, 0, nullptr, sorted, cands1, connectivity, nodes, enclosing,
+                                weights, num_failed, list, counters, stream));
+    if (k1 < k) {
+        double *b_pts = reinterpret_cast<double *>(ws + L.b_pts);
+        int32_t *b_cands = reinterpret_cast<int32_t *>(ws + L.b_cands);
+        const long long *n_un = reinterpret_cast<const long long *>(counters);
+        const int64_t cb = std::min<int64_t>(N, rerun_chunk(N));
+        for (int64_t at = 0; at < N; at += cb) {
+            const int64_t nb = std::min<int64_t>(cb, N - at);
+            gather_points_kernel<<<blocks_for(nb), 256, 0, stream>>>(3, nb, n_un, at, list + at, sorted, b_pts);
+            MM_CUDA(cudaGetLastError());
+            MM_TRY(mm_knn_strided(index, nb, b_pts, 3, k, 1, b_cands, nullptr, stream, counters, at));
+            MM_TRY(mm_trilinear_records(false, k, nb, counters, at, list + at, sorted, b_cands, connectivity, nodes,
+                                        enclosing, weights, num_failed, nullptr, nullptr, stream));
+        }
+    }
+    return MM_OK;
+}
+
 extern "C" int mm_profile_create(mm_profile_t **out, int max_calls)
 {
     MM_REQUIRE(out && max_calls > 0, MM_ERR_INVALID, "mm_profile_create: arguments");

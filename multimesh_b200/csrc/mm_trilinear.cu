@@ -125,6 +125,55 @@ __device__ __forceinline__ void load_vtx(const int64_t *__restrict__ conn,
     }
 }
 
+// Candidate loop of triLinearInterpolator (:40-148) for one point: the first candidate whose reference coordinates lie
+// within 1.025 wins; otherwise the candidate with the smallest overshoot below 1.5 gets a second chance (:113-131).
+// Returns the accepted element (sol = its reference coordinates) or -1.
+// PREFIX: `cands` is only a prefix of the k-NN list -- an acceptance is what the full list would have decided (the
+// loop stops at the first one), a miss decides nothing: no second chance, the caller re-runs the point with all k.
+template <typename CandT, bool PREFIX>
+__device__ __forceinline__ int64_t hex8_search(int64_t k, const CandT *__restrict__ cands,
+                                               const int64_t *__restrict__ conn, const double *__restrict__ nodes,
+                                               const double (&pnt)[3], double (&sol)[3])
+{
+    double vtx[8][3];
+    double smallest = 99999999.9;
+    int64_t best = -1, hit = -1;
+    for (int64_t j = 0; j < k && hit < 0; ++j) {
+        int64_t e = cands[j];
+        if (e < 0) continue;  // -1 padding of a k-NN list longer than the mesh (the C twin has no such case)
+        load_vtx(conn, nodes, e, vtx);
+        if (hex8_check_hull(pnt, vtx, sol)) {
+            double maxerr = 0.0;
+#pragma unroll
+            for (int c = 0; c < 3; ++c)
+                if (fabs(sol[c]) > maxerr) maxerr = fabs(sol[c]);
+            if (maxerr < (1 + 0.025)) hit = e;
+            else if (!PREFIX && maxerr < smallest) {
+                smallest = maxerr;
+                best = e;
+            }
+        }
+    }
+    if (!PREFIX && hit < 0 && smallest < 1.5 && best >= 0) {  // :113-131
+        load_vtx(conn, nodes, best, vtx);
+        if (hex8_check_hull(pnt, vtx, sol)) hit = best;
+    }
+    return hit;
+}
+
+__device__ __forceinline__ void hex8_store(int64_t row, int64_t hit, const double (&sol)[3],
+                                           const int64_t *__restrict__ conn, int64_t *__restrict__ enclosing,
+                                           double *__restrict__ weights)
+{
+    double w[8];
+    hex8_weights(sol, w);
+#pragma unroll
+    for (int a = 0; a < 8; ++a) {
+        weights[row * 8 + a] = w[a];
+        enclosing[row * 8 + a] = conn[hit * 8 + a];
+    }
+}
+
 __global__ void __launch_bounds__(128)
 trilinear_kernel(int64_t k, int64_t npoints, const int64_t *__restrict__ nearest,
                  const int64_t *__restrict__ conn, int64_t *__restrict__ enclosing,
@@ -135,42 +184,65 @@ trilinear_kernel(int64_t k, int64_t npoints, const int64_t *__restrict__ nearest
     for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < npoints;
          i += (int64_t)gridDim.x * blockDim.x) {
         double pnt[3] = {points[i * 3], points[i * 3 + 1], points[i * 3 + 2]};
-        double vtx[8][3], sol[3], w[8];
-        double smallest = 99999999.9;
-        int64_t best = -1, hit = -1;
-        for (int64_t j = 0; j < k && hit < 0; ++j) {
-            int64_t e = nearest[i * k + j];
-            if (e < 0) continue;  // -1 padding of a k-NN list longer than the mesh (the C twin has no such case)
-            load_vtx(conn, nodes, e, vtx);
-            if (hex8_check_hull(pnt, vtx, sol)) {
-                double maxerr = 0.0;
-#pragma unroll
-                for (int c = 0; c < 3; ++c)
-                    if (fabs(sol[c]) > maxerr) maxerr = fabs(sol[c]);
-                if (maxerr < (1 + 0.025)) hit = e;
-                else if (maxerr < smallest) {
-                    smallest = maxerr;
-                    best = e;
-                }
-            }
-        }
-        if (hit < 0 && smallest < 1.5 && best >= 0) {  // :113-131
-            load_vtx(conn, nodes, best, vtx);
-            if (hex8_check_hull(pnt, vtx, sol)) hit = best;
-        }
-        if (hit >= 0) {
-            hex8_weights(sol, w);
-#pragma unroll
-            for (int a = 0; a < 8; ++a) {
-                weights[i * 8 + a] = w[a];
-                enclosing[i * 8 + a] = conn[hit * 8 + a];
-            }
-        } else {
-            failed += 1;  // outputs stay as the caller initialised them (zeros), :132-145
-        }
+        double sol[3];
+        const int64_t hit = hex8_search<int64_t, false>(k, nearest + i * k, conn, nodes, pnt, sol);
+        if (hit >= 0) hex8_store(i, hit, sol, conn, enclosing, weights);
+        else failed += 1;  // outputs stay as the caller initialised them (zeros), :132-145
     }
     for (int o = 16; o > 0; o >>= 1) failed += __shfl_xor_sync(0xffffffffu, failed, o);
     if ((threadIdx.x & 31) == 0 && failed) atomicAdd(num_failed, failed);
+}
+
+// The same search inside the progressive pipeline (mm_trilinear_indexed): points come as the cell-sorted 32-byte
+// query records {x, y, z, caller's row}, candidates as int32 rows of the first pass (PREFIX, k = 4) or of the re-run
+// (all k).  list (optional): point i is record list[i] and owns candidate row i -- the re-run's work list, whose
+// length *n_dev lives on the device.  PREFIX: a point without acceptance is appended to the work list instead of
+// being counted as failed.
+template <bool PREFIX>
+__global__ void __launch_bounds__(128)
+trilinear_rec_kernel(int k, int64_t npoints, const long long *__restrict__ n_dev, int64_t n_off,
+                     const int32_t *__restrict__ list, const double4 *__restrict__ recs,
+                     const int32_t *__restrict__ cands, const int64_t *__restrict__ conn,
+                     const double *__restrict__ nodes, int64_t *__restrict__ enclosing, double *__restrict__ weights,
+                     unsigned long long *__restrict__ num_failed, int32_t *__restrict__ unresolved_list,
+                     unsigned long long *__restrict__ unresolved_count)
+{
+    if (n_dev) {
+        const long long have = *n_dev - n_off;
+        npoints = have < 0 ? 0 : (have < npoints ? have : npoints);
+    }
+    const int lane = threadIdx.x & 31;
+    unsigned long long failed = 0;
+    for (int64_t base = blockIdx.x * (int64_t)blockDim.x + threadIdx.x - lane; base < npoints;
+         base += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t i = base + lane;
+        const bool valid = i < npoints;
+        int64_t n = 0, hit = -1;
+        if (valid) {
+            n = list ? (int64_t)list[i] : i;
+            const double4 r = recs[n];
+            const double pnt[3] = {r.x, r.y, r.z};
+            double sol[3];
+            hit = hex8_search<int32_t, PREFIX>(k, cands + i * (int64_t)k, conn, nodes, pnt, sol);
+            if (hit >= 0) hex8_store((int64_t)(int32_t)__double_as_longlong(r.w), hit, sol, conn, enclosing, weights);
+            else if (!PREFIX) failed += 1;
+        }
+        if (PREFIX) {
+            const bool open = valid && hit < 0;
+            const unsigned mask = __ballot_sync(0xffffffffu, open);
+            if (mask) {
+                const int leader = __ffs(mask) - 1;
+                unsigned long long at = 0;
+                if (lane == leader) at = atomicAdd(unresolved_count, (unsigned long long)__popc(mask));
+                at = __shfl_sync(0xffffffffu, at, leader);
+                if (open) unresolved_list[at + __popc(mask & ((1u << lane) - 1u))] = (int32_t)n;
+            }
+        }
+    }
+    if (!PREFIX) {
+        for (int o = 16; o > 0; o >>= 1) failed += __shfl_xor_sync(0xffffffffu, failed, o);
+        if (lane == 0 && failed) atomicAdd(num_failed, failed);
+    }
 }
 
 // values[f][n] = sum_a param[f][enc[n][a]] * w[n][a], a ascending
@@ -223,6 +295,29 @@ extern "C" int mm_trilinear(int64_t k, int64_t npoints, const int64_t *nearest,
     trilinear_kernel<<<blocks_for(npoints, 128), 128, 0, stream>>>(
         k, npoints, nearest, connectivity, enclosing, nodes, weights, points,
         reinterpret_cast<unsigned long long *>(num_failed));
+    MM_CUDA(cudaGetLastError());
+    return MM_OK;
+}
+
+// launcher of trilinear_rec_kernel for mm_trilinear_indexed (mm_pipeline.cu)
+int mm_trilinear_records(bool prefix, int k, int64_t npoints, const int64_t *n_dev, int64_t n_off, const int32_t *list,
+                         const double *recs, const int32_t *cands, const int64_t *connectivity, const double *nodes,
+                         int64_t *enclosing, double *weights, int64_t *num_failed, int32_t *unresolved_list,
+                         int64_t *unresolved_count, void *stream_)
+{
+    cudaStream_t stream = (cudaStream_t)stream_;
+    if (npoints == 0) return MM_OK;
+    const int grid = blocks_for(npoints, 128);
+    auto nd = reinterpret_cast<const long long *>(n_dev);
+    auto r4 = reinterpret_cast<const double4 *>(recs);
+    auto nf = reinterpret_cast<unsigned long long *>(num_failed);
+    auto uc = reinterpret_cast<unsigned long long *>(unresolved_count);
+    if (prefix)
+        trilinear_rec_kernel<true><<<grid, 128, 0, stream>>>(k, npoints, nd, n_off, list, r4, cands, connectivity, nodes,
+                                                             enclosing, weights, nf, unresolved_list, uc);
+    else
+        trilinear_rec_kernel<false><<<grid, 128, 0, stream>>>(k, npoints, nd, n_off, list, r4, cands, connectivity,
+                                                              nodes, enclosing, weights, nf, unresolved_list, uc);
     MM_CUDA(cudaGetLastError());
     return MM_OK;
 }

@@ -372,6 +372,31 @@ def trilinear(nearest: torch.Tensor, connectivity: torch.Tensor, nodes: torch.Te
     return nfail, enc, w
 
 
+def trilinear_indexed(index: "GridIndex", connectivity: torch.Tensor, nodes: torch.Tensor, points: torch.Tensor,
+                      k: int = 20):
+    """`index.query_idx(points, k)` + `trilinear` as one stream-ordered call with the progressive search
+    (mm_trilinear_indexed): same (num_failed [1] i64, enclosing [N,8] i64, weights [N,8]), bit for bit, without the
+    [N,k] candidate array.  index: GridIndex over the HEX8 centroids (`centroid_conn`); connectivity [E,8] i64 in the C
+    routine's vertex order."""
+    connectivity = _need_cuda(connectivity, "connectivity", torch.int64)
+    nodes = _need_cuda(nodes, "nodes", torch.float64, align16=True)
+    points = _need_cuda(points, "points", torch.float64)
+    N = points.shape[0]
+    E = connectivity.shape[0]
+    dev = points.device
+    lib = load_lib()
+    with torch.cuda.device(dev):
+        enc = torch.zeros((N, 8), dtype=torch.int64, device=dev)
+        w = torch.zeros((N, 8), dtype=torch.float64, device=dev)
+        nfail = torch.zeros((1,), dtype=torch.int64, device=dev)
+        nbytes = lib.mm_trilinear_indexed_workspace_bytes(index._h, N, int(k))
+        ws = torch.empty((max(int(nbytes), 256),), dtype=torch.uint8, device=dev)
+        check(lib.mm_trilinear_indexed(index._h, E, _ptr(connectivity), _ptr(nodes), N, _ptr(points), int(k),
+                                       _ptr(enc), _ptr(w), _ptr(nfail), _ptr(ws), ws.numel(), _stream()),
+              "mm_trilinear_indexed")
+    return nfail, enc, w
+
+
 def centroid_conn(connectivity: torch.Tensor, points: torch.Tensor) -> torch.Tensor:
     connectivity = _need_cuda(connectivity, "connectivity", torch.int64)
     points = _need_cuda(points, "points", torch.float64)

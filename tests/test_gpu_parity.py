@@ -453,6 +453,47 @@ def test_trilinear_bit_exact(cuda, oracle):
     assert np.max(np.abs(vals - want)) < 1e-12
 
 
+@pytest.mark.parametrize("shape,warp,nq,k,env", [
+    ((7, 6, 5), 0.03, 3000, 20, {}),                        # few cells: per-thread first pass
+    ((24, 24, 24), 0.03, 60000, 20, {}),                    # CTA-tile first pass
+    ((24, 24, 24), 0.12, 60000, 20, {"MM_RERUN_CHUNK": "700"}),  # strong warp: many re-runs, several rounds
+    ((24, 24, 24), 0.03, 60000, 20, {"MM_KNN_TILE": "0"}),
+    ((9, 9, 9), 0.03, 5000, 4, {}),                         # k <= 4: no prefix, complete semantics at once
+    ((2, 2, 2), 0.0, 400, 20, {}),                          # k > number of elements: -1 padding
+])
+def test_trilinear_indexed_matches_knn_plus_trilinear(cuda, oracle, monkeypatch, shape, warp, nq, k, env):
+    """mm_trilinear_indexed (sort, 4-prefix, prefix search, re-run) == mm_knn(k) + mm_trilinear == oracle == compiled
+    reference C: enclosing node ids, weights and the failed count, bit for bit -- including points outside the mesh
+    (failed: rows stay zero) and points that need the second-chance candidate."""
+    import torch
+    from multimesh_b200 import ops
+
+    for name, val in env.items():
+        monkeypatch.setenv(name, val)
+    rng = np.random.default_rng(81)
+    points, conn = meshgen.hex8_mesh(shape, warp=warp)
+    connC = np.ascontiguousarray(conn[:, np.argsort([0, 3, 2, 1, 4, 5, 6, 7])])
+    t_conn, t_connC, t_points = _t(conn, cuda), _t(connC, cuda), _t(points, cuda)
+    cent = ops.centroid_conn(t_conn, t_points)
+    q = np.concatenate([rng.uniform(-0.08, 1.08, (nq, 3)), points[::3], cent.cpu().numpy()[::5]])
+    t_q = _t(q, cuda)
+    index = ops.GridIndex(cent)
+    nf1, enc1, w1 = ops.trilinear_indexed(index, t_connC, t_points, t_q, k)
+    nn = index.query_idx(t_q, k).to(torch.int64)
+    nf0, enc0, w0 = ops.trilinear(nn, t_connC, t_points, t_q)
+    assert int(nf1.item()) == int(nf0.item())
+    assert torch.equal(enc1, enc0) and torch.equal(w1, w0)
+    assert 0 < int(nf1.item()) < len(q)  # the box around the mesh: some points fail, most do not
+    sel = rng.choice(len(q), min(len(q), 6000), replace=False)
+    nn_h = nn.cpu().numpy()[sel]
+    o_nf, o_enc, o_w = oracle.trilinear_interpolator(k, nn_h, connC, points, q[sel])
+    assert np.array_equal(enc1.cpu().numpy()[sel], o_enc) and np.array_equal(w1.cpu().numpy()[sel], o_w)
+    if oracle.ref_lib() is not None and (nn_h >= 0).all():
+        r_nf, r_enc, r_w = oracle.ref_trilinear_interpolator(k, nn_h, connC, points, q[sel])
+        assert r_nf == o_nf
+        assert np.array_equal(enc1.cpu().numpy()[sel], r_enc) and np.array_equal(w1.cpu().numpy()[sel], r_w)
+
+
 def test_legacy_host_symbols(cuda, oracle):
     """helpers.load_lib()-style ctypes calls on HOST numpy buffers (helpers.py:43-81)."""
     import ctypes as C
