@@ -483,7 +483,9 @@ def test_trilinear_indexed_matches_knn_plus_trilinear(cuda, oracle, monkeypatch,
     nf0, enc0, w0 = ops.trilinear(nn, t_connC, t_points, t_q)
     assert int(nf1.item()) == int(nf0.item())
     assert torch.equal(enc1, enc0) and torch.equal(w1, w0)
-    assert 0 < int(nf1.item()) < len(q)  # the box around the mesh: some points fail, most do not
+    assert int(nf1.item()) < len(q)
+    if min(shape) >= 5:  # the box around the mesh: some points fail (coarser meshes accept them as second chances)
+        assert int(nf1.item()) > 0
     sel = rng.choice(len(q), min(len(q), 6000), replace=False)
     nn_h = nn.cpu().numpy()[sel]
     o_nf, o_enc, o_w = oracle.trilinear_interpolator(k, nn_h, connC, points, q[sel])
