@@ -860,11 +860,14 @@ long long mmo_trilinear_interpolator(long long nelem_to_search, long long npoint
         long long best = -1;
         for (long long j = 0; j < nelem_to_search; ++j) {
             long long e = nearest[i * nelem_to_search + j];
-            if (e < 0) continue; /* -1 padding when the k-NN list is longer than the mesh */
-            for (int a = 0; a < 8; ++a)
-                for (int c = 0; c < 3; ++c) vtx[a][c] = nodes[conn[e * 8 + a] * 3 + c];
             int done = 0;
-            if (hex8_check_hull(pnt, vtx, sol)) {
+            /* e < 0: -1 padding when the k-NN list is longer than the mesh (no such case in the reference, whose
+             * KD-tree would hand out an out-of-range id): the candidate is skipped, the end-of-list logic below
+             * still runs */
+            if (e >= 0)
+                for (int a = 0; a < 8; ++a)
+                    for (int c = 0; c < 3; ++c) vtx[a][c] = nodes[conn[e * 8 + a] * 3 + c];
+            if (e >= 0 && hex8_check_hull(pnt, vtx, sol)) {
                 double maxerr = 0.0;
                 for (int c = 0; c < 3; ++c)
                     if (fabs(sol[c]) > maxerr) maxerr = fabs(sol[c]);

@@ -459,7 +459,7 @@ def test_trilinear_bit_exact(cuda, oracle):
     ((24, 24, 24), 0.12, 60000, 20, {"MM_RERUN_CHUNK": "700"}),  # strong warp: many re-runs, several rounds
     ((24, 24, 24), 0.03, 60000, 20, {"MM_KNN_TILE": "0"}),
     ((9, 9, 9), 0.03, 5000, 4, {}),                         # k <= 4: no prefix, complete semantics at once
-    ((2, 2, 2), 0.0, 400, 20, {}),                          # k > number of elements: -1 padding
+    ((2, 2, 2), 0.0, 4000, 20, {}),                         # k > number of elements: -1 padding
 ])
 def test_trilinear_indexed_matches_knn_plus_trilinear(cuda, oracle, monkeypatch, shape, warp, nq, k, env):
     """mm_trilinear_indexed (sort, 4-prefix, prefix search, re-run) == mm_knn(k) + mm_trilinear == oracle == compiled
@@ -475,7 +475,8 @@ def test_trilinear_indexed_matches_knn_plus_trilinear(cuda, oracle, monkeypatch,
     connC = np.ascontiguousarray(conn[:, np.argsort([0, 3, 2, 1, 4, 5, 6, 7])])
     t_conn, t_connC, t_points = _t(conn, cuda), _t(connC, cuda), _t(points, cuda)
     cent = ops.centroid_conn(t_conn, t_points)
-    q = np.concatenate([rng.uniform(-0.08, 1.08, (nq, 3)), points[::3], cent.cpu().numpy()[::5]])
+    out = 0.08 if min(shape) >= 5 else 0.3  # coarse mesh: the second chance reaches far (|xi| < 1.5)
+    q = np.concatenate([rng.uniform(-out, 1 + out, (nq, 3)), points[::3], cent.cpu().numpy()[::5]])
     t_q = _t(q, cuda)
     index = ops.GridIndex(cent)
     nf1, enc1, w1 = ops.trilinear_indexed(index, t_connC, t_points, t_q, k)
@@ -483,9 +484,7 @@ def test_trilinear_indexed_matches_knn_plus_trilinear(cuda, oracle, monkeypatch,
     nf0, enc0, w0 = ops.trilinear(nn, t_connC, t_points, t_q)
     assert int(nf1.item()) == int(nf0.item())
     assert torch.equal(enc1, enc0) and torch.equal(w1, w0)
-    assert int(nf1.item()) < len(q)
-    if min(shape) >= 5:  # the box around the mesh: some points fail (coarser meshes accept them as second chances)
-        assert int(nf1.item()) > 0
+    assert 0 < int(nf1.item()) < len(q)  # the box around the mesh: some points fail, most do not
     sel = rng.choice(len(q), min(len(q), 6000), replace=False)
     nn_h = nn.cpu().numpy()[sel]
     o_nf, o_enc, o_w = oracle.trilinear_interpolator(k, nn_h, connC, points, q[sel])
