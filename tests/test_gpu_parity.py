@@ -447,7 +447,7 @@ def test_trilinear_bit_exact(cuda, oracle):
         r_nf, r_enc, r_w = oracle.ref_trilinear_interpolator(20, nn, connC, points, q)
         assert r_nf == int(nfail.item())
         assert np.array_equal(enc.cpu().numpy(), r_enc) and np.array_equal(w.cpu().numpy(), r_w)
-    param = rng.normal(size=(4, len(points)))
+    param = rng.normal(size=(7, len(points)))  # 4 + 2 + 1: every chunk width of the field loop
     vals = ops.gather_nodal(_t(param, cuda), enc, w).cpu().numpy()
     want = np.sum(param[:, o_enc] * o_w, axis=2)
     assert np.max(np.abs(vals - want)) < 1e-12
