@@ -13,7 +13,7 @@ SO = os.path.join(ROOT, "multimesh_b200", "lib", "multi_mesh_b200.so")
 COLS = ["UBLKCP", "SYNCS", "DFMA", "DADD", "DMUL", "FFMA", "FADD", "FMUL", "VIMNMX", "MATCH", "VOTE", "SHFL", "LDS", "STS",
         "LDG", "STG", "ATOMS", "ATOMG", "RED", "BAR"]
 KEEP = re.compile(r"knn_tile_kernel|interp_elem|elem_rank|elem_place|key_rank|key_place|knn_kernel|knn_sites|locate_kernel|interp_tile|interp_coherent|interp_kernel|"
-                  r"trilinear_kernel|radix_scatter|scatter_back|query_place|element_geometry|fluid_fixup")
+                  r"trilinear_kernel|trilinear_rec_kernel|gather_nodal|radix_scatter|scatter_back|query_place|element_geometry|fluid_fixup")
 EXTRACT = {"interp_elem_kernel<2, 3>": r"UBLKCP|SYNCS|LDS.128", "interp_tile_kernel<2, 3>": r"UBLKCP|SYNCS", "locate_kernel<2, 3, 4, 8, 4, false, true, false>": r"UBLKCP|SYNCS|MATCH",
            "knn_tile_kernel<true, 4, 8>": r"VIMNMX|LDS.128|FFMA"}
 
