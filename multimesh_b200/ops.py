@@ -9,6 +9,8 @@ Inner operator boundary of the reference that these ops replace:
     KDTree(...).query(pts, k)                       -> GridIndex.query          (K1)
     inverse_transform + _check_if_inside_element... -> locate                   (K2)
     get_coefficients + np.sum(data[elem] * coeffs)  -> interp / coeffs          (K3)
+    the three in one stream-ordered call             -> interpolate              (K1 -> K2 -> K3, progressive)
+    lib.triLinearInterpolator / + KDTree.query      -> trilinear / trilinear_indexed (V6, order-1 nodal path)
 """
 import ctypes as C
 from dataclasses import dataclass
@@ -23,7 +25,7 @@ from .gll import SUPPORTED_ORDERS
 
 __all__ = [
     "LocateSpec", "V1", "V2", "V3", "V4", "V5", "GridIndex", "element_geometry", "locate", "interp",
-    "coeffs", "gather_coeffs", "trilinear", "centroid_conn", "gather_nodal", "map_to_sphere_",
+    "coeffs", "gather_coeffs", "trilinear", "trilinear_indexed", "centroid_conn", "gather_nodal", "map_to_sphere_",
     "interpolate", "element_presolve", "ResidentSource", "unique_points", "scatter_back", "fluid_fixup_",
 ]
 
