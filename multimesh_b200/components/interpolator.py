@@ -67,7 +67,7 @@ class _Source:
     def locate(self, pts, cands, spec):
         return ops.locate(self.nodes, self.centroid, self.aabb, pts, cands, spec, presolve=self.presolve)
 
-    def find(self, pts, k, spec, form="centroid", fields=None, shard=True):
+    def find(self, pts, k, spec, form="centroid", fields=None, shard=True, want_location=True):
         """Fused k-NN -> locate (-> gather when `fields` [E,F,P] is given): the mm_interpolate
         pipeline (spatially sorted points, progressive search).  Same results as
         candidates() + locate() (+ ops.interp).  -> (values or None, elem, xi, status, nfail)
@@ -76,7 +76,11 @@ class _Source:
         per GPU, every rank calling the same driver with the same arguments) the target points are split into
         contiguous shards, each rank interpolates its own shard against its replica of the source mesh, and
         the shards are exchanged so that every rank returns the complete result -- bit-identical to the
-        single-GPU result, because no arithmetic depends on the partition."""
+        single-GPU result, because no arithmetic depends on the partition.
+
+        want_location=False (drivers that return values only): elem / xi / status come back as None -- K3 skips
+        the un-permuted location outputs (29 scattered bytes per point: a third of K3 on an unordered cloud) and
+        the ranks do not exchange them."""
         index, div = (self.gll_index(), self.P) if form == "gll" else (self.centroid_index(), 1)
         f = None if fields is None else _dev_f64(fields, self.device)
         world, rank = parallel._world()
@@ -84,13 +88,17 @@ class _Source:
         if shard and world > 1 and n >= world:
             sl = parallel.local_slice(n, rank, world)
             out, elem, xi, status, nfail = ops.interpolate(index, div, self.nodes, self.centroid, self.aabb, f,
-                                                            pts[sl].contiguous(), k, spec, presolve=self.presolve)
+                                                            pts[sl].contiguous(), k, spec, want_location,
+                                                            presolve=self.presolve)
             out = parallel.allgather_rows(out, n) if fields is not None else out
-            elem, xi, status = (parallel.allgather_rows(t, n) for t in (elem, xi, status))
+            if want_location:
+                elem, xi, status = (parallel.allgather_rows(t, n) for t in (elem, xi, status))
             torch.distributed.all_reduce(nfail)
         else:
             out, elem, xi, status, nfail = ops.interpolate(index, div, self.nodes, self.centroid, self.aabb, f,
-                                                            pts, k, spec, presolve=self.presolve)
+                                                            pts, k, spec, want_location, presolve=self.presolve)
+        if not want_location:
+            elem = xi = status = None
         return (out if fields is not None else None), elem, xi, status, nfail
 
 
@@ -290,7 +298,8 @@ def interpolate_to_points(mesh, points, params_to_interp, make_spherical=False):
     src = _Source(gll_points)
     print("Retrieving interpolation weights")
     pts = _dev_f64(points, src.device)
-    vals, elem, xi, _, nfail = src.find(pts, 25, ops.V2(), fields=_stack_fields(mesh, params_to_interp))
+    vals, _, _, _, nfail = src.find(pts, 25, ops.V2(), fields=_stack_fields(mesh, params_to_interp),
+                                    want_location=False)
     num_failed = int(nfail.item())
     if num_failed > 0:
         print(num_failed, "points could not find an enclosing element. These points will be set to zero. "
@@ -548,8 +557,9 @@ def gll_2_gll(from_gll, to_gll, nelem_to_search=20, parameters="ISO", from_model
             print("Now we start interpolating")
             pts = _dev_f64(unique_new_points, src.device)
             # V1, ignore_hard_elements=True (:781)
+            # (enclosing elements and reference coordinates are needed for the stored matrices only)
             vals, elem, xi, status, nfail = src.find(pts, nelem_to_search, ops.V1(), form="gll",
-                                                     fields=original_data)
+                                                     fields=original_data, want_location=bool(stored_array))
             print("Interpolation done, Need to organize the results and write to file")
             num_failed = int(nfail.item())
             if num_failed > 0:
@@ -625,7 +635,7 @@ def gll_2_exodus(gll_model, exodus_model, gll_order=4, dimensions=3, nelem_to_se
     exodus = exodus_model if isinstance(exodus_model, Exodus) else Exodus(exodus_model, mode="a")
     print("Querying the KDTree")
     pts = _dev_f64(exodus.points[:, :dimensions], src.device)
-    values, elem, xi, _, _ = src.find(pts, nelem_to_search, ops.V1(), fields=gll_data)
+    values, _, _, _, _ = src.find(pts, nelem_to_search, ops.V1(), fields=gll_data, want_location=False)
     values = values.cpu().numpy()
     for i, param in enumerate(parameters):
         exodus.attach_field(param, np.zeros_like(values[:, i]))
