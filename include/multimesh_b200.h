@@ -322,8 +322,8 @@ int mm_pool_trim(void);
  *   mm_source_set_fields_host: replace the fields (new model on the same geometry), host-owned sources
  *   mm_source_interpolate   : device pointers, one mm_interpolate on the caller's stream (stream-ordered,
  *                             no host synchronisation unless the internal workspace has to grow)
- *   mm_source_interpolate_host: HOST pointers; the points are cut into chunks (default 2 M points,
- *                             MM_HOST_CHUNK overrides) and pipelined over three streams -- H2D of chunk
+ *   mm_source_interpolate_host: HOST pointers; the points are cut into chunks (default 1 M points after a
+ *                             short ramp of smaller ones, MM_HOST_CHUNK / MM_HOST_RAMP=0 override) and pipelined over three streams -- H2D of chunk
  *                             i+1, K1-K3 of chunk i, D2H of chunk i-1 -- so both PCIe directions and the SMs
  *                             work concurrently.  Any N (chunks are < 2^31 points each).  values/elem/xi:
  *                             any may be NULL (not all).  Returns after the last byte has arrived.

@@ -80,7 +80,7 @@ cudaError_t sync_allocations(mm_source *s)
 
 int64_t host_chunk_points(int64_t N)
 {
-    int64_t c = (int64_t)1 << 21;  // 2 M points: 48 MB in, 80 MB out (F = 5) per chunk
+    int64_t c = (int64_t)1 << 20;  // 1 M points: 24 MB in, 40 MB out (F = 5) per chunk (S2: 20.0 ms; 2 M: 20.4, 4 M: 20.9)
     if (const char *e = getenv("MM_HOST_CHUNK")) {
         long long v = atoll(e);
         if (v > 0) c = v;
@@ -336,7 +336,21 @@ extern "C" int mm_source_interpolate_host(mm_source_t *s, int64_t N, const doubl
 
     const int d = s->dim, F = s->F;
     const int64_t C = host_chunk_points(N);  // any N: each chunk is one mm_interpolate of <= C < 2^31 points
-    const int64_t nchunks = (N + C - 1) / C;
+    // chunk schedule: the d2h stream is the bottleneck of the pipeline (F values out per point against d coordinates
+    // in) and idles until the first chunk is through h2d + K1-K3, so the first chunks are small (C/8, C/4, C/2) and
+    // the copy back starts after ~0.4 ms instead of ~1.7 ms
+    std::vector<int64_t> chunk_at;
+    {
+        const char *e = getenv("MM_HOST_RAMP");
+        const bool ramp = !(e && atoi(e) == 0);
+        int64_t n = ramp ? std::min<int64_t>(C, std::max<int64_t>(C / 8, 65536)) : C;
+        for (int64_t at = 0; at < N; at += n, n = std::min<int64_t>(C, n * 2)) {
+            chunk_at.push_back(at);
+            if (at + n >= N) break;
+        }
+        chunk_at.push_back(N);
+    }
+    const int64_t nchunks = (int64_t)chunk_at.size() - 1;
     const size_t ws_bytes = mm_interpolate_workspace_bytes(s->index, d, C, k);
     MM_CUDA(ensure(s, s->ws, ws_bytes));
     MM_CUDA(ensure(s, s->nf, sizeof(int64_t) * (size_t)nchunks));
@@ -352,7 +366,7 @@ extern "C" int mm_source_interpolate_host(mm_source_t *s, int64_t N, const doubl
 
     for (int64_t c = 0; c < nchunks; ++c) {
         const int b = (int)(c & 1);
-        const int64_t at = c * C, n = std::min<int64_t>(C, N - at);
+        const int64_t at = chunk_at[c], n = chunk_at[c + 1] - at;
         // h2d: the points buffer is free once the kernels of chunk c-2 are done
         if (c >= 2) MM_CUDA(cudaStreamWaitEvent(s->h2d, s->ev_comp[b], 0));
         MM_CUDA(cudaMemcpyAsync(s->pts[b].p, pts + at * d, sizeof(double) * n * d, cudaMemcpyHostToDevice, s->h2d));

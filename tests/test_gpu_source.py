@@ -64,6 +64,32 @@ def test_resident_source_host_pipeline_matches_oracle(cuda, oracle, order, form,
     src.close()
 
 
+def test_host_pipeline_ramped_chunks_match_device_path(cuda, monkeypatch):
+    """Default chunk schedule (small first chunks: 65 536, 131 072, ... points) on 300 k points == one device-side
+    mm_interpolate over all of them, bit for bit, values and locations; and == the un-ramped schedule."""
+    import torch
+    from multimesh_b200 import ops
+
+    monkeypatch.delenv("MM_HOST_CHUNK", raising=False)
+    monkeypatch.delenv("MM_HOST_RAMP", raising=False)
+    rng = np.random.default_rng(77)
+    nodes, fields, pts = _case(2, 12, rng, 300_000, lo=-0.02, hi=1.02)
+    src = ops.ResidentSource(nodes, fields, form="gll")
+    vals, elem, xi, nf = src.interpolate_host(pts, 20, ops.V1(), want_location=True)
+    monkeypatch.setenv("MM_HOST_RAMP", "0")
+    vals0, elem0, xi0, nf0 = src.interpolate_host(pts, 20, ops.V1(), want_location=True)
+    assert nf == nf0 and np.array_equal(vals, vals0) and np.array_equal(elem, elem0) and np.array_equal(xi, xi0)
+    tn, tf, tp = (torch.from_numpy(a).to(cuda) for a in (nodes, fields, pts))
+    cent, box = ops.element_geometry(tn)
+    E, P, _ = nodes.shape
+    index = ops.GridIndex(tn.view(E * P, 3)).prepare_sites()
+    d_vals, d_elem, d_xi, _, d_nf = ops.interpolate(index, P, tn, cent, box, tf, tp, 20, ops.V1(),
+                                                    presolve=ops.element_presolve(tn))
+    assert nf == int(d_nf.item())
+    assert np.array_equal(vals, d_vals.cpu().numpy()) and np.array_equal(elem, d_elem.cpu().numpy())
+    assert np.array_equal(xi, d_xi.cpu().numpy())
+
+
 def test_one_shot_host_entry_point_variants(cuda, oracle, monkeypatch):
     """mm_interpolate_host (upload + build + chunked pipeline + release) for V1 and V2-snap, chunked."""
     from multimesh_b200 import _lib, ops
