@@ -484,15 +484,18 @@ def measure_pipeline(lib, ops, step, steps, warmup, world, dev, sampler=None):
     return total_ms / steps, stages, res
 
 
-def launches_per_step(N, rerun):
-    """Kernels of ONE mm_interpolate call: query sort (rank, 3 scan kernels, place), first-pass k-NN, locate,
-    gather; plus 4 kernels per re-run round (gather points, full k-NN, locate, scatter) -- the host enqueues
-    ceil(N / max(2^20, N/4)) rounds because the number of unresolved points stays on the device."""
-    rounds = 0
-    if rerun:
-        chunk = max(1 << 20, (N + 3) // 4)
-        rounds = (N + chunk - 1) // chunk
-    return 8 + 4 * rounds
+def launches_per_step(N, rerun, gll_form=True):
+    """Kernels of ONE mm_interpolate call (profiles/r2_S2_fused_step_launches.txt): query sort (rank, 3 scan kernels,
+    place) 5, first-pass k-NN 1, [centroid form: grouping of the points by first candidate -- rank, 3 scan kernels,
+    place -- 5], locate 1, 4 per re-run round (gather points, full k-NN, locate, scatter: the host enqueues
+    ceil(N / max(2^20, N/4)) rounds because the number of unresolved points stays on the device), K3's grouping by
+    element (rank, 3 scan kernels, place) 5, gather 1."""
+    return 13 + (0 if gll_form else 5) + 4 * (rerun_rounds(N) if rerun else 0)
+
+
+def rerun_rounds(N):
+    chunk = max(1 << 20, (N + 3) // 4)
+    return (N + chunk - 1) // chunk
 
 
 def kernel_report(N, order, F, k, form, stages, peak, traffic_db):
@@ -663,7 +666,7 @@ def run_ours(args, w):
                 "roofline": {"bound": "hbm", "kernel": dom, "achieved": kernels[dom]["achieved_gbs"], "peak": peak,
                              "unit": "GB/s", "frac": kernels[dom]["frac"], "traffic": None, "peak_source": peak_src},
                 "kernels": kernels, "cpu_baseline": None, "e2e": None, "north_star": ns,
-                "gpu_launches": launches_per_step(N, True) * args.steps, "clocks": clocks, "nfailed": nfailed,
+                "gpu_launches": launches_per_step(N, True, gll_form) * args.steps, "clocks": clocks, "nfailed": nfailed,
                 "status_histogram": st, "parity_check": ns["parity_check"],
             }
             print(json.dumps(line), flush=True)
@@ -947,7 +950,7 @@ def run_ours(args, w):
                                           "geometry + index + site table inside every step"}},
         "gll_2_gll_flow": flow,
         "north_star": north_star, "other_configs": other_configs,
-        "gpu_launches": launches_per_step(N, True) * args.steps, "clocks": clocks, "index_build_ms": build_ms,
+        "gpu_launches": launches_per_step(N, True, gll_form) * args.steps, "clocks": clocks, "index_build_ms": build_ms,
         "nfailed": nfailed, "status_histogram": st, "checksum": checksum, "e2e_checksum": e2e_checksum,
     }
     print(json.dumps(line), flush=True)

@@ -93,7 +93,7 @@ def _events():
 
 def run_shell(args, w, lib, ops, world, rank, dev):
     import torch
-    from bench import ClockSampler, full_affinity, hbm_peak, measure_pipeline, workload_name
+    from bench import ClockSampler, full_affinity, hbm_peak, launches_per_step, measure_pipeline, workload_name
     from multimesh_b200 import _lib
 
     order, k = w["order"], w["k"]
@@ -224,13 +224,14 @@ def run_shell(args, w, lib, ops, world, rank, dev):
         "roofline": {"bound": "hbm", "peak": peak, "peak_source": peak_src, "unit": "GB/s",
                      "note": "per-layer kernel times in variants[*].per_layer; K3 algorithmic bytes 5 068 B/point"},
         "cpu_baseline": None, "e2e": None, "clocks": v1["clocks"],
-        "gpu_launches": None,
+        # V1 variant: one mm_interpolate per layer and step, centroid form
+        "gpu_launches": int(sum(launches_per_step(int(L["pts"].shape[0]), True, False) for L in layers) * args.steps),
     }
 
 
 def run_exodus(args, w, lib, ops, world, rank, dev):
     import torch
-    from bench import ClockSampler, full_affinity, hbm_peak, workload_name
+    from bench import ClockSampler, full_affinity, hbm_peak, launches_per_step, rerun_rounds, workload_name
     from multimesh_b200 import meshgen
 
     order, k = w["order"], w["k"]
@@ -368,7 +369,10 @@ def run_exodus(args, w, lib, ops, world, rank, dev):
                            "is the trilinear interpolation error of the smooth fields on the 128^3 HEX8 mesh",
         "parity_check": parity,
         "roofline": {"bound": "hbm", "peak": peak, "peak_source": peak_src, "unit": "GB/s"},
-        "cpu_baseline": None, "e2e": None, "clocks": clocks, "gpu_launches": None,
+        "cpu_baseline": None, "e2e": None, "clocks": clocks,
+        # exodus_2_gll: query sort 5, tile first pass 1, prefix search 1, 3 per re-run round, nodal gather 1;
+        # gll_2_exodus: one mm_interpolate, centroid form
+        "gpu_launches": int((8 + 3 * rerun_rounds(N1) + launches_per_step(N2, True, False)) * args.steps),
     }
 
 
@@ -378,7 +382,7 @@ def run_quads(args, w, lib, ops, world, rank, dev):
     VP, VS, RHO, targets = the GLL points of a non-nested 200 x 200 mesh, GLL-point k-NN form, V1 location.  The whole
     target set is also run through the CPU oracle (parity of every point) and timed there (`cpu_baseline`)."""
     import torch
-    from bench import ClockSampler, full_affinity, hbm_peak, measure_pipeline, workload_name
+    from bench import ClockSampler, full_affinity, hbm_peak, launches_per_step, measure_pipeline, workload_name
     from multimesh_b200 import meshgen
 
     order, k = w["order"], w["k"]
@@ -454,7 +458,7 @@ def run_quads(args, w, lib, ops, world, rank, dev):
         "other_stages": {"query_sort_ms": round(float(stages[0]), 4), "rerun_unresolved_ms": round(float(stages[3]), 4)},
         "parity_check": parity, "cpu_baseline": cpu, "e2e": None, "clocks": clocks, "geometry_index_build_s": build_s,
         "nfailed": int(nfail.item()), "status_histogram": torch.bincount(status.to(torch.int64), minlength=10).cpu().tolist(),
-        "gpu_launches": None,
+        "gpu_launches": int(launches_per_step(N, True, True) * args.steps),
     }
 
 
