@@ -10,12 +10,21 @@ sys.path.insert(0, root)
 import numpy as np  # noqa: E402
 import torch  # noqa: E402
 
+import torch.distributed as dist  # noqa: E402
+
 import bench  # noqa: E402  (workload generators only)
 from multimesh_b200 import _lib, ops  # noqa: E402
 
+# under torchrun: one rank per GPU, all ranks copy at the same time (the host side is shared)
+world, rank, local = (int(os.environ.get(k, d)) for k, d in (("WORLD_SIZE", "1"), ("RANK", "0"), ("LOCAL_RANK", "0")))
+torch.cuda.set_device(local)
+bench.bind_to_gpu_numa(local)
+if world > 1:
+    dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+
 w = dict(bench.WORKLOADS["S2"], name="S2")
 nodes_h, fields_h = bench.make_source(w)
-pts_h = bench.make_targets(w, 0)
+pts_h = bench.make_targets(w, rank)
 E, P = nodes_h.shape[0], nodes_h.shape[1]
 N, F = pts_h.shape[0], fields_h.shape[1]
 lib = _lib.load_lib()
@@ -28,8 +37,8 @@ src = C.c_void_p()
 _lib.check(lib.mm_source_create_host(C.byref(src), 2, 3, E, C.c_void_p(nodes_p.data_ptr()), F,
                                      C.c_void_p(fields_p.data_ptr()), 1), "create")
 sums = set()
-for ramp, chunk in (("0", None), ("1", None), ("0", None), ("1", None), ("1", str(1 << 22)), ("0", str(1 << 22)),
-                    ("1", str(1 << 20))):
+for ramp, chunk in (("0", str(1 << 21)), ("1", None), ("0", str(1 << 21)), ("1", None), ("1", str(1 << 21)),
+                    ("0", str(1 << 20)), ("1", str(1 << 22))):
     os.environ["MM_HOST_RAMP"] = ramp
     if chunk:
         os.environ["MM_HOST_CHUNK"] = chunk
@@ -38,12 +47,16 @@ for ramp, chunk in (("0", None), ("1", None), ("0", None), ("1", None), ("1", st
     ts = []
     for i in range(7):
         torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
         t = time.perf_counter()
         _lib.check(lib.mm_source_interpolate_host(src, N, C.c_void_p(pts_p.data_ptr()), 20, C.byref(prm),
                                                   C.c_void_p(vals_p.data_ptr()), None, None, C.byref(nf)), "run")
         torch.cuda.synchronize()
         ts.append((time.perf_counter() - t) * 1e3)
     sums.add(float(vals_p.sum()))
-    print(f"ramp={ramp} chunk={chunk or 'default'}: min {min(ts[2:]):.2f} median {np.median(ts[2:]):.2f} ms", flush=True)
+    print(f"rank {rank}/{world} ramp={ramp} chunk={chunk or 'default'}: min {min(ts[2:]):.2f} median {np.median(ts[2:]):.2f} ms", flush=True)
 print("checksums identical:", len(sums) == 1, sums)
 lib.mm_source_destroy(src)
+if world > 1:
+    dist.destroy_process_group()
