@@ -210,3 +210,15 @@ def test_bench_reference_arm_contract():
     assert set(d["config"]) == {"workload", "points_per_gpu", "source_elements", "fields", "l2"}
     assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1
     assert d["e2e"]["value"] == d["value"] and d["e2e"]["h2d_bytes_per_step"] == 0
+
+
+def test_bench_launch_count_matches_the_committed_launch_list():
+    """bench.py's `gpu_launches` claim per step == the kernels of one fused step in the committed ncu launch list."""
+    import bench
+
+    path = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "profiles",
+                        "r2_S2_fused_step_launches.txt")
+    lines = [ln for ln in open(path).read().splitlines() if ln.strip().endswith(" us")]
+    kernels = [ln for ln in lines if not ln.startswith("fused step total")]
+    assert len(kernels) == bench.launches_per_step(23_887_872, True, True) == 29
+    assert bench.launches_per_step(100_000_000, True, False) == 34  # centroid form: + grouping by first candidate
